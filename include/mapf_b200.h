@@ -1,0 +1,223 @@
+/* mapf_b200.h -- C ABI of the B200-native MAPF-GNN batched decentralized-policy step.
+ *
+ * One shared library (libmapf_b200.so, hand-written sm_100a CUDA) sits under the Python
+ * facade classes (GraphEnv / BatchedGraphEnv, GCNLayer, MessagePassingLayer, Network) and the
+ * `mapf::` torch custom ops.  Every entry point
+ *   - takes one plain-C argument struct of DEVICE pointers + int sizes and a cudaStream_t,
+ *   - is asynchronous on that stream, never allocates, never synchronises, never throws,
+ *   - keeps no global mutable state (re-entrant; thread-safe per stream),
+ *   - returns MAPF_OK (0) or a negative mapf_status code; mapf_last_error_string(code)
+ *     gives the message.  All buffers are caller-owned.
+ *
+ * The reference (RetamalVictor/MAPF-GNN) is pure Python and has no FFI seam; each entry point
+ * cites the reference Python interface it replaces (file:line under the reference root).
+ *
+ * Layout conventions (all row-major, contiguous):
+ *   pos / goal     int32 [E,N,2]   (x, y) per agent                     env_graph_gridv1.py:75-90
+ *   cells          uint8 [E,cell_stride]  board[y*H+x]; low 2 bits = board value 0 empty /
+ *                  1 agent / 2 obstacle (env_graph_gridv1.py:68-70,273-275); bit 7 = cell is in
+ *                  the (immutable) obstacle set used by check_collision_obstacle (:303-313).
+ *                  cell_stride >= H*H and a multiple of 16.
+ *   fov            f32 [E,N,2,5,5]                                       env_graph_gridv1.py:248-265
+ *   adj            f32 [E,N,N]    0/1, row-pruned closest-4              env_graph_gridv1.py:117-136,174-181
+ *   states         f32 [B,N,2,5,5] = fov; gso f32 [B,N,N] = adj (+I from the data loader)
+ *   node features  f32 [B*N, F] "agent-major" rows (row = b*N+n) inside the fused net; the
+ *                  standalone layer entry point also accepts the reference's [B,F,N] via strides.
+ */
+#ifndef MAPF_B200_H
+#define MAPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mapf_stream_t; /* cudaStream_t */
+
+typedef enum {
+  MAPF_OK = 0,
+  MAPF_ERR_NULL = -1,        /* a required pointer is NULL */
+  MAPF_ERR_SHAPE = -2,       /* a size is non-positive or inconsistent */
+  MAPF_ERR_UNSUPPORTED = -3, /* size outside what the kernels are built for */
+  MAPF_ERR_ALIGN = -4,       /* pointer / stride alignment requirement violated */
+  MAPF_ERR_CUDA = -5         /* the CUDA runtime reported a launch error */
+} mapf_status;
+
+const char* mapf_last_error_string(int code);
+/* library / build identification: "mapf_b200 <version> sm_100a" */
+const char* mapf_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Environment (reference: grid/env_graph_gridv1.py GraphEnv)
+ * ---------------------------------------------------------------------------------------- */
+
+/* GraphEnv.reset (env_graph_gridv1.py:65-95) for E episodes with explicit starts:
+ * cells <- obstacles only (value 2 | obstacle-set flag), pos <- starts, time <- 0, done <- 0.
+ * obstacles may be NULL when num_obstacles == 0.  Cells outside the board are ignored. */
+typedef struct {
+  int32_t episodes, agents, board, num_obstacles;
+  int32_t cell_stride;
+  const int32_t* starts;    /* [E,N,2] */
+  const int32_t* obstacles; /* [E,M,2] */
+  int32_t* pos;             /* [E,N,2] out */
+  uint8_t* cells;           /* [E,cell_stride] out */
+  int32_t* time;            /* [E] out */
+  uint8_t* done;            /* [E] out */
+} mapf_env_reset_args;
+int mapf_env_reset(const mapf_env_reset_args* a, mapf_stream_t stream);
+
+/* GraphEnv.step (env_graph_gridv1.py:183-198) = _updatePositions (:200-213) -> _computeDistance +
+ * _computeClosest (:117-136,174-181) -> preprocessObs (:248-265) -> time += 1 -> checkAllInGoal
+ * (:156-159), for E episodes in one fused kernel.  do_move == 0 gives getObservations() of the
+ * current state without moving (the observation reset() returns; actions may then be NULL).
+ * Episodes whose done flag is already set are frozen (callers of the reference `break`,
+ * evaluate.py:251): no move, no time increment, observation recomputed.
+ * d2_limit: smallest integer d2 with sqrt((double)d2) >= sensing_range. */
+typedef struct {
+  int32_t episodes, agents, board;
+  int32_t cell_stride;
+  int32_t d2_limit;
+  int32_t do_move;
+  int32_t* pos;           /* [E,N,2] in/out */
+  const int32_t* goal;    /* [E,N,2] */
+  const int32_t* actions; /* [E,N] 0 idle,1 +x,2 +y,3 -x,4 -y (:42-48) */
+  uint8_t* cells;         /* [E,cell_stride] in/out */
+  int32_t* time;          /* [E] in/out */
+  uint8_t* done;          /* [E] in/out */
+  float* fov;             /* [E,N,2,5,5] out (may be NULL) */
+  float* adj;             /* [E,N,N] out (may be NULL) */
+} mapf_env_step_args;
+int mapf_env_step(const mapf_env_step_args* a, mapf_stream_t stream);
+
+/* GraphEnv.computeMetrics (env_graph_gridv1.py:138-154,168-172): per episode
+ * success = (#agents on own goal)/N, flow_time = time if all on goal else N*max_time. */
+typedef struct {
+  int32_t episodes, agents, max_time;
+  const int32_t* pos;
+  const int32_t* goal;
+  const int32_t* time;
+  float* success;     /* [E] out */
+  int32_t* flow_time; /* [E] out */
+} mapf_env_metrics_args;
+int mapf_env_metrics(const mapf_env_metrics_args* a, mapf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Policy network (reference: models/framework_gnn.py, framework_gnn_message.py,
+ * framework_baseline.py, models/networks/gnn.py)
+ * ---------------------------------------------------------------------------------------- */
+
+#define MAPF_MAX_CONV 4
+
+/* Raw parameters in the reference state_dict layout.  conv_w[l] is
+ * convLayers.{3l}.weight [Cout,Cin,3,3]; bn_* are convLayers.{3l+1}.*; fc_* is compressMLP.0;
+ * gf_w is GFL.0.W [F,K,G]; gf_w2 is GFL.0.W2 [F,G] (message variant) or NULL; act_* is
+ * actionMLP.0 [A, G or F].  gf_w == NULL selects the no-communication baseline. */
+typedef struct {
+  int32_t num_conv;                   /* 1..MAPF_MAX_CONV */
+  int32_t channels[MAPF_MAX_CONV + 1];/* channels[0] = 2 input planes */
+  int32_t fc_in, fc_out;              /* 25*channels[num_conv], F */
+  int32_t taps, node_dim;             /* K, G (0 when baseline) */
+  int32_t num_actions;                /* 5 */
+  const float* conv_w[MAPF_MAX_CONV];
+  const float* conv_b[MAPF_MAX_CONV];
+  const float* bn_gamma[MAPF_MAX_CONV];
+  const float* bn_beta[MAPF_MAX_CONV];
+  const float* bn_mean[MAPF_MAX_CONV];
+  const float* bn_var[MAPF_MAX_CONV];
+  const float* fc_w;  /* [F, fc_in] */
+  const float* fc_b;  /* [F] */
+  const float* gf_w;  /* [F,K,G] or NULL */
+  const float* gf_w2; /* [F,G] or NULL */
+  const float* act_w; /* [A, G or F] */
+  const float* act_b; /* [A] */
+} mapf_net_params;
+
+/* Number of floats mapf_pack_weights writes for these dimensions (pointers are ignored). */
+int64_t mapf_packed_weights_size(const mapf_net_params* p);
+
+/* Inference-time weight preparation (one tiny kernel): folds eval-mode BatchNorm
+ * (framework_gnn.py:70, eps 1e-5) into the conv weights, regroups them per 4-output-channel
+ * group, transposes the encoder FC, and materialises W_eff^T = GFL.0.W.reshape(G,K*F)^T with the
+ * W2.reshape(G,F)^T rows appended (gnn.py:114-116,222 raw reinterpretations). */
+int mapf_pack_weights(const mapf_net_params* p, float* packed, mapf_stream_t stream);
+
+/* A5 eval: encoder of Network.forward (framework_gnn.py:156-166): per agent image
+ * 3x{conv3x3+BN+ReLU} -> flatten (C,H,W) -> Linear+ReLU.  x row r = b*N+n. */
+typedef struct {
+  int64_t rows;          /* B*N agent images */
+  const float* states;   /* [rows,2,5,5] */
+  const float* packed;   /* from mapf_pack_weights */
+  float* x;              /* [rows,F] out */
+} mapf_encoder_fwd_args;
+int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream);
+
+/* A6/A7 (+A8): GCNLayer.forward (gnn.py:72-126) / MessagePassingLayer.forward (gnn.py:178-235),
+ * optionally fused with the ReLU + actionMLP + argmax tail of Network.forward
+ * (framework_gnn.py:171-181; np.argmax first-max tie-break evaluate.py:238).
+ *   S = D^-1/2 (A [+ I]) D^-1/2 (row-sum degrees, inf -> 0); x_k = x_{k-1} S;
+ *   Y[n,g] = sum_{k,f} x_k[f,n] * W.reshape(G,K*F)[g, k*F+f]  (+ skip: X.reshape(B,N,F) W2.reshape(G,F)^T).
+ * Element (b,n,f) of x is at x[b*x_sb + n*x_sn + f*x_sf] (agent-major: N*F, F, 1; reference
+ * [B,F,N]: F*N, 1, N); likewise y with (y_sb, y_sn, y_sg).  wt is the packed
+ * [(K(+1))*F, G] matrix (mapf_pack_weights / mapf_pack_graph_weights). */
+typedef struct {
+  int32_t batch, agents, in_dim, out_dim, taps;
+  int32_t add_self_loop;  /* 1: GCNLayer (gnn.py:87); 0: MessagePassingLayer */
+  int32_t has_skip;       /* 1: W2 rows appended to wt (message variant) */
+  int32_t relu;           /* apply ReLU to Y before storing / before the head */
+  int32_t num_actions;    /* >0: fuse the action head */
+  const float* x; int64_t x_sb, x_sn, x_sf;
+  const float* gso;       /* [B,N,N] */
+  const float* wt;        /* [(K+has_skip)*F, G] */
+  float* y; int64_t y_sb, y_sn, y_sg; /* may be NULL when the head is fused */
+  float* z;               /* optional [B*N, (K+has_skip)*F] saved filter taps (training) or NULL */
+  const float* act_w;     /* [A,G] */
+  const float* act_b;     /* [A] */
+  float* logits;          /* [B*N, A] out */
+  int32_t* actions;       /* [B*N] out, may be NULL */
+} mapf_graph_filter_fwd_args;
+int mapf_graph_filter_fwd(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);
+
+/* Packs a standalone layer's W [F,K,G] (+ W2 [F,G]) into wt [(K(+1))*F, G]. */
+int mapf_pack_graph_weights(const float* w, const float* w2, int32_t in_dim, int32_t taps, int32_t out_dim,
+                            float* wt, mapf_stream_t stream);
+
+/* A9 head of the baseline: Linear(F->A) on the encoder output + argmax
+ * (framework_baseline.py:96,126). */
+typedef struct {
+  int64_t rows; int32_t in_dim, num_actions;
+  const float* x; const float* act_w; const float* act_b;
+  float* logits; int32_t* actions;
+} mapf_head_fwd_args;
+int mapf_head_fwd(const mapf_head_fwd_args* a, mapf_stream_t stream);
+
+/* Whole eval-mode Network.forward(states, gso) -> logits (+ greedy actions):
+ * encoder -> graph filter + ReLU -> head, or encoder -> head for the baseline.
+ * workspace_x: [B*N, F] floats. */
+typedef struct {
+  int32_t batch, agents;
+  int32_t message;        /* 1: framework_gnn_message.Network, 0: framework_gnn.Network */
+  const float* states;    /* [B,N,2,5,5] */
+  const float* gso;       /* [B,N,N] (ignored for the baseline) */
+  const float* packed;
+  float* workspace_x;
+  float* logits;          /* [B,N,A] */
+  int32_t* actions;       /* [B,N] or NULL */
+} mapf_policy_fwd_args;
+int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_args* a, mapf_stream_t stream);
+
+/* `steps` iterations of the rollout protocol of evaluate.py:223-241 for E resident episodes,
+ * entirely on the device: policy(fov, adj) -> argmax -> env step -> (fov, adj).  fov / adj must
+ * hold the current observation on entry (mapf_env_step with do_move = 0) and hold the last one on
+ * exit.  No host round trip, no collective. */
+typedef struct {
+  mapf_env_step_args env;     /* env.actions must point at `actions` below */
+  mapf_policy_fwd_args policy;/* policy.states == env.fov, policy.gso == env.adj, policy.actions == env.actions */
+  int32_t steps;
+} mapf_rollout_args;
+int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a, mapf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPF_B200_H */

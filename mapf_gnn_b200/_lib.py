@@ -1,0 +1,138 @@
+"""ctypes binding of ``include/mapf_b200.h`` -- the only way Python reaches the kernels.
+
+The structures below mirror the C header field for field.  ``check(rc)`` turns a non-zero status
+into ``RuntimeError`` with the library's own message.  There is deliberately no fallback: if the
+shared library cannot be loaded the import fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+MAX_CONV = 4
+c_f32p = C.c_void_p      # device pointers travel as integers
+c_i32p = C.c_void_p
+c_u8p = C.c_void_p
+
+
+class EnvResetArgs(C.Structure):
+    _fields_ = [("episodes", C.c_int32), ("agents", C.c_int32), ("board", C.c_int32), ("num_obstacles", C.c_int32),
+                ("cell_stride", C.c_int32),
+                ("starts", c_i32p), ("obstacles", c_i32p), ("pos", c_i32p), ("cells", c_u8p),
+                ("time", c_i32p), ("done", c_u8p)]
+
+
+class EnvStepArgs(C.Structure):
+    _fields_ = [("episodes", C.c_int32), ("agents", C.c_int32), ("board", C.c_int32), ("cell_stride", C.c_int32),
+                ("d2_limit", C.c_int32), ("do_move", C.c_int32),
+                ("pos", c_i32p), ("goal", c_i32p), ("actions", c_i32p), ("cells", c_u8p),
+                ("time", c_i32p), ("done", c_u8p), ("fov", c_f32p), ("adj", c_f32p)]
+
+
+class EnvMetricsArgs(C.Structure):
+    _fields_ = [("episodes", C.c_int32), ("agents", C.c_int32), ("max_time", C.c_int32),
+                ("pos", c_i32p), ("goal", c_i32p), ("time", c_i32p), ("success", c_f32p), ("flow_time", c_i32p)]
+
+
+class NetParams(C.Structure):
+    _fields_ = [("num_conv", C.c_int32), ("channels", C.c_int32 * (MAX_CONV + 1)),
+                ("fc_in", C.c_int32), ("fc_out", C.c_int32), ("taps", C.c_int32), ("node_dim", C.c_int32),
+                ("num_actions", C.c_int32),
+                ("conv_w", c_f32p * MAX_CONV), ("conv_b", c_f32p * MAX_CONV),
+                ("bn_gamma", c_f32p * MAX_CONV), ("bn_beta", c_f32p * MAX_CONV),
+                ("bn_mean", c_f32p * MAX_CONV), ("bn_var", c_f32p * MAX_CONV),
+                ("fc_w", c_f32p), ("fc_b", c_f32p), ("gf_w", c_f32p), ("gf_w2", c_f32p),
+                ("act_w", c_f32p), ("act_b", c_f32p)]
+
+
+class EncoderFwdArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("states", c_f32p), ("packed", c_f32p), ("x", c_f32p)]
+
+
+class GraphFilterFwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
+                ("taps", C.c_int32), ("add_self_loop", C.c_int32), ("has_skip", C.c_int32), ("relu", C.c_int32),
+                ("num_actions", C.c_int32),
+                ("x", c_f32p), ("x_sb", C.c_int64), ("x_sn", C.c_int64), ("x_sf", C.c_int64),
+                ("gso", c_f32p), ("wt", c_f32p),
+                ("y", c_f32p), ("y_sb", C.c_int64), ("y_sn", C.c_int64), ("y_sg", C.c_int64),
+                ("z", c_f32p), ("act_w", c_f32p), ("act_b", c_f32p), ("logits", c_f32p), ("actions", c_i32p)]
+
+
+class HeadFwdArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("in_dim", C.c_int32), ("num_actions", C.c_int32),
+                ("x", c_f32p), ("act_w", c_f32p), ("act_b", c_f32p), ("logits", c_f32p), ("actions", c_i32p)]
+
+
+class PolicyFwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32),
+                ("states", c_f32p), ("gso", c_f32p), ("packed", c_f32p), ("workspace_x", c_f32p),
+                ("logits", c_f32p), ("actions", c_i32p)]
+
+
+class RolloutArgs(C.Structure):
+    _fields_ = [("env", EnvStepArgs), ("policy", PolicyFwdArgs), ("steps", C.c_int32)]
+
+
+_SIGNATURES = {
+    "mapf_last_error_string": (C.c_char_p, [C.c_int]),
+    "mapf_version": (C.c_char_p, []),
+    "mapf_env_reset": (C.c_int, [C.POINTER(EnvResetArgs), C.c_void_p]),
+    "mapf_env_step": (C.c_int, [C.POINTER(EnvStepArgs), C.c_void_p]),
+    "mapf_env_metrics": (C.c_int, [C.POINTER(EnvMetricsArgs), C.c_void_p]),
+    "mapf_packed_weights_size": (C.c_int64, [C.POINTER(NetParams)]),
+    "mapf_pack_weights": (C.c_int, [C.POINTER(NetParams), C.c_void_p, C.c_void_p]),
+    "mapf_pack_graph_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p]),
+    "mapf_encoder_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(EncoderFwdArgs), C.c_void_p]),
+    "mapf_graph_filter_fwd": (C.c_int, [C.POINTER(GraphFilterFwdArgs), C.c_void_p]),
+    "mapf_head_fwd": (C.c_int, [C.POINTER(HeadFwdArgs), C.c_void_p]),
+    "mapf_policy_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(PolicyFwdArgs), C.c_void_p]),
+    "mapf_rollout": (C.c_int, [C.POINTER(NetParams), C.POINTER(RolloutArgs), C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every entry point ``include/mapf_b200.h`` declares."""
+    return sorted(_SIGNATURES)
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources changed) libmapf_b200.so.  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build_library()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m mapf_gnn_b200._build`")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().mapf_last_error_string(rc).decode()
+        raise RuntimeError(f"mapf_b200 {what}: {msg} (status {rc})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None) as an integer for a ctypes c_void_p field."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

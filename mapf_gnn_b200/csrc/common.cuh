@@ -1,0 +1,66 @@
+// Shared helpers for the sm_100a kernels behind include/mapf_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mapf_b200.h"
+
+#define MAPF_REQUIRE(cond, code) \
+  do {                           \
+    if (!(cond)) return (code);  \
+  } while (0)
+
+static inline int mapf_launch_status() {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return MAPF_ERR_CUDA;
+  }
+  return MAPF_OK;
+}
+
+static inline bool mapf_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+constexpr int kFov = 5;          // FOV side, env_graph_gridv1.py:252 with pad = 3
+constexpr int kFovHalf = 2;
+constexpr int kFovCells = 25;
+constexpr int kFovFloats = 50;   // 2 channels x 5 x 5
+constexpr uint8_t kObstacleFlag = 0x80;
+constexpr uint8_t kBoardValueMask = 0x03;
+
+// Packed-weight layout shared by pack_weights and the consumers (offsets in floats).
+struct PackedLayout {
+  int64_t conv_w[MAPF_MAX_CONV];  // [Cout/4][Cin][9][4]
+  int64_t conv_b[MAPF_MAX_CONV];  // [Cout]
+  int64_t fc_wt;                  // [fc_in][F]   (transposed compressMLP.0.weight)
+  int64_t fc_b;                   // [F]
+  int64_t gf_wt;                  // [(K(+1))*F][G]
+  int64_t act_w;                  // [A][G or F]
+  int64_t act_b;                  // [A]
+  int64_t total;
+};
+
+static inline __host__ __device__ int64_t mapf_round4(int64_t v) { return (v + 3) & ~int64_t(3); }
+
+static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net_params& p) {
+  PackedLayout L;
+  int64_t off = 0;
+  for (int l = 0; l < MAPF_MAX_CONV; ++l) {
+    L.conv_w[l] = off;
+    if (l < p.num_conv) off += mapf_round4(int64_t(p.channels[l + 1]) * p.channels[l] * 9);
+    L.conv_b[l] = off;
+    if (l < p.num_conv) off += mapf_round4(p.channels[l + 1]);
+  }
+  L.fc_wt = off;
+  off += mapf_round4(int64_t(p.fc_in) * p.fc_out);
+  L.fc_b = off;
+  off += mapf_round4(p.fc_out);
+  L.gf_wt = off;
+  if (p.taps > 0) off += mapf_round4(int64_t(p.taps + 1) * p.fc_out * p.node_dim);  // room for the W2 rows
+  L.act_w = off;
+  off += mapf_round4(int64_t(p.num_actions) * (p.taps > 0 ? p.node_dim : p.fc_out));
+  L.act_b = off;
+  off += mapf_round4(p.num_actions);
+  L.total = off;
+  return L;
+}

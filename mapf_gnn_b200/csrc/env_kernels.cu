@@ -1,0 +1,257 @@
+// Batched grid environment: reset, fused move + adjacency + FOV step, metrics.
+// New B200-first design of the semantics of the reference's single-episode numpy GraphEnv
+// (grid/env_graph_gridv1.py; exact rules restated in SURVEY.md 8a A1-A4).
+//
+// Work decomposition: one CTA of 128 threads owns EPB = 128/LANES consecutive episodes, LANES =
+// next power of two >= N lanes per episode.  The episodes' board cells are staged into shared
+// memory with 128-bit coalesced loads, all integer logic (move, obstacle revert, clamp, single-pass
+// collision revert, closest-4 threshold) runs on shared memory, and the two observation tensors of
+// the CTA's episodes -- contiguous ranges of fov[E,N,2,5,5] and adj[E,N,N] -- are written back
+// cooperatively with 128-bit coalesced stores.  HBM traffic per agent-step is the algorithmic
+// minimum: pos + goal + H*H/N board bytes in, 200 B FOV + 4N B adjacency + the 2 changed cells out.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEnvThreads = 128;
+
+__global__ void env_reset_kernel(mapf_env_reset_args a) {
+  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t n_agents = int64_t(a.episodes) * a.agents;
+  const int64_t n_obst = int64_t(a.episodes) * a.num_obstacles;
+  if (t < n_agents) {
+    reinterpret_cast<int2*>(a.pos)[t] = reinterpret_cast<const int2*>(a.starts)[t];
+  }
+  if (t < n_obst) {
+    const int e = int(t / a.num_obstacles);
+    const int2 o = reinterpret_cast<const int2*>(a.obstacles)[t];
+    if (o.x >= 0 && o.x < a.board && o.y >= 0 && o.y < a.board)
+      a.cells[int64_t(e) * a.cell_stride + o.y * a.board + o.x] = uint8_t(2) | kObstacleFlag;
+  }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_args a) {
+  constexpr int EPB = kEnvThreads / LANES;
+  extern __shared__ __align__(16) uint8_t s_cells[];
+  __shared__ int s_x[kEnvThreads], s_y[kEnvThreads], s_thr[kEnvThreads];
+  __shared__ int8_t s_gr[kEnvThreads], s_gc[kEnvThreads];
+  __shared__ int s_notgoal[EPB];
+
+  const int tid = threadIdx.x;
+  const int el = tid / LANES, lane = tid % LANES;
+  const int e0 = blockIdx.x * EPB;
+  const int nep = min(EPB, a.episodes - e0);
+  const int e = e0 + el;
+  const int N = a.agents, H = a.board, stride = a.cell_stride;
+  const bool agent = (el < nep) && (lane < N);
+
+  {  // stage this CTA's boards (contiguous, 16-byte aligned by construction)
+    const uint4* src = reinterpret_cast<const uint4*>(a.cells + int64_t(e0) * stride);
+    uint4* dst = reinterpret_cast<uint4*>(s_cells);
+    const int nvec = nep * (stride >> 4);
+    for (int i = tid; i < nvec; i += kEnvThreads) dst[i] = src[i];  // plain load: this kernel writes cells later
+  }
+  if (tid < EPB) s_notgoal[tid] = 0;
+
+  int ox = 0, oy = 0, gx = 0, gy = 0;
+  bool moving = false;
+  if (agent) {
+    const int2 p = reinterpret_cast<const int2*>(a.pos)[int64_t(e) * N + lane];
+    const int2 g = __ldg(reinterpret_cast<const int2*>(a.goal) + int64_t(e) * N + lane);
+    ox = p.x; oy = p.y; gx = g.x; gy = g.y;
+    moving = a.do_move && !a.done[e];
+  }
+  __syncthreads();
+
+  uint8_t* cells = s_cells + el * stride;
+  int nx = ox, ny = oy;
+  if (moving) {
+    // A1: delta -> obstacle-set revert -> clamp   (env_graph_gridv1.py:202-211)
+    const int act = __ldg(a.actions + int64_t(e) * N + lane);
+    nx = ox + (act == 1) - (act == 3);
+    ny = oy + (act == 2) - (act == 4);
+    if (nx >= 0 && nx < H && ny >= 0 && ny < H && (cells[ny * H + nx] & kObstacleFlag)) { nx = ox; ny = oy; }
+    nx = min(max(nx, 0), H - 1);
+    ny = min(max(ny, 0), H - 1);
+  }
+  s_x[tid] = nx; s_y[tid] = ny;
+  __syncthreads();
+  const int base = el * LANES;
+  if (moving) {
+    // single-pass collision revert of every member of a shared cell (:282-301)
+    int cnt = 0;
+    for (int j = 0; j < N; ++j) cnt += (s_x[base + j] == nx) & (s_y[base + j] == ny);
+    if (cnt > 1) { nx = ox; ny = oy; }
+  }
+  __syncthreads();
+  s_x[tid] = nx; s_y[tid] = ny;
+  if (moving) cells[oy * H + ox] &= kObstacleFlag;  // updateBoard: old cells <- 0 (:273-275)
+  __syncthreads();
+  if (moving) cells[ny * H + nx] = (cells[ny * H + nx] & kObstacleFlag) | uint8_t(1);  // new cells <- 1
+  __syncthreads();
+  if (moving) {
+    uint8_t* gcells = a.cells + int64_t(e) * stride;
+    gcells[oy * H + ox] = cells[oy * H + ox];
+    gcells[ny * H + nx] = cells[ny * H + nx];
+    reinterpret_cast<int2*>(a.pos)[int64_t(e) * N + lane] = make_int2(nx, ny);
+  }
+
+  // A2: per-row closest-4 threshold on integer squared distances (:117-136,174-181)
+  int thr = -1;
+  if (agent) {
+    int m0 = INT_MAX, m1 = INT_MAX, m2 = INT_MAX, m3 = INT_MAX, cnt = 0, mx = -1;
+    for (int j = 0; j < N; ++j) {
+      const int dx = s_x[base + j] - nx, dy = s_y[base + j] - ny;
+      const int d2 = dx * dx + dy * dy;
+      if (d2 > 0 && d2 < a.d2_limit) {
+        ++cnt;
+        mx = max(mx, d2);
+        if (d2 < m3) {
+          m3 = d2;
+          if (m3 < m2) { const int t = m2; m2 = m3; m3 = t; }
+          if (m2 < m1) { const int t = m1; m1 = m2; m2 = t; }
+          if (m1 < m0) { const int t = m0; m0 = m1; m1 = t; }
+        }
+      }
+    }
+    thr = cnt >= 4 ? m3 : mx;
+    // A3 goal channel: single mark, projected onto the FOV border (:218-246)
+    const int dgx = min(max(gx - nx, -kFovHalf), kFovHalf), dgy = min(max(gy - ny, -kFovHalf), kFovHalf);
+    s_gr[tid] = int8_t(kFovHalf - dgy);
+    s_gc[tid] = int8_t(kFovHalf + dgx);
+    if (nx != gx || ny != gy) s_notgoal[el] = 1;
+  }
+  s_thr[tid] = thr;
+  __syncthreads();
+
+  if (a.adj != nullptr) {
+    const int nn = N * N, total = nep * nn;
+    float* out = a.adj + int64_t(e0) * nn;
+    for (int idx = tid; idx < total; idx += kEnvThreads) {
+      const int el2 = idx / nn, rem = idx - el2 * nn;
+      const int i = rem / N, j = rem - i * N;
+      const int b = el2 * LANES;
+      const int dx = s_x[b + i] - s_x[b + j], dy = s_y[b + i] - s_y[b + j];
+      const int d2 = dx * dx + dy * dy;
+      out[idx] = (d2 > 0 && d2 < a.d2_limit && d2 <= s_thr[b + i]) ? 1.0f : 0.0f;
+    }
+  }
+
+  if (a.fov != nullptr) {
+    // A3 channel 0: fov[r,c] = board[y+2-r, x-2+c], zero outside (:248-265)
+    auto fov_value = [&](int idx) -> float {
+      const int ag = idx / kFovFloats;
+      int k = idx - ag * kFovFloats;
+      const int el2 = ag / N, ln = ag - el2 * N;
+      const int t = el2 * LANES + ln;
+      if (k < kFovCells) {
+        const int r = k / kFov, c = k - r * kFov;
+        const int by = s_y[t] + kFovHalf - r, bx = s_x[t] - kFovHalf + c;
+        if (by < 0 || by >= H || bx < 0 || bx >= H) return 0.0f;
+        return float(s_cells[el2 * stride + by * H + bx] & kBoardValueMask);
+      }
+      k -= kFovCells;
+      const int r = k / kFov, c = k - r * kFov;
+      return (r == s_gr[t] && c == s_gc[t]) ? 3.0f : 0.0f;
+    };
+    const int total = nep * N * kFovFloats;
+    float* out = a.fov + int64_t(e0) * N * kFovFloats;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      const int nq = total >> 2;
+      for (int q = tid; q < nq; q += kEnvThreads) {
+        const int i4 = q << 2;
+        reinterpret_cast<float4*>(out)[q] =
+            make_float4(fov_value(i4), fov_value(i4 + 1), fov_value(i4 + 2), fov_value(i4 + 3));
+      }
+      for (int idx = (nq << 2) + tid; idx < total; idx += kEnvThreads) out[idx] = fov_value(idx);
+    } else {
+      for (int idx = tid; idx < total; idx += kEnvThreads) out[idx] = fov_value(idx);
+    }
+  }
+
+  if (a.do_move && tid < nep) {  // time += 1; done = checkAllInGoal() (:195-197)
+    const int ee = e0 + tid;
+    if (!a.done[ee]) {
+      a.time[ee] += 1;
+      a.done[ee] = s_notgoal[tid] ? 0 : 1;
+    }
+  }
+}
+
+__global__ void env_metrics_kernel(mapf_env_metrics_args a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.episodes) return;
+  int hit = 0;
+  for (int n = 0; n < a.agents; ++n) {
+    const int2 p = reinterpret_cast<const int2*>(a.pos)[int64_t(e) * a.agents + n];
+    const int2 g = reinterpret_cast<const int2*>(a.goal)[int64_t(e) * a.agents + n];
+    hit += (p.x == g.x) & (p.y == g.y);
+  }
+  a.success[e] = float(hit) / float(a.agents);
+  a.flow_time[e] = (hit == a.agents) ? a.time[e] : a.agents * a.max_time;
+}
+
+template <int LANES>
+int launch_env_step(const mapf_env_step_args& a, cudaStream_t s) {
+  constexpr int EPB = kEnvThreads / LANES;
+  const size_t smem = size_t(EPB) * a.cell_stride;
+  if (smem > 200 * 1024) return MAPF_ERR_UNSUPPORTED;
+  if (smem > 40 * 1024) {
+    if (cudaFuncSetAttribute(env_step_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) !=
+        cudaSuccess)
+      return MAPF_ERR_CUDA;
+  }
+  const int grid = (a.episodes + EPB - 1) / EPB;
+  env_step_kernel<LANES><<<grid, kEnvThreads, smem, s>>>(a);
+  return mapf_launch_status();
+}
+
+}  // namespace
+
+extern "C" int mapf_env_reset(const mapf_env_reset_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a != nullptr, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->starts && a->pos && a->cells && a->time && a->done, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->num_obstacles == 0 || a->obstacles, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->episodes > 0 && a->agents > 0 && a->board > 0 && a->num_obstacles >= 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(a->cell_stride >= a->board * a->board && (a->cell_stride & 15) == 0, MAPF_ERR_ALIGN);
+  MAPF_REQUIRE(mapf_aligned(a->cells, 16) && mapf_aligned(a->pos, 8) && mapf_aligned(a->starts, 8), MAPF_ERR_ALIGN);
+  MAPF_REQUIRE(a->num_obstacles == 0 || mapf_aligned(a->obstacles, 8), MAPF_ERR_ALIGN);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(a->cells, 0, size_t(a->episodes) * a->cell_stride, s) != cudaSuccess) return MAPF_ERR_CUDA;
+  if (cudaMemsetAsync(a->time, 0, size_t(a->episodes) * sizeof(int32_t), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  if (cudaMemsetAsync(a->done, 0, size_t(a->episodes), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  const int64_t work = int64_t(a->episodes) * max(a->agents, a->num_obstacles);
+  const int threads = 256;
+  env_reset_kernel<<<unsigned((work + threads - 1) / threads), threads, 0, s>>>(*a);
+  return mapf_launch_status();
+}
+
+extern "C" int mapf_env_step(const mapf_env_step_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a != nullptr, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->pos && a->goal && a->cells && a->time && a->done, MAPF_ERR_NULL);
+  MAPF_REQUIRE(!a->do_move || a->actions, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->episodes > 0 && a->agents > 0 && a->board > 0 && a->d2_limit >= 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(a->cell_stride >= a->board * a->board && (a->cell_stride & 15) == 0, MAPF_ERR_ALIGN);
+  MAPF_REQUIRE(mapf_aligned(a->cells, 16) && mapf_aligned(a->pos, 8) && mapf_aligned(a->goal, 8), MAPF_ERR_ALIGN);
+  MAPF_REQUIRE(a->fov == nullptr || mapf_aligned(a->fov, 4), MAPF_ERR_ALIGN);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n = a->agents;
+  if (n <= 8) return launch_env_step<8>(*a, s);
+  if (n <= 16) return launch_env_step<16>(*a, s);
+  if (n <= 32) return launch_env_step<32>(*a, s);
+  if (n <= 64) return launch_env_step<64>(*a, s);
+  if (n <= 128) return launch_env_step<128>(*a, s);
+  return MAPF_ERR_UNSUPPORTED;
+}
+
+extern "C" int mapf_env_metrics(const mapf_env_metrics_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a != nullptr, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->pos && a->goal && a->time && a->success && a->flow_time, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->episodes > 0 && a->agents > 0, MAPF_ERR_SHAPE);
+  const int threads = 128;
+  env_metrics_kernel<<<(a->episodes + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  return mapf_launch_status();
+}

@@ -1,0 +1,177 @@
+"""``mapf::`` torch custom ops: typed schemas, CUDA-only dispatch, bodies = one C-ABI call each.
+
+The ops exist so that the facade modules (``Network``, ``GCNLayer`` ...) stay ordinary PyTorch
+modules (device placement, streams, autograd) while every number is produced by libmapf_b200.so.
+They are registered for the CUDA dispatch key only: calling one with CPU tensors raises
+``NotImplementedError`` from the dispatcher -- there is no CPU path.
+
+``dims`` is the flat description of a network that every model op takes:
+``[num_conv, c0, c1, c2, c3, c4, fc_in, fc_out, taps, node_dim, num_actions]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_LIB = torch.library.Library("mapf", "DEF")
+
+_LIB.define("pack_weights(int[] dims, Tensor[] conv_w, Tensor[] conv_b, Tensor[] bn_gamma, Tensor[] bn_beta, "
+            "Tensor[] bn_mean, Tensor[] bn_var, Tensor fc_w, Tensor fc_b, Tensor? gf_w, Tensor? gf_w2, "
+            "Tensor act_w, Tensor act_b) -> Tensor")
+_LIB.define("policy_fwd(int[] dims, bool message, Tensor states, Tensor? gso, Tensor packed) -> (Tensor, Tensor)")
+_LIB.define("encoder_fwd(int[] dims, Tensor states, Tensor packed) -> Tensor")
+_LIB.define("pack_graph_weights(Tensor w, Tensor? w2) -> Tensor")
+_LIB.define("graph_filter_fwd(Tensor x, Tensor gso, Tensor wt, int taps, bool add_self_loop, bool has_skip, "
+            "bool relu) -> Tensor")
+_LIB.define("head_fwd(Tensor x, Tensor act_w, Tensor act_b) -> (Tensor, Tensor)")
+_LIB.define("env_step(Tensor(a!) pos, Tensor goal, Tensor? actions, Tensor(b!) cells, Tensor(c!) time, "
+            "Tensor(d!) done, Tensor(e!) fov, Tensor(f!) adj, int board, int d2_limit, bool do_move) -> ()")
+
+
+def net_params(dims, tensors=None) -> _lib.NetParams:
+    p = _lib.NetParams()
+    p.num_conv = int(dims[0])
+    for i in range(_lib.MAX_CONV + 1):
+        p.channels[i] = int(dims[1 + i])
+    p.fc_in, p.fc_out, p.taps, p.node_dim, p.num_actions = (int(v) for v in dims[6:11])
+    if tensors is not None:
+        for l in range(p.num_conv):
+            for name in ("conv_w", "conv_b", "bn_gamma", "bn_beta", "bn_mean", "bn_var"):
+                getattr(p, name)[l] = tensors[name][l].data_ptr()
+        for name in ("fc_w", "fc_b", "gf_w", "gf_w2", "act_w", "act_b"):
+            t = tensors[name]
+            setattr(p, name, None if t is None else t.data_ptr())
+    return p
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32 tensor, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _pack_weights(dims, conv_w, conv_b, bn_gamma, bn_beta, bn_mean, bn_var, fc_w, fc_b, gf_w, gf_w2, act_w, act_b):
+    lib = _lib.load()
+    keep = {"conv_w": [_f32c(t) for t in conv_w], "conv_b": [_f32c(t) for t in conv_b],
+            "bn_gamma": [_f32c(t) for t in bn_gamma], "bn_beta": [_f32c(t) for t in bn_beta],
+            "bn_mean": [_f32c(t) for t in bn_mean], "bn_var": [_f32c(t) for t in bn_var],
+            "fc_w": _f32c(fc_w), "fc_b": _f32c(fc_b), "gf_w": None if gf_w is None else _f32c(gf_w),
+            "gf_w2": None if gf_w2 is None else _f32c(gf_w2), "act_w": _f32c(act_w), "act_b": _f32c(act_b)}
+    p = net_params(dims, keep)
+    size = lib.mapf_packed_weights_size(p)
+    if size < 0:
+        raise RuntimeError("mapf_b200 pack_weights: unsupported network dimensions")
+    packed = torch.empty((size,), dtype=torch.float32, device=fc_w.device)
+    with torch.cuda.device(fc_w.device):
+        _lib.check(lib.mapf_pack_weights(p, packed.data_ptr(), _stream()), "pack_weights")
+    return packed
+
+
+def _policy_fwd(dims, message, states, gso, packed):
+    lib = _lib.load()
+    states = _f32c(states)
+    B, N = int(states.shape[0]), int(states.shape[1])
+    p = net_params(dims)
+    dev = states.device
+    logits = torch.empty((B, N, p.num_actions), dtype=torch.float32, device=dev)
+    actions = torch.empty((B, N), dtype=torch.int32, device=dev)
+    work = torch.empty((B * N, p.fc_out), dtype=torch.float32, device=dev)
+    a = _lib.PolicyFwdArgs()
+    a.batch, a.agents, a.message = B, N, int(message)
+    a.states, a.packed, a.workspace_x = states.data_ptr(), packed.data_ptr(), work.data_ptr()
+    if p.taps > 0:
+        if gso is None:
+            raise ValueError("gso is required for the GNN variants")
+        gso = _f32c(gso)
+        if tuple(gso.shape) != (B, N, N):
+            raise ValueError(f"gso must be [{B},{N},{N}], got {tuple(gso.shape)}")
+        a.gso = gso.data_ptr()
+    a.logits, a.actions = logits.data_ptr(), actions.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mapf_policy_fwd(p, a, _stream()), "policy_fwd")
+    return logits, actions
+
+
+def _encoder_fwd(dims, states, packed):
+    lib = _lib.load()
+    states = _f32c(states)
+    p = net_params(dims)
+    rows = states.numel() // 50
+    x = torch.empty((rows, p.fc_out), dtype=torch.float32, device=states.device)
+    a = _lib.EncoderFwdArgs(rows, states.data_ptr(), packed.data_ptr(), x.data_ptr())
+    with torch.cuda.device(states.device):
+        _lib.check(lib.mapf_encoder_fwd(p, a, _stream()), "encoder_fwd")
+    return x
+
+
+def _pack_graph_weights(w, w2):
+    lib = _lib.load()
+    w = _f32c(w)
+    F, K, G = (int(v) for v in w.shape)
+    w2c = None if w2 is None else _f32c(w2)
+    wt = torch.empty(((K + (w2 is not None)) * F, G), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.mapf_pack_graph_weights(w.data_ptr(), None if w2c is None else w2c.data_ptr(), F, K, G,
+                                               wt.data_ptr(), _stream()), "pack_graph_weights")
+    return wt
+
+
+def _graph_filter_fwd(x, gso, wt, taps, add_self_loop, has_skip, relu):
+    """x in the reference layout [B,F,N] (gnn.py:72) -> y [B,G,N]."""
+    lib = _lib.load()
+    x, gso, wt = _f32c(x), _f32c(gso), _f32c(wt)
+    B, F, N = (int(v) for v in x.shape)
+    G = int(wt.shape[1])
+    y = torch.empty((B, G, N), dtype=torch.float32, device=x.device)
+    a = _lib.GraphFilterFwdArgs()
+    a.batch, a.agents, a.in_dim, a.out_dim, a.taps = B, N, F, G, int(taps)
+    a.add_self_loop, a.has_skip, a.relu, a.num_actions = int(add_self_loop), int(has_skip), int(relu), 0
+    a.x, a.x_sb, a.x_sn, a.x_sf = x.data_ptr(), F * N, 1, N
+    a.gso, a.wt = gso.data_ptr(), wt.data_ptr()
+    a.y, a.y_sb, a.y_sn, a.y_sg = y.data_ptr(), G * N, 1, N
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mapf_graph_filter_fwd(a, _stream()), "graph_filter_fwd")
+    return y
+
+
+def _head_fwd(x, act_w, act_b):
+    lib = _lib.load()
+    x, act_w, act_b = _f32c(x), _f32c(act_w), _f32c(act_b)
+    rows, D = int(x.shape[0]), int(x.shape[1])
+    A = int(act_w.shape[0])
+    logits = torch.empty((rows, A), dtype=torch.float32, device=x.device)
+    actions = torch.empty((rows,), dtype=torch.int32, device=x.device)
+    a = _lib.HeadFwdArgs(rows, D, A, x.data_ptr(), act_w.data_ptr(), act_b.data_ptr(), logits.data_ptr(),
+                         actions.data_ptr())
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mapf_head_fwd(a, _stream()), "head_fwd")
+    return logits, actions
+
+
+def _env_step(pos, goal, actions, cells, time, done, fov, adj, board, d2_limit, do_move):
+    lib = _lib.load()
+    E, N = int(pos.shape[0]), int(pos.shape[1])
+    a = _lib.EnvStepArgs()
+    a.episodes, a.agents, a.board, a.cell_stride = E, N, int(board), int(cells.shape[1])
+    a.d2_limit, a.do_move = int(d2_limit), int(do_move)
+    a.pos, a.goal, a.actions = pos.data_ptr(), goal.data_ptr(), None if actions is None else actions.data_ptr()
+    a.cells, a.time, a.done, a.fov, a.adj = (cells.data_ptr(), time.data_ptr(), done.data_ptr(), fov.data_ptr(),
+                                             adj.data_ptr())
+    with torch.cuda.device(pos.device):
+        _lib.check(lib.mapf_env_step(a, _stream()), "env_step")
+
+
+_LIB.impl("pack_weights", _pack_weights, "CUDA")
+_LIB.impl("policy_fwd", _policy_fwd, "CUDA")
+_LIB.impl("encoder_fwd", _encoder_fwd, "CUDA")
+_LIB.impl("pack_graph_weights", _pack_graph_weights, "CUDA")
+_LIB.impl("graph_filter_fwd", _graph_filter_fwd, "CUDA")
+_LIB.impl("head_fwd", _head_fwd, "CUDA")
+_LIB.impl("env_step", _env_step, "CUDA")

@@ -1,0 +1,141 @@
+"""GPU parity of the batched environment kernels (through the C ABI) against the reference's golden
+traces and the numpy oracle.  Integer work: everything must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import env_oracle as eo
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(n, h, max_time=32):
+    return {"num_agents": n, "board_size": [h, h], "max_time": max_time, "min_time": 1}
+
+
+def _run_case_batched(c, reps):
+    """Replicate one golden case `reps` times in one batch (covers multi-episode CTAs and tails)."""
+    import mapf_gnn_b200 as m
+    n, h, mm, T, max_time = (int(v) for v in c["meta"])
+    tile = lambda a: np.repeat(np.asarray(a)[None], reps, axis=0)
+    env = m.BatchedGraphEnv(_cfg(n, h, max_time), tile(c["goals"]), tile(c["starts"]),
+                            tile(c["obstacles"]) if mm else None, sensing_range=float(c["range"][0]))
+    obs = env.observe()
+    out = {"fov": [obs["fov"].cpu().numpy().copy()], "adj": [obs["adj_matrix"].cpu().numpy().copy()],
+           "pos": [env.pos.cpu().numpy().copy()], "done": []}
+    for t in range(T):
+        obs, done = env.step(tile(c["actions"][t]))
+        out["fov"].append(obs["fov"].cpu().numpy().copy())
+        out["adj"].append(obs["adj_matrix"].cpu().numpy().copy())
+        out["pos"].append(env.pos.cpu().numpy().copy())
+        out["done"].append(done.cpu().numpy().copy())
+    return env, out
+
+
+@pytest.mark.parametrize("reps", [1, 3, 37])
+def test_golden_traces_bit_exact(env_cases, reps):
+    for name, c in env_cases.items():
+        n, h, mm, T, max_time = (int(v) for v in c["meta"])
+        env, out = _run_case_batched(c, reps)
+        for r in (0, reps - 1):
+            for t in range(T + 1):
+                assert np.array_equal(out["pos"][t][r], c["pos"][t]), (name, t)
+                assert np.array_equal(out["fov"][t][r], c["fov"][t].astype(np.float32)), (name, t)
+                assert np.array_equal(out["adj"][t][r], c["adj"][t].astype(np.float32)), (name, t)
+        # golden traces keep stepping after done (the reference env does not freeze itself); the batched env
+        # freezes finished episodes, so compare done up to and including the first True
+        ref_done = c["done"].astype(bool)
+        first = int(np.argmax(ref_done)) if ref_done.any() else T
+        for t in range(min(first + 1, T)):
+            assert bool(out["done"][t][0]) == bool(ref_done[t]), (name, t)
+        if not ref_done.any():
+            assert np.array_equal(env.board()[0].cpu().numpy(), c["board_final"]), name
+            success, flow = env.computeMetrics()
+            assert abs(float(success[0]) - c["metrics"][0]) < 1e-7 and int(flow[0]) == int(c["metrics"][1]), name
+
+
+def test_done_freezes_episode(env_cases):
+    import mapf_gnn_b200 as m
+    c = env_cases["goalrun_3a_8"]
+    n, h, mm, T, max_time = (int(v) for v in c["meta"])
+    env = m.BatchedGraphEnv(_cfg(n, h, max_time), c["goals"][None], c["starts"][None], None,
+                            sensing_range=float(c["range"][0]))
+    first = int(np.argmax(c["done"]))
+    for t in range(first + 1):
+        _, done = env.step(c["actions"][t][None])
+    assert bool(done[0])
+    pos, time = env.pos.clone(), env.time.clone()
+    fov = env.fov.clone()
+    for _ in range(3):
+        env.step(np.full((1, n), 1))
+    assert torch.equal(env.pos, pos) and torch.equal(env.time, time) and torch.equal(env.fov, fov)
+    success, flow = env.computeMetrics()
+    assert float(success[0]) == 1.0 and int(flow[0]) == first + 1
+
+
+CONFIGS = [  # name, E, N, H, M, r, T, seed   (SURVEY 8d parity subsets)
+    ("C1", 64, 5, 18, 5, 6, 32, 0),
+    ("C2", 64, 5, 28, 8, 6, 32, 1),
+    ("C3", 48, 20, 32, 40, 6, 16, 2),
+    ("C5", 10, 64, 64, 200, 6, 8, 4),
+    ("r4", 33, 7, 9, 4, 4, 12, 5),
+    ("n100", 3, 100, 40, 30, 5, 4, 6),
+]
+
+
+@pytest.mark.parametrize("name,E,N,H,M,r,T,seed", CONFIGS)
+def test_random_rollouts_match_oracle(name, E, N, H, M, r, T, seed):
+    import mapf_gnn_b200 as m
+    rng = np.random.default_rng(seed)
+    starts, goals, obst = eo.make_scenarios(rng, E, N, H, M)
+    env = m.BatchedGraphEnv(_cfg(N, H), goals, starts, obst, sensing_range=r)
+    oracles = [eo.EnvOracle(N, H, goals[e], starts[e], obst[e], sensing_range=r) for e in range(E)]
+    obs = env.observe()
+    for e in range(E):
+        o = oracles[e].observe()
+        assert np.array_equal(obs["fov"][e].cpu().numpy(), o["fov"].astype(np.float32))
+        assert np.array_equal(obs["adj_matrix"][e].cpu().numpy(), o["adj_matrix"].astype(np.float32))
+    frozen = np.zeros(E, dtype=bool)
+    for t in range(T):
+        actions = rng.integers(0, 5, size=(E, N))
+        obs, done = env.step(actions)
+        fov, adj, pos = obs["fov"].cpu().numpy(), obs["adj_matrix"].cpu().numpy(), env.pos.cpu().numpy()
+        done = done.cpu().numpy().astype(bool)
+        for e in range(E):
+            if frozen[e]:
+                continue
+            o, d = oracles[e].step(actions[e])
+            assert np.array_equal(pos[e], oracles[e].positions), (name, t, e)
+            assert np.array_equal(fov[e], o["fov"].astype(np.float32)), (name, t, e)
+            assert np.array_equal(adj[e], o["adj_matrix"].astype(np.float32)), (name, t, e)
+            assert done[e] == d
+            frozen[e] = d
+    success, flow = env.computeMetrics()
+    for e in range(E):
+        s, f = oracles[e].metrics()
+        assert abs(float(success[e]) - s) < 1e-7 and int(flow[e]) == f
+
+
+def test_facade_matches_reference_known_answers():
+    """tests/test_env.py:196-220 (action map) and :77-122 (three-way collision) through the facade."""
+    import mapf_gnn_b200 as m
+    goals = np.array([[9, 9], [8, 8], [7, 7], [6, 6], [5, 5]])
+    starts = np.array([[5, 5], [4, 4], [3, 3], [2, 2], [1, 1]])
+    env = m.GraphEnv(_cfg(5, 10, 20), goal=goals, starting_positions=starts.copy())
+    obs, info, done, _ = env.step([0, 1, 2, 3, 4], np.ones((5, 1)))
+    assert env.getPositions().tolist() == [[5, 5], [5, 4], [3, 4], [1, 2], [1, 0]]
+    assert obs["fov"].shape == (5, 2, 5, 5) and obs["adj_matrix"].shape == (5, 5) and done is False
+    assert obs["distances"] is obs["adj_matrix"]
+    starts = np.array([[3, 4], [4, 5], [5, 4], [7, 7], [9, 9]])
+    env = m.GraphEnv(_cfg(5, 10, 20), goal=goals, starting_positions=starts.copy())
+    env.step([1, 4, 3, 0, 0], None)
+    assert env.getPositions().tolist() == starts.tolist()
+    assert env.computeMetrics()[0] == 0.0
+
+
+def test_bad_arguments_raise():
+    import mapf_gnn_b200 as m
+    with pytest.raises(ValueError):
+        m.BatchedGraphEnv(_cfg(5, 10), np.zeros((2, 4, 2)), np.zeros((2, 4, 2)))
+    with pytest.raises(RuntimeError):
+        m.BatchedGraphEnv(_cfg(200, 10), np.zeros((1, 200, 2)), np.zeros((1, 200, 2)))   # N > 128 unsupported

@@ -1,0 +1,160 @@
+"""GPU parity of the policy-network kernels (through the C ABI / torch ops) against logits produced by
+the unmodified reference on the shipped weights (tests/golden) and against the torch-CPU oracle.
+fp32: logits within 1e-4 relative (north star); chosen actions bit-exact wherever the reference's own
+top-2 margin exceeds the fp32 noise floor."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_network, model_config, oracle_params, rel_err, top2_margin
+from oracle import env_oracle as eo
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+MARGIN_FLOOR = 1e-4   # decisions closer than this in the reference may legitimately flip
+
+
+def _check_actions(mine, ref_logits):
+    ref_act = ref_logits.argmax(-1)
+    bad = mine != ref_act
+    if bad.any():
+        assert top2_margin(ref_logits)[bad].max() < MARGIN_FLOOR, "action flipped where the reference margin is wide"
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("name", ["gnn_k3", "gnn_k2", "gnn_msg_k3", "baseline", "gnn_k4_seed4"])
+def test_logits_match_reference_goldens(model_logits, name):
+    states = torch.from_numpy(model_logits[f"{name}/states"]).float().cuda()
+    gso = torch.from_numpy(model_logits[f"{name}/gso"]).float().cuda()
+    net = load_network(name, num_agents=states.shape[1]).eval()
+    with torch.no_grad():
+        logits = net(states) if name == "baseline" else net(states, gso)
+        logits2, actions = net.act(states, None if name == "baseline" else gso)
+    ref = model_logits[f"{name}/logits"]
+    assert tuple(logits.shape) == ref.shape
+    assert rel_err(logits.cpu().numpy(), ref) < REL
+    assert torch.equal(logits, logits2)
+    assert _check_actions(actions.cpu().numpy(), ref) == 0
+    assert np.array_equal(actions.cpu().numpy(), logits.cpu().numpy().argmax(-1))
+
+
+@pytest.mark.parametrize("name", ["gcn_k3_n5", "msg_k3_n5", "gcn_k4_n20", "msg_k2_n7"])
+def test_graph_layers_match_reference_goldens(graph_layers, name):
+    import mapf_gnn_b200 as m
+    g = graph_layers
+    x = torch.from_numpy(g[f"{name}/x"]).cuda()
+    adj = torch.from_numpy(g[f"{name}/adj"]).float().cuda()
+    W = g[f"{name}/W"]
+    F, K, G = W.shape
+    cls = m.MessagePassingLayer if f"{name}/W2" in g.files else m.GCNLayer
+    layer = cls(x.shape[2], F, G, K).cuda()
+    with torch.no_grad():
+        layer.W.copy_(torch.from_numpy(W))
+        if f"{name}/W2" in g.files:
+            layer.W2.copy_(torch.from_numpy(g[f"{name}/W2"]))
+        layer.addGSO(adj)
+        y = layer(x)
+    assert rel_err(y.cpu().numpy(), g[f"{name}/y"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,B,N", [("gnn_k3", 300, 5), ("gnn_msg_k3", 67, 20), ("gnn_k4_seed4", 9, 64),
+                                      ("baseline", 257, 5), ("gnn_k2", 1, 5), ("gnn_k3", 33, 13)])
+def test_logits_match_oracle_on_random_observations(name, B, N):
+    rng = np.random.default_rng(B * 31 + N)
+    H = 12 if N <= 20 else 24
+    starts, goals, obst = eo.make_scenarios(rng, B, N, H, 6)
+    S, A = [], []
+    for b in range(B):
+        env = eo.EnvOracle(N, H, goals[b], starts[b], obst[b], sensing_range=4)
+        o, _ = env.step(rng.integers(0, 5, size=N))
+        S.append(o["fov"]), A.append(o["adj_matrix"])
+    states = torch.tensor(np.stack(S)).float()
+    gso = torch.tensor(np.stack(A)).float()
+    with torch.no_grad():
+        ref = mo.forward(oracle_params(name), states, gso).numpy()
+    net = load_network(name, num_agents=N).eval()
+    logits, actions = net.act(states.cuda(), None if name == "baseline" else gso.cuda())
+    assert rel_err(logits.cpu().numpy(), ref) < REL
+    _check_actions(actions.cpu().numpy(), ref)
+
+
+def test_training_gso_convention_a_plus_i():
+    """The data loader feeds A + I (data_loader.py:74); GCNLayer adds I again -> diagonal 2."""
+    rng = np.random.default_rng(3)
+    B, N = 16, 5
+    states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+    adj = torch.tensor((rng.random((B, N, N)) < 0.4).astype(np.float32))
+    gso = adj + torch.eye(N)
+    for name in ("gnn_k3", "gnn_msg_k3"):
+        with torch.no_grad():
+            ref = mo.forward(oracle_params(name), states, gso).numpy()
+        net = load_network(name).eval()
+        with torch.no_grad():
+            out = net(states.cuda(), gso.cuda())
+        assert rel_err(out.cpu().numpy(), ref) < REL
+
+
+def test_weights_repack_after_update():
+    net = load_network("gnn_k3").eval()
+    states = torch.rand(4, 5, 2, 5, 5, device="cuda")
+    gso = torch.zeros(4, 5, 5, device="cuda")
+    with torch.no_grad():
+        a = net(states, gso).clone()
+        net.actionMLP[0].bias.add_(1.0)
+        b = net(states, gso)
+    assert torch.allclose(b, a + 1.0, atol=1e-5)
+
+
+def test_rollout_matches_teacher_forced_oracle():
+    """Full on-device rollout (policy -> argmax -> env step) vs oracle env + oracle model, teacher-forced:
+    the oracle follows the device's actions; device actions must equal the oracle's argmax wherever the
+    oracle's margin is above the fp32 noise floor, and states must stay bit-identical."""
+    import mapf_gnn_b200 as m
+    E, N, H, M, T = 48, 5, 18, 5, 12
+    rng = np.random.default_rng(0)
+    starts, goals, obst = eo.make_scenarios(rng, E, N, H, M)
+    cfg = model_config("gnn_k3", N, board_size=[H, H])
+    env = m.BatchedGraphEnv(cfg, goals, starts, obst, sensing_range=6)
+    net = load_network("gnn_k3").eval()
+    ro = m.Rollout(net, env)
+    params = oracle_params("gnn_k3")
+    oracles = [eo.EnvOracle(N, H, goals[e], starts[e], obst[e], sensing_range=6) for e in range(E)]
+    obs = [o.observe() for o in oracles]
+    alive = np.ones(E, dtype=bool)
+    flips = 0
+    for t in range(T):
+        ro.run(1)
+        acts = ro.actions.cpu().numpy()
+        states = torch.tensor(np.stack([o["fov"] for o in obs])).float()
+        gso = torch.tensor(np.stack([o["adj_matrix"] for o in obs])).float()
+        with torch.no_grad():
+            ref = mo.forward(params, states, gso).numpy()
+        assert rel_err(ro.logits.cpu().numpy()[alive], ref[alive]) < REL
+        flips += _check_actions(acts[alive], ref[alive])
+        pos = env.pos.cpu().numpy()
+        for e in range(E):
+            if not alive[e]:
+                continue
+            obs[e], d = oracles[e].step(acts[e])
+            assert np.array_equal(pos[e], oracles[e].positions)
+            alive[e] = not d
+        assert np.array_equal(env.done.cpu().numpy().astype(bool), ~alive)
+    assert flips <= 2
+
+
+def test_rollout_multi_step_equals_single_steps():
+    import mapf_gnn_b200 as m
+    E, N, H, M = 40, 20, 32, 40
+    rng = np.random.default_rng(2)
+    starts, goals, obst = eo.make_scenarios(rng, E, N, H, M)
+    cfg = model_config("gnn_msg_k3", N, board_size=[H, H])
+    net = load_network("gnn_msg_k3", num_agents=N).eval()
+    env_a = m.BatchedGraphEnv(cfg, goals, starts, obst)
+    env_b = m.BatchedGraphEnv(cfg, goals, starts, obst)
+    ra, rb = m.Rollout(net, env_a), m.Rollout(net, env_b)
+    ra.run(8)
+    for _ in range(8):
+        rb.run(1)
+    assert torch.equal(env_a.pos, env_b.pos) and torch.equal(env_a.fov, env_b.fov)
+    assert torch.equal(env_a.adj_matrix, env_b.adj_matrix) and torch.equal(env_a.time, env_b.time)
