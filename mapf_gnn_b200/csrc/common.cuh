@@ -64,3 +64,19 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
   L.total = off;
   return L;
 }
+
+constexpr int kMaxActions = 8;
+
+static inline int mapf_check_params(const mapf_net_params* p) {
+  MAPF_REQUIRE(p != nullptr, MAPF_ERR_NULL);
+  MAPF_REQUIRE(p->num_conv >= 1 && p->num_conv <= MAPF_MAX_CONV, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(p->channels[0] == 2, MAPF_ERR_SHAPE);
+  for (int l = 1; l <= p->num_conv; ++l)
+    MAPF_REQUIRE(p->channels[l] > 0 && p->channels[l] <= 64 && (p->channels[l] & 3) == 0, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(p->fc_in == kFovCells * p->channels[p->num_conv], MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(p->fc_out > 0 && (p->fc_out & 15) == 0, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(p->num_actions > 0 && p->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(p->taps >= 0 && p->taps <= 8, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(p->taps == 0 || (p->node_dim > 0 && (p->node_dim & 3) == 0), MAPF_ERR_UNSUPPORTED);
+  return MAPF_OK;
+}

@@ -1,0 +1,237 @@
+// Eval-mode observation encoder (reference models/framework_gnn.py:156-166):
+// per agent image [2,5,5]: 3 x {conv3x3 pad 1 + BatchNorm(eval, folded) + ReLU} -> flatten (C,H,W) ->
+// Linear + ReLU, for all B*N agent images of a batch.
+//
+// Design (B200): a PERSISTENT kernel, one 256-thread CTA per SM.  Every weight the encoder needs
+// (BN-folded conv filters 20-30 KB, transposed FC matrix 100 KB) is copied into shared memory once
+// per CTA and stays there while the CTA walks over tiles of 32 agent images, so the steady state
+// touches HBM/L2 only for the 200 B image and the 256 B feature row of each agent.  Inside a tile
+// lane = agent and warp = a pair of output channels: each thread keeps a 2 x 25 accumulator block
+// in registers, reads the 25 input pixels of one input channel with conflict-free LDS (activations
+// are stored [channel*25 + pixel][agent]) and the 9 x 2 filter taps with broadcast LDS.64, and the
+// 3x3 border handling is resolved at compile time (169 instead of 225 taps per channel pair).
+// The FC runs as a 32 x F x fc_in register-tiled GEMM (4 agents x 4 outputs per thread, K split
+// over the two halves of the CTA).  Everything is fp32 FFMA (bit-exact argmax requirement).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kEncAgents = 32;
+constexpr int kEncThreads = 256;
+constexpr int kEncWarps = kEncThreads / 32;
+
+struct EncoderDims {
+  int num_conv;
+  int channels[MAPF_MAX_CONV + 1];
+  int fc_in, fc_out;
+  int w_floats;      // floats of the packed prefix resident in shared memory
+  int fc_in_smem;    // 1: the FC matrix is part of that prefix
+  int buf0_floats;   // ping buffer 0: image staging, outputs of odd layers, FC split-K scratch
+  int buf1_floats;   // ping buffer 1: outputs of even layers
+};
+
+// One 3x3 / stride 1 / zero-pad 1 convolution (BN folded) + ReLU over the tile's 32 images.
+// Input element (ci, p) of this lane's image is at in[ci*in_cs + p*in_ps + in_off]; out is
+// [Cout*25][32].  w is the packed [Cout/4][Cin][9][4] filter bank in shared memory.
+__device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, int in_cs, int in_ps, int in_off,
+                                                  float* __restrict__ out, const float* __restrict__ w,
+                                                  const float* __restrict__ bias, int cin, int cout, int warp,
+                                                  int lane) {
+  for (int pr = warp; pr < (cout >> 1); pr += kEncWarps) {
+    float acc0[kFovCells], acc1[kFovCells];
+    {
+      const float2 b = *reinterpret_cast<const float2*>(bias + 2 * pr);
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) { acc0[p] = b.x; acc1[p] = b.y; }
+    }
+    // float2 view: element [(cog*cin + ci)*9 + t]*2 + h with cog = pr/2, h = pr&1
+    const float2* wp = reinterpret_cast<const float2*>(w) + (int64_t(pr >> 1) * cin * 9) * 2 + (pr & 1);
+#pragma unroll 2
+    for (int ci = 0; ci < cin; ++ci) {
+      float v[kFovCells];
+      const float* src = in + ci * in_cs + in_off;
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) v[p] = src[p * in_ps];
+      float2 wv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wv[t] = wp[(ci * 9 + t) * 2];
+#pragma unroll
+      for (int y = 0; y < kFov; ++y)
+#pragma unroll
+        for (int x = 0; x < kFov; ++x)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int yy = y + ky - 1, xx = x + kx - 1;
+              if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov) {  // resolved at compile time
+                const float a = v[yy * kFov + xx];
+                acc0[y * kFov + x] = fmaf(a, wv[ky * 3 + kx].x, acc0[y * kFov + x]);
+                acc1[y * kFov + x] = fmaf(a, wv[ky * 3 + kx].y, acc1[y * kFov + x]);
+              }
+            }
+    }
+#pragma unroll
+    for (int p = 0; p < kFovCells; ++p) {
+      out[((2 * pr) * kFovCells + p) * kEncAgents + lane] = fmaxf(acc0[p], 0.0f);
+      out[((2 * pr + 1) * kFovCells + p) * kEncAgents + lane] = fmaxf(acc1[p], 0.0f);
+    }
+  }
+}
+
+template <bool kFcSmem>
+__global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims d, PackedLayout L, int64_t rows,
+                                                                     const float* __restrict__ states,
+                                                                     const float* __restrict__ packed,
+                                                                     float* __restrict__ x) {
+  extern __shared__ __align__(16) float s_enc[];
+  float* const s_w = s_enc;                     // packed prefix: conv filters/biases (+ FC matrix and bias)
+  float* const s_b0 = s_enc + d.w_floats;
+  float* const s_b1 = s_b0 + d.buf0_floats;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < (d.w_floats >> 2); i += kEncThreads)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(packed) + i);
+
+  const int64_t ntiles = (rows + kEncAgents - 1) / kEncAgents;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kEncAgents;
+    const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
+    {  // stage the tile's images as they lie in memory: [agent][50]
+      const int nfl = nrows * kFovFloats;
+      const float* src = states + row0 * kFovFloats;
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int nq = nfl >> 2;
+        for (int q = tid; q < nq; q += kEncThreads)
+          reinterpret_cast<float4*>(s_b0)[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+      } else {
+        for (int i = tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+      }
+      for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) s_b0[i] = 0.0f;
+    }
+    __syncthreads();
+
+    // layer 0 reads the staging layout [agent][ci*25 + p]; later layers read [ci*25 + p][agent]
+    conv3x3_relu_pair(s_b0, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
+                      d.channels[0], d.channels[1], warp, lane);
+    __syncthreads();
+    bool in1 = true;  // current activations live in s_b1
+    for (int l = 1; l < d.num_conv; ++l) {
+      conv3x3_relu_pair(in1 ? s_b1 : s_b0, kFovCells * kEncAgents, kEncAgents, lane, in1 ? s_b0 : s_b1,
+                        s_w + L.conv_w[l], s_w + L.conv_b[l], d.channels[l], d.channels[l + 1], warp, lane);
+      in1 = !in1;
+      __syncthreads();
+    }
+    const float* act = in1 ? s_b1 : s_b0;   // [fc_in][32]
+    float* scratch = in1 ? s_b0 : s_b1;     // free buffer: split-K partials [128 threads][16]
+
+    // compressMLP: X[32, F] = relu(act^T Wt + b); thread tile 4 agents x 4 outputs, K split in two halves
+    const int kg = tid >> 7, t7 = tid & 127;
+    const int aq = t7 & 7, jq = t7 >> 3;
+    const int khalf = d.fc_in >> 1;
+    const int k0 = kg * khalf, k1 = kg ? d.fc_in : khalf;
+    const int wstride = d.fc_out >> 2;
+    for (int jb = 0; jb < d.fc_out; jb += 64) {
+      const int j = jb + jq * 4;
+      const bool jlive = j < d.fc_out;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+      if (jlive) {
+        const float4* wps = reinterpret_cast<const float4*>(s_w + L.fc_wt + j);
+        const float4* wpg = reinterpret_cast<const float4*>(packed + L.fc_wt + j);
+        const float4* ap = reinterpret_cast<const float4*>(act + aq * 4);
+#pragma unroll 8
+        for (int i = k0; i < k1; ++i) {
+          const float4 a4 = ap[i * (kEncAgents / 4)];
+          const float4 w4 = kFcSmem ? wps[i * wstride] : __ldg(wpg + i * wstride);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            acc[r][0] = fmaf(av[r], w4.x, acc[r][0]);
+            acc[r][1] = fmaf(av[r], w4.y, acc[r][1]);
+            acc[r][2] = fmaf(av[r], w4.z, acc[r][2]);
+            acc[r][3] = fmaf(av[r], w4.w, acc[r][3]);
+          }
+        }
+      }
+      if (kg == 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          reinterpret_cast<float4*>(scratch)[r * 128 + t7] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
+      __syncthreads();
+      if (kg == 0 && jlive) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j));
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int a = aq * 4 + r;
+          const float4 o2 = reinterpret_cast<const float4*>(scratch)[r * 128 + t7];
+          if (a < nrows) {
+            float4 o;
+            o.x = fmaxf(acc[r][0] + o2.x + b4.x, 0.0f);
+            o.y = fmaxf(acc[r][1] + o2.y + b4.y, 0.0f);
+            o.z = fmaxf(acc[r][2] + o2.z + b4.z, 0.0f);
+            o.w = fmaxf(acc[r][3] + o2.w + b4.w, 0.0f);
+            *reinterpret_cast<float4*>(x + (row0 + a) * d.fc_out + j) = o;
+          }
+        }
+      }
+      __syncthreads();  // scratch / staging buffer is rewritten by the next block or tile
+    }
+  }
+}
+
+}  // namespace
+
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return 148;
+    cached = n;
+  }
+  return cached;
+}
+
+extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream) {
+  const int st = mapf_check_params(p);
+  if (st != MAPF_OK) return st;
+  MAPF_REQUIRE(a && a->states && a->packed && a->x, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->rows > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(mapf_aligned(a->packed, 16) && mapf_aligned(a->x, 16) && mapf_aligned(a->states, 4), MAPF_ERR_ALIGN);
+  MAPF_REQUIRE((p->fc_in & 1) == 0, MAPF_ERR_UNSUPPORTED);
+  const PackedLayout L = mapf_packed_layout(*p);
+  EncoderDims d;
+  d.num_conv = p->num_conv;
+  for (int l = 0; l <= MAPF_MAX_CONV; ++l) d.channels[l] = l <= p->num_conv ? p->channels[l] : 0;
+  d.fc_in = p->fc_in;
+  d.fc_out = p->fc_out;
+  int b0 = kFovFloats, b1 = 0;
+  for (int l = 0; l < p->num_conv; ++l) {
+    const int out = kFovCells * p->channels[l + 1];
+    if (l & 1) b0 = max(b0, out); else b1 = max(b1, out);
+  }
+  b0 = max(b0, 64);  // FC split-K scratch: 128 threads x 16 floats = 2048 floats = 64 x 32
+  b1 = max(b1, 64);
+  d.buf0_floats = b0 * kEncAgents;
+  d.buf1_floats = b1 * kEncAgents;
+  const size_t act_bytes = size_t(d.buf0_floats + d.buf1_floats) * sizeof(float);
+  const size_t limit = 227 * 1024;
+  d.fc_in_smem = (size_t(L.gf_wt) * sizeof(float) + act_bytes <= limit) ? 1 : 0;
+  d.w_floats = int(d.fc_in_smem ? L.gf_wt : L.fc_wt);
+  const size_t smem = size_t(d.w_floats) * sizeof(float) + act_bytes;
+  MAPF_REQUIRE(smem <= limit, MAPF_ERR_UNSUPPORTED);
+  auto kernel = d.fc_in_smem ? encoder_fwd_kernel<true> : encoder_fwd_kernel<false>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return MAPF_ERR_CUDA;
+  const int64_t ntiles = (a->rows + kEncAgents - 1) / kEncAgents;
+  const int grid = int(ntiles < sm_count() ? ntiles : sm_count());
+  kernel<<<grid, kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(d, L, a->rows, a->states, a->packed, a->x);
+  return mapf_launch_status();
+}

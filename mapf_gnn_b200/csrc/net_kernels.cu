@@ -80,151 +80,6 @@ __global__ void pack_graph_weights_kernel(const float* __restrict__ w, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// encoder: 32 agent images per CTA, lane = agent, warp = group of 4 output channels
-// ---------------------------------------------------------------------------------------------
-constexpr int kEncAgents = 32;
-constexpr int kEncThreads = 128;
-
-struct EncoderDims {
-  int num_conv;
-  int channels[MAPF_MAX_CONV + 1];
-  int fc_in, fc_out;
-  int buf0_floats;  // per-CTA floats of ping buffer 0 (states staging, outputs of odd layers)
-  int buf1_floats;  // outputs of even layers
-};
-
-// One 3x3 / stride 1 / zero-pad 1 convolution (BN folded) + ReLU over the CTA's 32 images.
-// in element (ci, p) of this lane's image is at in[ci*in_cs + p*in_ps + in_off]; out is [Cout*25][32].
-__device__ __forceinline__ void conv3x3_relu(const float* __restrict__ in, int in_cs, int in_ps, int in_off,
-                                             float* __restrict__ out, const float* __restrict__ w,
-                                             const float* __restrict__ bias, int cin, int cout, int warp, int lane) {
-  for (int cog = warp; cog < (cout >> 2); cog += kEncThreads / 32) {
-    float acc[4][kFovCells];
-    {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + cog);
-#pragma unroll
-      for (int p = 0; p < kFovCells; ++p) { acc[0][p] = b.x; acc[1][p] = b.y; acc[2][p] = b.z; acc[3][p] = b.w; }
-    }
-    const float4* wp = reinterpret_cast<const float4*>(w) + int64_t(cog) * cin * 9;
-#pragma unroll 1
-    for (int ci = 0; ci < cin; ++ci) {
-      float v[kFovCells];
-      const float* src = in + ci * in_cs + in_off;
-#pragma unroll
-      for (int p = 0; p < kFovCells; ++p) v[p] = src[p * in_ps];
-      float4 wv[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) wv[t] = __ldg(wp + ci * 9 + t);
-#pragma unroll
-      for (int y = 0; y < kFov; ++y)
-#pragma unroll
-        for (int x = 0; x < kFov; ++x)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int yy = y + ky - 1, xx = x + kx - 1;
-              if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov) {  // resolved at compile time
-                const float a = v[yy * kFov + xx];
-                const float4 ww = wv[ky * 3 + kx];
-                acc[0][y * kFov + x] = fmaf(a, ww.x, acc[0][y * kFov + x]);
-                acc[1][y * kFov + x] = fmaf(a, ww.y, acc[1][y * kFov + x]);
-                acc[2][y * kFov + x] = fmaf(a, ww.z, acc[2][y * kFov + x]);
-                acc[3][y * kFov + x] = fmaf(a, ww.w, acc[3][y * kFov + x]);
-              }
-            }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int p = 0; p < kFovCells; ++p)
-        out[((cog * 4 + c) * kFovCells + p) * kEncAgents + lane] = fmaxf(acc[c][p], 0.0f);
-  }
-}
-
-__global__ void __launch_bounds__(kEncThreads) encoder_fwd_kernel(EncoderDims d, PackedLayout L, int64_t rows,
-                                                                  const float* __restrict__ states,
-                                                                  const float* __restrict__ packed,
-                                                                  float* __restrict__ x) {
-  extern __shared__ __align__(16) float s_enc[];
-  float* buf[2] = {s_enc, s_enc + d.buf0_floats};
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = int64_t(blockIdx.x) * kEncAgents;
-  const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
-
-  {  // stage the CTA's images as they lie in memory: [agent][50]
-    const int nfl = nrows * kFovFloats;
-    const float* src = states + row0 * kFovFloats;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      const int nq = nfl >> 2;
-      for (int q = tid; q < nq; q += kEncThreads)
-        reinterpret_cast<float4*>(buf[0])[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
-      for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) buf[0][i] = __ldg(src + i);
-    } else {
-      for (int i = tid; i < nfl; i += kEncThreads) buf[0][i] = __ldg(src + i);
-    }
-    for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) buf[0][i] = 0.0f;
-  }
-  __syncthreads();
-
-  int cur = 0;
-  for (int l = 0; l < d.num_conv; ++l) {
-    const float* in = buf[cur];
-    float* out = buf[cur ^ 1];
-    if (l == 0)
-      conv3x3_relu(in, kFovCells, 1, lane * kFovFloats, out, packed + L.conv_w[l], packed + L.conv_b[l],
-                   d.channels[l], d.channels[l + 1], warp, lane);
-    else
-      conv3x3_relu(in, kFovCells * kEncAgents, kEncAgents, lane, out, packed + L.conv_w[l], packed + L.conv_b[l],
-                   d.channels[l], d.channels[l + 1], warp, lane);
-    cur ^= 1;
-    __syncthreads();
-  }
-
-  // compressMLP: X[32, F] = relu(act[32, fc_in] @ Wt[fc_in, F] + b); thread tile 4 agents x 4 outputs
-  const float* act = buf[cur];  // [fc_in][32]
-  const int aq = tid & 7, jq = tid >> 3;
-  const float* wt = packed + L.fc_wt;
-  for (int jb = 0; jb < d.fc_out; jb += 64) {
-    const int j = jb + jq * 4;
-    if (j >= d.fc_out) continue;
-    float acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
-    const float4* wp = reinterpret_cast<const float4*>(wt + j);
-    const int wstride = d.fc_out >> 2;
-#pragma unroll 8
-    for (int i = 0; i < d.fc_in; ++i) {
-      const float4 a4 = *reinterpret_cast<const float4*>(act + i * kEncAgents + aq * 4);
-      const float4 w4 = __ldg(wp + int64_t(i) * wstride);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        acc[r][0] = fmaf(av[r], w4.x, acc[r][0]);
-        acc[r][1] = fmaf(av[r], w4.y, acc[r][1]);
-        acc[r][2] = fmaf(av[r], w4.z, acc[r][2]);
-        acc[r][3] = fmaf(av[r], w4.w, acc[r][3]);
-      }
-    }
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j));
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int a = aq * 4 + r;
-      if (a < nrows) {
-        float4 o;
-        o.x = fmaxf(acc[r][0] + b4.x, 0.0f);
-        o.y = fmaxf(acc[r][1] + b4.y, 0.0f);
-        o.z = fmaxf(acc[r][2] + b4.z, 0.0f);
-        o.w = fmaxf(acc[r][3] + b4.w, 0.0f);
-        *reinterpret_cast<float4*>(x + (row0 + a) * d.fc_out + j) = o;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // graph filter (+ head): 64 agent rows (whole episodes) per CTA
 // ---------------------------------------------------------------------------------------------
 constexpr int kGfRows = 64;
@@ -232,7 +87,6 @@ constexpr int kGfThreads = 256;
 constexpr int kGfZs = 68;      // row stride of the k-major tap matrix Zt[KT][kGfZs]
 constexpr int kGfColTile = 128;
 constexpr int kGfChunk = 16;   // k rows of W^T staged per cp.async stage
-constexpr int kMaxActions = 8;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -471,45 +325,16 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(mapf_head_fwd_args a) {
   }
 }
 
-int check_params(const mapf_net_params* p) {
-  MAPF_REQUIRE(p != nullptr, MAPF_ERR_NULL);
-  MAPF_REQUIRE(p->num_conv >= 1 && p->num_conv <= MAPF_MAX_CONV, MAPF_ERR_UNSUPPORTED);
-  MAPF_REQUIRE(p->channels[0] == 2, MAPF_ERR_SHAPE);
-  for (int l = 1; l <= p->num_conv; ++l)
-    MAPF_REQUIRE(p->channels[l] > 0 && p->channels[l] <= 64 && (p->channels[l] & 3) == 0, MAPF_ERR_UNSUPPORTED);
-  MAPF_REQUIRE(p->fc_in == kFovCells * p->channels[p->num_conv], MAPF_ERR_SHAPE);
-  MAPF_REQUIRE(p->fc_out > 0 && (p->fc_out & 15) == 0, MAPF_ERR_UNSUPPORTED);
-  MAPF_REQUIRE(p->num_actions > 0 && p->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
-  MAPF_REQUIRE(p->taps >= 0 && p->taps <= 8, MAPF_ERR_UNSUPPORTED);
-  MAPF_REQUIRE(p->taps == 0 || (p->node_dim > 0 && (p->node_dim & 3) == 0), MAPF_ERR_UNSUPPORTED);
-  return MAPF_OK;
-}
-
-EncoderDims encoder_dims(const mapf_net_params& p) {
-  EncoderDims d;
-  d.num_conv = p.num_conv;
-  for (int l = 0; l <= MAPF_MAX_CONV; ++l) d.channels[l] = l <= p.num_conv ? p.channels[l] : 0;
-  d.fc_in = p.fc_in;
-  d.fc_out = p.fc_out;
-  int b0 = kFovFloats, b1 = 0;
-  for (int l = 0; l < p.num_conv; ++l) {
-    const int out = kFovCells * p.channels[l + 1];
-    if (l & 1) b0 = max(b0, out); else b1 = max(b1, out);
-  }
-  d.buf0_floats = b0 * kEncAgents;
-  d.buf1_floats = b1 * kEncAgents;
-  return d;
-}
 
 }  // namespace
 
 extern "C" int64_t mapf_packed_weights_size(const mapf_net_params* p) {
-  if (check_params(p) != MAPF_OK) return -1;
+  if (mapf_check_params(p) != MAPF_OK) return -1;
   return mapf_packed_layout(*p).total;
 }
 
 extern "C" int mapf_pack_weights(const mapf_net_params* p, float* packed, mapf_stream_t stream) {
-  const int st = check_params(p);
+  const int st = mapf_check_params(p);
   if (st != MAPF_OK) return st;
   MAPF_REQUIRE(packed != nullptr && p->fc_w && p->fc_b && p->act_w && p->act_b, MAPF_ERR_NULL);
   for (int l = 0; l < p->num_conv; ++l)
@@ -529,23 +354,6 @@ extern "C" int mapf_pack_graph_weights(const float* w, const float* w2, int32_t 
   const int64_t total = int64_t(taps + (w2 ? 1 : 0)) * in_dim * out_dim;
   pack_graph_weights_kernel<<<int((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, w2, in_dim, taps,
                                                                                                    out_dim, wt);
-  return mapf_launch_status();
-}
-
-extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream) {
-  const int st = check_params(p);
-  if (st != MAPF_OK) return st;
-  MAPF_REQUIRE(a && a->states && a->packed && a->x, MAPF_ERR_NULL);
-  MAPF_REQUIRE(a->rows > 0, MAPF_ERR_SHAPE);
-  MAPF_REQUIRE(mapf_aligned(a->packed, 16) && mapf_aligned(a->x, 16) && mapf_aligned(a->states, 4), MAPF_ERR_ALIGN);
-  const EncoderDims d = encoder_dims(*p);
-  const size_t smem = size_t(d.buf0_floats + d.buf1_floats) * sizeof(float);
-  MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
-  if (cudaFuncSetAttribute(encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-    return MAPF_ERR_CUDA;
-  const int64_t grid = (a->rows + kEncAgents - 1) / kEncAgents;
-  encoder_fwd_kernel<<<unsigned(grid), kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      d, mapf_packed_layout(*p), a->rows, a->states, a->packed, a->x);
   return mapf_launch_status();
 }
 
@@ -583,7 +391,7 @@ extern "C" int mapf_head_fwd(const mapf_head_fwd_args* a, mapf_stream_t stream) 
 }
 
 extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_args* a, mapf_stream_t stream) {
-  const int st = check_params(p);
+  const int st = mapf_check_params(p);
   if (st != MAPF_OK) return st;
   MAPF_REQUIRE(a && a->states && a->packed && a->workspace_x && a->logits, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->batch > 0 && a->agents > 0, MAPF_ERR_SHAPE);
