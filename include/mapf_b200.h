@@ -217,6 +217,106 @@ typedef struct {
 } mapf_rollout_args;
 int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a, mapf_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Imitation-training step (reference: train.py:82-100)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Gradients, one buffer per parameter tensor, shapes as in mapf_net_params. */
+typedef struct {
+  float* conv_w[MAPF_MAX_CONV];
+  float* conv_b[MAPF_MAX_CONV];
+  float* bn_gamma[MAPF_MAX_CONV];
+  float* bn_beta[MAPF_MAX_CONV];
+  float* fc_w;
+  float* fc_b;
+  float* gf_w;  /* NULL for the baseline */
+  float* gf_w2; /* NULL unless message variant */
+  float* act_w;
+  float* act_b;
+} mapf_net_grads;
+
+/* Floats of caller-owned scratch the train-mode forward/backward pair needs for a [B,N] batch
+ * (saved activations, BatchNorm statistics, packed weights, gradient temporaries). -1 if unsupported. */
+int64_t mapf_train_workspace_size(const mapf_net_params* p, int32_t batch, int32_t agents);
+
+/* Train-mode Network.forward (train.py:87): BatchNorm uses batch statistics computed PER AGENT SLOT
+ * over B*25 values (the reference calls the conv stack once per agent, framework_gnn.py:160-163) and
+ * the running statistics receive N sequential momentum updates (p->bn_mean / p->bn_var are written
+ * through; bn_batches[l] += N when non-NULL).  gso is used as given (the loader's A + I,
+ * data_loader.py:74); GCNLayer adds its own I. */
+typedef struct {
+  int32_t batch, agents;
+  int32_t message;
+  float momentum;            /* 0.1 */
+  const float* states;       /* [B,N,2,5,5] */
+  const float* gso;          /* [B,N,N] (ignored for the baseline) */
+  float* workspace;          /* mapf_train_workspace_size floats, 16-byte aligned */
+  float* logits;             /* [B,N,A] out */
+  int64_t* bn_batches[MAPF_MAX_CONV];
+} mapf_train_fwd_args;
+int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream);
+
+/* Backward of the above from d(loss)/d(logits); must follow mapf_train_forward on the same
+ * workspace.  Every gradient buffer is overwritten. */
+typedef struct {
+  int32_t batch, agents;
+  int32_t message;
+  const float* states;
+  const float* gso;
+  float* workspace;
+  const float* dlogits;      /* [B,N,A] */
+  mapf_net_grads grads;
+} mapf_train_bwd_args;
+int mapf_train_backward(const mapf_net_params* p, const mapf_train_bwd_args* a, mapf_stream_t stream);
+
+/* nn.CrossEntropyLoss (mean) over rows = B*N (train.py:66,90-93): loss scalar and d loss / d logits. */
+typedef struct {
+  int64_t rows;
+  int32_t num_actions;
+  const float* logits;    /* [rows,A] */
+  const int32_t* targets; /* [rows] */
+  float* loss;            /* [1] out */
+  float* dlogits;         /* [rows,A] out */
+} mapf_ce_loss_args;
+int mapf_ce_loss(const mapf_ce_loss_args* a, mapf_stream_t stream);
+
+/* clip_grad_norm_(max_norm) followed by Adam with L2 weight decay (train.py:64,97,100; torch.optim.Adam
+ * defaults) over flat fp32 buffers; `step` is the 1-based step count.  grad_norm receives the
+ * pre-clip global L2 norm; scratch is one double owned by the caller. */
+typedef struct {
+  int64_t n;
+  float* params;
+  float* grads; /* scaled in place by the clip coefficient */
+  float* exp_avg;
+  float* exp_avg_sq;
+  float lr, beta1, beta2, eps, weight_decay, max_norm;
+  int32_t step;
+  float* grad_norm; /* [1] out */
+  double* scratch;  /* [1] */
+} mapf_clip_adam_args;
+int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream);
+
+/* Backward of the standalone GCNLayer / MessagePassingLayer (gnn.py:72-126,178-235) in the reference
+ * layouts: x [B,F,N], dy [B,G,N] -> dx [B,F,N], dw [F,K,G], dw2 [F,G] (w2/dw2 NULL for GCNLayer).
+ * workspace: mapf_graph_filter_bwd_workspace_size(B, N, F, G, K, has_skip) floats. */
+typedef struct {
+  int32_t batch, agents, in_dim, out_dim, taps;
+  int32_t add_self_loop;
+  const float* x;
+  const float* gso;
+  const float* w;
+  const float* w2;
+  const float* dy;
+  float* workspace;
+  float* dx;
+  float* dw;
+  float* dw2;
+} mapf_graph_filter_bwd_args;
+int64_t mapf_graph_filter_bwd_workspace_size(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim,
+                                             int32_t taps, int32_t has_skip);
+int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

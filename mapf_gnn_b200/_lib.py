@@ -72,6 +72,44 @@ class PolicyFwdArgs(C.Structure):
                 ("logits", c_f32p), ("actions", c_i32p)]
 
 
+class NetGrads(C.Structure):
+    _fields_ = [("conv_w", c_f32p * MAX_CONV), ("conv_b", c_f32p * MAX_CONV),
+                ("bn_gamma", c_f32p * MAX_CONV), ("bn_beta", c_f32p * MAX_CONV),
+                ("fc_w", c_f32p), ("fc_b", c_f32p), ("gf_w", c_f32p), ("gf_w2", c_f32p),
+                ("act_w", c_f32p), ("act_b", c_f32p)]
+
+
+class TrainFwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32), ("momentum", C.c_float),
+                ("states", c_f32p), ("gso", c_f32p), ("workspace", c_f32p), ("logits", c_f32p),
+                ("bn_batches", C.c_void_p * MAX_CONV)]
+
+
+class TrainBwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32),
+                ("states", c_f32p), ("gso", c_f32p), ("workspace", c_f32p), ("dlogits", c_f32p),
+                ("grads", NetGrads)]
+
+
+class CeLossArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("num_actions", C.c_int32), ("logits", c_f32p), ("targets", c_i32p),
+                ("loss", c_f32p), ("dlogits", c_f32p)]
+
+
+class ClipAdamArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("params", c_f32p), ("grads", c_f32p), ("exp_avg", c_f32p),
+                ("exp_avg_sq", c_f32p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float), ("step", C.c_int32),
+                ("grad_norm", c_f32p), ("scratch", C.c_void_p)]
+
+
+class GraphFilterBwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
+                ("taps", C.c_int32), ("add_self_loop", C.c_int32),
+                ("x", c_f32p), ("gso", c_f32p), ("w", c_f32p), ("w2", c_f32p), ("dy", c_f32p),
+                ("workspace", c_f32p), ("dx", c_f32p), ("dw", c_f32p), ("dw2", c_f32p)]
+
+
 class RolloutArgs(C.Structure):
     _fields_ = [("env", EnvStepArgs), ("policy", PolicyFwdArgs), ("steps", C.c_int32)]
 
@@ -91,6 +129,14 @@ _SIGNATURES = {
     "mapf_head_fwd": (C.c_int, [C.POINTER(HeadFwdArgs), C.c_void_p]),
     "mapf_policy_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(PolicyFwdArgs), C.c_void_p]),
     "mapf_rollout": (C.c_int, [C.POINTER(NetParams), C.POINTER(RolloutArgs), C.c_void_p]),
+    "mapf_train_workspace_size": (C.c_int64, [C.POINTER(NetParams), C.c_int32, C.c_int32]),
+    "mapf_train_forward": (C.c_int, [C.POINTER(NetParams), C.POINTER(TrainFwdArgs), C.c_void_p]),
+    "mapf_train_backward": (C.c_int, [C.POINTER(NetParams), C.POINTER(TrainBwdArgs), C.c_void_p]),
+    "mapf_ce_loss": (C.c_int, [C.POINTER(CeLossArgs), C.c_void_p]),
+    "mapf_clip_adam": (C.c_int, [C.POINTER(ClipAdamArgs), C.c_void_p]),
+    "mapf_graph_filter_bwd_workspace_size": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                          C.c_int32]),
+    "mapf_graph_filter_bwd": (C.c_int, [C.POINTER(GraphFilterBwdArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -364,7 +364,7 @@ extern "C" int mapf_graph_filter_fwd(const mapf_graph_filter_fwd_args* a, mapf_s
   MAPF_REQUIRE((a->in_dim & 15) == 0 && (a->out_dim & 3) == 0, MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(a->num_actions >= 0 && a->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(a->num_actions == 0 || (a->act_w && a->act_b && a->logits), MAPF_ERR_NULL);
-  MAPF_REQUIRE(a->num_actions > 0 || a->y, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->num_actions > 0 || a->y || a->z, MAPF_ERR_NULL);
   MAPF_REQUIRE(mapf_aligned(a->wt, 16), MAPF_ERR_ALIGN);
   const int epc = max(1, kGfRows / a->agents);
   const int KT = (a->taps + (a->has_skip ? 1 : 0)) * a->in_dim;

@@ -1,0 +1,856 @@
+// Imitation-training step on the GPU (reference semantics: train.py:82-100):
+// train-mode forward with per-agent-slot BatchNorm statistics, backward through head / graph filter /
+// encoder, cross-entropy, global-norm clip + Adam.  New decomposition; nothing here is a port.
+//
+// Activations live in HBM between layers (grid-wide BatchNorm statistics force a kernel boundary per
+// conv layer); rows are r = b*N + n.  Statistics are accumulated in fp64 (block-reduced, then one
+// atomicAdd(double) per (slot, channel)), matching the double accumulators of the reference's ATen
+// CPU BatchNorm.  Weight-gradient reductions over the batch use split-K GEMMs / persistent CTAs with
+// one fp32 atomicAdd per CTA and output element.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kBnEpsT = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout (offsets in floats)
+// ---------------------------------------------------------------------------------------------
+struct TrainLayout {
+  int64_t stat_fwd, stat_bwd;                 // fp64 [L][N][Cmax][2] each (offset in floats, 8-byte aligned)
+  int64_t meaninv[MAPF_MAX_CONV];             // [N][C][2]  (mean, invstd)
+  int64_t convpk[MAPF_MAX_CONV];              // [Cout/4][Cin][9][4]
+  int64_t convpk_bwd[MAPF_MAX_CONV];          // flipped / transposed filters for the data gradient
+  int64_t wt;                                 // [(K(+1))F][G]
+  int64_t u[MAPF_MAX_CONV], a[MAPF_MAX_CONV]; // pre-BN conv outputs, post BN+ReLU activations [rows][C*25]
+  int64_t x, z, y;                            // [rows][F], [rows][KT], [rows][G]
+  int64_t dy, dz, dx, da0, da1;
+  int64_t total;
+  int cmax;
+};
+
+__host__ __device__ inline int64_t r4(int64_t v) { return (v + 3) & ~int64_t(3); }
+inline int64_t mapf_min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
+  TrainLayout T{};
+  const int64_t rows = int64_t(B) * N;
+  int cmax = 0;
+  for (int l = 1; l <= p.num_conv; ++l) cmax = max(cmax, p.channels[l]);
+  T.cmax = cmax;
+  const int KT = (p.taps + (message ? 1 : 0)) * p.fc_out;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { const int64_t o = off; off += r4(n); return o; };
+  T.stat_fwd = take(int64_t(2) * p.num_conv * N * cmax * 2);
+  T.stat_bwd = take(int64_t(2) * p.num_conv * N * cmax * 2);
+  for (int l = 0; l < p.num_conv; ++l) {
+    const int64_t cin = p.channels[l], cout = p.channels[l + 1];
+    T.meaninv[l] = take(int64_t(N) * cout * 2);
+    T.convpk[l] = take(cout * cin * 9);
+    T.convpk_bwd[l] = take(cout * r4(cin) * 9);
+    T.u[l] = take(rows * cout * 25);
+    T.a[l] = take(rows * cout * 25);
+  }
+  T.wt = take(p.taps > 0 ? int64_t(KT) * p.node_dim : 0);
+  T.x = take(rows * p.fc_out);
+  T.z = take(p.taps > 0 ? rows * KT : 0);
+  T.y = take(p.taps > 0 ? rows * p.node_dim : 0);
+  T.dy = take(p.taps > 0 ? rows * p.node_dim : 0);
+  T.dz = take(p.taps > 0 ? rows * KT : 0);
+  T.dx = take(rows * p.fc_out);
+  T.da0 = take(rows * cmax * 25);
+  T.da1 = take(rows * cmax * 25);
+  T.total = off;
+  return T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// filters -> [Cout'/4][Cin'][9][4].  flip = 0: plain regrouping of w [Cout][Cin][9].  flip = 1: the
+// data-gradient filter bank, Cout' = Cin (padded to 4), Cin' = Cout, tap mirrored.
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int flip, float* __restrict__ out) {
+  const int co2 = flip ? int(r4(cin)) : cout, ci2 = flip ? cout : cin;
+  const int total = co2 * ci2 * 9;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int r = idx;
+    const int c4 = r & 3; r >>= 2;
+    const int t = r % 9; r /= 9;
+    const int ci = r % ci2;
+    const int co = (r / ci2) * 4 + c4;
+    float v;
+    if (!flip) v = w[(co * cin + ci) * 9 + t];
+    else v = co < cin ? w[(ci * cin + co) * 9 + (8 - t)] : 0.0f;
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv3x3 over one agent slot: grid (ceil(B/32), N), lane = batch item, warp = 4 output channels
+// ---------------------------------------------------------------------------------------------
+constexpr int kCtThreads = 128;
+constexpr int kCtPad = 33;
+
+__global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __restrict__ in, int cin, int cout,
+                                                                int B, int N, const float* __restrict__ wpk,
+                                                                const float* __restrict__ bias,
+                                                                float* __restrict__ out, double* __restrict__ stats,
+                                                                int stat_c) {
+  extern __shared__ __align__(16) float s_ct[];
+  float* s_in = s_ct;                               // [cin*25][33]
+  float* s_out = s_ct + cin * kFovCells * kCtPad;   // [cout*25][33]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y, b0 = blockIdx.x * 32;
+  const int nb = min(32, B - b0);
+  const int in_len = cin * kFovCells, out_len = cout * kFovCells;
+  for (int idx = tid; idx < 32 * in_len; idx += kCtThreads) {
+    const int r = idx / in_len, i = idx - r * in_len;
+    s_in[i * kCtPad + r] = r < nb ? __ldg(in + (int64_t(b0 + r) * N + n) * in_len + i) : 0.0f;
+  }
+  __syncthreads();
+  for (int cog = warp; cog < (cout >> 2); cog += kCtThreads / 32) {
+    float acc[4][kFovCells];
+    {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias) + cog);
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) { acc[0][p] = b.x; acc[1][p] = b.y; acc[2][p] = b.z; acc[3][p] = b.w; }
+    }
+    const float4* wp = reinterpret_cast<const float4*>(wpk) + int64_t(cog) * cin * 9;
+#pragma unroll 1
+    for (int ci = 0; ci < cin; ++ci) {
+      float v[kFovCells];
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) v[p] = s_in[(ci * kFovCells + p) * kCtPad + lane];
+      float4 wv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wv[t] = __ldg(wp + ci * 9 + t);
+#pragma unroll
+      for (int y = 0; y < kFov; ++y)
+#pragma unroll
+        for (int x = 0; x < kFov; ++x)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int yy = y + ky - 1, xx = x + kx - 1;
+              if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov) {
+                const float a = v[yy * kFov + xx];
+                const float4 ww = wv[ky * 3 + kx];
+                acc[0][y * kFov + x] = fmaf(a, ww.x, acc[0][y * kFov + x]);
+                acc[1][y * kFov + x] = fmaf(a, ww.y, acc[1][y * kFov + x]);
+                acc[2][y * kFov + x] = fmaf(a, ww.z, acc[2][y * kFov + x]);
+                acc[3][y * kFov + x] = fmaf(a, ww.w, acc[3][y * kFov + x]);
+              }
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float s1 = 0.0f;
+      double s2 = 0.0;
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) {
+        s_out[((cog * 4 + c) * kFovCells + p) * kCtPad + lane] = acc[c][p];
+        s1 += acc[c][p];
+        s2 += double(acc[c][p]) * double(acc[c][p]);
+      }
+      if (stats != nullptr) {
+        const double t1 = warp_sum(lane < nb ? double(s1) : 0.0);
+        const double t2 = warp_sum(lane < nb ? s2 : 0.0);
+        if (lane == 0) {
+          double* dst = stats + (int64_t(n) * stat_c + cog * 4 + c) * 2;
+          atomicAdd(dst, t1);
+          atomicAdd(dst + 1, t2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nb * out_len; idx += kCtThreads) {
+    const int r = idx / out_len, i = idx - r * out_len;
+    out[(int64_t(b0 + r) * N + n) * out_len + i] = s_out[i * kCtPad + r];
+  }
+}
+
+// batch statistics -> (mean, invstd) per (slot, channel); N sequential running-stat updates
+// (nn.BatchNorm2d momentum rule with the unbiased variance), framework_gnn.py:160-163
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int C, int stat_c, double count,
+                                   float momentum, float* __restrict__ meaninv, float* running_mean,
+                                   float* running_var, int64_t* batches) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float rm = running_mean ? running_mean[c] : 0.0f, rv = running_var ? running_var[c] : 0.0f;
+    for (int n = 0; n < N; ++n) {
+      const double s1 = stats[(int64_t(n) * stat_c + c) * 2], s2 = stats[(int64_t(n) * stat_c + c) * 2 + 1];
+      const double mean = s1 / count;
+      double var = s2 / count - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      const double invstd = 1.0 / sqrt(var + double(kBnEpsT));
+      meaninv[(n * C + c) * 2] = float(mean);
+      meaninv[(n * C + c) * 2 + 1] = float(invstd);
+      const float unbiased = float(count > 1.0 ? var * count / (count - 1.0) : var);
+      rm = (1.0f - momentum) * rm + momentum * float(mean);
+      rv = (1.0f - momentum) * rv + momentum * unbiased;
+    }
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+  }
+  if (c == 0 && batches != nullptr) *batches += N;
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ meaninv,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int N, int C,
+                                int64_t total, float* __restrict__ a) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t rc = idx / kFovCells;
+    const int c = int(rc % C);
+    const int n = int((rc / C) % N);
+    const float mean = meaninv[(n * C + c) * 2], invstd = meaninv[(n * C + c) * 2 + 1];
+    const float w = gamma[c] * invstd;
+    a[idx] = fmaxf(fmaf(u[idx], w, beta[c] - mean * w), 0.0f);
+  }
+}
+
+// sums over (batch, pixels) per (slot, channel) of dy and dy*xhat, dy = da * [a > 0]
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ a,
+                                                            const float* __restrict__ u,
+                                                            const float* __restrict__ meaninv, int B, int N, int C,
+                                                            int stat_c, double* __restrict__ stats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y, b0 = blockIdx.x * 32;
+  const int nb = min(32, B - b0);
+  for (int c = warp; c < C; c += 8) {
+    const float mean = meaninv[(n * C + c) * 2], invstd = meaninv[(n * C + c) * 2 + 1];
+    float s1 = 0.0f, s2 = 0.0f;
+    if (lane < kFovCells) {
+      for (int r = 0; r < nb; ++r) {
+        const int64_t idx = ((int64_t(b0 + r) * N + n) * C + c) * kFovCells + lane;
+        const float dy = a[idx] > 0.0f ? da[idx] : 0.0f;
+        s1 += dy;
+        s2 = fmaf(dy, (u[idx] - mean) * invstd, s2);
+      }
+    }
+    const double t1 = warp_sum(double(s1)), t2 = warp_sum(double(s2));
+    if (lane == 0) {
+      atomicAdd(stats + (int64_t(n) * stat_c + c) * 2, t1);
+      atomicAdd(stats + (int64_t(n) * stat_c + c) * 2 + 1, t2);
+    }
+  }
+}
+
+// du = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)), in place over da
+__global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ a, const float* __restrict__ u,
+                                    const float* __restrict__ meaninv, const float* __restrict__ gamma,
+                                    const double* __restrict__ stats, int N, int C, int stat_c, double count,
+                                    int64_t total) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t rc = idx / kFovCells;
+    const int c = int(rc % C);
+    const int n = int((rc / C) % N);
+    const float mean = meaninv[(n * C + c) * 2], invstd = meaninv[(n * C + c) * 2 + 1];
+    const float m1 = float(stats[(int64_t(n) * stat_c + c) * 2] / count);
+    const float m2 = float(stats[(int64_t(n) * stat_c + c) * 2 + 1] / count);
+    const float dy = a[idx] > 0.0f ? da[idx] : 0.0f;
+    const float xhat = (u[idx] - mean) * invstd;
+    da[idx] = gamma[c] * invstd * (dy - m1 - xhat * m2);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ stats, int N, int C, int stat_c,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double g = 0.0, b = 0.0;
+  for (int n = 0; n < N; ++n) {
+    b += stats[(int64_t(n) * stat_c + c) * 2];
+    g += stats[(int64_t(n) * stat_c + c) * 2 + 1];
+  }
+  dgamma[c] = float(g);
+  dbeta[c] = float(b);
+}
+
+// dW[co][ci][tap] = sum_{rows, pixels} du[r][co][p] * in[r][ci][p + tap], db[co] = sum du
+constexpr int kCwThreads = 256;
+constexpr int kCwRows = 32;
+constexpr int kCwSlots = 4;
+
+__global__ void __launch_bounds__(kCwThreads) conv_bwd_weight_kernel(const float* __restrict__ du,
+                                                                     const float* __restrict__ in, int cin, int cout,
+                                                                     int64_t rows, float* __restrict__ dw,
+                                                                     float* __restrict__ db) {
+  extern __shared__ __align__(16) float s_cw[];
+  const int in_len = cin * kFovCells, out_len = cout * kFovCells;
+  float* s_du = s_cw;                       // [32][out_len]
+  float* s_in = s_cw + kCwRows * out_len;   // [32][in_len]
+  const int tid = threadIdx.x;
+  const int npairs = cin * cout;
+  const bool small = npairs < kCwThreads;
+  const int rstep = small ? kCwThreads / npairs : 1;
+  const int rstart = small ? tid / npairs : 0;
+  const bool active = small ? tid < npairs * rstep : true;
+  float acc[kCwSlots][9];
+  float accb[kCwSlots];
+#pragma unroll
+  for (int s = 0; s < kCwSlots; ++s) {
+    accb[s] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[s][t] = 0.0f;
+  }
+  const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kCwRows;
+    const int nr = (rows - r0) < kCwRows ? int(rows - r0) : kCwRows;
+    __syncthreads();
+    for (int idx = tid; idx < nr * out_len; idx += kCwThreads) s_du[idx] = __ldg(du + r0 * out_len + idx);
+    for (int idx = tid; idx < nr * in_len; idx += kCwThreads) s_in[idx] = __ldg(in + r0 * in_len + idx);
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll
+    for (int s = 0; s < kCwSlots; ++s) {
+      const int pp = small ? tid % npairs : tid + s * kCwThreads;
+      if (pp >= npairs || (small && s > 0)) break;
+      const int co = pp / cin, ci = pp - co * cin;
+      for (int r = rstart; r < nr; r += rstep) {
+        float d[kFovCells], v[kFovCells];
+#pragma unroll
+        for (int p = 0; p < kFovCells; ++p) {
+          d[p] = s_du[r * out_len + co * kFovCells + p];
+          v[p] = s_in[r * in_len + ci * kFovCells + p];
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int y = 0; y < kFov; ++y)
+#pragma unroll
+              for (int x = 0; x < kFov; ++x) {
+                const int yy = y + ky - 1, xx = x + kx - 1;
+                if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov)
+                  acc[s][ky * 3 + kx] = fmaf(d[y * kFov + x], v[yy * kFov + xx], acc[s][ky * 3 + kx]);
+              }
+        if (ci == 0) {
+#pragma unroll
+          for (int p = 0; p < kFovCells; ++p) accb[s] += d[p];
+        }
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int s = 0; s < kCwSlots; ++s) {
+    const int pp = small ? tid % npairs : tid + s * kCwThreads;
+    if (pp >= npairs || (small && s > 0)) break;
+    const int co = pp / cin, ci = pp - co * cin;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(dw + int64_t(pp) * 9 + t, acc[s][t]);
+    if (ci == 0 && db != nullptr) atomicAdd(db + co, accb[s]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic fp32 GEMM  C[M,N] (+)= A[M,K] B[K,N]  with arbitrary element strides
+//   epilogue: + bias[n], ReLU, * [mask > 0]; split-K accumulates with atomicAdd into zeroed C
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+  int M, N, K;
+  const float* A; int64_t sam, sak;
+  const float* B; int64_t sbk, sbn;
+  float* C; int64_t ldc;
+  const float* bias;
+  const float* mask; int64_t ldmask;
+  int relu;
+  int splits;
+};
+constexpr int kGemmTile = 64, kGemmK = 16, kGemmThreads = 256;
+
+__global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[kGemmK][kGemmTile + 4];
+  __shared__ __align__(16) float Bs[kGemmK][kGemmTile + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * kGemmTile, n0 = blockIdx.x * kGemmTile;
+  const int kper = ((g.K + g.splits - 1) / g.splits + kGemmK - 1) / kGemmK * kGemmK;
+  const int kbeg = blockIdx.z * kper, kend = min(g.K, kbeg + kper);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
+  for (int k0 = kbeg; k0 < kend; k0 += kGemmK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * kGemmThreads;
+      int m, k;
+      if (a_kfast) { m = e >> 4; k = e & 15; } else { m = e & 63; k = e >> 6; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < g.M && gk < kend) ? __ldg(g.A + gm * g.sam + gk * g.sak) : 0.0f;
+      int n, kb;
+      if (b_nfast) { n = e & 63; kb = e >> 6; } else { n = e >> 4; kb = e & 15; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < g.N && gkb < kend) ? __ldg(g.B + gkb * g.sbk + gn * g.sbn) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kGemmK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.splits > 1) {
+        atomicAdd(g.C + m * g.ldc + n, v);
+      } else {
+        if (g.bias) v += __ldg(g.bias + n);
+        if (g.relu) v = fmaxf(v, 0.0f);
+        if (g.mask) v = __ldg(g.mask + m * g.ldmask + n) > 0.0f ? v : 0.0f;
+        g.C[m * g.ldc + n] = v;
+      }
+    }
+  }
+}
+
+int gemm(cudaStream_t s, int M, int N, int K, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
+         int64_t sbn, float* C, int64_t ldc, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
+         int64_t ldmask = 0, int splits = 1) {
+  GemmArgs g{M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, mask, ldmask, relu, splits};
+  dim3 grid((N + kGemmTile - 1) / kGemmTile, (M + kGemmTile - 1) / kGemmTile, splits);
+  sgemm_kernel<<<grid, kGemmThreads, 0, s>>>(g);
+  return mapf_launch_status();
+}
+
+// number of K splits for a reduction over `rows` with a small output
+int splits_for(int64_t rows, int tiles) {
+  int s = int((rows + 511) / 512);
+  const int cap = max(1, 592 / max(1, tiles));
+  return max(1, min(s, cap));
+}
+
+// out[c] = sum_r in[r][c]   (C <= 256)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, int64_t rows, int C,
+                                                     float* __restrict__ out) {
+  __shared__ float s_part[256];
+  const int tid = threadIdx.x;
+  const int per = 256 / C;                  // row lanes per block pass
+  const int c = tid % C, rl = tid / C;
+  float s = 0.0f;
+  if (rl < per)
+    for (int64_t r = blockIdx.x * int64_t(per) + rl; r < rows; r += int64_t(gridDim.x) * per) s += __ldg(in + r * C + c);
+  s_part[tid] = rl < per ? s : 0.0f;
+  __syncthreads();
+  if (tid < C) {
+    float t = 0.0f;
+    for (int q = 0; q < per; ++q) t += s_part[q * C + tid];
+    atomicAdd(out + tid, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph-filter recurrence backward: dZ [rows][KT] -> dX [rows][F] (one CTA per episode)
+//   x_k = x_{k-1} S  =>  dx_{k-1}[i] += sum_j S[i][j] dx_k[j];  skip: Xr = raw reshape of X[B,F,N]
+// then dh = dX * [x > 0] (ReLU of the encoder FC)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) recurrence_bwd_kernel(const float* __restrict__ dz,
+                                                             const float* __restrict__ gso,
+                                                             const float* __restrict__ x, int N, int F, int K,
+                                                             int has_skip, int add_self_loop, float* __restrict__ dx,
+                                                             int64_t dx_sb, int64_t dx_sn, int64_t dx_sf) {
+  extern __shared__ __align__(16) float s_rb[];
+  const int KT = (K + has_skip) * F;
+  float* sm = s_rb;                 // [N][N]
+  float* dinv = sm + N * N;         // [N]
+  float* d = dinv + ((N + 3) & ~3); // [N][KT]
+  const int tid = threadIdx.x, e = blockIdx.x;
+  for (int idx = tid; idx < N * N; idx += 128) {
+    const int i = idx / N, j = idx - i * N;
+    float v = __ldg(gso + int64_t(e) * N * N + idx);
+    if (add_self_loop && i == j) v += 1.0f;
+    sm[idx] = v;
+  }
+  for (int idx = tid; idx < N * KT; idx += 128) d[idx] = __ldg(dz + int64_t(e) * N * KT + idx);
+  __syncthreads();
+  if (tid < N) {
+    float deg = 0.0f;
+    for (int j = 0; j < N; ++j) deg += sm[tid * N + j];
+    dinv[tid] = deg > 0.0f ? __fdiv_rn(1.0f, __fsqrt_rn(deg)) : 0.0f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * N; idx += 128) {
+    const int i = idx / N, j = idx - i * N;
+    sm[idx] = (dinv[i] * sm[idx]) * dinv[j];
+  }
+  __syncthreads();
+  for (int k = K - 1; k >= 1; --k) {
+    for (int idx = tid; idx < N * F; idx += 128) {
+      const int i = idx / F, f = idx - i * F;
+      float s = 0.0f;
+      for (int j = 0; j < N; ++j) s = fmaf(sm[i * N + j], d[j * KT + k * F + f], s);
+      d[i * KT + (k - 1) * F + f] += s;
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < N * F; idx += 128) {
+    const int i = idx / F, f = idx - i * F;
+    float v = d[i * KT + f];
+    if (has_skip) {
+      const int q = f * N + i;  // X[b,f,n] sits at flat f*N+n = n'*F + f' of the reshaped [N,F] view
+      v += d[(q / F) * KT + K * F + (q % F)];
+    }
+    if (x != nullptr && !(__ldg(x + (int64_t(e) * N + i) * F + f) > 0.0f)) v = 0.0f;
+    dx[int64_t(e) * dx_sb + int64_t(i) * dx_sn + int64_t(f) * dx_sf] = v;
+  }
+}
+
+// [B,C,N] -> [B*N, C]
+__global__ void bcn_to_rows_kernel(const float* __restrict__ in, int B, int C, int N, float* __restrict__ out) {
+  const int64_t total = int64_t(B) * C * N;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % C);
+    const int64_t r = idx / C;
+    const int n = int(r % N);
+    const int64_t b = r / N;
+    out[idx] = __ldg(in + (b * C + c) * N + n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss and optimiser
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_loss_kernel(mapf_ce_loss_args a) {
+  const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int A = a.num_actions;
+  float loss = 0.0f;
+  if (r < a.rows) {
+    float v[kMaxActions];
+    float mx = -INFINITY;
+    for (int q = 0; q < A; ++q) { v[q] = a.logits[r * A + q]; mx = fmaxf(mx, v[q]); }
+    float sum = 0.0f;
+    for (int q = 0; q < A; ++q) { v[q] = expf(v[q] - mx); sum += v[q]; }
+    const int t = a.targets[r];
+    const float inv = 1.0f / sum, invn = 1.0f / float(a.rows);
+    for (int q = 0; q < A; ++q) a.dlogits[r * A + q] = (v[q] * inv - (q == t ? 1.0f : 0.0f)) * invn;
+    loss = (logf(sum) + mx - a.logits[r * A + t]) * invn;
+  }
+  loss = warp_sum(loss);
+  __shared__ float s_l[8];
+  if ((threadIdx.x & 31) == 0) s_l[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += s_l[w];
+    atomicAdd(a.loss, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    s += double(g[i]) * double(g[i]);
+  s = warp_sum(s);
+  __shared__ double s_s[8];
+  if ((threadIdx.x & 31) == 0) s_s[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_s[w];
+    atomicAdd(out, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, float bc1, float bc2_sqrt) {
+  const float total = float(sqrt(*a.scratch));
+  const float coef = fminf(a.max_norm / (total + 1e-6f), 1.0f);   // clip_grad_norm_ (train.py:97)
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.grad_norm = total;
+  const float step_size = a.lr / bc1;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < a.n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float p = a.params[i];
+    float g = a.grads[i] * coef;
+    a.grads[i] = g;
+    g = fmaf(a.weight_decay, p, g);                                 // Adam L2 weight decay
+    const float m = a.beta1 * a.exp_avg[i] + (1.0f - a.beta1) * g;
+    const float v = a.beta2 * a.exp_avg_sq[i] + (1.0f - a.beta2) * g * g;
+    a.exp_avg[i] = m;
+    a.exp_avg_sq[i] = v;
+    a.params[i] = p - step_size * (m / (sqrtf(v) / bc2_sqrt + a.eps));
+  }
+}
+
+int launch_conv_train(cudaStream_t s, const float* in, int cin, int cout, int B, int N, const float* wpk,
+                      const float* bias, float* out, double* stats, int stat_c) {
+  const size_t smem = sizeof(float) * size_t(cin + cout) * kFovCells * kCtPad;
+  if (smem > 220 * 1024) return MAPF_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(conv_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return MAPF_ERR_CUDA;
+  dim3 grid((B + 31) / 32, N);
+  conv_train_kernel<<<grid, kCtThreads, smem, s>>>(in, cin, cout, B, N, wpk, bias, out, stats, stat_c);
+  return mapf_launch_status();
+}
+
+#define MAPF_TRY(expr)              \
+  do {                              \
+    const int rc__ = (expr);        \
+    if (rc__ != MAPF_OK) return rc__; \
+  } while (0)
+
+int check_train(const mapf_net_params* p, int B, int N) {
+  const int st = mapf_check_params(p);
+  if (st != MAPF_OK) return st;
+  MAPF_REQUIRE(B > 0 && N > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(N <= 64 && N <= 65535, MAPF_ERR_UNSUPPORTED);
+  for (int l = 0; l < p->num_conv; ++l)
+    MAPF_REQUIRE(p->channels[l] * p->channels[l + 1] <= kCwSlots * kCwThreads, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(p->fc_out <= 256 && p->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
+  return MAPF_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t mapf_train_workspace_size(const mapf_net_params* p, int32_t batch, int32_t agents) {
+  if (check_train(p, batch, agents) != MAPF_OK) return -1;
+  return train_layout(*p, batch, agents, 1).total;
+}
+
+extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a != nullptr, MAPF_ERR_NULL);
+  MAPF_TRY(check_train(p, a->batch, a->agents));
+  MAPF_REQUIRE(a->states && a->workspace && a->logits && p->fc_w && p->fc_b && p->act_w && p->act_b, MAPF_ERR_NULL);
+  MAPF_REQUIRE(p->taps == 0 || (a->gso && p->gf_w), MAPF_ERR_NULL);
+  MAPF_REQUIRE(!a->message || p->gf_w2, MAPF_ERR_NULL);
+  MAPF_REQUIRE(mapf_aligned(a->workspace, 16), MAPF_ERR_ALIGN);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = a->batch, N = a->agents, L = p->num_conv;
+  const int64_t rows = int64_t(B) * N;
+  const TrainLayout T = train_layout(*p, B, N, 1);
+  float* ws = a->workspace;
+  double* stat = reinterpret_cast<double*>(ws + T.stat_fwd);
+  if (cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, s) != cudaSuccess) return MAPF_ERR_CUDA;
+  const double count = double(B) * kFovCells;
+  for (int l = 0; l < L; ++l) {
+    const int cin = p->channels[l], cout = p->channels[l + 1];
+    MAPF_REQUIRE(p->conv_w[l] && p->conv_b[l] && p->bn_gamma[l] && p->bn_beta[l], MAPF_ERR_NULL);
+    pack_conv_kernel<<<(cout * cin * 9 + 255) / 256, 256, 0, s>>>(p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
+    double* st = stat + int64_t(l) * N * T.cmax * 2;
+    MAPF_TRY(launch_conv_train(s, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, B, N, ws + T.convpk[l],
+                               p->conv_b[l], ws + T.u[l], st, T.cmax));
+    bn_finalize_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
+                                                      const_cast<float*>(p->bn_mean[l]),
+                                                      const_cast<float*>(p->bn_var[l]), a->bn_batches[l]);
+    const int64_t total = rows * cout * kFovCells;
+    bn_apply_kernel<<<unsigned(mapf_min64((total + 255) / 256, 148 * 16)), 256, 0, s>>>(
+        ws + T.u[l], ws + T.meaninv[l], p->bn_gamma[l], p->bn_beta[l], N, cout, total, ws + T.a[l]);
+  }
+  MAPF_TRY(mapf_launch_status());
+  const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
+  // compressMLP: x = relu(a_L Wfc^T + b)
+  MAPF_TRY(gemm(s, int(rows), F, fin, ws + T.a[L - 1], fin, 1, p->fc_w, 1, fin, ws + T.x, F, p->fc_b, 1));
+  if (p->taps == 0) return gemm(s, int(rows), A, F, ws + T.x, F, 1, p->act_w, 1, F, a->logits, A, p->act_b, 0);
+  MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, p->taps, p->node_dim, ws + T.wt, stream));
+  mapf_graph_filter_fwd_args g{};
+  g.batch = B; g.agents = N; g.in_dim = F; g.out_dim = p->node_dim; g.taps = p->taps;
+  g.add_self_loop = a->message ? 0 : 1;
+  g.has_skip = a->message ? 1 : 0;
+  g.relu = 1;
+  g.num_actions = A;
+  g.x = ws + T.x; g.x_sb = int64_t(N) * F; g.x_sn = F; g.x_sf = 1;
+  g.gso = a->gso;
+  g.wt = ws + T.wt;
+  g.y = ws + T.y; g.y_sb = int64_t(N) * p->node_dim; g.y_sn = p->node_dim; g.y_sg = 1;
+  g.z = ws + T.z;
+  g.act_w = p->act_w; g.act_b = p->act_b;
+  g.logits = a->logits; g.actions = nullptr;
+  return mapf_graph_filter_fwd(&g, stream);
+}
+
+extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bwd_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a != nullptr, MAPF_ERR_NULL);
+  MAPF_TRY(check_train(p, a->batch, a->agents));
+  MAPF_REQUIRE(a->states && a->workspace && a->dlogits, MAPF_ERR_NULL);
+  const mapf_net_grads& G = a->grads;
+  MAPF_REQUIRE(G.fc_w && G.fc_b && G.act_w && G.act_b, MAPF_ERR_NULL);
+  MAPF_REQUIRE(p->taps == 0 || (a->gso && G.gf_w), MAPF_ERR_NULL);
+  MAPF_REQUIRE(!a->message || G.gf_w2, MAPF_ERR_NULL);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = a->batch, N = a->agents, L = p->num_conv;
+  const int F = p->fc_out, fin = p->fc_in, A = p->num_actions, Gd = p->node_dim, K = p->taps;
+  const int64_t rows = int64_t(B) * N;
+  const TrainLayout T = train_layout(*p, B, N, 1);
+  float* ws = a->workspace;
+  const int head_in = K > 0 ? Gd : F;
+  auto zero = [&](float* ptr, int64_t n) { return cudaMemsetAsync(ptr, 0, sizeof(float) * size_t(n), s) == cudaSuccess; };
+  bool ok = zero(G.act_w, int64_t(A) * head_in) && zero(G.act_b, A) && zero(G.fc_w, int64_t(F) * fin) && zero(G.fc_b, F);
+  if (K > 0) ok = ok && zero(G.gf_w, int64_t(F) * K * Gd);
+  if (a->message) ok = ok && zero(G.gf_w2, int64_t(F) * Gd);
+  for (int l = 0; l < L; ++l) {
+    MAPF_REQUIRE(G.conv_w[l] && G.conv_b[l] && G.bn_gamma[l] && G.bn_beta[l], MAPF_ERR_NULL);
+    ok = ok && zero(G.conv_w[l], int64_t(p->channels[l]) * p->channels[l + 1] * 9) && zero(G.conv_b[l], p->channels[l + 1]);
+  }
+  double* stat = reinterpret_cast<double*>(ws + T.stat_bwd);
+  ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, s) == cudaSuccess;
+  if (!ok) return MAPF_ERR_CUDA;
+
+  const int row_splits = splits_for(rows, 4);
+  const float* head_act = K > 0 ? ws + T.y : ws + T.x;
+  // actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0]
+  colsum_kernel<<<int(mapf_min64((rows + 255) / 256, 296)), 256, 0, s>>>(a->dlogits, rows, A, G.act_b);
+  MAPF_TRY(gemm(s, A, head_in, int(rows), a->dlogits, 1, A, head_act, head_in, 1, G.act_w, head_in, nullptr, 0, nullptr,
+                0, splits_for(rows, (head_in + 63) / 64)));
+  if (K > 0) {
+    const int KF = K * F, KT = (K + (a->message ? 1 : 0)) * F;
+    MAPF_TRY(gemm(s, int(rows), Gd, A, a->dlogits, A, 1, p->act_w, Gd, 1, ws + T.dy, Gd, nullptr, 0, ws + T.y, Gd));
+    // dW_eff[g][j] = sum_r dy[r][g] z[r][j]  -- row-major [G][K*F] IS the memory of GFL.0.W [F,K,G] (gnn.py:114-116)
+    MAPF_TRY(gemm(s, Gd, KF, int(rows), ws + T.dy, 1, Gd, ws + T.z, KT, 1, G.gf_w, KF, nullptr, 0, nullptr, 0,
+                  splits_for(rows, ((Gd + 63) / 64) * ((KF + 63) / 64))));
+    // dz[r][j] = sum_g dy[r][g] W_eff[g][j]
+    MAPF_TRY(gemm(s, int(rows), KF, Gd, ws + T.dy, Gd, 1, p->gf_w, KF, 1, ws + T.dz, KT));
+    if (a->message) {
+      MAPF_TRY(gemm(s, Gd, F, int(rows), ws + T.dy, 1, Gd, ws + T.z + KF, KT, 1, G.gf_w2, F, nullptr, 0, nullptr, 0,
+                    splits_for(rows, ((Gd + 63) / 64) * ((F + 63) / 64))));
+      MAPF_TRY(gemm(s, int(rows), F, Gd, ws + T.dy, Gd, 1, p->gf_w2, F, 1, ws + T.dz + KF, KT));
+    }
+    const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
+    MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
+    if (cudaFuncSetAttribute(recurrence_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      return MAPF_ERR_CUDA;
+    recurrence_bwd_kernel<<<B, 128, smem, s>>>(ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
+                                               a->message ? 0 : 1, ws + T.dx, int64_t(N) * F, F, 1);
+  } else {
+    MAPF_TRY(gemm(s, int(rows), F, A, a->dlogits, A, 1, p->act_w, F, 1, ws + T.dx, F, nullptr, 0, ws + T.x, F));
+  }
+  // compressMLP backward
+  colsum_kernel<<<int(mapf_min64((rows + 255) / 256, 296)), 256, 0, s>>>(ws + T.dx, rows, F, G.fc_b);
+  MAPF_TRY(gemm(s, F, fin, int(rows), ws + T.dx, 1, F, ws + T.a[L - 1], fin, 1, G.fc_w, fin, nullptr, 0, nullptr, 0,
+                splits_for(rows, ((F + 63) / 64) * ((fin + 63) / 64))));
+  float* da = ws + T.da0;
+  float* da_next = ws + T.da1;
+  MAPF_TRY(gemm(s, int(rows), fin, F, ws + T.dx, F, 1, p->fc_w, fin, 1, da, fin));
+  (void)row_splits;
+  const double count = double(B) * kFovCells;
+  for (int l = L - 1; l >= 0; --l) {
+    const int cin = p->channels[l], cout = p->channels[l + 1];
+    double* st = stat + int64_t(l) * N * T.cmax * 2;
+    dim3 grid((B + 31) / 32, N);
+    bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
+    const int64_t total = rows * cout * kFovCells;
+    bn_bwd_apply_kernel<<<unsigned(mapf_min64((total + 255) / 256, 148 * 16)), 256, 0, s>>>(
+        da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], p->bn_gamma[l], st, N, cout, T.cmax, count, total);
+    bn_param_grads_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
+    {
+      const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
+      MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
+      if (cudaFuncSetAttribute(conv_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return MAPF_ERR_CUDA;
+      const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
+      const int gridw = int(mapf_min64(ntiles, 2 * 148));
+      conv_bwd_weight_kernel<<<gridw, kCwThreads, smem, s>>>(da, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, rows,
+                                                            G.conv_w[l], G.conv_b[l]);
+    }
+    if (l > 0) {
+      // data gradient = the same 3x3 convolution with mirrored, transposed filters
+      const int cin_pad = int(r4(cin));
+      pack_conv_kernel<<<(cin_pad * cout * 9 + 255) / 256, 256, 0, s>>>(p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
+      MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
+      MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
+      float* t = da; da = da_next; da_next = t;
+    }
+  }
+  return mapf_launch_status();
+}
+
+extern "C" int mapf_ce_loss(const mapf_ce_loss_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a && a->logits && a->targets && a->loss && a->dlogits, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->rows > 0 && a->num_actions > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(a->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(a->loss, 0, sizeof(float), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  ce_loss_kernel<<<unsigned((a->rows + 255) / 256), 256, 0, s>>>(*a);
+  return mapf_launch_status();
+}
+
+extern "C" int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a && a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->grad_norm && a->scratch, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->n > 0 && a->step >= 1, MAPF_ERR_SHAPE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(a->scratch, 0, sizeof(double), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  const int blocks = int(mapf_min64((a->n + 255) / 256, 148));
+  sumsq_kernel<<<blocks, 256, 0, s>>>(a->grads, a->n, a->scratch);
+  const double bc1 = 1.0 - pow(double(a->beta1), double(a->step));
+  const double bc2 = 1.0 - pow(double(a->beta2), double(a->step));
+  clip_adam_kernel<<<blocks, 256, 0, s>>>(*a, float(bc1), float(sqrt(bc2)));
+  return mapf_launch_status();
+}
+
+extern "C" int64_t mapf_graph_filter_bwd_workspace_size(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim,
+                                                        int32_t taps, int32_t has_skip) {
+  const int64_t rows = int64_t(batch) * agents, KT = int64_t(taps + (has_skip ? 1 : 0)) * in_dim;
+  return r4(KT * out_dim) + 2 * r4(rows * KT) + r4(rows * out_dim);
+}
+
+extern "C" int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a && a->x && a->gso && a->w && a->dy && a->workspace && a->dx && a->dw, MAPF_ERR_NULL);
+  MAPF_REQUIRE((a->w2 == nullptr) == (a->dw2 == nullptr), MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->batch > 0 && a->agents > 0 && a->in_dim > 0 && a->out_dim > 0 && a->taps > 0, MAPF_ERR_SHAPE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = a->batch, N = a->agents, F = a->in_dim, G = a->out_dim, K = a->taps;
+  const int skip = a->w2 ? 1 : 0, KF = K * F, KT = (K + skip) * F;
+  const int64_t rows = int64_t(B) * N;
+  float* wt = a->workspace;
+  float* z = wt + r4(int64_t(KT) * G);
+  float* dz = z + r4(rows * KT);
+  float* dyr = dz + r4(rows * KT);
+  // recompute the filter taps z with the forward kernel
+  MAPF_TRY(mapf_pack_graph_weights(a->w, a->w2, F, K, G, wt, stream));
+  bcn_to_rows_kernel<<<unsigned(mapf_min64((rows * G + 255) / 256, 148 * 16)), 256, 0, s>>>(a->dy, B, G, N, dyr);
+  mapf_graph_filter_fwd_args g{};
+  g.batch = B; g.agents = N; g.in_dim = F; g.out_dim = G; g.taps = K;
+  g.add_self_loop = a->add_self_loop; g.has_skip = skip; g.relu = 0; g.num_actions = 0;
+  g.x = a->x; g.x_sb = int64_t(F) * N; g.x_sn = 1; g.x_sf = N;
+  g.gso = a->gso; g.wt = wt;
+  g.y = nullptr;   // only the saved filter taps z are needed
+  g.z = z;
+  MAPF_TRY(mapf_graph_filter_fwd(&g, stream));
+  if (cudaMemsetAsync(a->dw, 0, sizeof(float) * size_t(KF) * G, s) != cudaSuccess) return MAPF_ERR_CUDA;
+  MAPF_TRY(gemm(s, G, KF, int(rows), dyr, 1, G, z, KT, 1, a->dw, KF, nullptr, 0, nullptr, 0,
+                splits_for(rows, ((G + 63) / 64) * ((KF + 63) / 64))));
+  MAPF_TRY(gemm(s, int(rows), KF, G, dyr, G, 1, a->w, KF, 1, dz, KT));
+  if (skip) {
+    if (cudaMemsetAsync(a->dw2, 0, sizeof(float) * size_t(F) * G, s) != cudaSuccess) return MAPF_ERR_CUDA;
+    MAPF_TRY(gemm(s, G, F, int(rows), dyr, 1, G, z + KF, KT, 1, a->dw2, F, nullptr, 0, nullptr, 0,
+                  splits_for(rows, ((G + 63) / 64) * ((F + 63) / 64))));
+    MAPF_TRY(gemm(s, int(rows), F, G, dyr, G, 1, a->w2, F, 1, dz + KF, KT));
+  }
+  const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
+  MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
+  if (cudaFuncSetAttribute(recurrence_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return MAPF_ERR_CUDA;
+  recurrence_bwd_kernel<<<B, 128, smem, s>>>(dz, a->gso, nullptr, N, F, K, skip, a->add_self_loop, a->dx, int64_t(F) * N,
+                                             1, N);
+  return mapf_launch_status();
+}

@@ -106,7 +106,7 @@ class _PolicyBase(nn.Module):
         """BatchNorm-folded, kernel-ordered weights; re-packed when any parameter/buffer changed."""
         g = self.param_groups()
         flat = [t for v in g.values() for t in (v if isinstance(v, list) else [v]) if t is not None]
-        key = tuple((t.data_ptr(), t._version) for t in flat)
+        key = (getattr(self, "_weights_epoch", 0),) + tuple((t.data_ptr(), t._version) for t in flat)
         if self._packed is None or key != self._packed_key:
             d = lambda ts: [t.detach() for t in ts]
             self._packed = torch.ops.mapf.pack_weights(

@@ -1,0 +1,158 @@
+"""GPU parity of the training step (train.py:82-100) against loss / gradients / BatchNorm statistics /
+post-Adam parameters recorded from the unmodified reference (tests/golden/train_step.npz) and against the
+torch-CPU oracle on other shapes.  fp32: gradients within 1e-4 relative per tensor (with the absolute floor
+of SURVEY 8d for the mathematically-zero conv-bias gradients)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_network, oracle_params, rel_err
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+GRAD_FLOOR = 1e-3   # x total gradient norm, see tests/test_oracle_model.py
+
+
+def _batch(t):
+    states = torch.from_numpy(t["states"]).float().cuda()
+    gso = (torch.from_numpy(t["adj"]).float() + torch.eye(5)).cuda()
+    targets = torch.from_numpy(t["targets"]).long().cuda()
+    return states, gso, targets
+
+
+@pytest.mark.parametrize("name", ["gnn_msg_k3", "gnn_k3", "baseline"])
+def test_autograd_step_matches_reference(train_step, name):
+    """The reference's own step body on top of our modules: model(states, gso) -> CrossEntropyLoss -> backward."""
+    t = train_step
+    net = load_network(name).train()
+    states, gso, targets = _batch(t)
+    out = net(states) if name == "baseline" else net(states, gso)
+    loss = torch.nn.functional.cross_entropy(out.reshape(-1, 5), targets.reshape(-1))
+    loss.backward()
+    assert rel_err(out.detach().cpu().numpy(), t[f"{name}/logits"]) < REL
+    assert abs(loss.item() - t[f"{name}/loss"][0]) < 1e-5 * abs(t[f"{name}/loss"][0])
+    floor = GRAD_FLOOR * t[f"{name}/total_norm"][0]
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        assert rel_err(p.grad.cpu().numpy(), t[f"{name}/grad/{k}"], floor) < REL, k
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert rel_err(v.cpu().numpy(), t[f"{name}/after/{k}"]) < 1e-5, k
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(t[f"{name}/after/{k}"]), k
+
+
+@pytest.mark.parametrize("name", ["gnn_msg_k3", "gnn_k3", "baseline"])
+def test_fused_trainer_step_matches_reference(train_step, name):
+    import mapf_gnn_b200.train as tr
+    t = train_step
+    net = load_network(name).train()
+    trainer = tr.Trainer(net, lr=3e-4, weight_decay=1e-4, max_norm=1.0)
+    states, gso, targets = _batch(t)
+    loss = trainer.step(states, None if name == "baseline" else gso, targets)
+    assert abs(loss.item() - t[f"{name}/loss"][0]) < 1e-5 * abs(t[f"{name}/loss"][0])
+    assert abs(trainer.grad_norm.item() - t[f"{name}/total_norm"][0]) < 1e-4 * t[f"{name}/total_norm"][0]
+    sd = net.state_dict()
+    for k, v in sd.items():
+        ref = t[f"{name}/after/{k}"]
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(ref)
+        elif k.startswith("convLayers") and k.endswith(".bias") and int(k.split(".")[1]) % 3 == 0:
+            # conv biases feed train-mode BatchNorm: their true gradient is 0, Adam's first step turns the
+            # reference's rounding noise into +-lr.  Bound the move instead of matching the noise.
+            assert np.abs(v.cpu().numpy() - ref).max() <= 2 * 3e-4 + 1e-7, k
+        else:
+            assert rel_err(v.cpu().numpy(), ref) < 2e-5, k
+
+
+def test_clip_adam_kernel_on_reference_gradients(train_step):
+    """Optimizer kernel alone, fed the reference's gradients: parameters must match torch.optim.Adam."""
+    from mapf_gnn_b200 import _lib
+    t = train_step
+    name = "gnn_msg_k3"
+    params = oracle_params(name)
+    keys = mo.trainable_keys(params)
+    flat = torch.cat([params[k].reshape(-1) for k in keys]).cuda()
+    grads = torch.cat([torch.from_numpy(t[f"{name}/grad/{k}"]).reshape(-1) for k in keys]).cuda()
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    norm = torch.zeros(1, device="cuda")
+    scratch = torch.zeros(1, dtype=torch.float64, device="cuda")
+    a = _lib.ClipAdamArgs()
+    a.n, a.params, a.grads, a.exp_avg, a.exp_avg_sq = flat.numel(), flat.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr()
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.max_norm, a.step = 3e-4, 0.9, 0.999, 1e-8, 1e-4, 1.0, 1
+    a.grad_norm, a.scratch = norm.data_ptr(), scratch.data_ptr()
+    _lib.check(_lib.load().mapf_clip_adam(a, _lib.current_stream()))
+    assert abs(norm.item() - t[f"{name}/total_norm"][0]) < 1e-5 * t[f"{name}/total_norm"][0]
+    off = 0
+    out = flat.cpu().numpy()
+    for k in keys:
+        n = params[k].numel()
+        assert rel_err(out[off:off + n].reshape(params[k].shape), t[f"{name}/after/{k}"]) < 1e-5, k
+        off += n
+
+
+@pytest.mark.parametrize("name,B,N", [("gnn_k3", 70, 5), ("gnn_msg_k3", 37, 9), ("gnn_k4_seed4", 6, 20),
+                                      ("baseline", 130, 5)])
+def test_gradients_match_oracle_other_shapes(name, B, N):
+    rng = np.random.default_rng(B + N)
+    states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+    adj = torch.tensor((rng.random((B, N, N)) < 0.3).astype(np.float32))
+    adj[:, torch.arange(N), torch.arange(N)] = 0
+    gso = adj + torch.eye(N)
+    targets = torch.tensor(rng.integers(0, 5, size=(B, N)))
+    params = oracle_params(name)
+    loss_ref, grads_ref, bn_ref = mo.loss_and_grads(params, states, gso, targets)
+    total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads_ref.values())))
+    net = load_network(name, num_agents=N).train()
+    out = net(states.cuda()) if name == "baseline" else net(states.cuda(), gso.cuda())
+    loss = torch.nn.functional.cross_entropy(out.reshape(-1, 5), targets.cuda().reshape(-1))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy(), GRAD_FLOOR * total) < REL, k
+    for k, v in bn_ref.items():
+        if "running" in k:
+            assert rel_err(net.state_dict()[k].cpu().numpy(), v.detach().numpy()) < 1e-5, k
+
+
+@pytest.mark.parametrize("cls_name,K,N", [("GCNLayer", 3, 5), ("MessagePassingLayer", 2, 7)])
+def test_standalone_layer_backward_matches_oracle(cls_name, K, N):
+    import mapf_gnn_b200 as m
+    torch.manual_seed(1)
+    B, F, G = 9, 64, 128
+    layer = getattr(m, cls_name)(N, F, G, K).cuda()
+    x = torch.randn(B, F, N, requires_grad=True)
+    adj = (torch.rand(B, N, N) < 0.4).float()
+    adj[0, 1, :] = 0
+    W = layer.W.detach().cpu().clone().requires_grad_(True)
+    W2 = layer.W2.detach().cpu().clone().requires_grad_(True) if cls_name == "MessagePassingLayer" else None
+    gy = torch.randn(B, G, N)
+    y_ref = mo.graph_filter(x, adj, W, W2)
+    y_ref.backward(gy)
+    xg = x.detach().cuda().requires_grad_(True)
+    layer.addGSO(adj.cuda())
+    y = layer(xg)
+    y.backward(gy.cuda())
+    assert rel_err(y.detach().cpu().numpy(), y_ref.detach().numpy()) < 1e-5
+    assert rel_err(xg.grad.cpu().numpy(), x.grad.numpy()) < REL
+    assert rel_err(layer.W.grad.cpu().numpy(), W.grad.numpy()) < REL
+    if W2 is not None:
+        assert rel_err(layer.W2.grad.cpu().numpy(), W2.grad.numpy()) < REL
+
+
+def test_eval_after_training_uses_updated_weights(train_step):
+    import mapf_gnn_b200.train as tr
+    net = load_network("gnn_k3").train()
+    trainer = tr.Trainer(net)
+    states, gso, targets = _batch(train_step)
+    with torch.no_grad():
+        before = net.eval()(states, gso).clone()
+    net.train()
+    for _ in range(3):
+        trainer.step(states, gso, targets)
+    with torch.no_grad():
+        after = net.eval()(states, gso)
+        ref = mo.forward({k: v.cpu() for k, v in net.state_dict().items()}, states.cpu(), gso.cpu())
+    assert not torch.allclose(before, after)
+    assert rel_err(after.cpu().numpy(), ref.numpy()) < REL
