@@ -298,6 +298,8 @@ def run_mine(args, w):
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
     e2e_value = float(u[0]) / float(t[0])
 
+    train = None if args.no_train else run_train(args, w, env, dev, rank, world, barrier)
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -329,10 +331,81 @@ def run_mine(args, w):
                     "d2h_bytes_per_step": E * N * 4 + E * N * 8 + E, "steps": ke},
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_train_steps(model, states, gso, targets, steps):
+    """train.py:82-100 on the host through the oracle port: train-mode forward, CE, backward, clip, Adam."""
+    import torch
+    from oracle import model_oracle as mo
+    params = {k: torch.from_numpy(v) for k, v in load_weights(model).items()}
+    keys = mo.trainable_keys(params)
+    m = {k: torch.zeros_like(params[k]) for k in keys}
+    v = {k: torch.zeros_like(params[k]) for k in keys}
+    total = 0.0
+    for it in range(steps + 1):
+        t0 = time.perf_counter()
+        loss, grads, bn = mo.loss_and_grads(params, states, gso, targets)
+        newp, m, v, _ = mo.clip_and_adam(params, grads, m, v, step=it + 1)
+        params = dict(params, **newp, **{k: t.detach() for k, t in bn.items()})
+        if it > 0:
+            total += time.perf_counter() - t0
+    return states.shape[0] * steps / total
+
+
+def run_train(args, w, env, dev, rank, world, barrier):
+    """Second BASELINE metric: train samples/sec of the full imitation step (train.py:82-100) on synthetic
+    CBS-shaped batches: observations recorded from the resident episodes, A + I as the loader feeds it
+    (data_loader.py:74), uniform random expert actions; the message-passing network train.py trains."""
+    import torch
+    import mapf_gnn_b200 as m
+    import mapf_gnn_b200.train as tr
+    model = "baseline" if w["model"] == "baseline" else ("gnn_msg_k3" if w["N"] == 5 else w["model"])
+    wl = dict(w, model=model)
+    cfg = model_config(wl)
+    N = w["N"]
+    env.reset()
+    results = []
+    eye = torch.eye(N, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3 + rank)
+    for B in args.train_batches:
+        net = m.build_network(cfg)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights(model).items()})
+        net = net.to(dev).train()
+        trainer = tr.Trainer(net)
+        reps = (B + env.episodes - 1) // env.episodes
+        states = env.fov.repeat(reps, 1, 1, 1, 1)[:B].contiguous()
+        gso = (env.adj_matrix + eye).repeat(reps, 1, 1)[:B].contiguous()
+        targets = torch.randint(0, 5, (B, N), device=dev, generator=gen, dtype=torch.int32)
+        for _ in range(3):
+            trainer.step(states, gso, targets)
+        barrier()
+        steps = 10
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss = trainer.step(states, gso, targets)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        entry = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms / steps,
+                 "samples_per_s": B * world * steps / (ms * 1e-3), "loss": float(loss.item())}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and B <= 1024:
+            entry["cpu_samples_per_s"] = cpu_train_steps(model, states.cpu(), gso.cpu(), targets.cpu().long(), 3)
+        results.append(entry)
+    return {"metric": "train samples/sec (forward + CE + backward + clip + Adam" + (" + NCCL all-reduce)" if world > 1
+                                                                                    else ")"),
+            "model": model, "agents": N, "results": results}
 
 
 def main():
@@ -347,6 +420,8 @@ def main():
     ap.add_argument("--cpu-episodes", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-batches", type=int, nargs="*", default=[128, 1024, 8192])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

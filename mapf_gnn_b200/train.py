@@ -220,8 +220,8 @@ class Trainer:
         loss, dlogits = cross_entropy(logits, targets)
         _backward(net, saved, dlogits, self.grad_views)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=self.group)
+            from .parallel import average_gradients
+            average_gradients(self.flat_grad, self.group)
         self.step_count += 1
         a = _lib.ClipAdamArgs()
         a.n = self.flat.numel()
