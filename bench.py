@@ -147,6 +147,7 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1; the CPU arm may use every core
     episodes = args.ref_episodes
     value, total = cpu_reference_steps(w, episodes, args.steps, args.warmup)
     cores = torch.get_num_threads()
@@ -303,6 +304,7 @@ def run_mine(args, w):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
             v, tot = cpu_reference_steps(w, args.cpu_episodes, args.cpu_steps, 1)
             cpu = {"value": v, "unit": "agent-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{args.cpu_episodes} episodes x {args.cpu_steps} steps of the same workload, "
@@ -417,8 +419,8 @@ def main():
     ap.add_argument("--workload", default="c2a", choices=sorted(WORKLOADS))
     ap.add_argument("--episodes", type=int, default=0, help="episodes per GPU (default: the workload's)")
     ap.add_argument("--ref-episodes", type=int, default=512, help="episodes per step of the --impl reference arm")
-    ap.add_argument("--cpu-episodes", type=int, default=1024)
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-episodes", type=int, default=4096)
+    ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-batches", type=int, nargs="*", default=[128, 1024, 8192])
