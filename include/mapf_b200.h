@@ -317,6 +317,13 @@ int64_t mapf_graph_filter_bwd_workspace_size(int32_t batch, int32_t agents, int3
                                              int32_t taps, int32_t has_skip);
 int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_stream_t stream);
 
+/* fp32-accurate tensor-core GEMM (3xTF32 on tcgen05, accumulators in TMEM):
+ * C[M,N] = act(A[M,K] B[N,K]^T + bias[N]); A, B row-major with K contiguous, lda/ldb multiples of 4, 16-byte
+ * aligned bases; bias may be NULL; relu != 0 applies max(0, .).  The building block behind the encoder FC
+ * (compressMLP, framework_gnn.py:93) and the graph-filter mix (gnn.py:117-118). */
+int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                 int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
