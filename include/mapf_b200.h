@@ -201,6 +201,7 @@ typedef struct {
   const float* gso;       /* [B,N,N] (ignored for the baseline) */
   const float* packed;
   float* workspace_x;
+  float* workspace_z;     /* [B*N, (K+1)*F] floats: enables the tensor-core graph-filter path; NULL = fused FFMA kernel */
   float* logits;          /* [B,N,A] */
   int32_t* actions;       /* [B,N] or NULL */
 } mapf_policy_fwd_args;
@@ -323,6 +324,16 @@ int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_stream_t str
  * (compressMLP, framework_gnn.py:93) and the graph-filter mix (gnn.py:117-118). */
 int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                  int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream);
+
+/* Tensor-core graph-filter tail: logits / greedy actions = actionMLP(relu(Z [W | W2]^T)) with Z [M, K0+K1] the
+ * row-major filter taps from mapf_graph_taps, W = GFL.0.W viewed as [G, K*F] and W2 = GFL.0.W2 viewed as [G, F]
+ * (the raw reshapes of gnn.py:114-116,222 -- no repacking needed).  y (optional) receives relu(...) [M, G]. */
+int mapf_tc_mix_head(int32_t M, int32_t N, const float* Z, int64_t ldz, const float* W, int32_t K0, const float* W2,
+                     int32_t K1, const float* act_w, const float* act_b, int32_t num_actions, float* logits,
+                     int32_t* actions, float* y, mapf_stream_t stream);
+/* Filter taps Z [B*N, (K+has_skip)*F] (x_k = x_{k-1} S, gnn.py:104-109, + skip columns gnn.py:201-204) from
+ * agent-major x; uses the x / gso / z / size / flag fields of the argument struct. */
+int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,7 @@ class HeadFwdArgs(C.Structure):
 class PolicyFwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32),
                 ("states", c_f32p), ("gso", c_f32p), ("packed", c_f32p), ("workspace_x", c_f32p),
-                ("logits", c_f32p), ("actions", c_i32p)]
+                ("workspace_z", c_f32p), ("logits", c_f32p), ("actions", c_i32p)]
 
 
 class NetGrads(C.Structure):
@@ -137,6 +137,10 @@ _SIGNATURES = {
     "mapf_graph_filter_bwd_workspace_size": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                           C.c_int32]),
     "mapf_graph_filter_bwd": (C.c_int, [C.POINTER(GraphFilterBwdArgs), C.c_void_p]),
+    "mapf_tc_mix_head": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "mapf_graph_taps": (C.c_int, [C.POINTER(GraphFilterFwdArgs), C.c_void_p]),
     "mapf_tc_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
 }

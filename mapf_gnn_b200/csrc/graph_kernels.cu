@@ -290,3 +290,151 @@ extern "C" int mapf_graph_filter_fwd(const mapf_graph_filter_fwd_args* a, mapf_s
   MAPF_REQUIRE(smem <= 227 * 1024, MAPF_ERR_UNSUPPORTED);
   return TM == 32 ? launch_gf<32>(*a, epc, ntiles, smem, s) : launch_gf<64>(*a, epc, ntiles, smem, s);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Filter taps only: Z[row][k*F+f] = x_k[f, n] (k < K) and the message-passing skip columns, row-major [B*N, KT].
+// Feeds the tensor-core mix (mapf_tc_mix_head).  Memory-light (reads 4F+4N, writes 4*KT bytes per agent), one
+// CTA of TZ*4 threads per tile of TZ rows of whole episodes; taps are kept row-major [row][KT] in shared memory so
+// that the hop reads are conflict-free (lanes over features) and the tile leaves as one contiguous block.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int TZ>
+__global__ void __launch_bounds__(TZ * 4) graph_taps_kernel(mapf_graph_filter_fwd_args a, int epc) {
+  constexpr int NT = TZ * 4;
+  extern __shared__ __align__(16) float s_gt[];
+  const int N = a.agents, F = a.in_dim, K = a.taps;
+  const int KT = (K + a.has_skip) * F;
+  const int ZR = KT + 4;                               // row stride (floats), keeps 16-byte alignment
+  float* z = s_gt;                                     // [TZ][ZR]
+  float* sm = z + TZ * ZR;                             // [epc][N][N]
+  float* dinv = sm + ((epc * N * N + 3) & ~3);         // [TZ]
+  const int tid = threadIdx.x;
+  const int e0 = blockIdx.x * epc;
+  const int nep = min(epc, a.batch - e0);
+  const int rows_used = nep * N;
+
+  for (int idx = tid; idx < nep * N * N; idx += NT) {
+    const int el = idx / (N * N), rem = idx - el * N * N;
+    const int i = rem / N, j = rem - i * N;
+    float v = __ldg(a.gso + int64_t(e0 + el) * N * N + rem);
+    if (a.add_self_loop && i == j) v += 1.0f;
+    sm[idx] = v;
+  }
+  {  // tap 0 (agent-major x rows are contiguous)
+    const float4* src = reinterpret_cast<const float4*>(a.x + int64_t(e0) * N * F);
+    const int f4 = F >> 2;
+    for (int idx = tid; idx < rows_used * f4; idx += NT) {
+      const int row = idx / f4, c = (idx - row * f4) << 2;
+      *reinterpret_cast<float4*>(z + row * ZR + c) = __ldg(src + idx);
+    }
+  }
+  __syncthreads();
+  if (tid < rows_used) {
+    const int el = tid / N, i = tid - el * N;
+    float deg = 0.0f;
+    for (int j = 0; j < N; ++j) deg += sm[(el * N + i) * N + j];
+    dinv[tid] = deg > 0.0f ? __fdiv_rn(1.0f, __fsqrt_rn(deg)) : 0.0f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nep * N * N; idx += NT) {
+    const int el = idx / (N * N), rem = idx - el * N * N;
+    const int i = rem / N, j = rem - i * N;
+    sm[idx] = (dinv[el * N + i] * sm[idx]) * dinv[el * N + j];
+  }
+  if (a.has_skip) {
+    for (int idx = tid; idx < rows_used * F; idx += NT) {
+      const int row = idx / F, fp = idx - row * F;
+      const int el = row / N, np = row - el * N;
+      const int q = np * F + fp;
+      z[row * ZR + K * F + fp] = z[(el * N + (q % N)) * ZR + (q / N)];
+    }
+  }
+  __syncthreads();
+  const int f4n = F >> 2;
+  for (int k = 1; k < K; ++k) {
+    if ((N & 3) == 0) {
+      // 4 rows j x 4 features per thread, i in steps of 1: S[i][j0..j0+3] and x[i][f0..f0+3] are both 128-bit loads
+      const int jt = N >> 2;
+      for (int t = tid; t < nep * jt * f4n; t += NT) {
+        const int fq = t % f4n, r = t / f4n;
+        const int el = r / jt, j0 = (r - el * jt) << 2;
+        const float* sp = sm + el * N * N + j0;
+        const float* xp = z + (el * N) * ZR + (k - 1) * F + (fq << 2);
+        float acc[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = 0.0f;
+        for (int i = 0; i < N; ++i) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sp + i * N);
+          const float4 x4 = *reinterpret_cast<const float4*>(xp + i * ZR);
+          const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[u][0] = fmaf(sv[u], x4.x, acc[u][0]);
+            acc[u][1] = fmaf(sv[u], x4.y, acc[u][1]);
+            acc[u][2] = fmaf(sv[u], x4.z, acc[u][2]);
+            acc[u][3] = fmaf(sv[u], x4.w, acc[u][3]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<float4*>(z + (el * N + j0 + u) * ZR + k * F + (fq << 2)) =
+              make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+      }
+    } else {
+      for (int t = tid; t < rows_used * f4n; t += NT) {
+        const int fq = t % f4n, row = t / f4n;
+        const int el = row / N, jl = row - el * N;
+        const float* sp = sm + el * N * N + jl;
+        const float* xp = z + (el * N) * ZR + (k - 1) * F + (fq << 2);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < N; ++i) {
+          const float s = sp[i * N];
+          const float4 x4 = *reinterpret_cast<const float4*>(xp + i * ZR);
+          acc.x = fmaf(s, x4.x, acc.x); acc.y = fmaf(s, x4.y, acc.y);
+          acc.z = fmaf(s, x4.z, acc.z); acc.w = fmaf(s, x4.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(z + row * ZR + k * F + (fq << 2)) = acc;
+      }
+    }
+    __syncthreads();
+  }
+  const int k4 = KT >> 2;
+  float4* dst = reinterpret_cast<float4*>(a.z + int64_t(e0) * N * KT);
+  for (int idx = tid; idx < rows_used * k4; idx += NT) {
+    const int row = idx / k4, c = (idx - row * k4) << 2;
+    dst[idx] = *reinterpret_cast<const float4*>(z + row * ZR + c);
+  }
+}
+
+template <int TZ>
+int launch_taps(const mapf_graph_filter_fwd_args& a, int epc, int ntiles, size_t smem, cudaStream_t s) {
+  auto kernel = graph_taps_kernel<TZ>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return MAPF_ERR_CUDA;
+  kernel<<<ntiles, TZ * 4, smem, s>>>(a, epc);
+  return mapf_launch_status();
+}
+
+}  // namespace
+
+// Z [B*N, (K+has_skip)*F] from agent-major x [B*N, F] and gso [B,N,N]; only x, gso, z and the size / flag fields of
+// the argument struct are used.
+extern "C" int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a && a->x && a->gso && a->z, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->batch > 0 && a->agents > 0 && a->in_dim > 0 && a->taps > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(a->agents <= 64 && (a->in_dim & 3) == 0, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(a->x_sf == 1 && a->x_sn == a->in_dim && a->x_sb == int64_t(a->agents) * a->in_dim, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(a->x, 16) && mapf_aligned(a->z, 16), MAPF_ERR_ALIGN);
+  const int N = a->agents;
+  const int TZ = N <= 16 ? 32 : 64;
+  const int epc = TZ / N;
+  const int ntiles = (a->batch + epc - 1) / epc;
+  const int KT = (a->taps + (a->has_skip ? 1 : 0)) * a->in_dim;
+  const size_t smem = sizeof(float) * (size_t(TZ) * (KT + 4) + ((size_t(epc) * N * N + 3) & ~size_t(3)) + TZ);
+  MAPF_REQUIRE(smem <= 227 * 1024, MAPF_ERR_UNSUPPORTED);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return TZ == 32 ? launch_taps<32>(*a, epc, ntiles, smem, s) : launch_taps<64>(*a, epc, ntiles, smem, s);
+}

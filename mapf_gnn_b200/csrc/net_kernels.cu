@@ -58,6 +58,10 @@ __global__ void pack_weights_kernel(mapf_net_params p, PackedLayout L, float* __
         const int j = int(r / G), g = int(r % G);
         if (j < KF) v = p.gf_w[int64_t(g) * KF + j];
         else if (p.gf_w2 != nullptr) v = p.gf_w2[int64_t(g) * F + (j - KF)];
+      } else if (p.taps > 0 && idx >= L.gf_raw && idx < L.gf_raw + int64_t(p.taps) * F * p.node_dim) {
+        v = p.gf_w[idx - L.gf_raw];
+      } else if (p.taps > 0 && p.gf_w2 != nullptr && idx >= L.gf2_raw && idx < L.gf2_raw + int64_t(F) * p.node_dim) {
+        v = p.gf_w2[idx - L.gf2_raw];
       } else if (idx >= L.act_w && idx < L.act_w + int64_t(p.num_actions) * head_in) {
         v = p.act_w[idx - L.act_w];
       } else if (idx >= L.act_b && idx < L.act_b + p.num_actions) {
@@ -183,7 +187,18 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
   g.y = nullptr; g.z = nullptr;
   g.act_w = a->packed + L.act_w; g.act_b = a->packed + L.act_b;
   g.logits = a->logits; g.actions = a->actions;
-  return mapf_graph_filter_fwd(&g, stream);
+  const bool tensor_path = a->workspace_z != nullptr && p->node_dim <= 128 && (p->node_dim & 15) == 0 &&
+                           (p->fc_out & 3) == 0 && a->agents <= 64;
+  if (!tensor_path) return mapf_graph_filter_fwd(&g, stream);   // fused fp32-FFMA kernel
+  // tensor-core path: filter taps -> Z (tiny kernel), then 3xTF32 tcgen05 mix + ReLU + head + argmax
+  g.z = a->workspace_z;
+  rc = mapf_graph_taps(&g, stream);
+  if (rc != MAPF_OK) return rc;
+  const int KF = p->taps * p->fc_out;
+  return mapf_tc_mix_head(int32_t(rows), p->node_dim, a->workspace_z, KF + (a->message ? p->fc_out : 0),
+                          a->packed + L.gf_raw, KF, a->message ? a->packed + L.gf2_raw : nullptr,
+                          a->message ? p->fc_out : 0, a->packed + L.act_w, a->packed + L.act_b, p->num_actions,
+                          a->logits, a->actions, nullptr, stream);
 }
 
 extern "C" int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a, mapf_stream_t stream) {

@@ -2,7 +2,7 @@
 //
 // The policy network must reproduce fp32 logits closely enough that the argmax is bit-exact (top-2 margins go
 // down to 3e-5), so plain TF32 (10-bit mantissa) is not usable.  We use the classic 3xTF32 split:
-//   a = a_hi + a_lo,  a_hi = a with the low 13 mantissa bits cleared (exactly representable in TF32),
+//   a = a_hi + a_lo,  a_hi = a rounded to TF32 (exactly representable, low 13 mantissa bits zero),
 //   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (dropped terms are O(2^-21) relative)
 // with fp32 accumulation in TMEM.  Operands are staged in shared memory in the canonical no-swizzle K-major
 // UMMA layout: 8x(16 byte) core matrices, [row/8][k/4][row%8][k%4].
@@ -103,10 +103,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ---- 3xTF32 operand split ---------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+// round-to-nearest TF32 (low 13 mantissa bits become zero): the hardware then sees exactly these values
+__device__ __forceinline__ float tf32_rn(float a) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split1(float a, float& hi, float& lo) {
+  hi = tf32_rn(a);
+  lo = tf32_rn(a - hi);   // a - hi is exact; rounding (instead of the hardware's truncation) keeps the error unbiased
+}
 __device__ __forceinline__ void split4(const float4& a, float4& hi, float4& lo) {
-  hi = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
-  lo = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+  split1(a.x, hi.x, lo.x);
+  split1(a.y, hi.y, lo.y);
+  split1(a.z, hi.z, lo.z);
+  split1(a.w, hi.w, lo.w);
 }
 
 // byte offset of element (row, k) inside a canonical K-major no-swizzle block with KC floats per row

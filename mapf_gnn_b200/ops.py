@@ -11,12 +11,16 @@ They are registered for the CUDA dispatch key only: calling one with CPU tensors
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 
 _LIB = torch.library.Library("mapf", "DEF")
+
+# graph-filter mix on tcgen05 (3xTF32) when True; the fused fp32-FFMA kernel when False (development switch)
+USE_TENSOR_CORES = os.environ.get("MAPF_B200_TENSOR_CORES", "1") != "0"
 
 _LIB.define("pack_weights(int[] dims, Tensor[] conv_w, Tensor[] conv_b, Tensor[] bn_gamma, Tensor[] bn_beta, "
             "Tensor[] bn_mean, Tensor[] bn_var, Tensor fc_w, Tensor fc_b, Tensor? gf_w, Tensor? gf_w2, "
@@ -93,6 +97,9 @@ def _policy_fwd(dims, message, states, gso, packed):
         if tuple(gso.shape) != (B, N, N):
             raise ValueError(f"gso must be [{B},{N},{N}], got {tuple(gso.shape)}")
         a.gso = gso.data_ptr()
+        if USE_TENSOR_CORES:
+            workz = torch.empty((B * N, (p.taps + 1) * p.fc_out), dtype=torch.float32, device=dev)
+            a.workspace_z = workz.data_ptr()
     a.logits, a.actions = logits.data_ptr(), actions.data_ptr()
     with torch.cuda.device(dev):
         _lib.check(lib.mapf_policy_fwd(p, a, _stream()), "policy_fwd")
