@@ -318,19 +318,23 @@ int64_t mapf_graph_filter_bwd_workspace_size(int32_t batch, int32_t agents, int3
                                              int32_t taps, int32_t has_skip);
 int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_stream_t stream);
 
-/* fp32-accurate tensor-core GEMM (3xTF32 on tcgen05, accumulators in TMEM):
- * C[M,N] = act(A[M,K] B[N,K]^T + bias[N]); A, B row-major with K contiguous, lda/ldb multiples of 4, 16-byte
- * aligned bases; bias may be NULL; relu != 0 applies max(0, .).  The building block behind the encoder FC
- * (compressMLP, framework_gnn.py:93) and the graph-filter mix (gnn.py:117-118). */
-int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
-                 int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream);
-
-/* Tensor-core graph-filter tail: logits / greedy actions = actionMLP(relu(Z [W | W2]^T)) with Z [M, K0+K1] the
- * row-major filter taps from mapf_graph_taps, W = GFL.0.W viewed as [G, K*F] and W2 = GFL.0.W2 viewed as [G, F]
- * (the raw reshapes of gnn.py:114-116,222 -- no repacking needed).  y (optional) receives relu(...) [M, G]. */
-int mapf_tc_mix_head(int32_t M, int32_t N, const float* Z, int64_t ldz, const float* W, int32_t K0, const float* W2,
-                     int32_t K1, const float* act_w, const float* act_b, int32_t num_actions, float* logits,
-                     int32_t* actions, float* y, mapf_stream_t stream);
+/* fp32-accurate tensor-core GEMMs (3xTF32 on tcgen05, accumulators in TMEM).
+ * mapf_tc_pack_b: B [N,K0] (optionally [N,K1] appended along K), row-major fp32 with K contiguous, N <= 128 ->
+ *   TF32 hi / lo parts tiled in the canonical UMMA shared-memory layout, one contiguous block per 16-wide K chunk
+ *   (what the kernel's TMA bulk copies fetch); out holds mapf_tc_packed_b_size(N, K0+K1) floats.
+ * mapf_tc_gemm: C[M,N] = act(A[M,K] B^T + bias[N]); A row-major fp32, lda multiple of 4, 16-byte aligned.  The
+ *   building block behind the encoder FC (compressMLP, framework_gnn.py:93).
+ * mapf_tc_mix_head: logits / greedy actions = actionMLP(relu(Z [W | W2]^T)) with Z [M,K] the row-major filter taps
+ *   of mapf_graph_taps and the packed B built from GFL.0.W viewed as [G, K*F] and GFL.0.W2 viewed as [G, F] (the raw
+ *   reshapes of gnn.py:114-116,222); y (optional) receives relu(...) [M,G]. */
+int64_t mapf_tc_packed_b_size(int32_t N, int32_t K);
+int mapf_tc_pack_b(const float* b0, int32_t K0, const float* b1, int32_t K1, int32_t N, float* out,
+                   mapf_stream_t stream);
+int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
+                 const float* bias, int32_t relu, mapf_stream_t stream);
+int mapf_tc_mix_head(int32_t M, int32_t N, int32_t K, const float* Z, int64_t ldz, const float* Wp, const float* act_w,
+                     const float* act_b, int32_t num_actions, float* logits, int32_t* actions, float* y,
+                     mapf_stream_t stream);
 /* Filter taps Z [B*N, (K+has_skip)*F] (x_k = x_{k-1} S, gnn.py:104-109, + skip columns gnn.py:201-204) from
  * agent-major x; uses the x / gso / z / size / flag fields of the argument struct. */
 int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);

@@ -137,12 +137,13 @@ _SIGNATURES = {
     "mapf_graph_filter_bwd_workspace_size": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                           C.c_int32]),
     "mapf_graph_filter_bwd": (C.c_int, [C.POINTER(GraphFilterBwdArgs), C.c_void_p]),
-    "mapf_tc_mix_head": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
-                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p]),
+    "mapf_tc_packed_b_size": (C.c_int64, [C.c_int32, C.c_int32]),
+    "mapf_tc_pack_b": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mapf_tc_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mapf_tc_mix_head": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mapf_graph_taps": (C.c_int, [C.POINTER(GraphFilterFwdArgs), C.c_void_p]),
-    "mapf_tc_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
-                               C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

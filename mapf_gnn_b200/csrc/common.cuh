@@ -35,14 +35,18 @@ struct PackedLayout {
   int64_t fc_wt;                  // [fc_in][F]   (transposed compressMLP.0.weight)
   int64_t fc_b;                   // [F]
   int64_t gf_wt;                  // [(K(+1))*F][G]
-  int64_t gf_raw;                 // [G][K*F]  raw GFL.0.W memory (K-major B operand of the tensor-core mix)
-  int64_t gf2_raw;                // [G][F]    raw GFL.0.W2 memory
+  int64_t tc_gf;                  // tensor-core B operand of the mix: [W | W2] as chunked canonical TF32 hi/lo blocks
   int64_t act_w;                  // [A][G or F]
   int64_t act_b;                  // [A]
   int64_t total;
 };
 
 static inline __host__ __device__ int64_t mapf_round4(int64_t v) { return (v + 3) & ~int64_t(3); }
+
+// floats of a pre-tiled tensor-core B operand [N, K] (tc_gemm.cu: KC = 16, NT = 64 or 128, hi | lo per chunk)
+static inline __host__ __device__ int64_t mapf_tc_b_floats(int N, int K) {
+  return int64_t((K + 15) / 16) * 2 * (N <= 64 ? 64 : 128) * 16;
+}
 
 static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net_params& p) {
   PackedLayout L;
@@ -59,10 +63,8 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
   off += mapf_round4(p.fc_out);
   L.gf_wt = off;
   if (p.taps > 0) off += mapf_round4(int64_t(p.taps + 1) * p.fc_out * p.node_dim);  // room for the W2 rows
-  L.gf_raw = off;
-  if (p.taps > 0) off += mapf_round4(int64_t(p.taps) * p.fc_out * p.node_dim);
-  L.gf2_raw = off;
-  if (p.taps > 0) off += mapf_round4(int64_t(p.fc_out) * p.node_dim);
+  L.tc_gf = off;
+  if (p.taps > 0 && p.node_dim <= 128) off += mapf_tc_b_floats(p.node_dim, (p.taps + 1) * p.fc_out);
   L.act_w = off;
   off += mapf_round4(int64_t(p.num_actions) * (p.taps > 0 ? p.node_dim : p.fc_out));
   L.act_b = off;

@@ -58,10 +58,6 @@ __global__ void pack_weights_kernel(mapf_net_params p, PackedLayout L, float* __
         const int j = int(r / G), g = int(r % G);
         if (j < KF) v = p.gf_w[int64_t(g) * KF + j];
         else if (p.gf_w2 != nullptr) v = p.gf_w2[int64_t(g) * F + (j - KF)];
-      } else if (p.taps > 0 && idx >= L.gf_raw && idx < L.gf_raw + int64_t(p.taps) * F * p.node_dim) {
-        v = p.gf_w[idx - L.gf_raw];
-      } else if (p.taps > 0 && p.gf_w2 != nullptr && idx >= L.gf2_raw && idx < L.gf2_raw + int64_t(F) * p.node_dim) {
-        v = p.gf_w2[idx - L.gf2_raw];
       } else if (idx >= L.act_w && idx < L.act_w + int64_t(p.num_actions) * head_in) {
         v = p.act_w[idx - L.act_w];
       } else if (idx >= L.act_b && idx < L.act_b + p.num_actions) {
@@ -134,6 +130,13 @@ extern "C" int mapf_pack_weights(const mapf_net_params* p, float* packed, mapf_s
   MAPF_REQUIRE(mapf_aligned(packed, 16), MAPF_ERR_ALIGN);
   const PackedLayout L = mapf_packed_layout(*p);
   pack_weights_kernel<<<int((L.total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*p, L, packed);
+  if (p->taps > 0 && p->node_dim <= 128) {
+    // B operand of the tensor-core mix: GFL.0.W viewed as [G, K*F] (+ W2 viewed as [G, F]) -- the raw reshapes of
+    // gnn.py:114-116,222 are exactly the K-major operand the MMA wants
+    const int rc = mapf_tc_pack_b(p->gf_w, p->taps * p->fc_out, p->gf_w2, p->gf_w2 ? p->fc_out : 0, p->node_dim,
+                                  packed + L.tc_gf, stream);
+    if (rc != MAPF_OK) return rc;
+  }
   return mapf_launch_status();
 }
 
@@ -194,11 +197,9 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
   g.z = a->workspace_z;
   rc = mapf_graph_taps(&g, stream);
   if (rc != MAPF_OK) return rc;
-  const int KF = p->taps * p->fc_out;
-  return mapf_tc_mix_head(int32_t(rows), p->node_dim, a->workspace_z, KF + (a->message ? p->fc_out : 0),
-                          a->packed + L.gf_raw, KF, a->message ? a->packed + L.gf2_raw : nullptr,
-                          a->message ? p->fc_out : 0, a->packed + L.act_w, a->packed + L.act_b, p->num_actions,
-                          a->logits, a->actions, nullptr, stream);
+  const int KT = (p->taps + (a->message ? 1 : 0)) * p->fc_out;
+  return mapf_tc_mix_head(int32_t(rows), p->node_dim, KT, a->workspace_z, KT, a->packed + L.tc_gf, a->packed + L.act_w,
+                          a->packed + L.act_b, p->num_actions, a->logits, a->actions, nullptr, stream);
 }
 
 extern "C" int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a, mapf_stream_t stream) {

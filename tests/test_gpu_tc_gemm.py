@@ -14,7 +14,9 @@ def tc_gemm(A, B, bias=None, relu=False):
     M, K = A.shape
     N = B.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    rc = lib.mapf_tc_gemm(M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(), N,
+    Bp = torch.empty((lib.mapf_tc_packed_b_size(N, K),), dtype=torch.float32, device=A.device)
+    _lib.check(lib.mapf_tc_pack_b(B.data_ptr(), K, None, 0, N, Bp.data_ptr(), _lib.current_stream()), "tc_pack_b")
+    rc = lib.mapf_tc_gemm(M, N, K, A.data_ptr(), A.stride(0), Bp.data_ptr(), out.data_ptr(), N,
                           None if bias is None else bias.data_ptr(), int(relu), _lib.current_stream())
     _lib.check(rc, "tc_gemm")
     torch.cuda.synchronize()
