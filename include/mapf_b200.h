@@ -151,6 +151,9 @@ typedef struct {
   float* x;              /* [rows,F] out */
 } mapf_encoder_fwd_args;
 int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream);
+/* Conv stack only: a->x receives the flattened (C,H,W) activations [rows, fc_in] (framework_gnn.py:160-163); the
+ * Linear + ReLU that follows is mapf_tc_gemm on the tensor cores. */
+int mapf_encoder_conv_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream);
 
 /* A6/A7 (+A8): GCNLayer.forward (gnn.py:72-126) / MessagePassingLayer.forward (gnn.py:178-235),
  * optionally fused with the ReLU + actionMLP + argmax tail of Network.forward
@@ -202,6 +205,7 @@ typedef struct {
   const float* packed;
   float* workspace_x;
   float* workspace_z;     /* [B*N, (K+1)*F] floats: enables the tensor-core graph-filter path; NULL = fused FFMA kernel */
+  float* workspace_act;   /* [B*N, fc_in] floats: enables the tensor-core encoder FC; NULL = FC fused in the conv kernel */
   float* logits;          /* [B,N,A] */
   int32_t* actions;       /* [B,N] or NULL */
 } mapf_policy_fwd_args;

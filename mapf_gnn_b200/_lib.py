@@ -69,7 +69,7 @@ class HeadFwdArgs(C.Structure):
 class PolicyFwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32),
                 ("states", c_f32p), ("gso", c_f32p), ("packed", c_f32p), ("workspace_x", c_f32p),
-                ("workspace_z", c_f32p), ("logits", c_f32p), ("actions", c_i32p)]
+                ("workspace_z", c_f32p), ("workspace_act", c_f32p), ("logits", c_f32p), ("actions", c_i32p)]
 
 
 class NetGrads(C.Structure):
@@ -125,6 +125,7 @@ _SIGNATURES = {
     "mapf_pack_graph_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                           C.c_void_p]),
     "mapf_encoder_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(EncoderFwdArgs), C.c_void_p]),
+    "mapf_encoder_conv_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(EncoderFwdArgs), C.c_void_p]),
     "mapf_graph_filter_fwd": (C.c_int, [C.POINTER(GraphFilterFwdArgs), C.c_void_p]),
     "mapf_head_fwd": (C.c_int, [C.POINTER(HeadFwdArgs), C.c_void_p]),
     "mapf_policy_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(PolicyFwdArgs), C.c_void_p]),

@@ -35,6 +35,7 @@ struct PackedLayout {
   int64_t fc_wt;                  // [fc_in][F]   (transposed compressMLP.0.weight)
   int64_t fc_b;                   // [F]
   int64_t gf_wt;                  // [(K(+1))*F][G]
+  int64_t tc_fc;                  // tensor-core B operand of the encoder FC (compressMLP.0.weight [F, fc_in])
   int64_t tc_gf;                  // tensor-core B operand of the mix: [W | W2] as chunked canonical TF32 hi/lo blocks
   int64_t act_w;                  // [A][G or F]
   int64_t act_b;                  // [A]
@@ -43,9 +44,9 @@ struct PackedLayout {
 
 static inline __host__ __device__ int64_t mapf_round4(int64_t v) { return (v + 3) & ~int64_t(3); }
 
-// floats of a pre-tiled tensor-core B operand [N, K] (tc_gemm.cu: KC = 16, NT = 64 or 128, hi | lo per chunk)
+// floats of a pre-tiled tensor-core B operand [N, K] (tc_gemm.cu: KC = 8, NT = 64 or 128, hi | lo per chunk)
 static inline __host__ __device__ int64_t mapf_tc_b_floats(int N, int K) {
-  return int64_t((K + 15) / 16) * 2 * (N <= 64 ? 64 : 128) * 16;
+  return int64_t((K + 7) / 8) * 2 * (N <= 64 ? 64 : 128) * 8;
 }
 
 static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net_params& p) {
@@ -63,6 +64,8 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
   off += mapf_round4(p.fc_out);
   L.gf_wt = off;
   if (p.taps > 0) off += mapf_round4(int64_t(p.taps + 1) * p.fc_out * p.node_dim);  // room for the W2 rows
+  L.tc_fc = off;
+  if (p.fc_out <= 128) off += mapf_tc_b_floats(p.fc_out, p.fc_in);
   L.tc_gf = off;
   if (p.taps > 0 && p.node_dim <= 128) off += mapf_tc_b_floats(p.node_dim, (p.taps + 1) * p.fc_out);
   L.act_w = off;
@@ -87,4 +90,17 @@ static inline int mapf_check_params(const mapf_net_params* p) {
   MAPF_REQUIRE(p->taps >= 0 && p->taps <= 8, MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(p->taps == 0 || (p->node_dim > 0 && (p->node_dim & 3) == 0), MAPF_ERR_UNSUPPORTED);
   return MAPF_OK;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs microseconds of host time per call; remember, per device and
+// per kernel call site, the largest size already granted.  Benign race: the attribute call is idempotent.
+template <typename F>
+static inline bool mapf_ensure_smem(F func, size_t bytes, int* cache /* [16] zero-initialised, one per call site */) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  const int slot = dev & 15;
+  if (int(bytes) <= cache[slot]) return true;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) != cudaSuccess) return false;
+  cache[slot] = int(bytes);
+  return true;
 }

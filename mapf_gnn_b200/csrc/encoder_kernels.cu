@@ -12,6 +12,8 @@
 // 3x3 border handling is resolved at compile time (169 instead of 225 taps per channel pair).
 // The FC runs as a 32 x F x fc_in register-tiled GEMM (4 agents x 4 outputs per thread, K split
 // over the two halves of the CTA).  Everything is fp32 FFMA (bit-exact argmax requirement).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -36,7 +38,7 @@ struct EncoderDims {
 __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, int in_cs, int in_ps, int in_off,
                                                   float* __restrict__ out, const float* __restrict__ w,
                                                   const float* __restrict__ bias, int cin, int cout, int warp,
-                                                  int lane) {
+                                                  int lane, int out_ps = kEncAgents) {
   for (int pr = warp; pr < (cout >> 1); pr += kEncWarps) {
     float acc0[kFovCells], acc1[kFovCells];
     {
@@ -73,8 +75,8 @@ __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, 
     }
 #pragma unroll
     for (int p = 0; p < kFovCells; ++p) {
-      out[((2 * pr) * kFovCells + p) * kEncAgents + lane] = fmaxf(acc0[p], 0.0f);
-      out[((2 * pr + 1) * kFovCells + p) * kEncAgents + lane] = fmaxf(acc1[p], 0.0f);
+      out[((2 * pr) * kFovCells + p) * out_ps + lane] = fmaxf(acc0[p], 0.0f);
+      out[((2 * pr + 1) * kFovCells + p) * out_ps + lane] = fmaxf(acc1[p], 0.0f);
     }
   }
 }
@@ -186,6 +188,70 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
   }
 }
 
+// Conv stack only (the FC runs on the tensor cores, tc_gemm.cu): NG independent groups of 256 threads per CTA, each
+// walking its own tiles of 32 agent images with its own ping-pong buffers and its own named barrier, so that the
+// load / barrier phases of one group overlap the FFMA phases of the other (16 warps per SM).
+template <int NG>
+__global__ void __launch_bounds__(kEncThreads * NG, 1) encoder_conv_kernel(EncoderDims d, PackedLayout L, int64_t rows,
+                                                                           const float* __restrict__ states,
+                                                                           const float* __restrict__ packed,
+                                                                           float* __restrict__ act) {
+  extern __shared__ __align__(16) float s_enc[];
+  float* const s_w = s_enc;
+  const int grp = threadIdx.x / kEncThreads, tid = threadIdx.x % kEncThreads;
+  float* const s_b0 = s_enc + d.w_floats + grp * (d.buf0_floats + d.buf1_floats);
+  float* const s_b1 = s_b0 + d.buf0_floats;
+  const int warp = tid >> 5, lane = tid & 31;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kEncThreads) : "memory"); };
+
+  for (int i = threadIdx.x; i < (d.w_floats >> 2); i += kEncThreads * NG)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(packed) + i);
+  __syncthreads();
+
+  const int64_t ntiles = (rows + kEncAgents - 1) / kEncAgents;
+  for (int64_t tile = int64_t(blockIdx.x) * NG + grp; tile < ntiles; tile += int64_t(gridDim.x) * NG) {
+    const int64_t row0 = tile * kEncAgents;
+    const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
+    {
+      const int nfl = nrows * kFovFloats;
+      const float* src = states + row0 * kFovFloats;
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int nq = nfl >> 2;
+        for (int q = tid; q < nq; q += kEncThreads)
+          reinterpret_cast<float4*>(s_b0)[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+      } else {
+        for (int i = tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+      }
+      for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) s_b0[i] = 0.0f;
+    }
+    group_sync();
+    // the last layer writes its [fc_in][32] block with a padded stride so that the row-major copy-out below
+    // reads shared memory conflict-free (lanes walk the feature index)
+    const bool single = d.num_conv == 1;
+    conv3x3_relu_pair(s_b0, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
+                      d.channels[0], d.channels[1], warp, lane, single ? kEncAgents + 1 : kEncAgents);
+    group_sync();
+    bool in1 = true;
+    for (int l = 1; l < d.num_conv; ++l) {
+      const bool last = l == d.num_conv - 1;
+      conv3x3_relu_pair(in1 ? s_b1 : s_b0, kFovCells * kEncAgents, kEncAgents, lane, in1 ? s_b0 : s_b1,
+                        s_w + L.conv_w[l], s_w + L.conv_b[l], d.channels[l], d.channels[l + 1], warp, lane,
+                        last ? kEncAgents + 1 : kEncAgents);
+      in1 = !in1;
+      group_sync();
+    }
+    {  // flatten (C,H,W) -> act[row][fc_in], coalesced: warp w copies rows w, w+8, ...
+      const float* src = in1 ? s_b1 : s_b0;
+      for (int r = warp; r < nrows; r += kEncWarps) {
+        float* dst = act + (row0 + r) * d.fc_in;
+        for (int i = lane; i < d.fc_in; i += 32) dst[i] = src[i * (kEncAgents + 1) + r];
+      }
+    }
+    group_sync();   // the buffers are rewritten by the next tile
+  }
+}
+
 }  // namespace
 
 static int sm_count() {
@@ -227,11 +293,64 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   d.w_floats = int(d.fc_in_smem ? L.gf_wt : L.fc_wt);
   const size_t smem = size_t(d.w_floats) * sizeof(float) + act_bytes;
   MAPF_REQUIRE(smem <= limit, MAPF_ERR_UNSUPPORTED);
-  auto kernel = d.fc_in_smem ? encoder_fwd_kernel<true> : encoder_fwd_kernel<false>;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-    return MAPF_ERR_CUDA;
   const int64_t ntiles = (a->rows + kEncAgents - 1) / kEncAgents;
   const int grid = int(ntiles < sm_count() ? ntiles : sm_count());
-  kernel<<<grid, kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(d, L, a->rows, a->states, a->packed, a->x);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d.fc_in_smem) {
+    static int cache_a[16] = {0};
+    if (!mapf_ensure_smem(encoder_fwd_kernel<true>, smem, cache_a)) return MAPF_ERR_CUDA;
+    encoder_fwd_kernel<true><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, a->states, a->packed, a->x);
+  } else {
+    static int cache_b[16] = {0};
+    if (!mapf_ensure_smem(encoder_fwd_kernel<false>, smem, cache_b)) return MAPF_ERR_CUDA;
+    encoder_fwd_kernel<false><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, a->states, a->packed, a->x);
+  }
+  return mapf_launch_status();
+}
+
+// Conv stack of the encoder only: act[rows, fc_in] = flatten(relu(bn(conv(...)))) (framework_gnn.py:160-163); the
+// Linear + ReLU that follows runs as a tensor-core GEMM (mapf_tc_gemm).
+extern "C" int mapf_encoder_conv_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream) {
+  const int st = mapf_check_params(p);
+  if (st != MAPF_OK) return st;
+  MAPF_REQUIRE(a && a->states && a->packed && a->x, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->rows > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(mapf_aligned(a->packed, 16) && mapf_aligned(a->x, 16) && mapf_aligned(a->states, 4), MAPF_ERR_ALIGN);
+  const PackedLayout L = mapf_packed_layout(*p);
+  EncoderDims d;
+  d.num_conv = p->num_conv;
+  for (int l = 0; l <= MAPF_MAX_CONV; ++l) d.channels[l] = l <= p->num_conv ? p->channels[l] : 0;
+  d.fc_in = p->fc_in;
+  d.fc_out = p->fc_out;
+  int b0 = kFovFloats * kEncAgents, b1 = 0;
+  for (int l = 0; l < p->num_conv; ++l) {
+    const int stride = l == p->num_conv - 1 ? kEncAgents + 1 : kEncAgents;   // padded copy-out layout for the last layer
+    const int out = kFovCells * p->channels[l + 1] * stride;
+    if (l & 1) b0 = max(b0, out); else b1 = max(b1, out);
+  }
+  d.buf0_floats = (b0 + 3) & ~3;
+  d.buf1_floats = (b1 + 3) & ~3;
+  d.fc_in_smem = 0;
+  d.w_floats = int(L.fc_wt);
+  const size_t wbytes = size_t(d.w_floats) * sizeof(float);
+  const size_t gbytes = size_t(d.buf0_floats + d.buf1_floats) * sizeof(float);
+  const size_t limit = 227 * 1024;
+  MAPF_REQUIRE(wbytes + gbytes <= limit, MAPF_ERR_UNSUPPORTED);
+  const char* force = getenv("MAPF_B200_ENC_GROUPS");   // development switch; one group measured faster
+  const int ng = (force && force[0] == '2' && wbytes + 2 * gbytes <= limit) ? 2 : 1;
+  const size_t smem = wbytes + ng * gbytes;
+  const int64_t ntiles = (a->rows + kEncAgents - 1) / kEncAgents;
+  const int64_t want = (ntiles + ng - 1) / ng;
+  const int grid = int(want < sm_count() ? want : sm_count());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ng == 2) {
+    if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(encoder_conv_kernel<2>, size_t(smem), cache__); }())
+      return MAPF_ERR_CUDA;
+    encoder_conv_kernel<2><<<grid, kEncThreads * 2, smem, s>>>(d, L, a->rows, a->states, a->packed, a->x);
+  } else {
+    if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(encoder_conv_kernel<1>, size_t(smem), cache__); }())
+      return MAPF_ERR_CUDA;
+    encoder_conv_kernel<1><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, a->states, a->packed, a->x);
+  }
   return mapf_launch_status();
 }

@@ -200,8 +200,7 @@ int launch_env_step(const mapf_env_step_args& a, cudaStream_t s) {
   const size_t smem = size_t(EPB) * a.cell_stride;
   if (smem > 200 * 1024) return MAPF_ERR_UNSUPPORTED;
   if (smem > 40 * 1024) {
-    if (cudaFuncSetAttribute(env_step_kernel<LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) !=
-        cudaSuccess)
+    if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(env_step_kernel<LANES>, size_t(smem), cache__); }())
       return MAPF_ERR_CUDA;
   }
   const int grid = (a.episodes + EPB - 1) / EPB;

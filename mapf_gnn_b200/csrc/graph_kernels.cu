@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(TM * 4) graph_filter_kernel(mapf_graph_filter_
 template <int TM>
 int launch_gf(const mapf_graph_filter_fwd_args& a, int epc, int ntiles, size_t smem, cudaStream_t s) {
   auto kernel = graph_filter_kernel<TM>;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+  if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   kernel<<<ntiles, TM * 4, smem, s>>>(a, epc);
   return mapf_launch_status();
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(TZ * 4) graph_taps_kernel(mapf_graph_filter_fw
 template <int TZ>
 int launch_taps(const mapf_graph_filter_fwd_args& a, int epc, int ntiles, size_t smem, cudaStream_t s) {
   auto kernel = graph_taps_kernel<TZ>;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+  if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   kernel<<<ntiles, TZ * 4, smem, s>>>(a, epc);
   return mapf_launch_status();

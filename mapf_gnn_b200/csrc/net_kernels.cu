@@ -130,6 +130,10 @@ extern "C" int mapf_pack_weights(const mapf_net_params* p, float* packed, mapf_s
   MAPF_REQUIRE(mapf_aligned(packed, 16), MAPF_ERR_ALIGN);
   const PackedLayout L = mapf_packed_layout(*p);
   pack_weights_kernel<<<int((L.total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*p, L, packed);
+  if (p->fc_out <= 128) {
+    const int rc = mapf_tc_pack_b(p->fc_w, p->fc_in, nullptr, 0, p->fc_out, packed + L.tc_fc, stream);
+    if (rc != MAPF_OK) return rc;
+  }
   if (p->taps > 0 && p->node_dim <= 128) {
     // B operand of the tensor-core mix: GFL.0.W viewed as [G, K*F] (+ W2 viewed as [G, F]) -- the raw reshapes of
     // gnn.py:114-116,222 are exactly the K-major operand the MMA wants
@@ -156,7 +160,7 @@ extern "C" int mapf_head_fwd(const mapf_head_fwd_args* a, mapf_stream_t stream) 
   MAPF_REQUIRE(a->num_actions > 0 && a->num_actions <= kMaxActions && a->in_dim <= 1024, MAPF_ERR_UNSUPPORTED);
   const size_t smem = sizeof(float) * 32 * (a->in_dim + 1);
   if (smem > 40 * 1024 &&
-      cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      [&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(head_fwd_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   head_fwd_kernel<<<unsigned((a->rows + 31) / 32), 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
   return mapf_launch_status();
@@ -169,8 +173,18 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
   MAPF_REQUIRE(a->batch > 0 && a->agents > 0, MAPF_ERR_SHAPE);
   const PackedLayout L = mapf_packed_layout(*p);
   const int64_t rows = int64_t(a->batch) * a->agents;
-  mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_x};
-  int rc = mapf_encoder_fwd(p, &e, stream);
+  int rc;
+  if (a->workspace_act != nullptr && p->fc_out <= 128) {
+    // conv stack on FFMA -> act [rows, fc_in]; Linear + ReLU as a 3xTF32 tcgen05 GEMM
+    mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_act};
+    rc = mapf_encoder_conv_fwd(p, &e, stream);
+    if (rc != MAPF_OK) return rc;
+    rc = mapf_tc_gemm(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, p->fc_in, a->packed + L.tc_fc,
+                      a->workspace_x, p->fc_out, a->packed + L.fc_b, 1, stream);
+  } else {
+    mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_x};
+    rc = mapf_encoder_fwd(p, &e, stream);
+  }
   if (rc != MAPF_OK) return rc;
   if (p->taps == 0) {
     mapf_head_fwd_args h{rows, p->fc_out, p->num_actions, a->workspace_x, a->packed + L.act_w,

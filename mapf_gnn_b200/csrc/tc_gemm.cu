@@ -5,13 +5,17 @@
 //   EPI_HEAD  : y = relu(D); logits = y Wa^T + ba; first-max argmax (graph-filter mix gnn.py:117-118 + ReLU +
 //               actionMLP framework_gnn.py:171-181 + np.argmax evaluate.py:238)
 //
-// Warp-specialised, one 256-thread CTA per 128-row tile, a ring of NSTAGE shared-memory stages of KC floats of K:
-//   warps 0-5  producers : load the A chunk (fp32, global), split it into TF32 hi / lo (round-to-nearest) and store
-//                          both in the canonical no-swizzle K-major UMMA layout; one of them also issues the TMA
-//                          bulk copy (cp.async.bulk, SASS UBLKCP) of the pre-tiled hi|lo B chunk; all arrive on the
-//                          stage's `full` mbarrier (the bulk copy through its transaction count)
-//   warp  6    MMA issuer: one elected lane waits `full`, issues 3 tcgen05.mma (128 x N x 8) per 8-wide K slice
-//                          (lo*hi, hi*lo, hi*hi) and commits them to the stage's `empty` mbarrier
+// Warp-specialised, one 256-thread CTA per 128-row tile, six shared-memory stages of KC floats of K:
+//   warps 0-5  producers : warp w owns stage w and the chunks c = w, w+6, ...: its lanes load the A chunk (fp32,
+//                          global, all loads of the chunk in flight at once), split it into TF32 hi / lo
+//                          (round-to-nearest) and store both in the canonical no-swizzle K-major UMMA layout; lane 0
+//                          also issues the TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the pre-tiled hi|lo B chunk;
+//                          the warp arrives on the stage's `full` mbarrier (the bulk copy through its byte count)
+//   warps 6,7  MMA issuers: one elected lane each (even / odd chunks, each with its own TMEM accumulator) waits
+//                          `full`, issues 3 tcgen05.mma (128 x N x 8) per 8-wide K slice (lo*hi, hi*lo, hi*hi) and
+//                          commits them to the stage's `empty` mbarrier.  Two issuers because the MMAs are small
+//                          (32-64 cycles of tensor work): one thread's wait/issue/commit loop (~500 cycles) would pace
+//                          the whole pipeline
 //   warps 0-3  epilogue  : after the final commit each thread owns one output row = one TMEM lane, reads it with
 //                          tcgen05.ld and applies the epilogue (no cross-thread reduction for the 5-way head)
 // The tensor core's fp32 accumulation loses a little precision per accumulate, so consecutive chunks rotate over
@@ -22,7 +26,7 @@
 namespace {
 
 constexpr int kTcThreads = 256;
-constexpr int kTcProducers = 192;   // warps 0-5
+constexpr int kTcProdWarps = 6;      // warps 0-5, one shared-memory stage each
 constexpr int kTcM = 128;
 
 enum { EPI_STORE = 0, EPI_HEAD = 1 };
@@ -69,8 +73,9 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ b0, int K0, const flo
   }
 }
 
-template <int NT, int KC, int NSTAGE, int NACC, int EPI>
+template <int NT, int KC, int NACC, int EPI>
 __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
+  constexpr int NSTAGE = kTcProdWarps;
   constexpr uint32_t kColsNeeded = NT * NACC;
   constexpr uint32_t kCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                              : kColsNeeded <= 256 ? 256 : 512;
@@ -80,17 +85,17 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   extern __shared__ __align__(128) uint8_t s_tc[];
   __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE], s_done;
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? kMaxActions * NT + kMaxActions : 4];
+  __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? kMaxActions * NT + kMaxActions : NT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * NT;
 
-  if (warp == 7) tc::tmem_alloc(&s_tmem, kCols);
+  if (warp == 0) tc::tmem_alloc(&s_tmem, kCols);
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      tc::mbar_init(&s_full[s], kTcProducers);
+      tc::mbar_init(&s_full[s], 32);
       tc::mbar_init(&s_empty[s], 1);
     }
-    tc::mbar_init(&s_done, 1);
+    tc::mbar_init(&s_done, 2);
     tc::fence_mbar_init();
   }
   if (EPI == EPI_HEAD) {
@@ -99,6 +104,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       s_head[i] = n < g.N ? __ldg(g.act_w + int64_t(q) * g.N + n) : 0.0f;
     }
     if (tid < g.num_actions) s_head[kMaxActions * NT + tid] = __ldg(g.act_b + tid);
+  } else {
+    for (int i = tid; i < NT; i += kTcThreads) s_head[i] = (g.bias != nullptr && i < g.N) ? __ldg(g.bias + i) : 0.0f;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -106,82 +113,91 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   const uint32_t tmem = s_tmem;
   const int nchunks = (g.K + KC - 1) / KC;
 
-  if (warp < 6) {
-    // ===== producers =====
-    const float* bsrc = g.Bp;
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % NSTAGE;
-      const uint32_t ph = uint32_t(c / NSTAGE) & 1;
-      uint8_t* a_hi = s_tc + s * kStageBytes;
-      uint8_t* a_lo = a_hi + kABytes;
-      uint8_t* b_hi = a_lo + kABytes;
-      // global loads first (they do not touch the stage), then wait for the stage to be free
-      constexpr int kPerThread = (kTcM * KQ + kTcProducers - 1) / kTcProducers;
-      float4 v[kPerThread];
+  if (warp < kTcProdWarps) {
+    // ===== producers: warp w owns stage w =====
+    const int s = warp;
+    uint8_t* a_hi = s_tc + s * kStageBytes;
+    uint8_t* a_lo = a_hi + kABytes;
+    uint8_t* b_hi = a_lo + kABytes;
+    constexpr int kPerLane = kTcM * KQ / 32;
+    // kPerLane independent 128-bit loads of one chunk in flight per lane
+    auto load_chunk = [&](int c, float4* v) {
 #pragma unroll
-      for (int it = 0; it < kPerThread; ++it) {
-        const int idx = tid + it * kTcProducers;
+      for (int it = 0; it < kPerLane; ++it) {
+        const int idx = lane + it * 32;
+        const int r8 = idx & 7, k4 = (idx >> 3) % KQ, rg = idx / (8 * KQ);
+        const int grow = m0 + rg * 8 + r8, gk = c * KC + k4 * 4;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < kTcM * KQ) {
-          const int r8 = idx & 7, k4 = (idx >> 3) % KQ, rg = idx / (8 * KQ);
-          const int grow = m0 + rg * 8 + r8, gk = c * KC + k4 * 4;
-          if (grow < g.M) {
-            const float* p = g.A + int64_t(grow) * g.lda;
-            if (gk + 3 < g.K) {
-              v[it] = __ldg(reinterpret_cast<const float4*>(p + gk));
-            } else {
-              if (gk + 0 < g.K) v[it].x = __ldg(p + gk + 0);
-              if (gk + 1 < g.K) v[it].y = __ldg(p + gk + 1);
-              if (gk + 2 < g.K) v[it].z = __ldg(p + gk + 2);
-            }
+        if (c < nchunks && grow < g.M) {
+          const float* p = g.A + int64_t(grow) * g.lda;
+          if (gk + 3 < g.K) {
+            v[it] = __ldg(reinterpret_cast<const float4*>(p + gk));
+          } else {
+            if (gk + 0 < g.K) v[it].x = __ldg(p + gk + 0);
+            if (gk + 1 < g.K) v[it].y = __ldg(p + gk + 1);
+            if (gk + 2 < g.K) v[it].z = __ldg(p + gk + 2);
           }
         }
       }
+    };
+    float4 v[kPerLane], vn[kPerLane];
+    load_chunk(warp, v);
+    uint32_t ph = 0;
+    for (int c = warp; c < nchunks; c += kTcProdWarps, ph ^= 1) {
+      load_chunk(c + kTcProdWarps, vn);   // next chunk's loads overlap this chunk's wait / convert / store
       tc::mbar_wait(&s_empty[s], ph ^ 1);
-      if (tid == 0) {
+      if (lane == 0) {
         tc::mbar_expect_tx(&s_full[s], 2 * kBBytes);
-        tc::bulk_g2s(b_hi, bsrc + int64_t(c) * (2 * NT * KC), 2 * kBBytes, &s_full[s]);
+        tc::bulk_g2s(b_hi, g.Bp + int64_t(c) * (2 * NT * KC), 2 * kBBytes, &s_full[s]);
       }
 #pragma unroll
-      for (int it = 0; it < kPerThread; ++it) {
-        const int idx = tid + it * kTcProducers;
-        if (idx < kTcM * KQ) {
-          const int r8 = idx & 7, k4 = (idx >> 3) % KQ, rg = idx / (8 * KQ);
-          float4 h, l;
-          tc::split4(v[it], h, l);
-          const uint32_t off = tc::canon_off(rg * 8 + r8, k4 * 4, KC);
-          *reinterpret_cast<float4*>(a_hi + off) = h;
-          *reinterpret_cast<float4*>(a_lo + off) = l;
-        }
+      for (int it = 0; it < kPerLane; ++it) {
+        const int idx = lane + it * 32;
+        const int r8 = idx & 7, k4 = (idx >> 3) % KQ, rg = idx / (8 * KQ);
+        float4 h, l;
+        tc::split4(v[it], h, l);
+        const uint32_t off = tc::canon_off(rg * 8 + r8, k4 * 4, KC);
+        *reinterpret_cast<float4*>(a_hi + off) = h;
+        *reinterpret_cast<float4*>(a_lo + off) = l;
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&s_full[s]);
+#pragma unroll
+      for (int it = 0; it < kPerLane; ++it) v[it] = vn[it];
     }
-  } else if (warp == 6) {
-    // ===== MMA issuer =====
+  } else {
+    // ===== MMA issuers (warps 6 and 7: even / odd chunks) =====
+    // A single thread issues every tcgen05.mma, so its instruction stream is the critical path: descriptors are
+    // built once (stage 0) and advanced by adding the stage / K-slice byte offset to the 14-bit address field.
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(kTcM, NT);
       constexpr uint32_t sbo = KQ * 128, lbo = 128;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % NSTAGE;
-        const uint32_t ph = uint32_t(c / NSTAGE) & 1;
+      const uint32_t base = tc::smem_u32(s_tc);
+      const uint64_t dah0 = tc::smem_desc(base, lbo, sbo);
+      const uint64_t dal0 = tc::smem_desc(base + kABytes, lbo, sbo);
+      const uint64_t dbh0 = tc::smem_desc(base + 2 * kABytes, lbo, sbo);
+      const uint64_t dbl0 = tc::smem_desc(base + 2 * kABytes + kBBytes, lbo, sbo);
+      static_assert(NACC == 2 && (NSTAGE % 2) == 0, "issuer w owns accumulator w and the stages of its parity");
+      const int which = warp - kTcProdWarps;   // 0: even chunks, 1: odd chunks
+      int s = which;
+      uint32_t ph = 0;
+      const uint32_t accsel = which;
+      for (int c = which; c < nchunks; c += 2) {
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
-        const uint32_t a_hi = tc::smem_u32(s_tc + s * kStageBytes);
-        const uint32_t a_lo = a_hi + kABytes, b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
-        const uint32_t acc = tmem + uint32_t(c % NACC) * NT;
-        const bool first = c < NACC;   // first touch of this accumulator overwrites
+        const uint64_t soff = uint64_t(uint32_t(s) * (kStageBytes >> 4));
+        const uint32_t acc = tmem + accsel * NT;
+        const bool first = c < 2;   // first touch of this accumulator overwrites
 #pragma unroll
         for (int ks = 0; ks < KC / 8; ++ks) {
-          const uint64_t dah = tc::smem_desc(a_hi + ks * 256, lbo, sbo);
-          const uint64_t dal = tc::smem_desc(a_lo + ks * 256, lbo, sbo);
-          const uint64_t dbh = tc::smem_desc(b_hi + ks * 256, lbo, sbo);
-          const uint64_t dbl = tc::smem_desc(b_lo + ks * 256, lbo, sbo);
-          tc::mma_tf32(acc, dal, dbh, idesc, !(first && ks == 0));   // small terms first
-          tc::mma_tf32(acc, dah, dbl, idesc, true);
-          tc::mma_tf32(acc, dah, dbh, idesc, true);
+          const uint64_t o = soff + uint64_t(ks * 16);   // one 8-wide K slice = 2 core matrices = 256 bytes
+          tc::mma_tf32(acc, dal0 + o, dbh0 + o, idesc, !(first && ks == 0));   // small terms first
+          tc::mma_tf32(acc, dah0 + o, dbl0 + o, idesc, true);
+          tc::mma_tf32(acc, dah0 + o, dbh0 + o, idesc, true);
         }
         tc::mma_commit(&s_empty[s]);
+        s += 2;
+        if (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
       }
       tc::mma_commit(&s_done);
     }
@@ -198,25 +214,28 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     for (int q = 0; q < kMaxActions; ++q) part[q] = 0.0f;
 #pragma unroll
     for (int cb = 0; cb < NT; cb += 32) {
+      // all accumulators of this 32-column block in flight, one wait
+      uint32_t raw[NACC][32];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a)
+        if (a < nacc_used) tc::tmem_ld32_nowait(tmem + (uint32_t(warp * 32) << 16) + a * NT + cb, raw[a]);   // warp-uniform
+      tc::tmem_ld_wait();
       float v[32];
-      tc::tmem_ld32(tmem + (uint32_t(warp * 32) << 16) + cb, v);
 #pragma unroll
-      for (int a = 1; a < NACC; ++a) {
-        if (a < nacc_used) {   // warp-uniform
-          float w[32];
-          tc::tmem_ld32(tmem + (uint32_t(warp * 32) << 16) + a * NT + cb, w);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[0][j]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += w[j];
+      for (int a = 1; a < NACC; ++a)
+        if (a < nacc_used) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[a][j]);
         }
-      }
       if (EPI == EPI_STORE) {
         if (row < g.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + cb + j;
             if (n < g.N) {
-              float o = v[j];
-              if (g.bias) o += __ldg(g.bias + n);
+              float o = v[j] + s_head[cb + j];
               if (g.relu) o = fmaxf(o, 0.0f);
               v[j] = o;
             }
@@ -273,14 +292,14 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 7) tc::tmem_dealloc(tmem, kCols);
+  if (warp == 0) tc::tmem_dealloc(tmem, kCols);
 }
 
-template <int NT, int KC, int NSTAGE, int NACC, int EPI>
+template <int NT, int KC, int NACC, int EPI>
 int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
-  constexpr size_t smem = size_t(NSTAGE) * (2 * kTcM * KC * 4 + 2 * NT * KC * 4);
-  auto kernel = tc_gemm_kernel<NT, KC, NSTAGE, NACC, EPI>;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+  constexpr size_t smem = size_t(kTcProdWarps) * (2 * kTcM * KC * 4 + 2 * NT * KC * 4);
+  auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI>;
+  if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   dim3 grid((g.M + kTcM - 1) / kTcM, 1);
   kernel<<<grid, kTcThreads, smem, s>>>(g);
@@ -289,9 +308,9 @@ int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
 
 }  // namespace
 
-// tile shapes: N <= 64 -> (NT 64, KC 16, 4 stages, 4 accumulators); N <= 128 -> (NT 128, KC 16, 3 stages, 2 accumulators)
+// tile shapes: N <= 64 -> (NT 64, 4 accumulators); N <= 128 -> (NT 128, 2 accumulators); KC = 8 floats per stage
 static inline int tc_nt(int N) { return N <= 64 ? 64 : 128; }
-constexpr int kTcKC = 16;
+constexpr int kTcKC = 8;
 
 extern "C" int64_t mapf_tc_packed_b_size(int32_t N, int32_t K) {
   if (N <= 0 || N > 128 || K <= 0) return -1;
@@ -322,8 +341,8 @@ extern "C" int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int
   g.A = A; g.lda = lda; g.Bp = Bp;
   g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (N <= 64) return launch_tc<64, kTcKC, 4, 4, EPI_STORE>(g, s);
-  return launch_tc<128, kTcKC, 3, 2, EPI_STORE>(g, s);
+  if (N <= 64) return launch_tc<64, kTcKC, 2, EPI_STORE>(g, s);
+  return launch_tc<128, kTcKC, 2, EPI_STORE>(g, s);
 }
 
 // logits / greedy actions = head(relu(Z Wp^T)): Z [M, K] row-major filter taps, Wp = packed [W | W2] (mapf_tc_pack_b).
@@ -340,6 +359,6 @@ extern "C" int mapf_tc_mix_head(int32_t M, int32_t N, int32_t K, const float* Z,
   g.act_w = act_w; g.act_b = act_b; g.num_actions = num_actions;
   g.logits = logits; g.actions = actions; g.y = y;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (N <= 64) return launch_tc<64, kTcKC, 4, 4, EPI_HEAD>(g, s);
-  return launch_tc<128, kTcKC, 3, 2, EPI_HEAD>(g, s);
+  if (N <= 64) return launch_tc<64, kTcKC, 2, EPI_HEAD>(g, s);
+  return launch_tc<128, kTcKC, 2, EPI_HEAD>(g, s);
 }

@@ -117,13 +117,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// same without waiting: the caller issues several loads and then one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- 3xTF32 operand split ---------------------------------------------------------------------------------
-// round-to-nearest TF32 (low 13 mantissa bits become zero): the hardware then sees exactly these values
+// round-to-nearest TF32 (low 13 mantissa bits become zero) with two integer ops on the fast ALU pipe: add half an
+// ulp of TF32 to the magnitude bits and clear the tail (ties away from zero, like cvt.rna.tf32.f32).  The hardware
+// then sees exactly these values.
 __device__ __forceinline__ float tf32_rn(float a) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split1(float a, float& hi, float& lo) {
   hi = tf32_rn(a);

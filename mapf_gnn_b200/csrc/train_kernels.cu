@@ -607,7 +607,7 @@ int launch_conv_train(cudaStream_t s, const float* in, int cin, int cout, int B,
                       const float* bias, float* out, double* stats, int stat_c) {
   const size_t smem = sizeof(float) * size_t(cin + cout) * kFovCells * kCtPad;
   if (smem > 220 * 1024) return MAPF_ERR_UNSUPPORTED;
-  if (cudaFuncSetAttribute(conv_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+  if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_train_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   dim3 grid((B + 31) / 32, N);
   conv_train_kernel<<<grid, kCtThreads, smem, s>>>(in, cin, cout, B, N, wpk, bias, out, stats, stat_c);
@@ -737,7 +737,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     }
     const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
     MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
-    if (cudaFuncSetAttribute(recurrence_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(recurrence_bwd_kernel, size_t(smem), cache__); }())
       return MAPF_ERR_CUDA;
     recurrence_bwd_kernel<<<B, 128, smem, s>>>(ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
                                                a->message ? 0 : 1, ws + T.dx, int64_t(N) * F, F, 1);
@@ -765,7 +765,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     {
       const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
       MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
-      if (cudaFuncSetAttribute(conv_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel, size_t(smem), cache__); }())
         return MAPF_ERR_CUDA;
       const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
       const int gridw = int(mapf_min64(ntiles, 2 * 148));
@@ -848,7 +848,7 @@ extern "C" int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_s
   }
   const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
   MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
-  if (cudaFuncSetAttribute(recurrence_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+  if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(recurrence_bwd_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   recurrence_bwd_kernel<<<B, 128, smem, s>>>(dz, a->gso, nullptr, N, F, K, skip, a->add_self_loop, a->dx, int64_t(F) * N,
                                              1, N);

@@ -21,6 +21,9 @@ _LIB = torch.library.Library("mapf", "DEF")
 
 # graph-filter mix on tcgen05 (3xTF32) when True; the fused fp32-FFMA kernel when False (development switch)
 USE_TENSOR_CORES = os.environ.get("MAPF_B200_TENSOR_CORES", "1") != "0"
+# encoder FC on tcgen05 as well (conv-only encoder kernel + tensor-core GEMM).  Off by default: at the benchmark
+# sizes the fused FFMA FC inside the persistent encoder kernel is as fast (see DESIGN.md 3.2 / profiles/)
+USE_TENSOR_CORE_FC = os.environ.get("MAPF_B200_TENSOR_CORE_FC", "0") == "1"
 
 _LIB.define("pack_weights(int[] dims, Tensor[] conv_w, Tensor[] conv_b, Tensor[] bn_gamma, Tensor[] bn_beta, "
             "Tensor[] bn_mean, Tensor[] bn_var, Tensor fc_w, Tensor fc_b, Tensor? gf_w, Tensor? gf_w2, "
@@ -90,6 +93,9 @@ def _policy_fwd(dims, message, states, gso, packed):
     a = _lib.PolicyFwdArgs()
     a.batch, a.agents, a.message = B, N, int(message)
     a.states, a.packed, a.workspace_x = states.data_ptr(), packed.data_ptr(), work.data_ptr()
+    if USE_TENSOR_CORES and USE_TENSOR_CORE_FC:
+        worka = torch.empty((B * N, p.fc_in), dtype=torch.float32, device=dev)
+        a.workspace_act = worka.data_ptr()
     if p.taps > 0:
         if gso is None:
             raise ValueError("gso is required for the GNN variants")

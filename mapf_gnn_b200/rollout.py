@@ -36,6 +36,7 @@ class Rollout:
         self.logits = torch.empty((E, N, dims[10]), dtype=torch.float32, device=dev)
         self.work = torch.empty((E * N, dims[7]), dtype=torch.float32, device=dev)
         from . import ops
+        self.worka = (torch.empty((E * N, dims[6]), dtype=torch.float32, device=dev) if ops.USE_TENSOR_CORES and ops.USE_TENSOR_CORE_FC else None)
         self.workz = (torch.empty((E * N, (dims[8] + 1) * dims[7]), dtype=torch.float32, device=dev)
                       if dims[8] > 0 and ops.USE_TENSOR_CORES else None)
         self.params = net_params(dims)
@@ -49,6 +50,7 @@ class Rollout:
         p.states, p.gso = env.fov.data_ptr(), env.adj_matrix.data_ptr()
         p.packed, p.workspace_x = self.net.packed_weights().data_ptr(), self.work.data_ptr()
         p.workspace_z = None if self.workz is None else self.workz.data_ptr()
+        p.workspace_act = None if self.worka is None else self.worka.data_ptr()
         p.logits, p.actions = self.logits.data_ptr(), self.actions.data_ptr()
         a.steps = int(steps)
         return a
