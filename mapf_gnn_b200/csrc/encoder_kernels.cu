@@ -40,11 +40,11 @@ __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, 
                                                   const float* __restrict__ bias, int cin, int cout, int warp,
                                                   int lane, int out_ps = kEncAgents) {
   for (int pr = warp; pr < (cout >> 1); pr += kEncWarps) {
-    float acc0[kFovCells], acc1[kFovCells];
+    float2 acc[kFovCells];   // (channel 2pr, channel 2pr+1) per pixel: one FFMA2 updates both
     {
       const float2 b = *reinterpret_cast<const float2*>(bias + 2 * pr);
 #pragma unroll
-      for (int p = 0; p < kFovCells; ++p) { acc0[p] = b.x; acc1[p] = b.y; }
+      for (int p = 0; p < kFovCells; ++p) acc[p] = b;
     }
     // float2 view: element [(cog*cin + ci)*9 + t]*2 + h with cog = pr/2, h = pr&1
     const float2* wp = reinterpret_cast<const float2*>(w) + (int64_t(pr >> 1) * cin * 9) * 2 + (pr & 1);
@@ -57,26 +57,24 @@ __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, 
       float2 wv[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) wv[t] = wp[(ci * 9 + t) * 2];
+      // taps outermost: consecutive FFMA2 hit 25 different accumulator pairs (no back-to-back dependency)
 #pragma unroll
-      for (int y = 0; y < kFov; ++y)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int x = 0; x < kFov; ++x)
+        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+          for (int y = 0; y < kFov; ++y)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+            for (int x = 0; x < kFov; ++x) {
               const int yy = y + ky - 1, xx = x + kx - 1;
-              if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov) {  // resolved at compile time
-                const float a = v[yy * kFov + xx];
-                acc0[y * kFov + x] = fmaf(a, wv[ky * 3 + kx].x, acc0[y * kFov + x]);
-                acc1[y * kFov + x] = fmaf(a, wv[ky * 3 + kx].y, acc1[y * kFov + x]);
-              }
+              if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov)   // resolved at compile time
+                mapf_ffma2(acc[y * kFov + x], v[yy * kFov + xx], wv[ky * 3 + kx]);
             }
     }
 #pragma unroll
     for (int p = 0; p < kFovCells; ++p) {
-      out[((2 * pr) * kFovCells + p) * out_ps + lane] = fmaxf(acc0[p], 0.0f);
-      out[((2 * pr + 1) * kFovCells + p) * out_ps + lane] = fmaxf(acc1[p], 0.0f);
+      out[((2 * pr) * kFovCells + p) * out_ps + lane] = fmaxf(acc[p].x, 0.0f);
+      out[((2 * pr + 1) * kFovCells + p) * out_ps + lane] = fmaxf(acc[p].y, 0.0f);
     }
   }
 }
@@ -138,11 +136,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
     for (int jb = 0; jb < d.fc_out; jb += 64) {
       const int j = jb + jq * 4;
       const bool jlive = j < d.fc_out;
-      float acc[4][4];
+      float2 acc[4][2];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+      for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.0f, 0.0f);
       if (jlive) {
         const float4* wps = reinterpret_cast<const float4*>(s_w + L.fc_wt + j);
         const float4* wpg = reinterpret_cast<const float4*>(packed + L.fc_wt + j);
@@ -152,19 +148,18 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
           const float4 a4 = ap[i * (kEncAgents / 4)];
           const float4 w4 = kFcSmem ? wps[i * wstride] : __ldg(wpg + i * wstride);
           const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            acc[r][0] = fmaf(av[r], w4.x, acc[r][0]);
-            acc[r][1] = fmaf(av[r], w4.y, acc[r][1]);
-            acc[r][2] = fmaf(av[r], w4.z, acc[r][2]);
-            acc[r][3] = fmaf(av[r], w4.w, acc[r][3]);
+            mapf_ffma2(acc[r][0], av[r], wlo);
+            mapf_ffma2(acc[r][1], av[r], whi);
           }
         }
       }
       if (kg == 1) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-          reinterpret_cast<float4*>(scratch)[r * 128 + t7] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          reinterpret_cast<float4*>(scratch)[r * 128 + t7] = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
       }
       __syncthreads();
       if (kg == 0 && jlive) {
@@ -175,10 +170,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
           const float4 o2 = reinterpret_cast<const float4*>(scratch)[r * 128 + t7];
           if (a < nrows) {
             float4 o;
-            o.x = fmaxf(acc[r][0] + o2.x + b4.x, 0.0f);
-            o.y = fmaxf(acc[r][1] + o2.y + b4.y, 0.0f);
-            o.z = fmaxf(acc[r][2] + o2.z + b4.z, 0.0f);
-            o.w = fmaxf(acc[r][3] + o2.w + b4.w, 0.0f);
+            o.x = fmaxf(acc[r][0].x + o2.x + b4.x, 0.0f);
+            o.y = fmaxf(acc[r][0].y + o2.y + b4.y, 0.0f);
+            o.z = fmaxf(acc[r][1].x + o2.z + b4.z, 0.0f);
+            o.w = fmaxf(acc[r][1].y + o2.w + b4.w, 0.0f);
             *reinterpret_cast<float4*>(x + (row0 + a) * d.fc_out + j) = o;
           }
         }
