@@ -266,32 +266,36 @@ def run_mine(args, w):
     env_gbs = E * N * w["env_bytes"] / (env_ms * 1e-3) / 1e9
 
     # ---- end to end through the public API with HOST buffers (pinned), every step ----
+    # Per step: the state (positions) is uploaded from pinned host memory, the step runs, and actions, new positions
+    # and done flags are read back into pinned host memory and waited for; the next step's upload uses those host
+    # values (host round trip).  No host arithmetic inside the loop: done flags land in a [steps, E] pinned log.
     env.reset()
-    pos_up = torch.empty((E, N, 2), dtype=torch.int32).pin_memory()
-    pos_dn = torch.empty((E, N, 2), dtype=torch.int32).pin_memory()
-    act_dn = torch.empty((E, N), dtype=torch.int32).pin_memory()
-    done_dn = torch.empty((E,), dtype=torch.uint8).pin_memory()
-    pos_up.copy_(env.pos.cpu())
     ke = max(8, min(K, 64))
+    host_pos = [torch.empty((E, N, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+    act_dn = torch.empty((E, N), dtype=torch.int32).pin_memory()
+    done_log = torch.empty((ke + 1, E), dtype=torch.uint8).pin_memory()
+    host_pos[0].copy_(env.pos.cpu())
+    done_log[0].zero_()
     for i in range(3):
-        env.pos.copy_(pos_up, non_blocking=True)
+        env.pos.copy_(host_pos[0], non_blocking=True)
         ro.run(1)
-        pos_dn.copy_(env.pos, non_blocking=True)
+        host_pos[1].copy_(env.pos, non_blocking=True)
         torch.cuda.synchronize()
-        pos_up.copy_(pos_dn)
+        host_pos[0].copy_(host_pos[1])
+    env.reset()
+    host_pos[0].copy_(env.pos.cpu())
     barrier()
-    e2e_units = 0.0
     t0 = time.perf_counter()
     for i in range(ke):
-        env.pos.copy_(pos_up, non_blocking=True)          # H2D: this step's state
+        src, dst = host_pos[i & 1], host_pos[(i + 1) & 1]
+        env.pos.copy_(src, non_blocking=True)              # H2D: this step's state
         ro.run(1)
         act_dn.copy_(ro.actions, non_blocking=True)       # D2H: actions, new state, done
-        pos_dn.copy_(env.pos, non_blocking=True)
-        done_dn.copy_(env.done, non_blocking=True)
+        dst.copy_(env.pos, non_blocking=True)
+        done_log[i + 1].copy_(env.done, non_blocking=True)
         torch.cuda.synchronize()
-        e2e_units += float(E - int(done_dn.sum())) * N
-        pos_up.copy_(pos_dn)                               # host round trip
     e2e_s = time.perf_counter() - t0
+    e2e_units = float((E - done_log[:ke].to(torch.int64).sum(dim=1)).sum()) * N   # episodes alive before each step
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     u = torch.tensor([e2e_units], dtype=torch.float64, device=dev)
     if world > 1:

@@ -16,8 +16,9 @@
 //                          commits them to the stage's `empty` mbarrier.  Two issuers because the MMAs are small
 //                          (32-64 cycles of tensor work): one thread's wait/issue/commit loop (~500 cycles) would pace
 //                          the whole pipeline
-//   warps 0-3  epilogue  : after the final commit each thread owns one output row = one TMEM lane, reads it with
-//                          tcgen05.ld and applies the epilogue (no cross-thread reduction for the 5-way head)
+//   all warps  epilogue  : after the final commit warp w reads TMEM lanes 32(w%4).. (= 32 output rows, one per thread)
+//                          and column half w/4 with tcgen05.ld; EPI_STORE transposes through shared memory so that
+//                          global stores are 128-byte coalesced; EPI_HEAD needs one exchange between the two halves
 // The tensor core's fp32 accumulation loses a little precision per accumulate, so consecutive chunks rotate over
 // NACC independent TMEM accumulators that are summed in registers in the epilogue.
 #include "common.cuh"
@@ -201,24 +202,29 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       }
       tc::mma_commit(&s_done);
     }
+    __syncwarp();   // lanes 1-31 park here instead of spinning on s_done next to the issuing lane
   }
 
-  if (warp < 4) {
-    // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows m0 + 32w + lane =====
+  {
+    // ===== epilogue (all 8 warps): warp w owns TMEM lanes [32(w%4), +32) = rows m0 + 32(w%4) + lane and the column
+    // half w/4.  The operand stages are free once s_done fires and are reused as transpose / exchange scratch. =====
     tc::mbar_wait(&s_done, 0);
     tc::fence_after_sync();
-    const int row = m0 + warp * 32 + lane;
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = m0 + quad * 32 + lane;
     const int nacc_used = nchunks < NACC ? nchunks : NACC;
+    constexpr int kHalfCols = NT / 2;
+    float* s_scr = reinterpret_cast<float*>(s_tc);
     float part[kMaxActions];
 #pragma unroll
     for (int q = 0; q < kMaxActions; ++q) part[q] = 0.0f;
 #pragma unroll
-    for (int cb = 0; cb < NT; cb += 32) {
-      // all accumulators of this 32-column block in flight, one wait
+    for (int cbl = 0; cbl < kHalfCols; cbl += 32) {
+      const int cb = half * kHalfCols + cbl;
       uint32_t raw[NACC][32];
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
-        if (a < nacc_used) tc::tmem_ld32_nowait(tmem + (uint32_t(warp * 32) << 16) + a * NT + cb, raw[a]);   // warp-uniform
+        if (a < nacc_used) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + a * NT + cb, raw[a]);   // warp-uniform
       tc::tmem_ld_wait();
       float v[32];
 #pragma unroll
@@ -230,35 +236,38 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
           for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[a][j]);
         }
       if (EPI == EPI_STORE) {
-        if (row < g.M) {
+        // bias / ReLU, then a warp-private 32x32 transpose through shared memory so that every global store
+        // instruction writes 128 contiguous bytes of one output row
+        float* t = s_scr + warp * (32 * 33);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + cb + j;
-            if (n < g.N) {
-              float o = v[j] + s_head[cb + j];
-              if (g.relu) o = fmaxf(o, 0.0f);
-              v[j] = o;
-            }
-          }
-          float* dst = g.C + int64_t(row) * g.ldc + n0 + cb;
-          if (n0 + cb + 32 <= g.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + cb + j < g.N) dst[j] = v[j];
-          }
+        for (int j = 0; j < 32; ++j) {
+          float o = v[j] + s_head[cb + j];
+          if (g.relu) o = fmaxf(o, 0.0f);
+          t[lane * 33 + j] = o;
         }
+        __syncwarp();
+        const int n = n0 + cb + lane;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int grow = m0 + quad * 32 + r;
+          if (grow < g.M && n < g.N) g.C[int64_t(grow) * g.ldc + n] = t[r * 33 + lane];
+        }
+        __syncwarp();
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        if (g.y != nullptr && row < g.M) {
-          float* dst = g.y + int64_t(row) * g.N + cb;
+        if (g.y != nullptr) {
+          float* t = s_scr + warp * (32 * 33);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j < g.N) dst[j] = v[j];
+          for (int j = 0; j < 32; ++j) t[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int n = cb + lane;
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int grow = m0 + quad * 32 + r;
+            if (grow < g.M && n < g.N) g.y[int64_t(grow) * g.N + n] = t[r * 33 + lane];
+          }
+          __syncwarp();
         }
 #pragma unroll
         for (int q = 0; q < kMaxActions; ++q) {
@@ -276,18 +285,27 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
         }
       }
     }
-    if (EPI == EPI_HEAD && row < g.M) {
-      float best = 0.0f;
-      int arg = 0;
+    if (EPI == EPI_HEAD) {
+      // the two column halves of a row meet in shared memory (after the y transposes are done with it)
+      float* ex = s_scr + 8 * (32 * 33);   // [128 rows][kMaxActions]
+      if (half == 1) {
 #pragma unroll
-      for (int q = 0; q < kMaxActions; ++q) {
-        if (q < g.num_actions) {
-          const float o = part[q] + s_head[kMaxActions * NT + q];
-          g.logits[int64_t(row) * g.num_actions + q] = o;
-          if (q == 0 || o > best) { best = o; arg = q; }   // first max wins (np.argmax)
-        }
+        for (int q = 0; q < kMaxActions; ++q) ex[(quad * 32 + lane) * kMaxActions + q] = part[q];
       }
-      if (g.actions != nullptr) g.actions[row] = arg;
+      __syncthreads();
+      if (half == 0 && row < g.M) {
+        float best = 0.0f;
+        int arg = 0;
+#pragma unroll
+        for (int q = 0; q < kMaxActions; ++q) {
+          if (q < g.num_actions) {
+            const float o = part[q] + ex[(quad * 32 + lane) * kMaxActions + q] + s_head[kMaxActions * NT + q];
+            g.logits[int64_t(row) * g.num_actions + q] = o;
+            if (q == 0 || o > best) { best = o; arg = q; }   // first max wins (np.argmax)
+          }
+        }
+        if (g.actions != nullptr) g.actions[row] = arg;
+      }
     }
   }
   tc::fence_before_sync();
