@@ -383,7 +383,7 @@ def run_train(args, w, env, dev, rank, world, barrier):
         net = m.build_network(cfg)
         net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights(model).items()})
         net = net.to(dev).train()
-        trainer = tr.Trainer(net)
+        trainer = tr.Trainer(net, use_graph=(world == 1 and not args.no_train_graph))
         reps = (B + env.episodes - 1) // env.episodes
         states = env.fov.repeat(reps, 1, 1, 1, 1)[:B].contiguous()
         gso = (env.adj_matrix + eye).repeat(reps, 1, 1)[:B].contiguous()
@@ -404,7 +404,7 @@ def run_train(args, w, env, dev, rank, world, barrier):
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
-        entry = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms / steps,
+        entry = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms / steps, "cuda_graph": trainer.use_graph,
                  "samples_per_s": B * world * steps / (ms * 1e-3), "loss": float(loss.item())}
         if rank == 0 and world == 1 and not args.no_cpu_baseline and B <= 1024:
             entry["cpu_samples_per_s"] = cpu_train_steps(model, states.cpu(), gso.cpu(), targets.cpu().long(), 3)
@@ -427,6 +427,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-train-graph", action="store_true", help="do not replay the training step as a CUDA graph")
     ap.add_argument("--train-batches", type=int, nargs="*", default=[128, 1024, 8192])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -299,6 +299,10 @@ typedef struct {
   int32_t step;
   float* grad_norm; /* [1] out */
   double* scratch;  /* [1] */
+  /* optional device-resident hyper-state, so that a captured CUDA graph can be replayed unchanged every step:
+   * step_dev (int32, incremented by the call and used instead of `step`), lr_dev (float, used instead of `lr`) */
+  int32_t* step_dev;
+  const float* lr_dev;
 } mapf_clip_adam_args;
 int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream);
 

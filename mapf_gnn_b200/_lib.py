@@ -100,7 +100,7 @@ class ClipAdamArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("params", c_f32p), ("grads", c_f32p), ("exp_avg", c_f32p),
                 ("exp_avg_sq", c_f32p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float), ("step", C.c_int32),
-                ("grad_norm", c_f32p), ("scratch", C.c_void_p)]
+                ("grad_norm", c_f32p), ("scratch", C.c_void_p), ("step_dev", C.c_void_p), ("lr_dev", C.c_void_p)]
 
 
 class GraphFilterBwdArgs(C.Structure):

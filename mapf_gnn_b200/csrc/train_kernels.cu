@@ -570,7 +570,9 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(mapf_ce_loss_args a) {
   }
 }
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out,
+                                                    int32_t* step_dev) {
+  if (step_dev != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;   // read by the next kernel
   double s = 0.0;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     s += double(g[i]) * double(g[i]);
@@ -586,6 +588,12 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, float bc1, float bc2_sqrt) {
+  if (a.step_dev != nullptr) {   // device-resident step count (CUDA-graph replay): bias corrections computed here
+    const double t = double(*a.step_dev);
+    bc1 = float(1.0 - pow(double(a.beta1), t));
+    bc2_sqrt = float(sqrt(1.0 - pow(double(a.beta2), t)));
+  }
+  if (a.lr_dev != nullptr) a.lr = *a.lr_dev;
   const float total = float(sqrt(*a.scratch));
   const float coef = fminf(a.max_norm / (total + 1e-6f), 1.0f);   // clip_grad_norm_ (train.py:97)
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.grad_norm = total;
@@ -796,11 +804,11 @@ extern "C" int mapf_ce_loss(const mapf_ce_loss_args* a, mapf_stream_t stream) {
 
 extern "C" int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream) {
   MAPF_REQUIRE(a && a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->grad_norm && a->scratch, MAPF_ERR_NULL);
-  MAPF_REQUIRE(a->n > 0 && a->step >= 1, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(a->n > 0 && (a->step >= 1 || a->step_dev != nullptr), MAPF_ERR_SHAPE);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(a->scratch, 0, sizeof(double), s) != cudaSuccess) return MAPF_ERR_CUDA;
   const int blocks = int(mapf_min64((a->n + 255) / 256, 148));
-  sumsq_kernel<<<blocks, 256, 0, s>>>(a->grads, a->n, a->scratch);
+  sumsq_kernel<<<blocks, 256, 0, s>>>(a->grads, a->n, a->scratch, a->step_dev);
   const double bc1 = 1.0 - pow(double(a->beta1), double(a->step));
   const double bc2 = 1.0 - pow(double(a->beta2), double(a->step));
   clip_adam_kernel<<<blocks, 256, 0, s>>>(*a, float(bc1), float(sqrt(bc2)));

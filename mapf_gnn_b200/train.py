@@ -171,7 +171,7 @@ class Trainer:
     """
 
     def __init__(self, net, lr=3e-4, weight_decay=1e-4, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, world_size=None):
+                 process_group=None, world_size=None, use_graph=False):
         self.net, self.lib = net, _lib.load()
         self.lr, self.weight_decay, self.max_norm, self.betas, self.eps = lr, weight_decay, max_norm, betas, eps
         self.slots = _param_list(net.param_groups())
@@ -199,6 +199,10 @@ class Trainer:
         self.grad_norm = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.scratch = torch.zeros((1,), dtype=torch.float64, device=dev)
         self.step_count = 0
+        self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)     # device-resident Adam step count
+        self.lr_dev = torch.full((1,), lr, dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self._graph, self._graph_key = None, None
         self.ws = _Workspace()
         self.group = process_group
         if world_size is None:
@@ -209,28 +213,77 @@ class Trainer:
     def set_lr(self, lr):
         """CosineAnnealingLR is stepped per epoch by the caller (train.py:65,151)."""
         self.lr = lr
+        self.lr_dev.fill_(lr)
 
-    @torch.no_grad()
-    def step(self, states, gso, targets):
-        """One optimisation step; returns the (local) mean cross-entropy as a device scalar."""
+    def _step_body(self, states, gso, targets):
         net = self.net
-        if not net.training:
-            raise RuntimeError("Trainer.step needs the network in train() mode (train.py:80)")
         logits, saved = _forward(net, states, gso, self.ws)
         loss, dlogits = cross_entropy(logits, targets)
         _backward(net, saved, dlogits, self.grad_views)
         if self.world > 1:
             from .parallel import average_gradients
             average_gradients(self.flat_grad, self.group)
-        self.step_count += 1
         a = _lib.ClipAdamArgs()
         a.n = self.flat.numel()
         a.params, a.grads = self.flat.data_ptr(), self.flat_grad.data_ptr()
         a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
         a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        a.weight_decay, a.max_norm, a.step = self.weight_decay, self.max_norm, self.step_count
+        a.weight_decay, a.max_norm, a.step = self.weight_decay, self.max_norm, 0
         a.grad_norm, a.scratch = self.grad_norm.data_ptr(), self.scratch.data_ptr()
+        a.step_dev, a.lr_dev = self.step_dev.data_ptr(), self.lr_dev.data_ptr()
         with torch.cuda.device(self.flat.device):
             _lib.check(self.lib.mapf_clip_adam(a, _stream()), "clip_adam")
+        return loss
+
+    @torch.no_grad()
+    def step(self, states, gso, targets):
+        """One optimisation step; returns the (local) mean cross-entropy as a device scalar.  With ``use_graph`` the
+        launch sequence (~50 kernels) is captured once per input shape into a CUDA graph and replayed: the small-batch
+        regime of train.py (batch 128) is launch-bound otherwise."""
+        net = self.net
+        if not net.training:
+            raise RuntimeError("Trainer.step needs the network in train() mode (train.py:80)")
+        targets = targets.to(device=self.flat.device, dtype=torch.int32)
+        if not self.use_graph:
+            loss = self._step_body(states, gso, targets)
+        else:
+            key = (tuple(states.shape), None if gso is None else tuple(gso.shape))
+            if self._graph_key != key:
+                self._capture(key, states, gso, targets)
+            self._g_states.copy_(states)
+            if gso is not None:
+                self._g_gso.copy_(gso)
+            self._g_targets.copy_(targets)
+            self._graph.replay()
+            loss = self._g_loss
+        self.step_count += 1
         net._weights_epoch = getattr(net, "_weights_epoch", 0) + 1   # parameters changed behind torch's back
         return loss
+
+    def _capture(self, key, states, gso, targets):
+        self._g_states = states.clone()
+        self._g_gso = None if gso is None else gso.to(torch.float32).clone()
+        self._g_targets = targets.clone()
+        # everything the replay touches must already exist: allocate the workspace with an eager forward on a copy
+        # of the optimiser state, then restore it (warm-up must not count as training steps)
+        snap = (self.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone(),
+                [b.clone() for b in self.net.buffers()])
+        side = torch.cuda.Stream(device=self.flat.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step_body(self._g_states, self._g_gso, self._g_targets)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+        def restore():
+            self.flat.copy_(snap[0]), self.exp_avg.copy_(snap[1]), self.exp_avg_sq.copy_(snap[2])
+            self.step_dev.copy_(snap[3])
+            for b, old in zip(self.net.buffers(), snap[4]):
+                b.copy_(old)
+        restore()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = self._step_body(self._g_states, self._g_gso, self._g_targets)
+        restore()       # capture does not execute, but keep the state exactly as before for safety
+        self._graph_key = key
