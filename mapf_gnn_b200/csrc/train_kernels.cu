@@ -19,6 +19,8 @@ constexpr float kBnEpsT = 1e-5f;
 struct TrainLayout {
   int64_t stat_fwd, stat_bwd;                 // fp64 [L][N][Cmax][2] each (offset in floats, 8-byte aligned)
   int64_t meaninv[MAPF_MAX_CONV];             // [N][C][2]  (mean, invstd)
+  int64_t scsh[MAPF_MAX_CONV];                // [N][C][2]  (gamma*invstd, beta - mean*gamma*invstd)
+  int64_t coef[MAPF_MAX_CONV];                // [N][C][4]  backward coefficients
   int64_t convpk[MAPF_MAX_CONV];              // [Cout/4][Cin][9][4]
   int64_t convpk_bwd[MAPF_MAX_CONV];          // flipped / transposed filters for the data gradient
   int64_t wt;                                 // [(K(+1))F][G]
@@ -46,6 +48,8 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
   for (int l = 0; l < p.num_conv; ++l) {
     const int64_t cin = p.channels[l], cout = p.channels[l + 1];
     T.meaninv[l] = take(int64_t(N) * cout * 2);
+    T.scsh[l] = take(int64_t(N) * cout * 2);
+    T.coef[l] = take(int64_t(N) * cout * 4);
     T.convpk[l] = take(cout * cin * 9);
     T.convpk_bwd[l] = take(cout * r4(cin) * 9);
     T.u[l] = take(rows * cout * 25);
@@ -187,7 +191,8 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
 // (nn.BatchNorm2d momentum rule with the unbiased variance), framework_gnn.py:160-163
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int C, int stat_c, double count,
                                    float momentum, float* __restrict__ meaninv, float* running_mean,
-                                   float* running_var, int64_t* batches) {
+                                   float* running_var, int64_t* batches, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale_shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     float rm = running_mean ? running_mean[c] : 0.0f, rv = running_var ? running_var[c] : 0.0f;
@@ -199,6 +204,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
       const double invstd = 1.0 / sqrt(var + double(kBnEpsT));
       meaninv[(n * C + c) * 2] = float(mean);
       meaninv[(n * C + c) * 2 + 1] = float(invstd);
+      const float w = gamma[c] * float(invstd);
+      scale_shift[(n * C + c) * 2] = w;
+      scale_shift[(n * C + c) * 2 + 1] = beta[c] - float(mean) * w;
       const float unbiased = float(count > 1.0 ? var * count / (count - 1.0) : var);
       rm = (1.0f - momentum) * rm + momentum * float(mean);
       rv = (1.0f - momentum) * rv + momentum * unbiased;
@@ -209,17 +217,15 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
   if (c == 0 && batches != nullptr) *batches += N;
 }
 
-__global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ meaninv,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int N, int C,
-                                int64_t total, float* __restrict__ a) {
-  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
-       idx += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t rc = idx / kFovCells;
-    const int c = int(rc % C);
-    const int n = int((rc / C) % N);
-    const float mean = meaninv[(n * C + c) * 2], invstd = meaninv[(n * C + c) * 2 + 1];
-    const float w = gamma[c] * invstd;
-    a[idx] = fmaxf(fmaf(u[idx], w, beta[c] - mean * w), 0.0f);
+__global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ scale_shift, int N, int C,
+                                int64_t planes, float* __restrict__ a) {
+  // coalesced, one element per thread and iteration; the (slot, channel) coefficients come from a tiny L1-resident table
+  const int64_t total = planes * kFovCells;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t pl = uint32_t(idx / kFovCells);
+    const uint32_t c = pl % uint32_t(C), n = (pl / uint32_t(C)) % uint32_t(N);
+    const float2 ws = __ldg(reinterpret_cast<const float2*>(scale_shift) + (n * C + c));
+    a[idx] = fmaxf(fmaf(u[idx], ws.x, ws.y), 0.0f);
   }
 }
 
@@ -250,22 +256,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
   }
 }
 
-// du = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)), in place over da
+// per (slot, channel): k0 = gamma*invstd, m1 = mean(dy), m2 = mean(dy*xhat)   (fp64 sums -> fp32 coefficients)
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ stats, const float* __restrict__ meaninv,
+                                   const float* __restrict__ gamma, int N, int C, int stat_c, double count,
+                                   float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  coef[i * 4 + 0] = gamma[c] * meaninv[i * 2 + 1];
+  coef[i * 4 + 1] = float(stats[(int64_t(n) * stat_c + c) * 2] / count);
+  coef[i * 4 + 2] = float(stats[(int64_t(n) * stat_c + c) * 2 + 1] / count);
+  coef[i * 4 + 3] = 0.0f;
+}
+
+// du = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)), in place over da (coalesced, element per thread)
 __global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ a, const float* __restrict__ u,
-                                    const float* __restrict__ meaninv, const float* __restrict__ gamma,
-                                    const double* __restrict__ stats, int N, int C, int stat_c, double count,
-                                    int64_t total) {
-  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
-       idx += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t rc = idx / kFovCells;
-    const int c = int(rc % C);
-    const int n = int((rc / C) % N);
-    const float mean = meaninv[(n * C + c) * 2], invstd = meaninv[(n * C + c) * 2 + 1];
-    const float m1 = float(stats[(int64_t(n) * stat_c + c) * 2] / count);
-    const float m2 = float(stats[(int64_t(n) * stat_c + c) * 2 + 1] / count);
+                                    const float* __restrict__ meaninv, const float* __restrict__ coef, int N, int C,
+                                    int64_t planes) {
+  const int64_t total = planes * kFovCells;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t pl = uint32_t(idx / kFovCells);
+    const uint32_t c = pl % uint32_t(C), n = (pl / uint32_t(C)) % uint32_t(N);
+    const float2 mi = __ldg(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
+    const float4 k = __ldg(reinterpret_cast<const float4*>(coef) + (n * C + c));
     const float dy = a[idx] > 0.0f ? da[idx] : 0.0f;
-    const float xhat = (u[idx] - mean) * invstd;
-    da[idx] = gamma[c] * invstd * (dy - m1 - xhat * m2);
+    const float xhat = (u[idx] - mi.x) * mi.y;
+    da[idx] = k.x * (dy - k.y - xhat * k.z);
   }
 }
 
@@ -375,56 +391,82 @@ struct GemmArgs {
   int relu;
   int splits;
 };
-constexpr int kGemmTile = 64, kGemmK = 16, kGemmThreads = 256;
+constexpr int kGemmTM = 128, kGemmTN = 64, kGemmK = 16, kGemmThreads = 256;
 
+// 128 x 64 tile, 8 x 4 outputs per thread kept as FFMA2 pairs along n, global -> register prefetch of the next K slab
+// while the current one is multiplied out of shared memory.
 __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
-  __shared__ __align__(16) float As[kGemmK][kGemmTile + 4];
-  __shared__ __align__(16) float Bs[kGemmK][kGemmTile + 4];
+  __shared__ __align__(16) float As[kGemmK][kGemmTM + 4];
+  __shared__ __align__(16) float Bs[kGemmK][kGemmTN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * kGemmTile, n0 = blockIdx.x * kGemmTile;
+  const int m0 = blockIdx.y * kGemmTM, n0 = blockIdx.x * kGemmTN;
   const int kper = ((g.K + g.splits - 1) / g.splits + kGemmK - 1) / kGemmK * kGemmK;
   const int kbeg = blockIdx.z * kper, kend = min(g.K, kbeg + kper);
-  float acc[4][4];
+  float2 acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = make_float2(0.0f, 0.0f);
   const bool a_kfast = g.sak == 1, b_nfast = g.sbn == 1;
-  for (int k0 = kbeg; k0 < kend; k0 += kGemmK) {
+  float ra[8], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = tid + i * kGemmThreads;
+      int m, k;
+      if (a_kfast) { m = e >> 4; k = e & 15; } else { m = e & 127; k = e >> 7; }
+      const int gm = m0 + m, gk = k0 + k;
+      ra[i] = (gm < g.M && gk < kend) ? __ldg(g.A + gm * g.sam + gk * g.sak) : 0.0f;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + i * kGemmThreads;
-      int m, k;
-      if (a_kfast) { m = e >> 4; k = e & 15; } else { m = e & 63; k = e >> 6; }
-      const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < g.M && gk < kend) ? __ldg(g.A + gm * g.sam + gk * g.sak) : 0.0f;
       int n, kb;
       if (b_nfast) { n = e & 63; kb = e >> 6; } else { n = e >> 4; kb = e & 15; }
       const int gn = n0 + n, gkb = k0 + kb;
-      Bs[kb][n] = (gn < g.N && gkb < kend) ? __ldg(g.B + gkb * g.sbk + gn * g.sbn) : 0.0f;
+      rb[i] = (gn < g.N && gkb < kend) ? __ldg(g.B + gkb * g.sbk + gn * g.sbn) : 0.0f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = tid + i * kGemmThreads;
+      if (a_kfast) As[e & 15][e >> 4] = ra[i]; else As[e >> 7][e & 127] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * kGemmThreads;
+      if (b_nfast) Bs[e >> 6][e & 63] = rb[i]; else Bs[e & 15][e >> 4] = rb[i];
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += kGemmK) {
+    stash();
     __syncthreads();
+    if (k0 + kGemmK < kend) fetch(k0 + kGemmK);
 #pragma unroll
     for (int k = 0; k < kGemmK; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 blo = make_float2(b4.x, b4.y), bhi = make_float2(b4.z, b4.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < 8; ++i) {
+        mapf_ffma2(acc[i][0], av[i], blo);
+        mapf_ffma2(acc[i][1], av[i], bhi);
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= g.M) continue;
+    const float vals[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
-      float v = acc[i][j];
+      float v = vals[j];
       if (g.splits > 1) {
         atomicAdd(g.C + m * g.ldc + n, v);
       } else {
@@ -441,15 +483,15 @@ int gemm(cudaStream_t s, int M, int N, int K, const float* A, int64_t sam, int64
          int64_t sbn, float* C, int64_t ldc, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
          int64_t ldmask = 0, int splits = 1) {
   GemmArgs g{M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, mask, ldmask, relu, splits};
-  dim3 grid((N + kGemmTile - 1) / kGemmTile, (M + kGemmTile - 1) / kGemmTile, splits);
+  dim3 grid((N + kGemmTN - 1) / kGemmTN, (M + kGemmTM - 1) / kGemmTM, splits);
   sgemm_kernel<<<grid, kGemmThreads, 0, s>>>(g);
   return mapf_launch_status();
 }
 
 // number of K splits for a reduction over `rows` with a small output
 int splits_for(int64_t rows, int tiles) {
-  int s = int((rows + 511) / 512);
-  const int cap = max(1, 592 / max(1, tiles));
+  int s = int((rows + 127) / 128);               // >= 128 rows of the reduction per split
+  const int cap = max(1, 592 / max(1, tiles));   // ~4 CTAs per SM in total
   return max(1, min(s, cap));
 }
 
@@ -670,10 +712,11 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
                                p->conv_b[l], ws + T.u[l], st, T.cmax));
     bn_finalize_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
                                                       const_cast<float*>(p->bn_mean[l]),
-                                                      const_cast<float*>(p->bn_var[l]), a->bn_batches[l]);
-    const int64_t total = rows * cout * kFovCells;
-    bn_apply_kernel<<<unsigned(mapf_min64((total + 255) / 256, 148 * 16)), 256, 0, s>>>(
-        ws + T.u[l], ws + T.meaninv[l], p->bn_gamma[l], p->bn_beta[l], N, cout, total, ws + T.a[l]);
+                                                      const_cast<float*>(p->bn_var[l]), a->bn_batches[l], p->bn_gamma[l],
+                                                      p->bn_beta[l], ws + T.scsh[l]);
+    const int64_t planes = rows * cout;
+    bn_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(ws + T.u[l], ws + T.scsh[l], N,
+                                                                                      cout, planes, ws + T.a[l]);
   }
   MAPF_TRY(mapf_launch_status());
   const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
@@ -735,12 +778,12 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     MAPF_TRY(gemm(s, int(rows), Gd, A, a->dlogits, A, 1, p->act_w, Gd, 1, ws + T.dy, Gd, nullptr, 0, ws + T.y, Gd));
     // dW_eff[g][j] = sum_r dy[r][g] z[r][j]  -- row-major [G][K*F] IS the memory of GFL.0.W [F,K,G] (gnn.py:114-116)
     MAPF_TRY(gemm(s, Gd, KF, int(rows), ws + T.dy, 1, Gd, ws + T.z, KT, 1, G.gf_w, KF, nullptr, 0, nullptr, 0,
-                  splits_for(rows, ((Gd + 63) / 64) * ((KF + 63) / 64))));
+                  splits_for(rows, ((Gd + 127) / 128) * ((KF + 63) / 64))));
     // dz[r][j] = sum_g dy[r][g] W_eff[g][j]
     MAPF_TRY(gemm(s, int(rows), KF, Gd, ws + T.dy, Gd, 1, p->gf_w, KF, 1, ws + T.dz, KT));
     if (a->message) {
       MAPF_TRY(gemm(s, Gd, F, int(rows), ws + T.dy, 1, Gd, ws + T.z + KF, KT, 1, G.gf_w2, F, nullptr, 0, nullptr, 0,
-                    splits_for(rows, ((Gd + 63) / 64) * ((F + 63) / 64))));
+                    splits_for(rows, ((Gd + 127) / 128) * ((F + 63) / 64))));
       MAPF_TRY(gemm(s, int(rows), F, Gd, ws + T.dy, Gd, 1, p->gf_w2, F, 1, ws + T.dz + KF, KT));
     }
     const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
@@ -755,7 +798,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   // compressMLP backward
   colsum_kernel<<<int(mapf_min64((rows + 255) / 256, 296)), 256, 0, s>>>(ws + T.dx, rows, F, G.fc_b);
   MAPF_TRY(gemm(s, F, fin, int(rows), ws + T.dx, 1, F, ws + T.a[L - 1], fin, 1, G.fc_w, fin, nullptr, 0, nullptr, 0,
-                splits_for(rows, ((F + 63) / 64) * ((fin + 63) / 64))));
+                splits_for(rows, ((F + 127) / 128) * ((fin + 63) / 64))));
   float* da = ws + T.da0;
   float* da_next = ws + T.da1;
   MAPF_TRY(gemm(s, int(rows), fin, F, ws + T.dx, F, 1, p->fc_w, fin, 1, da, fin));
@@ -766,9 +809,11 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     double* st = stat + int64_t(l) * N * T.cmax * 2;
     dim3 grid((B + 31) / 32, N);
     bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
-    const int64_t total = rows * cout * kFovCells;
-    bn_bwd_apply_kernel<<<unsigned(mapf_min64((total + 255) / 256, 148 * 16)), 256, 0, s>>>(
-        da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], p->bn_gamma[l], st, N, cout, T.cmax, count, total);
+    bn_bwd_coef_kernel<<<(N * cout + 127) / 128, 128, 0, s>>>(st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
+                                                             ws + T.coef[l]);
+    const int64_t planes = rows * cout;
+    bn_bwd_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(
+        da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
     bn_param_grads_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
       const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
@@ -846,12 +891,12 @@ extern "C" int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_s
   MAPF_TRY(mapf_graph_filter_fwd(&g, stream));
   if (cudaMemsetAsync(a->dw, 0, sizeof(float) * size_t(KF) * G, s) != cudaSuccess) return MAPF_ERR_CUDA;
   MAPF_TRY(gemm(s, G, KF, int(rows), dyr, 1, G, z, KT, 1, a->dw, KF, nullptr, 0, nullptr, 0,
-                splits_for(rows, ((G + 63) / 64) * ((KF + 63) / 64))));
+                splits_for(rows, ((G + 127) / 128) * ((KF + 63) / 64))));
   MAPF_TRY(gemm(s, int(rows), KF, G, dyr, G, 1, a->w, KF, 1, dz, KT));
   if (skip) {
     if (cudaMemsetAsync(a->dw2, 0, sizeof(float) * size_t(F) * G, s) != cudaSuccess) return MAPF_ERR_CUDA;
     MAPF_TRY(gemm(s, G, F, int(rows), dyr, 1, G, z + KF, KT, 1, a->dw2, F, nullptr, 0, nullptr, 0,
-                  splits_for(rows, ((G + 63) / 64) * ((F + 63) / 64))));
+                  splits_for(rows, ((G + 127) / 128) * ((F + 63) / 64))));
     MAPF_TRY(gemm(s, int(rows), F, G, dyr, G, 1, a->w2, F, 1, dz + KF, KT));
   }
   const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
