@@ -5,7 +5,8 @@
  * `mapf::` torch custom ops.  Every entry point
  *   - takes one plain-C argument struct of DEVICE pointers + int sizes and a cudaStream_t,
  *   - is asynchronous on that stream, never allocates, never synchronises, never throws,
- *   - keeps no global mutable state (re-entrant; thread-safe per stream),
+ *   - keeps no global mutable state apart from an idempotent per-device cache of "dynamic shared memory already
+ *     granted" flags (re-entrant; thread-safe per stream),
  *   - returns MAPF_OK (0) or a negative mapf_status code; mapf_last_error_string(code)
  *     gives the message.  All buffers are caller-owned.
  *
