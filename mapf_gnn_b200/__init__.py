@@ -15,7 +15,8 @@ from .layers import GCNLayer, MessagePassingLayer  # noqa: E402,F401
 from .network import BaselineNetwork, GNNNetwork, MessageNetwork, weights_init  # noqa: E402,F401
 from .rollout import Rollout, build_network  # noqa: E402,F401
 from .scenarios import make_scenarios  # noqa: E402,F401
+from .evaluate import evaluate  # noqa: E402,F401
 
 __all__ = ["BatchedGraphEnv", "GraphEnv", "create_goals", "create_obstacles", "d2_limit_from_range", "GCNLayer",
            "MessagePassingLayer", "GNNNetwork", "MessageNetwork", "BaselineNetwork", "weights_init", "Rollout",
-           "build_network", "make_scenarios"]
+           "build_network", "make_scenarios", "evaluate"]

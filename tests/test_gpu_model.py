@@ -158,3 +158,36 @@ def test_rollout_multi_step_equals_single_steps():
         rb.run(1)
     assert torch.equal(env_a.pos, env_b.pos) and torch.equal(env_a.fov, env_b.fov)
     assert torch.equal(env_a.adj_matrix, env_b.adj_matrix) and torch.equal(env_a.time, env_b.time)
+
+
+def test_batched_evaluator_matches_oracle_protocol():
+    """evaluate.py:201-271 for a whole batch at once: metrics must equal the oracle env driven by the oracle net
+    (teacher-forcing is not possible here, so compare only episodes whose every decision had a wide margin)."""
+    import mapf_gnn_b200 as m
+    cfg = model_config("gnn_k3", 5, board_size=[18, 18], obstacles=5, max_steps=12, tests_episodes=40, sensing_range=6)
+    net = load_network("gnn_k3").eval()
+    summary, per = m.evaluate(net, cfg, seed=5)
+    assert summary["episodes"] == 40 and 0.0 <= summary["avg_success_rate"] <= 1.0
+    assert per["steps_taken"].max() <= 22 and per["flow_time"].shape == (40,)
+    rng = np.random.default_rng(5)
+    starts, goals, obst = m.make_scenarios(rng, 40, 5, 18, 5)
+    params = oracle_params("gnn_k3")
+    checked = 0
+    for e in range(40):
+        env = eo.EnvOracle(5, 18, goals[e], starts[e], obst[e], sensing_range=6, max_time=cfg["max_time"])
+        obs, safe, done = env.observe(), True, False
+        for t in range(22):
+            st = torch.tensor(obs["fov"]).float()[None]
+            gs = torch.tensor(obs["adj_matrix"]).float()[None]
+            with torch.no_grad():
+                lg = mo.forward(params, st, gs).numpy()[0]
+            safe = safe and top2_margin(lg).min() > 1e-3
+            obs, done = env.step(lg.argmax(-1))
+            if done:
+                break
+        if safe:
+            s, f = env.metrics()
+            assert abs(per["success_rate"][e] - s) < 1e-6 and int(per["flow_time"][e]) == f
+            assert int(per["steps_taken"][e]) == env.time and bool(per["completed"][e]) == done
+            checked += 1
+    assert checked >= 20
