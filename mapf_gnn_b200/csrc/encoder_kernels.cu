@@ -94,29 +94,42 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(packed) + i);
 
   const int64_t ntiles = (rows + kEncAgents - 1) / kEncAgents;
+  float* const s_st = s_b1 + d.buf1_floats;     // [32][50] image staging, filled by cp.async one tile ahead
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kEncAgents;
-    const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
-    {  // stage the tile's images as they lie in memory: [agent][50]
+  // stage a tile's images as they lie in memory ([agent][50]); rows past the end are zero-filled after the wait
+  auto prefetch = [&](int64_t tile) {
+    if (tile < ntiles) {
+      const int64_t row0 = tile * kEncAgents;
+      const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
       const int nfl = nrows * kFovFloats;
       const float* src = states + row0 * kFovFloats;
       if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const int nq = nfl >> 2;
-        for (int q = tid; q < nq; q += kEncThreads)
-          reinterpret_cast<float4*>(s_b0)[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
-        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+        for (int q = tid; q < nq; q += kEncThreads) {
+          const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_st + 4 * q));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + 4 * q));
+        }
+        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_st[i] = __ldg(src + i);
       } else {
-        for (int i = tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+        for (int i = tid; i < nfl; i += kEncThreads) s_st[i] = __ldg(src + i);
       }
-      for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) s_b0[i] = 0.0f;
+      for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) s_st[i] = 0.0f;
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  prefetch(blockIdx.x);
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kEncAgents;
+    const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
 
     // layer 0 reads the staging layout [agent][ci*25 + p]; later layers read [ci*25 + p][agent]
-    conv3x3_relu_pair(s_b0, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
+    conv3x3_relu_pair(s_st, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
                       d.channels[0], d.channels[1], warp, lane);
     __syncthreads();
+    prefetch(tile + gridDim.x);   // the staging buffer is free: the next tile's images land during conv2 / conv3 / FC
     bool in1 = true;  // current activations live in s_b1
     for (int l = 1; l < d.num_conv; ++l) {
       conv3x3_relu_pair(in1 ? s_b1 : s_b0, kFovCells * kEncAgents, kEncAgents, lane, in1 ? s_b0 : s_b1,
@@ -282,7 +295,7 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   b1 = max(b1, 64);
   d.buf0_floats = b0 * kEncAgents;
   d.buf1_floats = b1 * kEncAgents;
-  const size_t act_bytes = size_t(d.buf0_floats + d.buf1_floats) * sizeof(float);
+  const size_t act_bytes = size_t(d.buf0_floats + d.buf1_floats + kEncAgents * kFovFloats) * sizeof(float);
   const size_t limit = 227 * 1024;
   d.fc_in_smem = (size_t(L.gf_wt) * sizeof(float) + act_bytes <= limit) ? 1 : 0;
   d.w_floats = int(d.fc_in_smem ? L.gf_wt : L.fc_wt);
