@@ -6,6 +6,7 @@ library is missing and cannot be built, importing the ops fails.
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
@@ -35,10 +36,10 @@ def _digest():
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files.append(os.path.join(ROOT, "include", "mapf_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # not the absolute path: the repo lives elsewhere on the GPU box
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(a for a in NVCC_FLAGS if not os.path.isabs(a)).encode())
     return h.hexdigest()
 
 
@@ -57,7 +58,8 @@ def is_fresh():
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Build (if stale) and return the path of the shared library."""
+    """Build (if stale) and return the path of the shared library.  Safe under concurrent ranks: an exclusive file
+    lock serialises builders and the library is moved into place atomically."""
     if not force and is_fresh():
         return LIB
     nvcc = nvcc_path()
@@ -66,6 +68,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             return LIB
         raise RuntimeError("nvcc not found and libmapf_b200.so is not built")
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():          # another rank built it while we waited
+                return LIB
+            return _build_locked(nvcc, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(nvcc, verbose):
     objs = []
     procs = []
     for src in sources():
@@ -80,11 +93,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if pr.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         sys.stderr.write(out.stdout)
         raise RuntimeError("link failed")
+    os.replace(tmp, LIB)                          # atomic: a concurrent dlopen never sees a short file
     with open(os.path.join(LIBDIR, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(STAMP, "w") as fh:
