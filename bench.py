@@ -271,31 +271,21 @@ def run_mine(args, w):
     # values (host round trip).  No host arithmetic inside the loop: done flags land in a [steps, E] pinned log.
     env.reset()
     ke = max(8, min(K, 64))
-    host_pos = [torch.empty((E, N, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
-    act_dn = torch.empty((E, N), dtype=torch.int32).pin_memory()
-    done_log = torch.empty((ke + 1, E), dtype=torch.uint8).pin_memory()
-    host_pos[0].copy_(env.pos.cpu())
-    done_log[0].zero_()
+    hs = m.HostSteppedRollout(ro)                 # public API: pinned host buffers + one CUDA-graph replay per step
+    done_log = np.zeros((ke + 1, E), dtype=np.uint8)
     for i in range(3):
-        env.pos.copy_(host_pos[0], non_blocking=True)
-        ro.run(1)
-        host_pos[1].copy_(env.pos, non_blocking=True)
-        torch.cuda.synchronize()
-        host_pos[0].copy_(host_pos[1])
+        hs.step()
+        hs.pos_in.copy_(hs.pos_out)
     env.reset()
-    host_pos[0].copy_(env.pos.cpu())
+    hs.pos_in.copy_(env.pos.cpu())
     barrier()
     t0 = time.perf_counter()
     for i in range(ke):
-        src, dst = host_pos[i & 1], host_pos[(i + 1) & 1]
-        env.pos.copy_(src, non_blocking=True)              # H2D: this step's state
-        ro.run(1)
-        act_dn.copy_(ro.actions, non_blocking=True)       # D2H: actions, new state, done
-        dst.copy_(env.pos, non_blocking=True)
-        done_log[i + 1].copy_(env.done, non_blocking=True)
-        torch.cuda.synchronize()
+        _, pos_out, done_out = hs.step()                  # H2D state, 4 kernels, D2H actions / state / done, sync
+        hs.pos_in.copy_(pos_out)                          # host round trip: next step's input is this step's output
+        done_log[i + 1] = done_out.numpy()
     e2e_s = time.perf_counter() - t0
-    e2e_units = float((E - done_log[:ke].to(torch.int64).sum(dim=1)).sum()) * N   # episodes alive before each step
+    e2e_units = float((E - done_log[:ke].astype(np.int64).sum(axis=1)).sum()) * N   # episodes alive before each step
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     u = torch.tensor([e2e_units], dtype=torch.float64, device=dev)
     if world > 1:
@@ -333,8 +323,9 @@ def run_mine(args, w):
                              "unit": "GB/s", "frac": env_gbs / pk["hbm_gbs"], "ms_per_launch": env_ms,
                              "peak_source": pk["source"]},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * N * 8,
-                    "d2h_bytes_per_step": E * N * 4 + E * N * 8 + E, "steps": ke},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": hs.h2d_bytes,
+                    "d2h_bytes_per_step": hs.d2h_bytes, "steps": ke,
+                    "api": "HostSteppedRollout.step(): pinned host buffers, CUDA-graph replay, sync per step"},
             "gpu_launches": K * launches_per_step,
             "clocks": clocks,
             "train": train,

@@ -69,10 +69,15 @@ class BatchedGraphEnv:
             self.obstacles = None
         self.cell_stride = (H * H + 15) // 16 * 16
         dev = self.device
-        self.pos = torch.empty((E, N, 2), dtype=torch.int32, device=dev)
+        # positions, the action slot used by Rollout and the done flags share ONE allocation so that a host-driven
+        # caller can fetch all three with a single device-to-host copy (HostSteppedRollout)
+        nb_pos, nb_act = E * N * 8, E * N * 4
+        self.host_block = torch.zeros((nb_pos + nb_act + (E + 15) // 16 * 16,), dtype=torch.uint8, device=dev)
+        self.pos = self.host_block[:nb_pos].view(torch.int32).view(E, N, 2)
+        self.actions = self.host_block[nb_pos:nb_pos + nb_act].view(torch.int32).view(E, N)
+        self.done = self.host_block[nb_pos + nb_act:nb_pos + nb_act + E]
         self.cells = torch.empty((E, self.cell_stride), dtype=torch.uint8, device=dev)
         self.time = torch.empty((E,), dtype=torch.int32, device=dev)
-        self.done = torch.empty((E,), dtype=torch.uint8, device=dev)
         self.fov = torch.empty((E, N, 2, 5, 5), dtype=torch.float32, device=dev)
         self.adj_matrix = torch.empty((E, N, N), dtype=torch.float32, device=dev)
         self.reset()

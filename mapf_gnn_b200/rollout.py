@@ -32,7 +32,7 @@ class Rollout:
         E, N = env.episodes, env.nb_agents
         dims = net.dims()
         dev = env.device
-        self.actions = torch.zeros((E, N), dtype=torch.int32, device=dev)
+        self.actions = env.actions          # lives next to env.pos / env.done (one block for host-driven callers)
         self.logits = torch.empty((E, N, dims[10]), dtype=torch.float32, device=dev)
         self.work = torch.empty((E * N, dims[7]), dtype=torch.float32, device=dev)
         from . import ops
@@ -64,3 +64,54 @@ class Rollout:
             stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(self.lib.mapf_rollout(self.params, args, stream), "rollout")
         return self.env.done
+
+
+class HostSteppedRollout:
+    """The step protocol of evaluate.py:223-241 driven from HOST buffers, the way an external caller holding numpy
+    state would use it: per step the positions go up from pinned memory, the policy + environment step runs, and the
+    chosen actions, the new positions and the done flags come back to pinned memory.
+
+    The whole sequence (1 host-to-device copy, 4 kernels, 1 device-to-host copy) is captured once into a CUDA graph
+    and replayed per step, so the host pays one graph launch and one stream synchronisation per step.
+    Buffers (pinned): ``pos_in`` int32[E,N,2] (written by the caller), ``actions`` int32[E,N], ``pos_out``
+    int32[E,N,2], ``done`` uint8[E] (read by the caller after ``step()`` returns)."""
+
+    def __init__(self, rollout: Rollout):
+        self.ro, env = rollout, rollout.env
+        E, N = env.episodes, env.nb_agents
+        nb_pos, nb_act = E * N * 8, E * N * 4
+        self.pos_in = torch.empty((E, N, 2), dtype=torch.int32).pin_memory()
+        self.out_block = torch.empty((env.host_block.numel(),), dtype=torch.uint8).pin_memory()
+        self.pos_out = self.out_block[:nb_pos].view(torch.int32).view(E, N, 2)
+        self.actions = self.out_block[nb_pos:nb_pos + nb_act].view(torch.int32).view(E, N)
+        self.done = self.out_block[nb_pos + nb_act:nb_pos + nb_act + E]
+        self.pos_in.copy_(env.pos.cpu())
+        self.h2d_bytes = self.pos_in.numel() * 4
+        self.d2h_bytes = self.out_block.numel()
+        snap = (env.pos.clone(), env.cells.clone(), env.time.clone(), env.done.clone(), env.fov.clone(),
+                env.adj_matrix.clone())
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                         # warm-up: first-launch attributes, lazy module loading
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for dst, src in zip((env.pos, env.cells, env.time, env.done, env.fov, env.adj_matrix), snap):
+            dst.copy_(src)
+        self.pos_in.copy_(env.pos.cpu())
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+
+    def _body(self):
+        env, ro = self.ro.env, self.ro
+        env.pos.copy_(self.pos_in, non_blocking=True)
+        ro.run(1)
+        self.out_block.copy_(env.host_block, non_blocking=True)      # actions + new positions + done in one copy
+
+    def step(self):
+        """One host-driven step; returns after the results are visible in the pinned output buffers."""
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        return self.actions, self.pos_out, self.done

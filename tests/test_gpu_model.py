@@ -191,3 +191,24 @@ def test_batched_evaluator_matches_oracle_protocol():
             assert int(per["steps_taken"][e]) == env.time and bool(per["completed"][e]) == done
             checked += 1
     assert checked >= 20
+
+
+def test_host_stepped_rollout_matches_device_rollout():
+    """HostSteppedRollout (pinned host buffers + CUDA-graph replay) must walk the same trajectory as Rollout.run."""
+    import mapf_gnn_b200 as m
+    E, N, H, M = 64, 5, 18, 5
+    rng = np.random.default_rng(9)
+    starts, goals, obst = m.make_scenarios(rng, E, N, H, M)
+    cfg = model_config("gnn_k3", N, board_size=[H, H])
+    net = load_network("gnn_k3").eval()
+    env_a = m.BatchedGraphEnv(cfg, goals, starts, obst)
+    env_b = m.BatchedGraphEnv(cfg, goals, starts, obst)
+    ra, rb = m.Rollout(net, env_a), m.Rollout(net, env_b)
+    hs = m.HostSteppedRollout(rb)
+    for t in range(6):
+        ra.run(1)
+        actions, pos_out, done = hs.step()
+        assert torch.equal(actions, ra.actions.cpu()) and torch.equal(pos_out, env_a.pos.cpu())
+        assert torch.equal(done, env_a.done.cpu())
+        hs.pos_in.copy_(pos_out)
+    assert torch.equal(env_a.fov, env_b.fov) and torch.equal(env_a.time, env_b.time)
