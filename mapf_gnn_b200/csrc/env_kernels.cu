@@ -141,34 +141,33 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
   }
 
   if (a.fov != nullptr) {
-    // A3 channel 0: fov[r,c] = board[y+2-r, x-2+c], zero outside (:248-265)
-    auto fov_value = [&](int idx) -> float {
-      const int ag = idx / kFovFloats;
-      int k = idx - ag * kFovFloats;
+    // A3 channel 0: fov[r,c] = board[y+2-r, x-2+c], zero outside (:248-265); channel 1: the goal mark.
+    // One work item = one 5-float row of one channel of one agent (10 items per agent): the per-agent state is
+    // decoded once per item and consecutive items write consecutive floats, so a warp writes one contiguous span.
+    const int items = nep * N * 10;
+    float* out = a.fov + int64_t(e0) * N * kFovFloats;
+    for (int it = tid; it < items; it += kEnvThreads) {
+      const int ag = it / 10, rr = it - ag * 10;
       const int el2 = ag / N, ln = ag - el2 * N;
       const int t = el2 * LANES + ln;
-      if (k < kFovCells) {
-        const int r = k / kFov, c = k - r * kFov;
-        const int by = s_y[t] + kFovHalf - r, bx = s_x[t] - kFovHalf + c;
-        if (by < 0 || by >= H || bx < 0 || bx >= H) return 0.0f;
-        return float(s_cells[el2 * stride + by * H + bx] & kBoardValueMask);
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+      if (rr < kFov) {
+        const int by = s_y[t] + kFovHalf - rr, bx = s_x[t] - kFovHalf;
+        if (by >= 0 && by < H) {
+          const uint8_t* row = s_cells + el2 * stride + by * H;
+          if (bx >= 0 && bx < H) v0 = float(row[bx] & kBoardValueMask);
+          if (bx + 1 >= 0 && bx + 1 < H) v1 = float(row[bx + 1] & kBoardValueMask);
+          if (bx + 2 >= 0 && bx + 2 < H) v2 = float(row[bx + 2] & kBoardValueMask);
+          if (bx + 3 >= 0 && bx + 3 < H) v3 = float(row[bx + 3] & kBoardValueMask);
+          if (bx + 4 >= 0 && bx + 4 < H) v4 = float(row[bx + 4] & kBoardValueMask);
+        }
+      } else if (rr - kFov == s_gr[t]) {
+        const int gc = s_gc[t];
+        v0 = gc == 0 ? 3.0f : 0.0f; v1 = gc == 1 ? 3.0f : 0.0f; v2 = gc == 2 ? 3.0f : 0.0f;
+        v3 = gc == 3 ? 3.0f : 0.0f; v4 = gc == 4 ? 3.0f : 0.0f;
       }
-      k -= kFovCells;
-      const int r = k / kFov, c = k - r * kFov;
-      return (r == s_gr[t] && c == s_gc[t]) ? 3.0f : 0.0f;
-    };
-    const int total = nep * N * kFovFloats;
-    float* out = a.fov + int64_t(e0) * N * kFovFloats;
-    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-      const int nq = total >> 2;
-      for (int q = tid; q < nq; q += kEnvThreads) {
-        const int i4 = q << 2;
-        reinterpret_cast<float4*>(out)[q] =
-            make_float4(fov_value(i4), fov_value(i4 + 1), fov_value(i4 + 2), fov_value(i4 + 3));
-      }
-      for (int idx = (nq << 2) + tid; idx < total; idx += kEnvThreads) out[idx] = fov_value(idx);
-    } else {
-      for (int idx = tid; idx < total; idx += kEnvThreads) out[idx] = fov_value(idx);
+      float* dst = out + it * kFov;
+      dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3; dst[4] = v4;
     }
   }
 
