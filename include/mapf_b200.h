@@ -344,6 +344,14 @@ int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, c
 int mapf_tc_mix_head(int32_t M, int32_t N, int32_t K, const float* Z, int64_t ldz, const float* Wp, const float* act_w,
                      const float* act_b, int32_t num_actions, float* logits, int32_t* actions, float* y,
                      mapf_stream_t stream);
+/* Fused graph filter + head on the tensor cores: S, hops, mix, ReLU, actionMLP, argmax in ONE kernel per 128-row tile
+ * of whole episodes (the taps never touch HBM).  x agent-major [B*N, F]; Wp as for mapf_tc_mix_head.
+ * mapf_tc_graph_supported tells whether the dimensions fit (N <= 64, F % 32 == 0, 64 < G <= 128). */
+int mapf_tc_graph_supported(int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps);
+int mapf_tc_graph_head(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
+                       int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
+                       const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
+                       mapf_stream_t stream);
 /* Filter taps Z [B*N, (K+has_skip)*F] (x_k = x_{k-1} S, gnn.py:104-109, + skip columns gnn.py:201-204) from
  * agent-major x; uses the x / gso / z / size / flag fields of the argument struct. */
 int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);

@@ -144,6 +144,10 @@ _SIGNATURES = {
                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_tc_mix_head": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mapf_tc_graph_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "mapf_tc_graph_head": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "mapf_graph_taps": (C.c_int, [C.POINTER(GraphFilterFwdArgs), C.c_void_p]),
 }
 

@@ -7,6 +7,8 @@
 // 8a A5-A9); the decomposition below is new.  All arithmetic is fp32 FFMA: the action argmax must be
 // bit-exact against fp32 logits whose top-2 margin goes down to 3e-5, which rules out
 // TF32/BF16 tensor-core inputs without error-compensating splits.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -207,7 +209,16 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
   const bool tensor_path = a->workspace_z != nullptr && p->node_dim <= 128 && (p->node_dim & 15) == 0 &&
                            (p->fc_out & 3) == 0 && a->agents <= 64;
   if (!tensor_path) return mapf_graph_filter_fwd(&g, stream);   // fused fp32-FFMA kernel
-  // tensor-core path: filter taps -> Z (tiny kernel), then 3xTF32 tcgen05 mix + ReLU + head + argmax
+  // The fused kernel runs the hops inside its 4 producer warps: right for small teams, too serial for N = 64 where the
+  // hops are 37 % of the MACs (measured: C5 987 us unfused vs 1415 us fused; C2a 24.7 vs 18.5 us).
+  if (a->agents <= 32 && mapf_tc_graph_supported(a->agents, p->fc_out, p->node_dim, p->taps) &&
+      getenv("MAPF_B200_UNFUSED_GRAPH") == nullptr) {
+    // fused tensor-core path: S, hops, 3xTF32 tcgen05 mix, ReLU, head, argmax in one kernel
+    return mapf_tc_graph_head(a->batch, a->agents, p->fc_out, p->node_dim, p->taps, a->message ? 0 : 1,
+                              a->message ? 1 : 0, a->workspace_x, a->gso, a->packed + L.tc_gf, a->packed + L.act_w,
+                              a->packed + L.act_b, p->num_actions, a->logits, a->actions, stream);
+  }
+  // two-kernel tensor-core path: filter taps -> Z (tiny kernel), then 3xTF32 tcgen05 mix + ReLU + head + argmax
   g.z = a->workspace_z;
   rc = mapf_graph_taps(&g, stream);
   if (rc != MAPF_OK) return rc;

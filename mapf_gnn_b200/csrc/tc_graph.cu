@@ -1,0 +1,324 @@
+// Fused graph filter on the tensor cores (A6/A7/A8): per 128-row tile of whole episodes, ONE kernel builds the graph
+// shift operator, runs the hops, feeds every filter tap straight into tcgen05 MMAs and finishes with ReLU + action head +
+// argmax.  The taps never touch HBM (the unfused path writes and re-reads Z [rows, K*F]).
+//
+//   S = D^-1/2 (A [+ I]) D^-1/2, x_k = x_{k-1} S                         gnn.py:87-109 / :185-199
+//   logits = actionMLP(relu([x_0 .. x_{K-1} (, Xr)] [W | W2]^T))          gnn.py:111-118,201-227; framework_gnn.py:171-181
+//
+// The hops act on the node axis independently per feature, so the K taps of an 8-feature slice can be produced from
+// that slice alone.  Warp roles (256 threads):
+//   warps 0-3  producers : warp p owns shared-memory stage p and the feature slices j = p, p+4, ...  For each slice it
+//                          loads x[:, 8j..8j+8) (128 rows, 4 per lane), and for k = 0..K-1 emits the chunk (tap k,
+//                          slice j) -- TF32 hi/lo split, canonical UMMA layout, B chunk by TMA bulk copy -- then
+//                          advances the slice one hop through a warp-private shared-memory exchange (a lane needs the
+//                          rows of its episode that other lanes hold).  The message-passing skip chunk is gathered from
+//                          global memory (raw [B,F,N]->[B,N,F] reshape).
+//   warps 4,5  MMA issuers (stages {0,2} / {1,3}, one TMEM accumulator each): wait `full`, 3 x tcgen05.mma 128xGx8
+//                          (lo*hi, hi*lo, hi*hi), commit to `empty`.
+//   all warps  epilogue  : tcgen05.ld, ReLU, 5-way head, exchange of the two column halves, first-max argmax.
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace {
+
+constexpr int kTgThreads = 256;
+constexpr int kTgProd = 4;
+constexpr int kTgM = 128;
+constexpr int kTgNT = 128;
+constexpr int kTgABytes = kTgM * 8 * 4, kTgBBytes = kTgNT * 8 * 4;
+constexpr int kTgStageBytes = 2 * kTgABytes + 2 * kTgBBytes;   // 16 KB
+
+struct TcGraphArgs {
+  int batch, agents, F, K, G;
+  int has_skip, add_self_loop, num_actions;
+  const float* x;       // [B*N, F] agent-major
+  const float* gso;     // [B, N, N]
+  const float* Bp;      // packed [W | W2] (mapf_tc_pack_b, NT = 128, KC = 8)
+  const float* act_w;   // [A, G]
+  const float* act_b;   // [A]
+  float* logits;        // [B*N, A]
+  int32_t* actions;     // [B*N] or NULL
+};
+
+__global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int epc) {
+  extern __shared__ __align__(128) uint8_t s_tg[];
+  __shared__ __align__(8) uint64_t s_full[kTgProd], s_empty[kTgProd], s_done;
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_head[kMaxActions * kTgNT + kMaxActions];
+  const int N = g.agents, F = g.F, K = g.K;
+  uint8_t* stages = s_tg;                                                     // [4][16 KB]
+  float* scratch = reinterpret_cast<float*>(s_tg + kTgProd * kTgStageBytes);  // [4 warps][128][8]
+  float* sm = scratch + kTgProd * kTgM * 8;                                   // [epc][N][N]
+  float* dinv = sm + ((epc * N * N + 3) & ~3);                                // [128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int e0 = blockIdx.x * epc;
+  const int nep = min(epc, g.batch - e0);
+  const int rows_used = nep * N;
+  const int64_t row0 = int64_t(e0) * N;
+
+  if (warp == 0) tc::tmem_alloc(&s_tmem, 256);
+  if (tid == 0) {
+    for (int s = 0; s < kTgProd; ++s) { tc::mbar_init(&s_full[s], 32); tc::mbar_init(&s_empty[s], 1); }
+    tc::mbar_init(&s_done, 2);
+    tc::fence_mbar_init();
+  }
+  for (int i = tid; i < g.num_actions * kTgNT; i += kTgThreads) {
+    const int q = i / kTgNT, n = i - q * kTgNT;
+    s_head[i] = n < g.G ? __ldg(g.act_w + int64_t(q) * g.G + n) : 0.0f;
+  }
+  if (tid < g.num_actions) s_head[kMaxActions * kTgNT + tid] = __ldg(g.act_b + tid);
+  // ---- graph shift operator of the tile's episodes ----
+  for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
+    const int el = idx / (N * N), rem = idx - el * N * N;
+    const int i = rem / N, j = rem - i * N;
+    float v = __ldg(g.gso + int64_t(e0 + el) * N * N + rem);
+    if (g.add_self_loop && i == j) v += 1.0f;
+    sm[idx] = v;
+  }
+  __syncthreads();
+  if (tid < rows_used) {
+    const int el = tid / N, i = tid - el * N;
+    float deg = 0.0f;
+    for (int j = 0; j < N; ++j) deg += sm[(el * N + i) * N + j];
+    dinv[tid] = deg > 0.0f ? __fdiv_rn(1.0f, __fsqrt_rn(deg)) : 0.0f;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
+    const int el = idx / (N * N), rem = idx - el * N * N;
+    const int i = rem / N, j = rem - i * N;
+    sm[idx] = (dinv[el * N + i] * sm[idx]) * dinv[el * N + j];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const int slices = F >> 3;                       // 8-feature slices (host guarantees slices % 4 == 0)
+  const int per_warp = slices / kTgProd;
+  const int chunks_per_slice = K + g.has_skip;
+
+  if (warp < kTgProd) {
+    // ===================== producers =====================
+    const int p = warp;
+    uint8_t* a_hi = stages + p * kTgStageBytes;
+    uint8_t* a_lo = a_hi + kTgABytes;
+    uint8_t* b_hi = a_lo + kTgABytes;
+    float* xs = scratch + p * kTgM * 8;
+    uint32_t ne = 0;
+    // per own row: episode-local bookkeeping
+    int rr[4], rep[4], rjl[4];
+    bool rlive[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rr[i] = lane + 32 * i;
+      rlive[i] = rr[i] < rows_used;
+      rep[i] = rlive[i] ? rr[i] / N : 0;
+      rjl[i] = rr[i] - rep[i] * N;
+    }
+    auto emit = [&](int c, const float (*v)[8]) {
+      tc::mbar_wait(&s_empty[p], (ne & 1) ^ 1);
+      ++ne;
+      if (lane == 0) {
+        tc::mbar_expect_tx(&s_full[p], 2 * kTgBBytes);
+        tc::bulk_g2s(b_hi, g.Bp + int64_t(c) * (2 * kTgNT * 8), 2 * kTgBBytes, &s_full[p]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 h0, l0, h1, l1;
+        tc::split4(make_float4(v[i][0], v[i][1], v[i][2], v[i][3]), h0, l0);
+        tc::split4(make_float4(v[i][4], v[i][5], v[i][6], v[i][7]), h1, l1);
+        const uint32_t off = tc::canon_off(rr[i], 0, 8);
+        *reinterpret_cast<float4*>(a_hi + off) = h0;
+        *reinterpret_cast<float4*>(a_hi + off + 128) = h1;
+        *reinterpret_cast<float4*>(a_lo + off) = l0;
+        *reinterpret_cast<float4*>(a_lo + off + 128) = l1;
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&s_full[p]);
+    };
+    for (int si = 0; si < per_warp; ++si) {
+      const int j = p + kTgProd * si;
+      float xv[4][8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (rlive[i]) {
+          const float4* src = reinterpret_cast<const float4*>(g.x + (row0 + rr[i]) * F + 8 * j);
+          v0 = __ldg(src);
+          v1 = __ldg(src + 1);
+        }
+        xv[i][0] = v0.x; xv[i][1] = v0.y; xv[i][2] = v0.z; xv[i][3] = v0.w;
+        xv[i][4] = v1.x; xv[i][5] = v1.y; xv[i][6] = v1.z; xv[i][7] = v1.w;
+      }
+      for (int k = 0; k < K; ++k) {
+        if (k > 0) {
+          // x_k[row j] = sum_i S[i][j] x_{k-1}[row i] over the rows of the same episode (held by other lanes)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<float4*>(xs + rr[i] * 8) = make_float4(xv[i][0], xv[i][1], xv[i][2], xv[i][3]);
+            *reinterpret_cast<float4*>(xs + rr[i] * 8 + 4) = make_float4(xv[i][4], xv[i][5], xv[i][6], xv[i][7]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float acc[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = 0.0f;
+            if (rlive[i]) {
+              const float* scol = sm + rep[i] * N * N + rjl[i];
+              const float* prev = xs + rep[i] * N * 8;
+              for (int n = 0; n < N; ++n) {
+                const float s = scol[n * N];
+                const float4 p0 = *reinterpret_cast<const float4*>(prev + n * 8);
+                const float4 p1 = *reinterpret_cast<const float4*>(prev + n * 8 + 4);
+                acc[0] = fmaf(s, p0.x, acc[0]); acc[1] = fmaf(s, p0.y, acc[1]);
+                acc[2] = fmaf(s, p0.z, acc[2]); acc[3] = fmaf(s, p0.w, acc[3]);
+                acc[4] = fmaf(s, p1.x, acc[4]); acc[5] = fmaf(s, p1.y, acc[5]);
+                acc[6] = fmaf(s, p1.z, acc[6]); acc[7] = fmaf(s, p1.w, acc[7]);
+              }
+            }
+#pragma unroll
+            for (int f = 0; f < 8; ++f) xv[i][f] = acc[f];
+          }
+          __syncwarp();   // everyone has read the exchange buffer before it is overwritten
+        }
+        emit(k * slices + j, xv);
+      }
+      if (g.has_skip) {
+        // Xr[n'][f'] = X_flat[n'F + f'] with X_flat index of X[b,f,n] = f*N + n   (gnn.py:201-204)
+        float sv[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int f = 0; f < 8; ++f) {
+            float v = 0.0f;
+            if (rlive[i]) {
+              const int q = rjl[i] * F + 8 * j + f;
+              v = __ldg(g.x + (row0 + rep[i] * N + (q % N)) * F + (q / N));
+            }
+            sv[i][f] = v;
+          }
+        emit(K * slices + j, sv);
+      }
+    }
+  } else if (warp < kTgProd + 2) {
+    // ===================== MMA issuers =====================
+    if (lane == 0) {
+      const int which = warp - kTgProd;
+      constexpr uint32_t idesc = tc::idesc_tf32(kTgM, kTgNT);
+      constexpr uint32_t sbo = 256, lbo = 128;
+      const uint32_t base = tc::smem_u32(stages);
+      const uint64_t dah0 = tc::smem_desc(base, lbo, sbo);
+      const uint64_t dal0 = tc::smem_desc(base + kTgABytes, lbo, sbo);
+      const uint64_t dbh0 = tc::smem_desc(base + 2 * kTgABytes, lbo, sbo);
+      const uint64_t dbl0 = tc::smem_desc(base + 2 * kTgABytes + kTgBBytes, lbo, sbo);
+      const uint32_t acc = tmem + uint32_t(which) * kTgNT;
+      const int T = per_warp * chunks_per_slice;
+      bool first = true;
+      for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int s = which + 2 * h;
+          tc::mbar_wait(&s_full[s], uint32_t(t & 1));
+          tc::fence_after_sync();
+          const uint64_t o = uint64_t(uint32_t(s) * (kTgStageBytes >> 4));
+          tc::mma_tf32(acc, dal0 + o, dbh0 + o, idesc, !first);
+          tc::mma_tf32(acc, dah0 + o, dbl0 + o, idesc, true);
+          tc::mma_tf32(acc, dah0 + o, dbh0 + o, idesc, true);
+          first = false;
+          tc::mma_commit(&s_empty[s]);
+        }
+      }
+      tc::mma_commit(&s_done);
+    }
+    __syncwarp();
+  }
+
+  {
+    // ===================== epilogue (all 8 warps) =====================
+    tc::mbar_wait(&s_done, 0);
+    tc::fence_after_sync();
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    float part[kMaxActions];
+#pragma unroll
+    for (int q = 0; q < kMaxActions; ++q) part[q] = 0.0f;
+#pragma unroll
+    for (int cbl = 0; cbl < kTgNT / 2; cbl += 32) {
+      const int cb = half * (kTgNT / 2) + cbl;
+      uint32_t r0[32], r1[32];
+      tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + cb, r0);
+      tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + kTgNT + cb, r1);
+      tc::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r0[j]) + __uint_as_float(r1[j]), 0.0f);
+#pragma unroll
+      for (int q = 0; q < kMaxActions; ++q) {
+        if (q < g.num_actions) {
+          const float4* wq = reinterpret_cast<const float4*>(s_head + q * kTgNT + cb);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 w4 = wq[j >> 2];
+            part[q] = fmaf(v[j], w4.x, part[q]);
+            part[q] = fmaf(v[j + 1], w4.y, part[q]);
+            part[q] = fmaf(v[j + 2], w4.z, part[q]);
+            part[q] = fmaf(v[j + 3], w4.w, part[q]);
+          }
+        }
+      }
+    }
+    float* ex = reinterpret_cast<float*>(stages);   // [128 rows][kMaxActions], the stages are idle now
+    if (half == 1) {
+#pragma unroll
+      for (int q = 0; q < kMaxActions; ++q) ex[row * kMaxActions + q] = part[q];
+    }
+    __syncthreads();
+    if (half == 0 && row < rows_used) {
+      float best = 0.0f;
+      int arg = 0;
+#pragma unroll
+      for (int q = 0; q < kMaxActions; ++q) {
+        if (q < g.num_actions) {
+          const float o = part[q] + ex[row * kMaxActions + q] + s_head[kMaxActions * kTgNT + q];
+          g.logits[(row0 + row) * g.num_actions + q] = o;
+          if (q == 0 || o > best) { best = o; arg = q; }   // first max wins (np.argmax)
+        }
+      }
+      if (g.actions != nullptr) g.actions[row0 + row] = arg;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+// 1 if mapf_tc_graph_head supports these dimensions (else use mapf_graph_taps + mapf_tc_mix_head)
+extern "C" int mapf_tc_graph_supported(int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps) {
+  return agents >= 1 && agents <= 64 && in_dim >= 32 && (in_dim & 31) == 0 && out_dim > 64 && out_dim <= 128 &&
+         (out_dim & 15) == 0 && taps >= 1;   // out_dim > 64: the packed B uses the 128-row tiling
+}
+
+// Whole graph-filter + head tail of Network.forward from agent-major x [B*N, F] and gso [B,N,N]; Wp = packed [W | W2].
+extern "C" int mapf_tc_graph_head(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
+                                  int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso,
+                                  const float* Wp, const float* act_w, const float* act_b, int32_t num_actions,
+                                  float* logits, int32_t* actions, mapf_stream_t stream) {
+  MAPF_REQUIRE(x && gso && Wp && act_w && act_b && logits, MAPF_ERR_NULL);
+  MAPF_REQUIRE(batch > 0 && num_actions > 0 && num_actions <= kMaxActions, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(mapf_tc_graph_supported(agents, in_dim, out_dim, taps), MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(x, 16) && mapf_aligned(Wp, 16), MAPF_ERR_ALIGN);
+  TcGraphArgs g{batch, agents, in_dim, taps, out_dim, has_skip ? 1 : 0, add_self_loop ? 1 : 0, num_actions,
+                x, gso, Wp, act_w, act_b, logits, actions};
+  const int epc = kTgM / agents;
+  const int ntiles = (batch + epc - 1) / epc;
+  const size_t smem = size_t(kTgProd) * kTgStageBytes + sizeof(float) * (size_t(kTgProd) * kTgM * 8 +
+                      ((size_t(epc) * agents * agents + 3) & ~size_t(3)) + kTgM);
+  MAPF_REQUIRE(smem <= 227 * 1024, MAPF_ERR_UNSUPPORTED);
+  static int cache[16] = {0};
+  if (!mapf_ensure_smem(tc_graph_kernel, smem, cache)) return MAPF_ERR_CUDA;
+  tc_graph_kernel<<<ntiles, kTgThreads, smem, static_cast<cudaStream_t>(stream)>>>(g, epc);
+  return mapf_launch_status();
+}
