@@ -212,3 +212,29 @@ def test_host_stepped_rollout_matches_device_rollout():
         assert torch.equal(done, env_a.done.cpu())
         hs.pos_in.copy_(pos_out)
     assert torch.equal(env_a.fov, env_b.fov) and torch.equal(env_a.time, env_b.time)
+
+
+@pytest.mark.parametrize("path", ["fused_tc", "unfused_tc", "ffma", "tc_fc"])
+@pytest.mark.parametrize("name,N", [("gnn_k3", 5), ("gnn_msg_k3", 20)])
+def test_every_policy_path_matches_oracle(monkeypatch, path, name, N):
+    """The graph-filter / FC stage has several implementations (fused tcgen05 kernel, taps + tcgen05 GEMM, fused FFMA
+    kernel, tensor-core FC): each must reproduce the oracle logits."""
+    from mapf_gnn_b200 import ops
+    if path == "unfused_tc":
+        monkeypatch.setenv("MAPF_B200_UNFUSED_GRAPH", "1")
+    if path == "ffma":
+        monkeypatch.setattr(ops, "USE_TENSOR_CORES", False)
+    if path == "tc_fc":
+        monkeypatch.setattr(ops, "USE_TENSOR_CORE_FC", True)
+    rng = np.random.default_rng(17 + N)
+    B = 70
+    states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+    adj = torch.tensor((rng.random((B, N, N)) < 0.3).astype(np.float32))
+    adj[:, torch.arange(N), torch.arange(N)] = 0
+    adj[3, 2, :] = 0
+    with torch.no_grad():
+        ref = mo.forward(oracle_params(name), states, adj).numpy()
+    net = load_network(name, num_agents=N).eval()
+    logits, actions = net.act(states.cuda(), adj.cuda())
+    assert rel_err(logits.cpu().numpy(), ref) < REL
+    _check_actions(actions.cpu().numpy(), ref)
