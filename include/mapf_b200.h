@@ -73,7 +73,8 @@ int mapf_env_reset(const mapf_env_reset_args* a, mapf_stream_t stream);
  * (:156-159), for E episodes in one fused kernel.  do_move == 0 gives getObservations() of the
  * current state without moving (the observation reset() returns; actions may then be NULL).
  * Episodes whose done flag is already set are frozen (callers of the reference `break`,
- * evaluate.py:251): no move, no time increment, observation recomputed.
+ * evaluate.py:251): no move, no time increment, observation recomputed.  do_move == 3 steps finished episodes too
+ * (the reference env itself never freezes; data_generation/record.py:78-88 keeps stepping).
  * d2_limit: smallest integer d2 with sqrt((double)d2) >= sensing_range. */
 typedef struct {
   int32_t episodes, agents, board;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
     const int2 p = reinterpret_cast<const int2*>(a.pos)[int64_t(e) * N + lane];
     const int2 g = __ldg(reinterpret_cast<const int2*>(a.goal) + int64_t(e) * N + lane);
     ox = p.x; oy = p.y; gx = g.x; gy = g.y;
-    moving = a.do_move && !a.done[e];
+    moving = a.do_move && (!a.done[e] || (a.do_move & 2));   // do_move & 2: keep stepping finished episodes
   }
   __syncthreads();
 
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
 
   if (a.do_move && tid < nep) {  // time += 1; done = checkAllInGoal() (:195-197)
     const int ee = e0 + tid;
-    if (!a.done[ee]) {
+    if (!a.done[ee] || (a.do_move & 2)) {
       a.time[ee] += 1;
       a.done[ee] = s_notgoal[tid] ? 0 : 1;
     }

@@ -1,0 +1,107 @@
+"""Dataset wire format of the reference: recording expert trajectories into
+``case_*/{states,gso,trajectory_record}.npy`` (``data_generation/record.py:39-97``) and loading them back the way
+``data_loader.py:24-125`` does.  Recording is the batched GPU environment replaying expert actions for all cases at
+once; loading is host-side numpy (file I/O), followed by pinned-memory uploads of whole batches.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from .env import BatchedGraphEnv
+
+
+@torch.no_grad()
+def record_cases(config, goals, starts, obstacles, trajectories, sensing_range=6, device="cuda"):
+    """Replay expert action matrices through the environment (record.py:66-88) for E cases of equal length.
+
+    trajectories: int [E, N, T+1] expert actions per agent (``trajectory.npy``); the first action is dropped
+    (record.py:67).  Returns numpy arrays in the on-disk layout: states f64 [E, T, N, 2, 5, 5], gso f64
+    [E, T, N, N, N] (the adjacency repeated along the first agent axis, record.py:80), trajectory_record [E, N, T].
+    Quirk kept (record.py:87-88): the observation after the last action overwrites the last slot."""
+    traj = np.asarray(trajectories)[:, :, 1:]
+    E, N, T = traj.shape
+    env = BatchedGraphEnv(config, goals, starts, obstacles, sensing_range=sensing_range, device=device)
+    states = torch.empty((T, E, N, 2, 5, 5), dtype=torch.float32, device=env.device)
+    adj = torch.empty((T, E, N, N), dtype=torch.float32, device=env.device)
+    actions = torch.as_tensor(traj, device=env.device).to(torch.int32)
+    for i in range(T):
+        states[i].copy_(env.fov)
+        adj[i].copy_(env.adj_matrix)
+        env.step(actions[:, :, i].contiguous(), freeze_done=False)
+    if T > 0:
+        states[T - 1].copy_(env.fov)
+        adj[T - 1].copy_(env.adj_matrix)
+    states_np = states.permute(1, 0, 2, 3, 4, 5).cpu().numpy().astype(np.float64)
+    adj_np = adj.permute(1, 0, 2, 3).cpu().numpy().astype(np.float64)
+    gso_np = np.broadcast_to(adj_np[:, :, None, :, :], (E, T, N, N, N)).copy()
+    return states_np, gso_np, traj
+
+
+def save_case(case_dir, states, gso, trajectory_record):
+    """Write one case in the reference's file layout (record.py:90-94)."""
+    os.makedirs(case_dir, exist_ok=True)
+    np.save(os.path.join(case_dir, "states.npy"), states)
+    np.save(os.path.join(case_dir, "gso.npy"), gso)
+    np.save(os.path.join(case_dir, "trajectory_record.npy"), trajectory_record)
+
+
+def load_cases(dir_path, min_time, nb_agents, max_time_dl):
+    """``CreateDataset.__init__`` (data_loader.py:24-101): per case keep states[1:min_time+1], the first min_time
+    expert actions and gso[:min_time, 0] + I; skip cases shorter than min_time or longer than max_time_dl; flatten
+    time into the sample axis.  Like the reference, skipped cases leave holes that shift later cases out of the
+    kept prefix (`states[:count]`, :95-97) -- reproduced, not fixed.
+    Returns (states f32 [S,N,2,5,5], targets f32 [S,N], gso f32 [S,N,N], count)."""
+    cases = os.listdir(dir_path)
+    states = np.zeros((len(cases), min_time, nb_agents, 2, 5, 5))
+    trajectories = np.zeros((len(cases), min_time, nb_agents))
+    gsos = np.zeros((len(cases), min_time, nb_agents, nb_agents))
+    count = 0
+    for i, case in enumerate(cases):
+        path = os.path.join(dir_path, case, "states.npy")
+        if not os.path.exists(path):
+            continue
+        state = np.load(path)[1:min_time + 1]
+        tray = np.load(os.path.join(dir_path, case, "trajectory_record.npy"))[:, :min_time]
+        gso = np.load(os.path.join(dir_path, case, "gso.npy"))[:min_time, 0, :, :] + np.eye(nb_agents)
+        if state.shape[0] < min_time or tray.shape[1] < min_time:
+            continue
+        if state.shape[0] > max_time_dl or tray.shape[1] > max_time_dl:
+            continue
+        states[i], trajectories[i], gsos[i] = state, tray.T, gso
+        count += 1
+    states = states[:count].reshape((-1, nb_agents, 2, 5, 5))
+    trajectories = trajectories[:count].reshape((-1, nb_agents))
+    gsos = gsos[:count].reshape((-1, nb_agents, nb_agents))
+    return (torch.from_numpy(states).float(), torch.from_numpy(trajectories).float(), torch.from_numpy(gsos).float(),
+            count)
+
+
+class GNNDataLoader:
+    """``GNNDataLoader(config).train_loader`` (data_loader.py:9-21): iterating yields
+    ``(states[B,N,2,5,5], actions[B,N], gso[B,N,N])`` float32 batches.  The whole dataset is kept in pinned host
+    memory and every batch is one asynchronous upload to ``device`` (the reference uses DataLoader workers +
+    pin_memory; here a batch is a contiguous gather, so no worker processes are needed)."""
+
+    def __init__(self, config, mode="train", device="cuda", seed=None):
+        cfg = config[mode]
+        sub = {"train": "train", "valid": "val"}.get(mode, mode)
+        self.states, self.targets, self.gso, self.count = load_cases(
+            os.path.join(cfg["root_dir"], sub), cfg["min_time"], cfg["nb_agents"], cfg["max_time_dl"])
+        self.batch_size = int(config["batch_size"])
+        self.device = torch.device(device)
+        self.rng = np.random.default_rng(seed)
+        if self.device.type == "cuda":
+            self.states, self.targets, self.gso = (t.pin_memory() for t in (self.states, self.targets, self.gso))
+        self.train_loader = self
+
+    def __len__(self):
+        return (self.states.shape[0] + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        order = torch.from_numpy(self.rng.permutation(self.states.shape[0]))      # shuffle=True (data_loader.py:17)
+        for lo in range(0, len(order), self.batch_size):
+            idx = order[lo:lo + self.batch_size]
+            yield tuple(t[idx].to(self.device, non_blocking=True) for t in (self.states, self.targets, self.gso))

@@ -111,12 +111,15 @@ class BatchedGraphEnv:
         return {"fov": self.fov, "adj_matrix": self.adj_matrix, "distances": self.adj_matrix}
 
     # -- reference: GraphEnv.step, env_graph_gridv1.py:183-198 -----------------------------------
-    def step(self, actions):
+    def step(self, actions, freeze_done=True):
+        """freeze_done=False reproduces the raw reference env, which keeps moving agents after all of them reached
+        their goals (only its callers stop, evaluate.py:251); used when replaying expert trajectories."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions))
         actions = actions.to(device=self.device, dtype=torch.int32).reshape(self.episodes, self.nb_agents).contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.mapf_env_step(self.step_args(actions, 1), _lib.current_stream()), "env_step")
+            _lib.check(self.lib.mapf_env_step(self.step_args(actions, 1 if freeze_done else 3), _lib.current_stream()),
+                       "env_step")
         obs = {"fov": self.fov, "adj_matrix": self.adj_matrix, "distances": self.adj_matrix}
         return obs, self.done
 

@@ -1,0 +1,85 @@
+"""Dataset wire format: loader logic on CPU (files written in the reference layout), cross-checked against the
+reference's own CreateDataset when /root/reference is present; recording parity on the GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import env_oracle as eo
+
+
+def _write_cases(root, rng, n_cases, N, lengths):
+    os.makedirs(root, exist_ok=True)
+    for i, T in enumerate(lengths[:n_cases]):
+        d = os.path.join(root, f"case_{i}")
+        os.makedirs(d)
+        np.save(os.path.join(d, "states.npy"), rng.integers(0, 4, size=(T, N, 2, 5, 5)).astype(np.float64))
+        np.save(os.path.join(d, "gso.npy"), (rng.random((T, N, N, N)) < 0.3).astype(np.float64))
+        np.save(os.path.join(d, "trajectory_record.npy"), rng.integers(0, 5, size=(N, T)).astype(np.float64))
+    os.makedirs(os.path.join(root, "case_without_files"))
+
+
+def test_loader_matches_reference_semantics(tmp_path):
+    from mapf_gnn_b200.dataset import GNNDataLoader, load_cases
+    rng = np.random.default_rng(0)
+    N, min_time = 5, 6
+    root = str(tmp_path / "ds" / "train")
+    _write_cases(root, rng, 7, N, [12, 9, 4, 30, 8, 7, 10])     # one too short (4), all within max_time_dl
+    states, targets, gso, count = load_cases(root, min_time, N, 25)
+    assert states.shape[1:] == (N, 2, 5, 5) and targets.shape[1] == N and gso.shape[1:] == (N, N)
+    assert states.shape[0] == count * min_time == targets.shape[0] == gso.shape[0]
+    assert count == 6
+    ref_path = "/root/reference"
+    if os.path.isdir(ref_path):
+        sys.path.insert(0, ref_path)
+        try:
+            from data_loader import CreateDataset
+        finally:
+            sys.path.remove(ref_path)
+        cfg = {"train": {"root_dir": str(tmp_path / "ds"), "min_time": min_time, "nb_agents": N, "max_time_dl": 25}}
+        ds = CreateDataset(cfg, "train")
+        assert ds.count == count
+        assert np.array_equal(ds.states.astype(np.float32), states.numpy())
+        assert np.array_equal(ds.trajectories.astype(np.float32), targets.numpy())
+        assert np.array_equal(ds.gsos.astype(np.float32), gso.numpy())
+    cfg = {"train": {"root_dir": str(tmp_path / "ds"), "min_time": min_time, "nb_agents": N, "max_time_dl": 25},
+           "batch_size": 16}
+    loader = GNNDataLoader(cfg, "train", device="cpu", seed=1)
+    seen = 0
+    for s, t, g in loader.train_loader:
+        assert s.shape[0] == t.shape[0] == g.shape[0] <= 16 and s.dtype == torch.float32
+        diag_ok = g.diagonal(dim1=1, dim2=2).min(dim=1).values >= 1.0          # + I (data_loader.py:74)
+        hole = g.abs().sum(dim=(1, 2)) == 0     # the reference's skipped-case holes stay zero (reproduced quirk)
+        assert bool((diag_ok | hole).all())
+        seen += s.shape[0]
+    assert seen == count * min_time and len(loader) == (seen + 15) // 16
+
+
+@pytest.mark.gpu
+def test_record_cases_matches_oracle_replay():
+    """record.py:66-88 on the GPU vs the numpy oracle env replaying the same expert actions (incl. the quirks:
+    first action dropped, last slot overwritten, no freezing after done)."""
+    import mapf_gnn_b200 as m
+    from mapf_gnn_b200.dataset import record_cases
+    E, N, H, M, T = 12, 5, 10, 4, 9
+    rng = np.random.default_rng(4)
+    starts, goals, obst = m.make_scenarios(rng, E, N, H, M)
+    traj = rng.integers(0, 5, size=(E, N, T + 1))
+    traj[0, :, 3:] = 0
+    cfg = {"num_agents": N, "board_size": [H, H], "max_time": 32, "min_time": 1}
+    states, gso, rec = record_cases(cfg, goals, starts, obst, traj, sensing_range=4)
+    assert states.shape == (E, T, N, 2, 5, 5) and gso.shape == (E, T, N, N, N) and rec.shape == (E, N, T)
+    for e in range(E):
+        env = eo.EnvOracle(N, H, goals[e], starts[e], obst[e], sensing_range=4)
+        obs = env.observe()
+        exp_s, exp_a = np.zeros((T, N, 2, 5, 5)), np.zeros((T, N, N))
+        for i in range(T):
+            exp_s[i], exp_a[i] = obs["fov"], obs["adj_matrix"]
+            obs, _ = env.step(traj[e, :, 1 + i])
+        exp_s[T - 1], exp_a[T - 1] = obs["fov"], obs["adj_matrix"]
+        assert np.array_equal(states[e], exp_s), e
+        for a in range(N):
+            assert np.array_equal(gso[e, :, a], exp_a), e
+        assert np.array_equal(rec[e], traj[e, :, 1:])
