@@ -140,54 +140,71 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
     const float* act = in1 ? s_b1 : s_b0;   // [fc_in][32]
     float* scratch = in1 ? s_b0 : s_b1;     // free buffer: split-K partials [128 threads][16]
 
-    // compressMLP: X[32, F] = relu(act^T Wt + b); thread tile 4 agents x 4 outputs, K split in two halves
-    const int kg = tid >> 7, t7 = tid & 127;
-    const int aq = t7 & 7, jq = t7 >> 3;
-    const int khalf = d.fc_in >> 1;
-    const int k0 = kg * khalf, k1 = kg ? d.fc_in : khalf;
+    // compressMLP: X[32, F] = relu(act^T Wt + b); thread tile 4 agents x 8 outputs (16 FFMA2 per 3 LDS.128), K split
+    // four ways over the CTA, partial sums meet in the free ping buffer
+    const int kg = tid >> 6, t6 = tid & 63;
+    const int aq = t6 & 7, jq = t6 >> 3;
+    const int kq = d.fc_in >> 2;
+    const int k0 = kg * kq, k1 = kg == 3 ? d.fc_in : k0 + kq;
     const int wstride = d.fc_out >> 2;
     for (int jb = 0; jb < d.fc_out; jb += 64) {
-      const int j = jb + jq * 4;
+      const int j = jb + jq * 8;
       const bool jlive = j < d.fc_out;
-      float2 acc[4][2];
+      float2 acc[4][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.0f, 0.0f);
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) acc[r][h] = make_float2(0.0f, 0.0f);
       if (jlive) {
         const float4* wps = reinterpret_cast<const float4*>(s_w + L.fc_wt + j);
         const float4* wpg = reinterpret_cast<const float4*>(packed + L.fc_wt + j);
         const float4* ap = reinterpret_cast<const float4*>(act + aq * 4);
-#pragma unroll 8
+#pragma unroll 4
         for (int i = k0; i < k1; ++i) {
           const float4 a4 = ap[i * (kEncAgents / 4)];
-          const float4 w4 = kFcSmem ? wps[i * wstride] : __ldg(wpg + i * wstride);
+          const float4 w0 = kFcSmem ? wps[i * wstride] : __ldg(wpg + i * wstride);
+          const float4 w1 = kFcSmem ? wps[i * wstride + 1] : __ldg(wpg + i * wstride + 1);
           const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-          const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
+          const float2 wp0 = make_float2(w0.x, w0.y), wp1 = make_float2(w0.z, w0.w);
+          const float2 wp2 = make_float2(w1.x, w1.y), wp3 = make_float2(w1.z, w1.w);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            mapf_ffma2(acc[r][0], av[r], wlo);
-            mapf_ffma2(acc[r][1], av[r], whi);
+            mapf_ffma2(acc[r][0], av[r], wp0);
+            mapf_ffma2(acc[r][1], av[r], wp1);
+            mapf_ffma2(acc[r][2], av[r], wp2);
+            mapf_ffma2(acc[r][3], av[r], wp3);
           }
         }
       }
-      if (kg == 1) {
+      float4* sc = reinterpret_cast<float4*>(scratch);
+      if (kg > 0) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          reinterpret_cast<float4*>(scratch)[r * 128 + t7] = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+        for (int r = 0; r < 4; ++r) {
+          sc[((kg - 1) * 8 + r * 2 + 0) * 64 + t6] = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+          sc[((kg - 1) * 8 + r * 2 + 1) * 64 + t6] = make_float4(acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y);
+        }
       }
       __syncthreads();
       if (kg == 0 && jlive) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j) + 1);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int a = aq * 4 + r;
-          const float4 o2 = reinterpret_cast<const float4*>(scratch)[r * 128 + t7];
+          float4 lo = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
+          float4 hi = make_float4(acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y);
+#pragma unroll
+          for (int g2 = 0; g2 < 3; ++g2) {
+            const float4 p0 = sc[(g2 * 8 + r * 2 + 0) * 64 + t6], p1 = sc[(g2 * 8 + r * 2 + 1) * 64 + t6];
+            lo.x += p0.x; lo.y += p0.y; lo.z += p0.z; lo.w += p0.w;
+            hi.x += p1.x; hi.y += p1.y; hi.z += p1.z; hi.w += p1.w;
+          }
           if (a < nrows) {
-            float4 o;
-            o.x = fmaxf(acc[r][0].x + o2.x + b4.x, 0.0f);
-            o.y = fmaxf(acc[r][0].y + o2.y + b4.y, 0.0f);
-            o.z = fmaxf(acc[r][1].x + o2.z + b4.z, 0.0f);
-            o.w = fmaxf(acc[r][1].y + o2.w + b4.w, 0.0f);
-            *reinterpret_cast<float4*>(x + (row0 + a) * d.fc_out + j) = o;
+            float* dst = x + (row0 + a) * d.fc_out + j;
+            *reinterpret_cast<float4*>(dst) = make_float4(fmaxf(lo.x + b0.x, 0.0f), fmaxf(lo.y + b0.y, 0.0f),
+                                                          fmaxf(lo.z + b0.z, 0.0f), fmaxf(lo.w + b0.w, 0.0f));
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(fmaxf(hi.x + b1.x, 0.0f), fmaxf(hi.y + b1.y, 0.0f),
+                                                              fmaxf(hi.z + b1.z, 0.0f), fmaxf(hi.w + b1.w, 0.0f));
           }
         }
       }
@@ -279,7 +296,7 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   MAPF_REQUIRE(a && a->states && a->packed && a->x, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->rows > 0, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(mapf_aligned(a->packed, 16) && mapf_aligned(a->x, 16) && mapf_aligned(a->states, 4), MAPF_ERR_ALIGN);
-  MAPF_REQUIRE((p->fc_in & 1) == 0, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE((p->fc_in & 3) == 0 && (p->fc_out & 7) == 0, MAPF_ERR_UNSUPPORTED);
   const PackedLayout L = mapf_packed_layout(*p);
   EncoderDims d;
   d.num_conv = p->num_conv;
@@ -291,8 +308,8 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
     const int out = kFovCells * p->channels[l + 1];
     if (l & 1) b0 = max(b0, out); else b1 = max(b1, out);
   }
-  b0 = max(b0, 64);  // FC split-K scratch: 128 threads x 16 floats = 2048 floats = 64 x 32
-  b1 = max(b1, 64);
+  b0 = max(b0, 192);  // FC split-K scratch: 3 partial groups x 64 threads x 32 floats = 6144 floats = 192 x 32
+  b1 = max(b1, 192);
   d.buf0_floats = b0 * kEncAgents;
   d.buf1_floats = b1 * kEncAgents;
   const size_t act_bytes = size_t(d.buf0_floats + d.buf1_floats + kEncAgents * kFovFloats) * sizeof(float);
