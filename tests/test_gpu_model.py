@@ -238,3 +238,47 @@ def test_every_policy_path_matches_oracle(monkeypatch, path, name, N):
     logits, actions = net.act(states.cuda(), adj.cuda())
     assert rel_err(logits.cpu().numpy(), ref) < REL
     _check_actions(actions.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 8, 16, 17, 31, 32, 33, 48, 64])
+@pytest.mark.parametrize("name", ["gnn_k3", "gnn_msg_k3"])
+def test_team_sizes_sweep(name, N):
+    """Every tiling branch of the graph stage (tile of 32 / 64 / 128 rows, fused vs two-kernel tensor-core path,
+    4-aligned vs generic hops) against the oracle, including N = 1 (no neighbours) and ragged last tiles."""
+    rng = np.random.default_rng(100 + N)
+    B = 37 if N <= 16 else 9
+    states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+    adj = torch.tensor((rng.random((B, N, N)) < min(0.5, 4.0 / max(N, 1))).astype(np.float32))
+    adj[:, torch.arange(N), torch.arange(N)] = 0
+    with torch.no_grad():
+        ref = mo.forward(oracle_params(name), states, adj).numpy()
+    net = load_network(name, num_agents=N).eval()
+    logits, actions = net.act(states.cuda(), adj.cuda())
+    assert rel_err(logits.cpu().numpy(), ref) < REL
+    _check_actions(actions.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("E,N,H", [(1, 1, 3), (1, 5, 18), (3, 2, 4), (129, 3, 6), (17, 128, 40)])
+def test_env_edge_sizes(E, N, H):
+    """Single episode, single agent, episode counts that do not fill a CTA, the largest supported team."""
+    import mapf_gnn_b200 as m
+    rng = np.random.default_rng(E * 7 + N)
+    M = min(3, H * H - 2 * N) if H * H > 2 * N + 3 else 0
+    starts, goals, obst = m.make_scenarios(rng, E, N, H, M)
+    cfg = {"num_agents": N, "board_size": [H, H], "max_time": 16, "min_time": 1}
+    env = m.BatchedGraphEnv(cfg, goals, starts, obst if M else None, sensing_range=3)
+    oracles = [eo.EnvOracle(N, H, goals[e], starts[e], obst[e] if M else None, sensing_range=3, max_time=16)
+               for e in range(E)]
+    alive = np.ones(E, dtype=bool)
+    for t in range(5):
+        actions = rng.integers(0, 5, size=(E, N))
+        obs, done = env.step(actions)
+        fov, adj, pos = obs["fov"].cpu().numpy(), obs["adj_matrix"].cpu().numpy(), env.pos.cpu().numpy()
+        for e in range(E):
+            if not alive[e]:
+                continue
+            o, d = oracles[e].step(actions[e])
+            assert np.array_equal(pos[e], oracles[e].positions)
+            assert np.array_equal(fov[e], o["fov"].astype(np.float32))
+            assert np.array_equal(adj[e], o["adj_matrix"].astype(np.float32))
+            alive[e] = not d
