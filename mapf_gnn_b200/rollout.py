@@ -71,47 +71,61 @@ class HostSteppedRollout:
     state would use it: per step the positions go up from pinned memory, the policy + environment step runs, and the
     chosen actions, the new positions and the done flags come back to pinned memory.
 
-    The whole sequence (1 host-to-device copy, 4 kernels, 1 device-to-host copy) is captured once into a CUDA graph
-    and replayed per step, so the host pays one graph launch and one stream synchronisation per step.
-    Buffers (pinned): ``pos_in`` int32[E,N,2] (written by the caller), ``actions`` int32[E,N], ``pos_out``
-    int32[E,N,2], ``done`` uint8[E] (read by the caller after ``step()`` returns)."""
+    The whole sequence (1 host-to-device copy, 3-4 kernels, 1 device-to-host copy) is captured into CUDA graphs and
+    replayed per step, so the host pays one graph launch and one stream synchronisation per step.  Two pinned result
+    blocks alternate: the positions returned by step t are, in place, the input of step t+1 (the caller may edit them
+    in between), so no host-side copy is needed to close the loop.
+    ``pos_in`` int32[E,N,2] is the input of the next ``step()``; ``step()`` returns views ``(actions int32[E,N],
+    pos_out int32[E,N,2], done uint8[E])`` of the block it just filled."""
 
     def __init__(self, rollout: Rollout):
         self.ro, env = rollout, rollout.env
         E, N = env.episodes, env.nb_agents
         nb_pos, nb_act = E * N * 8, E * N * 4
-        self.pos_in = torch.empty((E, N, 2), dtype=torch.int32).pin_memory()
-        self.out_block = torch.empty((env.host_block.numel(),), dtype=torch.uint8).pin_memory()
-        self.pos_out = self.out_block[:nb_pos].view(torch.int32).view(E, N, 2)
-        self.actions = self.out_block[nb_pos:nb_pos + nb_act].view(torch.int32).view(E, N)
-        self.done = self.out_block[nb_pos + nb_act:nb_pos + nb_act + E]
-        self.pos_in.copy_(env.pos.cpu())
-        self.h2d_bytes = self.pos_in.numel() * 4
-        self.d2h_bytes = self.out_block.numel()
+        self.blocks = [torch.empty((env.host_block.numel(),), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        view = lambda b: (b[nb_pos:nb_pos + nb_act].view(torch.int32).view(E, N),
+                          b[:nb_pos].view(torch.int32).view(E, N, 2), b[nb_pos + nb_act:nb_pos + nb_act + E])
+        self.views = [view(b) for b in self.blocks]
+        self.h2d_bytes = nb_pos
+        self.d2h_bytes = self.blocks[0].numel()
+        self.cur = 0                                   # block that the next step() fills; its input is the other one
         snap = (env.pos.clone(), env.cells.clone(), env.time.clone(), env.done.clone(), env.fov.clone(),
                 env.adj_matrix.clone())
+        for b in self.blocks:
+            b.copy_(env.host_block.cpu())
         side = torch.cuda.Stream(device=env.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(2):                         # warm-up: first-launch attributes, lazy module loading
-                self._body()
+            for k in range(2):                         # warm-up: first-launch attributes, lazy module loading
+                self._body(k)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         for dst, src in zip((env.pos, env.cells, env.time, env.done, env.fov, env.adj_matrix), snap):
             dst.copy_(src)
-        self.pos_in.copy_(env.pos.cpu())
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        for b in self.blocks:
+            b.copy_(env.host_block.cpu())
+        self.graphs = []
+        for k in range(2):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                self._body(k)
+            self.graphs.append(gph)
 
-    def _body(self):
+    @property
+    def pos_in(self):
+        """Pinned int32[E,N,2]: positions the next step() uploads (= the positions the previous step returned)."""
+        return self.views[1 - self.cur][1]
+
+    def _body(self, k):
         env, ro = self.ro.env, self.ro
-        env.pos.copy_(self.pos_in, non_blocking=True)
+        env.pos.copy_(self.views[1 - k][1], non_blocking=True)           # H2D: this step's state
         ro.run(1)
-        self.out_block.copy_(env.host_block, non_blocking=True)      # actions + new positions + done in one copy
+        self.blocks[k].copy_(env.host_block, non_blocking=True)           # D2H: actions + new positions + done
 
     def step(self):
-        """One host-driven step; returns after the results are visible in the pinned output buffers."""
-        self.graph.replay()
+        """One host-driven step; returns after the results are visible in pinned host memory."""
+        k = self.cur
+        self.graphs[k].replay()
         torch.cuda.current_stream().synchronize()
-        return self.actions, self.pos_out, self.done
+        self.cur = 1 - k
+        return self.views[k]

@@ -210,7 +210,7 @@ def test_host_stepped_rollout_matches_device_rollout():
         actions, pos_out, done = hs.step()
         assert torch.equal(actions, ra.actions.cpu()) and torch.equal(pos_out, env_a.pos.cpu())
         assert torch.equal(done, env_a.done.cpu())
-        hs.pos_in.copy_(pos_out)
+        assert hs.pos_in.data_ptr() == pos_out.data_ptr()      # the result is, in place, the next step's input
     assert torch.equal(env_a.fov, env_b.fov) and torch.equal(env_a.time, env_b.time)
 
 
