@@ -7,6 +7,8 @@
 // atomicAdd(double) per (slot, channel)), matching the double accumulators of the reference's ATen
 // CPU BatchNorm.  Weight-gradient reductions over the batch use split-K GEMMs / persistent CTAs with
 // one fp32 atomicAdd per CTA and output element.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -55,7 +57,9 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
     T.u[l] = take(rows * cout * 25);
     T.a[l] = take(rows * cout * 25);
   }
-  T.wt = take(p.taps > 0 ? int64_t(KT) * p.node_dim : 0);
+  T.wt = take(p.taps > 0 ? (int64_t(KT) * p.node_dim > mapf_tc_b_floats(p.node_dim, KT) ? int64_t(KT) * p.node_dim
+                                                                                  : mapf_tc_b_floats(p.node_dim, KT))
+                         : 0);
   T.x = take(rows * p.fc_out);
   T.z = take(p.taps > 0 ? rows * KT : 0);
   T.y = take(p.taps > 0 ? rows * p.node_dim : 0);
@@ -124,12 +128,12 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
   }
   __syncthreads();
   for (int cog = warp; cog < (cout >> 2); cog += kCtThreads / 32) {
-    float acc[4][kFovCells];
+    float2 acc[2][kFovCells];   // channel pairs (4cog, 4cog+1), (4cog+2, 4cog+3): one FFMA2 each per tap
     {
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias) + cog);
 #pragma unroll
-      for (int p = 0; p < kFovCells; ++p) { acc[0][p] = b.x; acc[1][p] = b.y; acc[2][p] = b.z; acc[3][p] = b.w; }
+      for (int p = 0; p < kFovCells; ++p) { acc[0][p] = make_float2(b.x, b.y); acc[1][p] = make_float2(b.z, b.w); }
     }
     const float4* wp = reinterpret_cast<const float4*>(wpk) + int64_t(cog) * cin * 9;
 #pragma unroll 1
@@ -141,21 +145,19 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
 #pragma unroll
       for (int t = 0; t < 9; ++t) wv[t] = __ldg(wp + ci * 9 + t);
 #pragma unroll
-      for (int y = 0; y < kFov; ++y)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int x = 0; x < kFov; ++x)
+        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+          for (int y = 0; y < kFov; ++y)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+            for (int x = 0; x < kFov; ++x) {
               const int yy = y + ky - 1, xx = x + kx - 1;
               if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov) {
                 const float a = v[yy * kFov + xx];
                 const float4 ww = wv[ky * 3 + kx];
-                acc[0][y * kFov + x] = fmaf(a, ww.x, acc[0][y * kFov + x]);
-                acc[1][y * kFov + x] = fmaf(a, ww.y, acc[1][y * kFov + x]);
-                acc[2][y * kFov + x] = fmaf(a, ww.z, acc[2][y * kFov + x]);
-                acc[3][y * kFov + x] = fmaf(a, ww.w, acc[3][y * kFov + x]);
+                mapf_ffma2(acc[0][y * kFov + x], a, make_float2(ww.x, ww.y));
+                mapf_ffma2(acc[1][y * kFov + x], a, make_float2(ww.z, ww.w));
               }
             }
     }
@@ -165,9 +167,10 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
       double s2 = 0.0;
 #pragma unroll
       for (int p = 0; p < kFovCells; ++p) {
-        s_out[((cog * 4 + c) * kFovCells + p) * kCtPad + lane] = acc[c][p];
-        s1 += acc[c][p];
-        s2 += double(acc[c][p]) * double(acc[c][p]);
+        const float val = (c & 1) ? acc[c >> 1][p].y : acc[c >> 1][p].x;
+        s_out[((cog * 4 + c) * kFovCells + p) * kCtPad + lane] = val;
+        s1 += val;
+        s2 += double(val) * double(val);
       }
       if (stats != nullptr) {
         const double t1 = warp_sum(lane < nb ? double(s1) : 0.0);
@@ -723,7 +726,6 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   // compressMLP: x = relu(a_L Wfc^T + b)
   MAPF_TRY(gemm(s, int(rows), F, fin, ws + T.a[L - 1], fin, 1, p->fc_w, 1, fin, ws + T.x, F, p->fc_b, 1));
   if (p->taps == 0) return gemm(s, int(rows), A, F, ws + T.x, F, 1, p->act_w, 1, F, a->logits, A, p->act_b, 0);
-  MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, p->taps, p->node_dim, ws + T.wt, stream));
   mapf_graph_filter_fwd_args g{};
   g.batch = B; g.agents = N; g.in_dim = F; g.out_dim = p->node_dim; g.taps = p->taps;
   g.add_self_loop = a->message ? 0 : 1;
@@ -737,6 +739,18 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   g.z = ws + T.z;
   g.act_w = p->act_w; g.act_b = p->act_b;
   g.logits = a->logits; g.actions = nullptr;
+  const int KT = (p->taps + (a->message ? 1 : 0)) * F;
+  const bool tensor_path = N <= 64 && p->node_dim <= 128 && (p->node_dim & 15) == 0 && (F & 3) == 0 &&
+                           mapf_aligned(p->act_w, 16) && getenv("MAPF_B200_TRAIN_FFMA_GRAPH") == nullptr;
+  if (tensor_path) {
+    // filter taps Z (saved for the weight gradient) + 3xTF32 tcgen05 mix with relu(Y) stored for the backward pass
+    MAPF_TRY(mapf_tc_pack_b(p->gf_w, p->taps * F, a->message ? p->gf_w2 : nullptr, a->message ? F : 0, p->node_dim,
+                            ws + T.wt, stream));
+    MAPF_TRY(mapf_graph_taps(&g, stream));
+    return mapf_tc_mix_head(int32_t(rows), p->node_dim, KT, ws + T.z, KT, ws + T.wt, p->act_w, p->act_b, A, a->logits,
+                            nullptr, ws + T.y, stream);
+  }
+  MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, p->taps, p->node_dim, ws + T.wt, stream));
   return mapf_graph_filter_fwd(&g, stream);
 }
 

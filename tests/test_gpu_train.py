@@ -63,7 +63,7 @@ def test_fused_trainer_step_matches_reference(train_step, name):
             # reference's rounding noise into +-lr.  Bound the move instead of matching the noise.
             assert np.abs(v.cpu().numpy() - ref).max() <= 2 * 3e-4 + 1e-7, k
         else:
-            assert rel_err(v.cpu().numpy(), ref) < 2e-5, k
+            assert rel_err(v.cpu().numpy(), ref) < REL, k     # Adam normalises every element to ~lr: tiny gradients amplify rounding
 
 
 def test_clip_adam_kernel_on_reference_gradients(train_step):
