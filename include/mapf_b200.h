@@ -68,6 +68,13 @@ typedef struct {
 } mapf_env_reset_args;
 int mapf_env_reset(const mapf_env_reset_args* a, mapf_stream_t stream);
 
+/* On-device scenario generation for E episodes: M unique obstacles, then N unique obstacle-free goals
+ * (evaluate.py:207-208: create_obstacles env_graph_gridv1.py:504-529, create_goals :465-501), then N unique
+ * obstacle-free starts.  Deterministic in (seed, episode index); distributional (not stream-exact) parity with the
+ * reference's numpy generator.  MAPF_ERR_SHAPE when M + N exceeds the number of cells (create_goals' ValueError). */
+int mapf_make_scenarios(int32_t episodes, int32_t agents, int32_t board, int32_t num_obstacles, uint64_t seed,
+                        int32_t* starts, int32_t* goals, int32_t* obstacles, mapf_stream_t stream);
+
 /* GraphEnv.step (env_graph_gridv1.py:183-198) = _updatePositions (:200-213) -> _computeDistance +
  * _computeClosest (:117-136,174-181) -> preprocessObs (:248-265) -> time += 1 -> checkAllInGoal
  * (:156-159), for E episodes in one fused kernel.  do_move == 0 gives getObservations() of the

@@ -253,3 +253,74 @@ extern "C" int mapf_env_metrics(const mapf_env_metrics_args* a, mapf_stream_t st
   env_metrics_kernel<<<(a->episodes + threads - 1) / threads, threads, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   return mapf_launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// On-device scenario generation: per episode, M unique obstacle cells, then N unique obstacle-free
+// goal cells (evaluate.py:207-208 order: create_obstacles :504-529, create_goals :465-501), then N unique
+// obstacle-free start cells (explicit starts instead of reset()'s row/column draw :77-90, which fails on dense maps).
+// One CTA per episode: the cell permutation lives in shared memory, a partial Fisher-Yates driven by a counter-based
+// hash (no state carried between launches: the stream of episode e depends only on (seed, e)).
+// Distributional, not stream-exact, parity with the reference's numpy generator.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // lowbias32 integer hash
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(128) scenario_kernel(int episodes, int agents, int board, int num_obstacles,
+                                                       uint64_t seed, int32_t* __restrict__ starts,
+                                                       int32_t* __restrict__ goals, int32_t* __restrict__ obstacles) {
+  extern __shared__ int s_perm[];
+  const int e = blockIdx.x, cells = board * board;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) s_perm[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t ctr = 0;
+    const uint32_t k0 = mix32(uint32_t(seed) ^ mix32(uint32_t(e) * 0x9E3779B9U + 1U));
+    const uint32_t k1 = mix32(uint32_t(seed >> 32) + 0x85EBCA6BU + uint32_t(e));
+    auto draw = [&](uint32_t n) -> uint32_t {   // uniform in [0, n) (multiply-shift; bias < 2^-20 for n <= 4096)
+      const uint32_t r = mix32(k0 + 0x9E3779B9U * (++ctr)) ^ mix32(k1 ^ ctr);
+      return uint32_t((uint64_t(r) * n) >> 32);
+    };
+    auto swap_to = [&](int i, int lo_end) {
+      const int j = i + int(draw(uint32_t(lo_end - i)));
+      const int t = s_perm[i]; s_perm[i] = s_perm[j]; s_perm[j] = t;
+    };
+    const int M = num_obstacles, N = agents;
+    for (int i = 0; i < M + N; ++i) swap_to(i, cells);            // obstacles, then goals
+    for (int i = 0; i < M; ++i) {
+      const int c = s_perm[i];
+      obstacles[(int64_t(e) * M + i) * 2] = c % board;
+      obstacles[(int64_t(e) * M + i) * 2 + 1] = c / board;
+    }
+    for (int i = 0; i < N; ++i) {
+      const int c = s_perm[M + i];
+      goals[(int64_t(e) * N + i) * 2] = c % board;
+      goals[(int64_t(e) * N + i) * 2 + 1] = c / board;
+    }
+    for (int i = M; i < M + N; ++i) swap_to(i, cells);            // starts: N fresh draws among the obstacle-free cells
+    for (int i = 0; i < N; ++i) {
+      const int c = s_perm[M + i];
+      starts[(int64_t(e) * N + i) * 2] = c % board;
+      starts[(int64_t(e) * N + i) * 2 + 1] = c / board;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mapf_make_scenarios(int32_t episodes, int32_t agents, int32_t board, int32_t num_obstacles, uint64_t seed,
+                                   int32_t* starts, int32_t* goals, int32_t* obstacles, mapf_stream_t stream) {
+  MAPF_REQUIRE(starts && goals && (num_obstacles == 0 || obstacles), MAPF_ERR_NULL);
+  MAPF_REQUIRE(episodes > 0 && agents > 0 && board > 0 && num_obstacles >= 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(int64_t(num_obstacles) + agents <= int64_t(board) * board, MAPF_ERR_SHAPE);   // create_goals ValueError
+  const size_t smem = sizeof(int) * size_t(board) * board;
+  MAPF_REQUIRE(smem <= 200 * 1024, MAPF_ERR_UNSUPPORTED);
+  static int cache[16] = {0};
+  if (smem > 40 * 1024 && !mapf_ensure_smem(scenario_kernel, smem, cache)) return MAPF_ERR_CUDA;
+  scenario_kernel<<<episodes, 128, smem, static_cast<cudaStream_t>(stream)>>>(episodes, agents, board, num_obstacles,
+                                                                               seed, starts, goals, obstacles);
+  return mapf_launch_status();
+}

@@ -31,3 +31,23 @@ def make_scenarios(rng: np.random.Generator, episodes, num_agents, board_size, n
         goals[lo:hi, :, 0], goals[lo:hi, :, 1] = g % H, g // H
         starts[lo:hi, :, 0], starts[lo:hi, :, 1] = s % H, s // H
     return starts, goals, obst
+
+
+def make_scenarios_device(episodes, num_agents, board_size, num_obstacles, seed=0, device="cuda"):
+    """Same contract as ``make_scenarios`` but generated on the GPU (one kernel, no host work): int32 device tensors
+    starts [E,N,2], goals [E,N,2], obstacles [E,M,2].  Raises ValueError like ``create_goals`` when the board is too
+    small (env_graph_gridv1.py:494-495)."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    E, N, H, M = int(episodes), int(num_agents), int(board_size), int(num_obstacles)
+    if M + N > H * H:
+        raise ValueError(f"Not enough valid positions ({H * H - M}) for {N} agents")
+    dev = torch.device(device)
+    starts = torch.empty((E, N, 2), dtype=torch.int32, device=dev)
+    goals = torch.empty((E, N, 2), dtype=torch.int32, device=dev)
+    obst = torch.empty((E, M, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mapf_make_scenarios(E, N, H, M, int(seed) & (2 ** 64 - 1), starts.data_ptr(), goals.data_ptr(),
+                                           obst.data_ptr() if M else None, _lib.current_stream()), "make_scenarios")
+    return starts, goals, obst

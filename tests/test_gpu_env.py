@@ -139,3 +139,41 @@ def test_bad_arguments_raise():
         m.BatchedGraphEnv(_cfg(5, 10), np.zeros((2, 4, 2)), np.zeros((2, 4, 2)))
     with pytest.raises(RuntimeError):
         m.BatchedGraphEnv(_cfg(200, 10), np.zeros((1, 200, 2)), np.zeros((1, 200, 2)))   # N > 128 unsupported
+
+
+@pytest.mark.parametrize("E,N,H,M", [(64, 5, 18, 5), (33, 20, 32, 40), (16, 64, 64, 200), (200, 6, 4, 4), (8, 1, 2, 3)])
+def test_device_scenario_generation(E, N, H, M):
+    """Validity properties of the on-device generator (distributional parity with create_obstacles / create_goals):
+    in-board, obstacles unique, goals unique and obstacle-free, starts unique and obstacle-free, deterministic in the
+    seed, different across episodes and seeds; roughly uniform cell usage."""
+    import mapf_gnn_b200 as m
+    s, g, o = (t.cpu().numpy() for t in m.make_scenarios_device(E, N, H, M, seed=7))
+    s2, g2, o2 = (t.cpu().numpy() for t in m.make_scenarios_device(E, N, H, M, seed=7))
+    s3, g3, o3 = (t.cpu().numpy() for t in m.make_scenarios_device(E, N, H, M, seed=8))
+    assert np.array_equal(s, s2) and np.array_equal(g, g2) and np.array_equal(o, o2)
+    assert not (np.array_equal(g, g3) and np.array_equal(s, s3))
+    for arr in (s, g, o):
+        assert arr.min() >= 0 and arr.max() < H
+    for e in range(E):
+        so = set(map(tuple, o[e]))
+        assert len(so) == M
+        for pts in (g[e], s[e]):
+            sp = set(map(tuple, pts))
+            assert len(sp) == N and not (sp & so)
+    if E >= 33:
+        assert len({tuple(map(tuple, g[e])) for e in range(E)}) > E // 2
+    if E * N >= 300 and H * H <= 400:
+        counts = np.bincount(g[:, :, 1].ravel() * H + g[:, :, 0].ravel(), minlength=H * H)
+        assert counts.max() <= 12 * max(1.0, E * N / (H * H))
+
+
+def test_device_scenarios_drive_a_rollout():
+    import mapf_gnn_b200 as m
+    with pytest.raises(ValueError):
+        m.make_scenarios_device(4, 10, 3, 5)
+    s, g, o = m.make_scenarios_device(50, 5, 12, 6, seed=1)
+    env = m.BatchedGraphEnv(_cfg(5, 12), g, s, o, sensing_range=6)
+    orc = [eo.EnvOracle(5, 12, g[e].cpu().numpy(), s[e].cpu().numpy(), o[e].cpu().numpy(), sensing_range=6) for e in range(50)]
+    for e in range(50):
+        ob = orc[e].observe()
+        assert np.array_equal(env.fov[e].cpu().numpy(), ob["fov"].astype(np.float32))
