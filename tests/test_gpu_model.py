@@ -193,6 +193,18 @@ def test_batched_evaluator_matches_oracle_protocol():
     assert checked >= 20
 
 
+def test_evaluator_with_device_scenarios():
+    """Same evaluator fed by the on-device scenario generator: deterministic in the seed, plausible summary."""
+    import mapf_gnn_b200 as m
+    cfg = model_config("gnn_k3", 5, board_size=[18, 18], obstacles=5, max_steps=12, sensing_range=6)
+    net = load_network("gnn_k3").eval()
+    s1, p1 = m.evaluate(net, cfg, episodes=300, seed=3, device_scenarios=True)
+    s2, p2 = m.evaluate(net, cfg, episodes=300, seed=3, device_scenarios=True)
+    assert s1 == s2 and np.array_equal(p1["flow_time"], p2["flow_time"])
+    s3, _ = m.evaluate(net, cfg, episodes=300, seed=3)
+    assert abs(s1["avg_success_rate"] - s3["avg_success_rate"]) < 0.12      # same distribution family
+
+
 def test_host_stepped_rollout_matches_device_rollout():
     """HostSteppedRollout (pinned host buffers + CUDA-graph replay) must walk the same trajectory as Rollout.run."""
     import mapf_gnn_b200 as m
