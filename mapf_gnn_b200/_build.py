@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
 ]
+# development only (e.g. "-DMAPF_ENC_DEBUG" for the phase-timing hooks used by tools/enc_dbg.py); part of the digest
+NVCC_FLAGS += os.environ.get("MAPF_B200_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -79,8 +79,96 @@ __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, 
   }
 }
 
+#ifdef MAPF_ENC_DEBUG
+__device__ long long* g_enc_dbg = nullptr;   // [tile][phase 0..7][warp][arrive, leave] clocks of block 0
+#endif
+
+// Same layer for a HALF tile of 16 agent images (the ragged last round of the persistent loop, see mapf_encoder_fwd):
+// lane = (agent = lane & 15, h = lane >> 4); the two half-warps split the INPUT channels of the warp's output pair,
+// exchange their partial sums with one shuffle per pixel, and half h finishes channel 2*pr + h.  Per-warp FFMA2 count is
+// half that of a full tile, so a half tile costs about half a tile.  Activations are [channel][25][16] with 16 floats of
+// padding from channel `mid` on, which puts the two half-warps on disjoint banks.
+__device__ __forceinline__ void conv3x3_relu_half(const float* __restrict__ in, int in_cs, int in_ps, int in_off,
+                                                  int in_pad, float* __restrict__ out, int out_ps, int out_mid,
+                                                  int out_pad, const float* __restrict__ w,
+                                                  const float* __restrict__ bias, int cin, int cout, int warp,
+                                                  int lane) {
+  const int ag = lane & 15, h = lane >> 4;
+  const int cmid = (cin + 1) >> 1;
+  for (int pr = warp; pr < (cout >> 1); pr += kEncWarps) {
+    float2 acc[kFovCells];
+    {
+      float2 b = *reinterpret_cast<const float2*>(bias + 2 * pr);
+      if (h) b = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) acc[p] = b;
+    }
+    const float2* wp = reinterpret_cast<const float2*>(w) + (int64_t(pr >> 1) * cin * 9) * 2 + (pr & 1);
+#ifdef MAPF_ENC_DEBUG
+    const long long t_a = clock64();
+#endif
+#pragma unroll 2
+    for (int i = 0; i < cmid; ++i) {
+      const int ci = h * cmid + i;
+      const bool live = ci < cin;                       // odd channel counts: the upper half runs one dummy round
+      const int cc = live ? ci : cin - 1;
+      float v[kFovCells];
+      const float* src = in + cc * in_cs + (cc >= cmid ? in_pad : 0) + in_off;
+#pragma unroll
+      for (int p = 0; p < kFovCells; ++p) v[p] = src[p * in_ps];
+      float2 wv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wv[t] = live ? wp[(cc * 9 + t) * 2] : make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int y = 0; y < kFov; ++y)
+#pragma unroll
+            for (int x = 0; x < kFov; ++x) {
+              const int yy = y + ky - 1, xx = x + kx - 1;
+              if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov)
+                mapf_ffma2(acc[y * kFov + x], v[yy * kFov + xx], wv[ky * 3 + kx]);
+            }
+    }
+#ifdef MAPF_ENC_DEBUG
+    const long long t_b = clock64();
+#endif
+    const int co = 2 * pr + h;
+    float* dst = out + co * kFovCells * out_ps + (co >= out_mid ? out_pad : 0) + ag;
+#pragma unroll
+    for (int p = 0; p < kFovCells; ++p) {
+      const float give = h ? acc[p].x : acc[p].y;       // the partner's channel
+      const float got = __shfl_xor_sync(0xffffffffu, give, 16);
+      dst[p * out_ps] = fmaxf((h ? acc[p].y : acc[p].x) + got, 0.0f);
+    }
+#ifdef MAPF_ENC_DEBUG
+    if (g_enc_dbg && blockIdx.x == 0 && lane == 0) {
+      g_enc_dbg[900 + warp * 3] = t_a; g_enc_dbg[901 + warp * 3] = t_b; g_enc_dbg[902 + warp * 3] = clock64();
+    }
+#endif
+  }
+}
+
+// Development hooks (MAPF_B200_NVCC_EXTRA=-DMAPF_ENC_DEBUG, tools/enc_dbg.py): per-phase, per-warp barrier clocks.
+#ifdef MAPF_ENC_DEBUG
+#define ENC_SYNC(phase)                                                                                    \
+  do {                                                                                                     \
+    long long t_arr__ = clock64();                                                                         \
+    __syncthreads();                                                                                       \
+    if (g_enc_dbg && blockIdx.x == 0 && lane == 0 && dbg_tile < 8) {                                       \
+      g_enc_dbg[((dbg_tile * 8 + (phase)) * 8 + warp) * 2] = t_arr__;                                      \
+      g_enc_dbg[((dbg_tile * 8 + (phase)) * 8 + warp) * 2 + 1] = clock64();                                \
+    }                                                                                                      \
+  } while (0)
+#else
+#define ENC_SYNC(phase) __syncthreads()
+#endif
+
 template <bool kFcSmem>
 __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims d, PackedLayout L, int64_t rows,
+                                                                     int64_t nfull, int nhalf,
                                                                      const float* __restrict__ states,
                                                                      const float* __restrict__ packed,
                                                                      float* __restrict__ x) {
@@ -93,14 +181,31 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
   for (int i = tid; i < (d.w_floats >> 2); i += kEncThreads)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(packed) + i);
 
-  const int64_t ntiles = (rows + kEncAgents - 1) / kEncAgents;
-  float* const s_st = s_b1 + d.buf1_floats;     // [32][50] image staging, filled by cp.async one tile ahead
+  float* const s_st = s_b1 + d.buf1_floats;     // [32][50] image staging, filled by cp.async one item ahead
 
-  // stage a tile's images as they lie in memory ([agent][50]); rows past the end are zero-filled after the wait
-  auto prefetch = [&](int64_t tile) {
-    if (tile < ntiles) {
-      const int64_t row0 = tile * kEncAgents;
-      const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
+  // Work items of this CTA: full tiles b, b + G, ... (< nfull) of 32 agent images, then half tile b (< nhalf) of 16.
+  // Item ids: [0, nfull) full tiles, nfull + h half tiles (rows nfull*32 + 16 h ...).
+  const int64_t first = blockIdx.x < nfull ? int64_t(blockIdx.x) : (int(blockIdx.x) < nhalf ? nfull + blockIdx.x : -1);
+  auto next_item = [&](int64_t it) -> int64_t {
+    if (it < nfull) {
+      if (it + gridDim.x < nfull) return it + gridDim.x;
+      return int(blockIdx.x) < nhalf ? nfull + blockIdx.x : -1;
+    }
+    return -1;
+  };
+  auto item_rows = [&](int64_t it, int64_t& row0, int& nrows) {
+    const bool full = it < nfull;
+    row0 = full ? it * kEncAgents : nfull * kEncAgents + (it - nfull) * (kEncAgents / 2);
+    const int cap = full ? kEncAgents : kEncAgents / 2;
+    nrows = (rows - row0) < cap ? int(rows - row0) : cap;
+  };
+
+  // stage an item's images as they lie in memory ([agent][50]); rows past the end are zero-filled
+  auto prefetch = [&](int64_t it) {
+    if (it >= 0) {
+      int64_t row0;
+      int nrows;
+      item_rows(it, row0, nrows);
       const int nfl = nrows * kFovFloats;
       const float* src = states + row0 * kFovFloats;
       if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -117,25 +222,48 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
-  prefetch(blockIdx.x);
+  prefetch(first);
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kEncAgents;
-    const int nrows = (rows - row0) < kEncAgents ? int(rows - row0) : kEncAgents;
+#ifdef MAPF_ENC_DEBUG
+  int dbg_tile = 0;
+  if (g_enc_dbg && blockIdx.x == 0 && tid == 0) g_enc_dbg[1023] = clock64();
+#endif
+  for (int64_t item = first; item >= 0; item = next_item(item)) {
+    int64_t row0;
+    int nrows;
+    item_rows(item, row0, nrows);
     asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
+    ENC_SYNC(0);
 
-    // layer 0 reads the staging layout [agent][ci*25 + p]; later layers read [ci*25 + p][agent]
-    conv3x3_relu_pair(s_st, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
-                      d.channels[0], d.channels[1], warp, lane);
-    __syncthreads();
-    prefetch(tile + gridDim.x);   // the staging buffer is free: the next tile's images land during conv2 / conv3 / FC
     bool in1 = true;  // current activations live in s_b1
-    for (int l = 1; l < d.num_conv; ++l) {
-      conv3x3_relu_pair(in1 ? s_b1 : s_b0, kFovCells * kEncAgents, kEncAgents, lane, in1 ? s_b0 : s_b1,
-                        s_w + L.conv_w[l], s_w + L.conv_b[l], d.channels[l], d.channels[l + 1], warp, lane);
-      in1 = !in1;
-      __syncthreads();
+    if (item < nfull) {
+      // layer 0 reads the staging layout [agent][ci*25 + p]; later layers read [ci*25 + p][agent]
+      conv3x3_relu_pair(s_st, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
+                        d.channels[0], d.channels[1], warp, lane);
+      ENC_SYNC(1);
+      prefetch(next_item(item));   // the staging buffer is free: the next images land during conv2 / conv3 / FC
+      for (int l = 1; l < d.num_conv; ++l) {
+        conv3x3_relu_pair(in1 ? s_b1 : s_b0, kFovCells * kEncAgents, kEncAgents, lane, in1 ? s_b0 : s_b1,
+                          s_w + L.conv_w[l], s_w + L.conv_b[l], d.channels[l], d.channels[l + 1], warp, lane);
+        in1 = !in1;
+        ENC_SYNC(1 + l);
+      }
+    } else {
+      // half tile: intermediate activations [channel][25][16] (+16 from the next layer's split channel on); the last
+      // layer writes the FC layout [fc_in][32] (columns 16..31 are never stored)
+      constexpr int kHalf = kEncAgents / 2;
+      const int ag = lane & 15;
+      for (int l = 0; l < d.num_conv; ++l) {
+        const bool last = l == d.num_conv - 1;
+        const float* src = l == 0 ? s_st : (in1 ? s_b1 : s_b0);
+        float* dst = l == 0 ? s_b1 : (in1 ? s_b0 : s_b1);
+        conv3x3_relu_half(src, l == 0 ? kFovCells : kFovCells * kHalf, l == 0 ? 1 : kHalf,
+                          l == 0 ? ag * kFovFloats : ag, l == 0 ? 0 : kHalf, dst, last ? kEncAgents : kHalf,
+                          last ? (1 << 30) : (d.channels[l + 1] + 1) >> 1, kHalf, s_w + L.conv_w[l], s_w + L.conv_b[l],
+                          d.channels[l], d.channels[l + 1], warp, lane);
+        if (l > 0) in1 = !in1;
+        ENC_SYNC(1 + l);
+      }
     }
     const float* act = in1 ? s_b1 : s_b0;   // [fc_in][32]
     float* scratch = in1 ? s_b0 : s_b1;     // free buffer: split-K partials [128 threads][16]
@@ -184,7 +312,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
           sc[((kg - 1) * 8 + r * 2 + 1) * 64 + t6] = make_float4(acc[r][2].x, acc[r][2].y, acc[r][3].x, acc[r][3].y);
         }
       }
-      __syncthreads();
+      ENC_SYNC(4 + (jb >> 6) * 2);
       if (kg == 0 && jlive) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(packed + L.fc_b + j) + 1);
@@ -208,8 +336,11 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
           }
         }
       }
-      __syncthreads();  // scratch / staging buffer is rewritten by the next block or tile
+      ENC_SYNC(5 + (jb >> 6) * 2);  // scratch / staging buffer is rewritten by the next block or tile
     }
+#ifdef MAPF_ENC_DEBUG
+    ++dbg_tile;
+#endif
   }
 }
 
@@ -279,6 +410,12 @@ __global__ void __launch_bounds__(kEncThreads * NG, 1) encoder_conv_kernel(Encod
 
 }  // namespace
 
+#ifdef MAPF_ENC_DEBUG
+extern "C" int mapf_enc_set_debug(long long* p) {
+  return cudaMemcpyToSymbol(g_enc_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 static int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -318,17 +455,29 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   d.w_floats = int(d.fc_in_smem ? L.gf_wt : L.fc_wt);
   const size_t smem = size_t(d.w_floats) * sizeof(float) + act_bytes;
   MAPF_REQUIRE(smem <= limit, MAPF_ERR_UNSUPPORTED);
+  // Persistent grid of G = min(tiles, SMs) CTAs.  When the last round of 32-image tiles would leave at least half of
+  // the CTAs idle, that round is cut into 16-image half tiles (one per CTA, about half the time of a full tile).
   const int64_t ntiles = (a->rows + kEncAgents - 1) / kEncAgents;
-  const int grid = int(ntiles < sm_count() ? ntiles : sm_count());
+  const int sms = sm_count();
+  int64_t nfull = ntiles;
+  int nhalf = 0;
+  {
+    const int64_t rounds = ntiles / sms, rem = ntiles - rounds * sms;
+    if (rem > 0 && 2 * rem <= sms && !getenv("MAPF_B200_ENC_NO_HALF_TILES")) {
+      nfull = rounds * sms;
+      nhalf = int((a->rows - nfull * kEncAgents + kEncAgents / 2 - 1) / (kEncAgents / 2));
+    }
+  }
+  const int grid = int(nfull >= sms ? sms : (nfull > nhalf ? nfull : nhalf));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d.fc_in_smem) {
     static int cache_a[16] = {0};
     if (!mapf_ensure_smem(encoder_fwd_kernel<true>, smem, cache_a)) return MAPF_ERR_CUDA;
-    encoder_fwd_kernel<true><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, a->states, a->packed, a->x);
+    encoder_fwd_kernel<true><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
   } else {
     static int cache_b[16] = {0};
     if (!mapf_ensure_smem(encoder_fwd_kernel<false>, smem, cache_b)) return MAPF_ERR_CUDA;
-    encoder_fwd_kernel<false><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, a->states, a->packed, a->x);
+    encoder_fwd_kernel<false><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
   }
   return mapf_launch_status();
 }

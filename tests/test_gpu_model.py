@@ -79,6 +79,23 @@ def test_logits_match_oracle_on_random_observations(name, B, N):
     _check_actions(actions.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("rows", [1, 15, 16, 17, 33, 640, 2368, 2400, 4736 + 300, 4736 + 74 * 32, 4736 + 75 * 32 + 5, 2 * 4736 + 16])
+def test_encoder_tile_schedules(rows):
+    """The persistent encoder walks full 32-image tiles and, for a ragged last round, 16-image half tiles (different
+    lane mapping); every schedule must give the oracle's features (framework_gnn.py:156-166), row for row."""
+    rng = np.random.default_rng(rows)
+    states = torch.tensor(rng.integers(0, 4, size=(rows, 1, 2, 5, 5))).float()
+    states[:: 7] *= 0.37                                   # not only small integers
+    params = oracle_params("gnn_k3")
+    with torch.no_grad():
+        ref = mo.encode_agents(params, states)[:, :, 0].numpy()
+    net = load_network("gnn_k3", num_agents=1).eval()
+    x = torch.ops.mapf.encoder_fwd(net.dims(), states.cuda(), net.packed_weights()).cpu().numpy()
+    assert x.shape == ref.shape
+    assert rel_err(x, ref) < REL
+    assert np.abs(x - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
 def test_training_gso_convention_a_plus_i():
     """The data loader feeds A + I (data_loader.py:74); GCNLayer adds I again -> diagonal 2."""
     rng = np.random.default_rng(3)
