@@ -260,6 +260,12 @@ def run_mine(args, w):
             env_ms.append(a.elapsed_time(b))
     env_ms = float(np.mean(env_ms))
     pk = peaks()
+    traffic = None
+    try:       # ncu-measured DRAM bytes per launch of the dominant kernel (committed summary; null when not captured)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch") if E == w["E"] else None
+    except OSError:
+        pass
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     enc_tflops = E * N * w["enc_flops"] / (enc_ms * 1e-3) / 1e12
     env_gbs = E * N * w["env_bytes"] / (env_ms * 1e-3) / 1e9
@@ -315,7 +321,7 @@ def run_mine(args, w):
                                   f"nominal E*N*K = {units_nominal:.0f}",
                        "wall_s_incl_flush": wall},
             "roofline": {"bound": "fp32_ffma", "kernel": "encoder_fwd_kernel", "achieved": enc_tflops,
-                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": enc_tflops / fp32_peak, "traffic": None,
+                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": enc_tflops / fp32_peak, "traffic": traffic,
                          "ms_per_launch": enc_ms, "share_of_step": enc_ms / (dev_ms_max / K),
                          "peak_source": f"148 SM x 128 FFMA x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})"},
             "roofline_env": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": env_gbs, "peak": pk["hbm_gbs"],
