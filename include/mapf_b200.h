@@ -49,6 +49,13 @@ const char* mapf_last_error_string(int code);
 /* library / build identification: "mapf_b200 <version> sm_100a" */
 const char* mapf_version(void);
 
+/* Host-stepping helpers for callers that drive the evaluate.py:223-241 loop from the host with a captured launch
+ * sequence (HostSteppedRollout): launch an instantiated cudaGraphExec_t on `stream` and record `event` (may be NULL)
+ * behind it; block the calling thread until `event` has completed.  Two plain driver calls each -- they exist so that
+ * the per-step host cost is not dominated by an interpreter's stream / graph wrappers. */
+int mapf_graph_launch(void* graph_exec, mapf_stream_t stream, void* event);
+int mapf_event_wait(void* event);
+
 /* ------------------------------------------------------------------------------------------
  * Environment (reference: grid/env_graph_gridv1.py GraphEnv)
  * ---------------------------------------------------------------------------------------- */

@@ -13,10 +13,10 @@ from . import ops  # noqa: E402,F401
 from .env import BatchedGraphEnv, GraphEnv, create_goals, create_obstacles, d2_limit_from_range  # noqa: E402,F401
 from .layers import GCNLayer, MessagePassingLayer  # noqa: E402,F401
 from .network import BaselineNetwork, GNNNetwork, MessageNetwork, weights_init  # noqa: E402,F401
-from .rollout import HostSteppedRollout, Rollout, build_network  # noqa: E402,F401
+from .rollout import HostSteppedRollout, PipelinedHostRollout, Rollout, build_network  # noqa: E402,F401
 from .scenarios import make_scenarios, make_scenarios_device  # noqa: E402,F401
 from .evaluate import evaluate  # noqa: E402,F401
 
 __all__ = ["BatchedGraphEnv", "GraphEnv", "create_goals", "create_obstacles", "d2_limit_from_range", "GCNLayer",
-           "MessagePassingLayer", "GNNNetwork", "MessageNetwork", "BaselineNetwork", "weights_init", "Rollout", "HostSteppedRollout",
+           "MessagePassingLayer", "GNNNetwork", "MessageNetwork", "BaselineNetwork", "weights_init", "Rollout", "HostSteppedRollout", "PipelinedHostRollout",
            "build_network", "make_scenarios", "make_scenarios_device", "evaluate"]

@@ -117,6 +117,8 @@ class RolloutArgs(C.Structure):
 _SIGNATURES = {
     "mapf_last_error_string": (C.c_char_p, [C.c_int]),
     "mapf_version": (C.c_char_p, []),
+    "mapf_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mapf_event_wait": (C.c_int, [C.c_void_p]),
     "mapf_make_scenarios": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "mapf_env_reset": (C.c_int, [C.POINTER(EnvResetArgs), C.c_void_p]),

@@ -257,3 +257,16 @@ extern "C" const char* mapf_last_error_string(int code) {
 }
 
 extern "C" const char* mapf_version(void) { return "mapf_b200 0.1 sm_100a"; }
+
+extern "C" int mapf_graph_launch(void* graph_exec, mapf_stream_t stream, void* event) {
+  MAPF_REQUIRE(graph_exec, MAPF_ERR_NULL);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  if (event && cudaEventRecord(static_cast<cudaEvent_t>(event), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  return MAPF_OK;
+}
+
+extern "C" int mapf_event_wait(void* event) {
+  MAPF_REQUIRE(event, MAPF_ERR_NULL);
+  return cudaEventSynchronize(static_cast<cudaEvent_t>(event)) == cudaSuccess ? MAPF_OK : MAPF_ERR_CUDA;
+}

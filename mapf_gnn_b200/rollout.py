@@ -110,6 +110,17 @@ class HostSteppedRollout:
             with torch.cuda.graph(gph):
                 self._body(k)
             self.graphs.append(gph)
+        self.stream = torch.cuda.Stream(device=env.device)     # replays run here, so several rollouts can overlap
+        self.event = torch.cuda.Event()
+        with torch.cuda.stream(self.stream):
+            self.event.record()                                 # materialises the cudaEvent_t handle
+        self.stream.wait_stream(torch.cuda.current_stream())
+        # raw handles: launch / wait are two C calls each (mapf_graph_launch, mapf_event_wait), not torch wrappers
+        self._exec = [C.c_void_p(g.raw_cuda_graph_exec()) for g in self.graphs]
+        self._stream = C.c_void_p(self.stream.cuda_stream)
+        self._event = C.c_void_p(self.event.cuda_event)
+        self._lib = _lib.load()
+        self.in_flight = False
 
     @property
     def pos_in(self):
@@ -122,10 +133,102 @@ class HostSteppedRollout:
         ro.run(1)
         self.blocks[k].copy_(env.host_block, non_blocking=True)           # D2H: actions + new positions + done
 
-    def step(self):
-        """One host-driven step; returns after the results are visible in pinned host memory."""
+    def launch(self):
+        """Enqueue one step (upload, kernels, download) on this rollout's own stream and return immediately.  Work
+        the caller issued on other streams (e.g. ``env.reset()``) is NOT waited for here -- ``step()`` does that."""
+        if self.in_flight:
+            raise RuntimeError("HostSteppedRollout.launch(): the previous step has not been waited for")
+        rc = self._lib.mapf_graph_launch(self._exec[self.cur], self._stream, self._event)
+        if rc:
+            _lib.check(rc, "graph_launch")
+        self.in_flight = True
+
+    def wait(self):
+        """Block until the step enqueued by ``launch()`` is visible in pinned host memory; returns its views."""
+        if not self.in_flight:
+            raise RuntimeError("HostSteppedRollout.wait(): nothing in flight")
+        rc = self._lib.mapf_event_wait(self._event)
+        if rc:
+            _lib.check(rc, "event_wait")
+        self.in_flight = False
         k = self.cur
-        self.graphs[k].replay()
-        torch.cuda.current_stream().synchronize()
         self.cur = 1 - k
         return self.views[k]
+
+    def step(self):
+        """One host-driven step; returns after the results are visible in pinned host memory."""
+        self.stream.wait_stream(torch.cuda.current_stream())   # e.g. an env.reset() issued by the caller
+        self.launch()
+        return self.wait()
+
+
+class PipelinedHostRollout:
+    """Host-driven stepping of G independent episode groups with their host round trips overlapped: every group is a
+    ``HostSteppedRollout`` on its own stream (own environment shard, own pinned blocks, same network), so while the
+    host consumes the results of one group and uploads its next state, the GPU runs the step of another.  Each group
+    still performs the full protocol of evaluate.py:223-241 per step -- state up from pinned memory, policy + env
+    step, actions / positions / done back to pinned memory.
+
+    ``start()`` launches the first step of every group; ``advance(g)`` waits for group g's step, returns its views
+    ``(actions, pos_out, done)`` and, unless ``relaunch=False``, immediately enqueues its next step (the caller may
+    edit ``groups[g].pos_in`` first by passing ``relaunch=False`` and calling ``groups[g].launch()`` itself)."""
+
+    @staticmethod
+    def round_aligned_sizes(episodes, agents, groups, sm_count, tile=32):
+        """Group sizes whose encoder launches are whole rounds of the persistent kernel (``sm_count`` tiles of ``tile``
+        agent images each) for all groups but the last, so that splitting the batch does not add ragged rounds."""
+        E, N = int(episodes), int(agents)
+        per_round = sm_count * tile
+        rounds = max(1, round(E * N / per_round / groups))
+        size = per_round * rounds // N
+        if size < 1 or size * (groups - 1) >= E:
+            return [E * (g + 1) // groups - E * g // groups for g in range(groups)]
+        return [size] * (groups - 1) + [E - size * (groups - 1)]
+
+    def __init__(self, net, config, goals, starts, obstacles=None, groups=2, sensing_range=6, device="cuda",
+                 group_sizes=None):
+        import numpy as np
+        goals, starts = np.asarray(goals), np.asarray(starts)
+        E = goals.shape[0]
+        if not 1 <= groups <= E:
+            raise ValueError("groups must be in [1, episodes]")
+        if group_sizes is None:
+            sms = torch.cuda.get_device_properties(torch.device(device)).multi_processor_count
+            group_sizes = self.round_aligned_sizes(E, goals.shape[1], groups, sms)
+        if len(group_sizes) != groups or sum(group_sizes) != E or min(group_sizes) < 1:
+            raise ValueError("group_sizes must be positive and sum to the number of episodes")
+        bounds = [0]
+        for n in group_sizes:
+            bounds.append(bounds[-1] + int(n))
+        self.slices = [slice(bounds[g], bounds[g + 1]) for g in range(groups)]
+        self.envs, self.rollouts, self.groups = [], [], []
+        for sl in self.slices:
+            ob = None if obstacles is None or np.asarray(obstacles).shape[1] == 0 else np.asarray(obstacles)[sl]
+            env = BatchedGraphEnv(config, goals[sl], starts[sl], ob, sensing_range=sensing_range, device=device)
+            ro = Rollout(net, env)
+            self.envs.append(env), self.rollouts.append(ro), self.groups.append(HostSteppedRollout(ro))
+        self.h2d_bytes = sum(h.h2d_bytes for h in self.groups)
+        self.d2h_bytes = sum(h.d2h_bytes for h in self.groups)
+
+    def reset(self):
+        """Back to the initial scenario in every group (device state and pinned input positions)."""
+        for env, h in zip(self.envs, self.groups):
+            if h.in_flight:
+                h.wait()
+            env.reset()
+            h.pos_in.copy_(env.pos.cpu())
+        torch.cuda.synchronize()
+
+    def start(self):
+        for h in self.groups:
+            h.launch()
+
+    def advance(self, g, relaunch=True):
+        h = self.groups[g]
+        out = h.wait()
+        if relaunch:
+            h.launch()
+        return out
+
+    def drain(self):
+        return [h.wait() if h.in_flight else None for h in self.groups]

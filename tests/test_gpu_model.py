@@ -311,3 +311,32 @@ def test_env_edge_sizes(E, N, H):
             assert np.array_equal(fov[e], o["fov"].astype(np.float32))
             assert np.array_equal(adj[e], o["adj_matrix"].astype(np.float32))
             alive[e] = not d
+
+
+def test_pipelined_host_rollout_matches_device_rollout():
+    """PipelinedHostRollout: groups stepped with overlapping host round trips walk the same trajectories as one
+    on-device Rollout over all episodes (episodes are independent)."""
+    import mapf_gnn_b200 as m
+    E, N, H, M = 90, 5, 18, 5
+    rng = np.random.default_rng(21)
+    starts, goals, obst = m.make_scenarios(rng, E, N, H, M)
+    cfg = model_config("gnn_k3", N, board_size=[H, H])
+    net = load_network("gnn_k3").eval()
+    env = m.BatchedGraphEnv(cfg, goals, starts, obst)
+    ro = m.Rollout(net, env)
+    assert m.PipelinedHostRollout.round_aligned_sizes(4096, 5, 2, 148) == [1894, 2202]
+    assert m.PipelinedHostRollout.round_aligned_sizes(90, 5, 3, 148) == [30, 30, 30]
+    pl = m.PipelinedHostRollout(net, cfg, goals, starts, obst, groups=3)
+    assert [s.stop - s.start for s in pl.slices] == [30, 30, 30]
+    pl.start()
+    for t in range(5):
+        ro.run(1)
+        for g, sl in enumerate(pl.slices):
+            actions, pos_out, done = pl.advance(g, relaunch=t < 4)
+            assert torch.equal(actions, ro.actions.cpu()[sl]) and torch.equal(pos_out, env.pos.cpu()[sl])
+            assert torch.equal(done, env.done.cpu()[sl])
+    assert pl.drain() == [None, None, None]
+    pl.reset()
+    assert torch.equal(pl.envs[1].pos.cpu(), torch.as_tensor(starts[30:60]).int())
+    with pytest.raises(RuntimeError):
+        pl.groups[0].wait()
