@@ -7,8 +7,12 @@ from __future__ import annotations
 import numpy as np
 
 
-def make_scenarios(rng: np.random.Generator, episodes, num_agents, board_size, num_obstacles, chunk=4096):
-    """Returns starts int32[E,N,2], goals int32[E,N,2], obstacles int32[E,M,2] as (x, y)."""
+def make_scenarios(rng: np.random.Generator, episodes, num_agents, board_size, num_obstacles, chunk=4096,
+                   goals_ignore_obstacles=False):
+    """Returns starts int32[E,N,2], goals int32[E,N,2], obstacles int32[E,M,2] as (x, y).
+
+    ``goals_ignore_obstacles=True`` is the train-time validation order (train.py:111-112): goals are drawn first and
+    independently of the obstacles, so a goal may lie under an obstacle (that agent can then never finish)."""
     H = int(board_size)
     cells = H * H
     N, M = int(num_agents), int(num_obstacles)
@@ -23,6 +27,8 @@ def make_scenarios(rng: np.random.Generator, episodes, num_agents, board_size, n
         # the first N obstacle-free cells of the second order
         order = np.argsort(rng.random((hi - lo, cells), dtype=np.float32), axis=1)
         o, g = order[:, :M], order[:, M:M + N]
+        if goals_ignore_obstacles:
+            g = np.argsort(rng.random((hi - lo, cells), dtype=np.float32), axis=1)[:, :N]
         is_obst = np.zeros((hi - lo, cells), dtype=bool)
         np.put_along_axis(is_obst, o, True, axis=1)
         key = rng.random((hi - lo, cells), dtype=np.float32) + is_obst * 2.0

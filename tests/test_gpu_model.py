@@ -217,7 +217,18 @@ def test_evaluator_with_device_scenarios():
     net = load_network("gnn_k3").eval()
     s1, p1 = m.evaluate(net, cfg, episodes=300, seed=3, device_scenarios=True)
     s2, p2 = m.evaluate(net, cfg, episodes=300, seed=3, device_scenarios=True)
-    assert s1 == s2 and np.array_equal(p1["flow_time"], p2["flow_time"])
+    strip = lambda d: {k: v for k, v in d.items() if k != "batch_time_s"}
+    assert strip(s1) == strip(s2) and np.array_equal(p1["flow_time"], p2["flow_time"])
+    from mapf_gnn_b200.evaluate import results_dict
+    import json
+    doc = json.loads(json.dumps(results_dict(cfg, s1, p1)))                  # evaluate.py:401-422 schema
+    assert set(doc) == {"timestamp", "config", "summary", "episodes"} and len(doc["episodes"]) == 300
+    assert set(doc["episodes"][0]) == {"success_rate", "flow_time", "steps_taken", "inference_time_ms", "episode_time_s",
+                                       "collisions", "agents_at_goal", "total_agents"}
+    assert set(doc["summary"]) == {"complete_success", "avg_success_rate", "std_success_rate", "avg_flow_time", "avg_steps",
+                                   "avg_inference_ms"}
+    sv, pv = m.evaluate(net, cfg, episodes=300, seed=3, validation=True)      # train.py:105-141: max_steps, no +10
+    assert pv["steps_taken"].max() <= cfg["max_steps"] and 0.0 <= sv["avg_success_rate"] <= 1.0
     s3, _ = m.evaluate(net, cfg, episodes=300, seed=3)
     assert abs(s1["avg_success_rate"] - s3["avg_success_rate"]) < 0.12      # same distribution family
 
