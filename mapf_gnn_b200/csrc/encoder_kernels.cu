@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace {
 
@@ -178,8 +179,28 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
   float* const s_b1 = s_b0 + d.buf0_floats;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < (d.w_floats >> 2); i += kEncThreads)
-    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(packed) + i);
+  // Weights -> shared memory by TMA bulk copies issued by one thread: the conv filters (first barrier) are needed
+  // before conv1 of the first item, the FC matrix (second barrier) only at its FC, so most of the 120 KB lands while
+  // the first convolutions run.
+  __shared__ __align__(8) uint64_t s_wbar[2];
+  const uint32_t conv_bytes = uint32_t(L.fc_wt) * 4u, all_bytes = uint32_t(d.w_floats) * 4u;
+  if (tid == 0) {
+    tc::mbar_init(&s_wbar[0], 1);
+    tc::mbar_init(&s_wbar[1], 1);
+    tc::fence_mbar_init();
+    constexpr uint32_t kChunk = 16 * 1024;
+    tc::mbar_expect_tx(&s_wbar[0], conv_bytes);
+    for (uint32_t o = 0; o < conv_bytes; o += kChunk)
+      tc::bulk_g2s(reinterpret_cast<char*>(s_w) + o, reinterpret_cast<const char*>(packed) + o,
+                   conv_bytes - o < kChunk ? conv_bytes - o : kChunk, &s_wbar[0]);
+    tc::mbar_arrive(&s_wbar[0]);
+    tc::mbar_expect_tx(&s_wbar[1], all_bytes - conv_bytes);
+    for (uint32_t o = conv_bytes; o < all_bytes; o += kChunk)
+      tc::bulk_g2s(reinterpret_cast<char*>(s_w) + o, reinterpret_cast<const char*>(packed) + o,
+                   all_bytes - o < kChunk ? all_bytes - o : kChunk, &s_wbar[1]);
+    tc::mbar_arrive(&s_wbar[1]);
+  }
+  __syncthreads();   // barrier words initialised before anyone polls them
 
   float* const s_st = s_b1 + d.buf1_floats;     // [32][50] image staging, filled by cp.async one item ahead
 
@@ -234,6 +255,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
     item_rows(item, row0, nrows);
     asm volatile("cp.async.wait_group 0;\n" ::);
     ENC_SYNC(0);
+    tc::mbar_wait(&s_wbar[0], 0);   // conv filters resident (returns at once after the first item)
 
     bool in1 = true;  // current activations live in s_b1
     if (item < nfull) {
@@ -265,6 +287,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
         ENC_SYNC(1 + l);
       }
     }
+    tc::mbar_wait(&s_wbar[1], 0);           // FC matrix resident
     const float* act = in1 ? s_b1 : s_b0;   // [fc_in][32]
     float* scratch = in1 ? s_b0 : s_b1;     // free buffer: split-K partials [128 threads][16]
 
@@ -450,7 +473,7 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   d.buf0_floats = b0 * kEncAgents;
   d.buf1_floats = b1 * kEncAgents;
   const size_t act_bytes = size_t(d.buf0_floats + d.buf1_floats + kEncAgents * kFovFloats) * sizeof(float);
-  const size_t limit = 227 * 1024;
+  const size_t limit = 227 * 1024 - 64;   // minus the kernel's static shared memory (two mbarriers)
   d.fc_in_smem = (size_t(L.gf_wt) * sizeof(float) + act_bytes <= limit) ? 1 : 0;
   d.w_floats = int(d.fc_in_smem ? L.gf_wt : L.fc_wt);
   const size_t smem = size_t(d.w_floats) * sizeof(float) + act_bytes;
