@@ -232,6 +232,23 @@ __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __rest
   }
 }
 
+// 128-bit variant for C*25 % 4 == 0 (a row's C*25 floats are 16-byte aligned, so a float4 never leaves its row)
+__global__ void bn_apply4_kernel(const float4* __restrict__ u, const float* __restrict__ scale_shift, int N, int C,
+                                 int64_t rows, float4* __restrict__ a) {
+  const uint32_t row4 = uint32_t(C * kFovCells) >> 2;
+  const int64_t total = rows * row4;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / row4;
+    const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
+    const float2* tab = reinterpret_cast<const float2*>(scale_shift) + n * C;
+    const float4 v = u[idx];
+    const float2 w0 = __ldg(tab + o / kFovCells), w1 = __ldg(tab + (o + 1) / kFovCells);
+    const float2 w2 = __ldg(tab + (o + 2) / kFovCells), w3 = __ldg(tab + (o + 3) / kFovCells);
+    a[idx] = make_float4(fmaxf(fmaf(v.x, w0.x, w0.y), 0.0f), fmaxf(fmaf(v.y, w1.x, w1.y), 0.0f),
+                         fmaxf(fmaf(v.z, w2.x, w2.y), 0.0f), fmaxf(fmaf(v.w, w3.x, w3.y), 0.0f));
+  }
+}
+
 // sums over (batch, pixels) per (slot, channel) of dy and dy*xhat, dy = da * [a > 0]
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ a,
                                                             const float* __restrict__ u,
@@ -286,6 +303,86 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restr
     const float xhat = (u[idx] - mi.x) * mi.y;
     da[idx] = k.x * (dy - k.y - xhat * k.z);
   }
+}
+
+__global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __restrict__ a, const float4* __restrict__ u,
+                                     const float* __restrict__ meaninv, const float* __restrict__ coef, int N, int C,
+                                     int64_t rows) {
+  const uint32_t row4 = uint32_t(C * kFovCells) >> 2;
+  const int64_t total = rows * row4;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / row4;
+    const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
+    const float4 av = a[idx], dv = da[idx], uv = u[idx];
+    const float aa[4] = {av.x, av.y, av.z, av.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t c = (o + j) / kFovCells;
+      const float2 mi = __ldg(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
+      const float4 k = __ldg(reinterpret_cast<const float4*>(coef) + (n * C + c));
+      const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
+      const float xhat = (uu[j] - mi.x) * mi.y;
+      r[j] = k.x * (dy - k.y - xhat * k.z);
+    }
+    da[idx] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// bn_bwd_reduce for C*25 % 4 == 0: one CTA per (32 batch rows, slot); thread t < 2*row4 owns the float4 column
+// t % row4 of the rows of its parity, so every warp reads whole 512-byte pieces of a row; a float4 touches at most two
+// channels, whose partial sums meet in shared memory before one fp64 atomic per (CTA, channel).
+__global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __restrict__ da, const float4* __restrict__ a,
+                                                             const float4* __restrict__ u,
+                                                             const float* __restrict__ meaninv, int B, int N, int C,
+                                                             int stat_c, double* __restrict__ stats) {
+  __shared__ float s_sum[64 * 2];
+  const int n = blockIdx.y, b0 = blockIdx.x * 32;
+  const int nb = min(32, B - b0);
+  const int row4 = (C * kFovCells) >> 2;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) s_sum[i] = 0.0f;
+  __syncthreads();
+  const int groups = blockDim.x / row4;                 // row-parity groups that fit the CTA (2 for C = 16)
+  const int grp = threadIdx.x / row4, f4 = threadIdx.x - grp * row4;
+  if (grp < groups) {
+    const int o = f4 * 4;
+    int ch[4];
+    float mean[4], inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ch[j] = (o + j) / kFovCells;
+      mean[j] = meaninv[(n * C + ch[j]) * 2];
+      inv[j] = meaninv[(n * C + ch[j]) * 2 + 1];
+    }
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int r = grp; r < nb; r += groups) {
+      const int64_t idx = (int64_t(b0 + r) * N + n) * row4 + f4;
+      const float4 av = a[idx], dv = da[idx], uv = u[idx];
+      const float aa[4] = {av.x, av.y, av.z, av.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
+        s1[j] += dy;
+        s2[j] = fmaf(dy, (uu[j] - mean[j]) * inv[j], s2[j]);
+      }
+    }
+    // elements of the same channel first (a float4 spans at most two channels)
+    float c0s1 = s1[0], c0s2 = s2[0], c1s1 = 0.f, c1s2 = 0.f;
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      if (ch[j] == ch[0]) { c0s1 += s1[j]; c0s2 += s2[j]; } else { c1s1 += s1[j]; c1s2 += s2[j]; }
+    }
+    atomicAdd(&s_sum[ch[0] * 2], c0s1);
+    atomicAdd(&s_sum[ch[0] * 2 + 1], c0s2);
+    if (ch[3] != ch[0]) {
+      atomicAdd(&s_sum[ch[3] * 2], c1s1);
+      atomicAdd(&s_sum[ch[3] * 2 + 1], c1s2);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
+    atomicAdd(stats + (int64_t(n) * stat_c + (i >> 1)) * 2 + (i & 1), double(s_sum[i]));
 }
 
 __global__ void bn_param_grads_kernel(const double* __restrict__ stats, int N, int C, int stat_c,
@@ -718,8 +815,12 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
                                                       const_cast<float*>(p->bn_var[l]), a->bn_batches[l], p->bn_gamma[l],
                                                       p->bn_beta[l], ws + T.scsh[l]);
     const int64_t planes = rows * cout;
-    bn_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(ws + T.u[l], ws + T.scsh[l], N,
-                                                                                      cout, planes, ws + T.a[l]);
+    if ((cout * kFovCells) % 4 == 0)
+      bn_apply4_kernel<<<unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16)), 256, 0, s>>>(
+          reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.scsh[l], N, cout, rows, reinterpret_cast<float4*>(ws + T.a[l]));
+    else
+      bn_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(ws + T.u[l], ws + T.scsh[l], N,
+                                                                                        cout, planes, ws + T.a[l]);
   }
   MAPF_TRY(mapf_launch_status());
   const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
@@ -822,12 +923,23 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     const int cin = p->channels[l], cout = p->channels[l + 1];
     double* st = stat + int64_t(l) * N * T.cmax * 2;
     dim3 grid((B + 31) / 32, N);
-    bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
+    const bool vec4 = (cout * kFovCells) % 4 == 0 && cout * kFovCells / 4 <= 256 && cout <= 64;
+    if (vec4)
+      bn_bwd_reduce4_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]),
+                                                 reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.meaninv[l], B, N, cout,
+                                                 T.cmax, st);
+    else
+      bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
     bn_bwd_coef_kernel<<<(N * cout + 127) / 128, 128, 0, s>>>(st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
                                                              ws + T.coef[l]);
     const int64_t planes = rows * cout;
-    bn_bwd_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(
-        da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
+    if ((cout * kFovCells) % 4 == 0)
+      bn_bwd_apply4_kernel<<<unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16)), 256, 0, s>>>(
+          reinterpret_cast<float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]), reinterpret_cast<const float4*>(ws + T.u[l]),
+          ws + T.meaninv[l], ws + T.coef[l], N, cout, rows);
+    else
+      bn_bwd_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(
+          da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
     bn_param_grads_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
       const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
