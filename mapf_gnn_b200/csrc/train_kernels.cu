@@ -105,7 +105,10 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
 }
 
 // ---------------------------------------------------------------------------------------------
-// conv3x3 over one agent slot: grid (ceil(B/32), N), lane = batch item, warp = 4 output channels
+// conv3x3 over one agent slot: grid (ceil(B/32), N), lane = batch item, warp = 4 output channels.  The 32 input images
+// are staged transposed ([cin*25][33], conflict-free both ways), the packed filters sit in shared memory, and every lane
+// stores its 4 finished channels (100 contiguous floats of its row) straight from registers, so a CTA needs
+// (cin*25*33 + cout*cin*9) floats and three of them fit an SM.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCtThreads = 128;
 constexpr int kCtPad = 33;
@@ -116,15 +119,31 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
                                                                 float* __restrict__ out, double* __restrict__ stats,
                                                                 int stat_c) {
   extern __shared__ __align__(16) float s_ct[];
-  float* s_in = s_ct;                               // [cin*25][33]
-  float* s_out = s_ct + cin * kFovCells * kCtPad;   // [cout*25][33]
+  float* s_w = s_ct;                                 // [cout/4][cin][9][4]
+  float* s_in = s_ct + ((cout * cin * 9 + 3) & ~3);  // [cin*25][33]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y, b0 = blockIdx.x * 32;
   const int nb = min(32, B - b0);
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
-  for (int idx = tid; idx < 32 * in_len; idx += kCtThreads) {
-    const int r = idx / in_len, i = idx - r * in_len;
-    s_in[i * kCtPad + r] = r < nb ? __ldg(in + (int64_t(b0 + r) * N + n) * in_len + i) : 0.0f;
+  for (int i = tid; i < cout * cin * 9; i += kCtThreads) s_w[i] = __ldg(wpk + i);
+  {
+    // staging: 8 independent global loads in flight per thread before the transposing stores
+    const int total = 32 * in_len;
+    for (int base = 0; base < total; base += kCtThreads * 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = base + k * kCtThreads + tid;
+        const int r = idx / in_len, i = idx - r * in_len;
+        v[k] = (idx < total && r < nb) ? __ldg(in + (int64_t(b0 + r) * N + n) * in_len + i) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = base + k * kCtThreads + tid;
+        const int r = idx / in_len, i = idx - r * in_len;
+        if (idx < total) s_in[i * kCtPad + r] = v[k];
+      }
+    }
   }
   __syncthreads();
   for (int cog = warp; cog < (cout >> 2); cog += kCtThreads / 32) {
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
 #pragma unroll
       for (int p = 0; p < kFovCells; ++p) { acc[0][p] = make_float2(b.x, b.y); acc[1][p] = make_float2(b.z, b.w); }
     }
-    const float4* wp = reinterpret_cast<const float4*>(wpk) + int64_t(cog) * cin * 9;
+    const float4* wp = reinterpret_cast<const float4*>(s_w) + cog * cin * 9;
 #pragma unroll 1
     for (int ci = 0; ci < cin; ++ci) {
       float v[kFovCells];
@@ -143,7 +162,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
       for (int p = 0; p < kFovCells; ++p) v[p] = s_in[(ci * kFovCells + p) * kCtPad + lane];
       float4 wv[9];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) wv[t] = __ldg(wp + ci * 9 + t);
+      for (int t = 0; t < 9; ++t) wv[t] = wp[ci * 9 + t];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -161,32 +180,38 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
               }
             }
     }
+    // the lane's row holds its 4 channels as 100 contiguous floats (16-byte aligned: row and channel offsets are
+    // multiples of 100 floats)
+    float4* dst = reinterpret_cast<float4*>(out + (int64_t(b0 + lane) * N + n) * out_len + cog * 4 * kFovCells);
+    float flat[4 * kFovCells];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float s1 = 0.0f;
-      double s2 = 0.0;
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int p = 0; p < kFovCells; ++p) {
-        const float val = (c & 1) ? acc[c >> 1][p].y : acc[c >> 1][p].x;
-        s_out[((cog * 4 + c) * kFovCells + p) * kCtPad + lane] = val;
-        s1 += val;
-        s2 += double(val) * double(val);
-      }
-      if (stats != nullptr) {
+      for (int p = 0; p < kFovCells; ++p) flat[c * kFovCells + p] = (c & 1) ? acc[c >> 1][p].y : acc[c >> 1][p].x;
+    if (lane < nb) {
+#pragma unroll
+      for (int q = 0; q < kFovCells; ++q) dst[q] = make_float4(flat[4 * q], flat[4 * q + 1], flat[4 * q + 2], flat[4 * q + 3]);
+    }
+    if (stats != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float s1 = 0.0f;
+        double s2 = 0.0;
+#pragma unroll
+        for (int p = 0; p < kFovCells; ++p) {
+          const float val = flat[c * kFovCells + p];
+          s1 += val;
+          s2 += double(val) * double(val);
+        }
         const double t1 = warp_sum(lane < nb ? double(s1) : 0.0);
         const double t2 = warp_sum(lane < nb ? s2 : 0.0);
         if (lane == 0) {
-          double* dst = stats + (int64_t(n) * stat_c + cog * 4 + c) * 2;
-          atomicAdd(dst, t1);
-          atomicAdd(dst + 1, t2);
+          double* dstat = stats + (int64_t(n) * stat_c + cog * 4 + c) * 2;
+          atomicAdd(dstat, t1);
+          atomicAdd(dstat + 1, t2);
         }
       }
     }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < nb * out_len; idx += kCtThreads) {
-    const int r = idx / out_len, i = idx - r * out_len;
-    out[(int64_t(b0 + r) * N + n) * out_len + i] = s_out[i * kCtPad + r];
   }
 }
 
@@ -755,7 +780,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, f
 
 int launch_conv_train(cudaStream_t s, const float* in, int cin, int cout, int B, int N, const float* wpk,
                       const float* bias, float* out, double* stats, int stat_c) {
-  const size_t smem = sizeof(float) * size_t(cin + cout) * kFovCells * kCtPad;
+  const size_t smem = sizeof(float) * (size_t(cin) * kFovCells * kCtPad + ((size_t(cout) * cin * 9 + 3) & ~size_t(3)));
   if (smem > 220 * 1024) return MAPF_ERR_UNSUPPORTED;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_train_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
