@@ -107,6 +107,16 @@ static inline bool mapf_ensure_smem(F func, size_t bytes, int* cache /* [16] zer
 
 // Packed fp32 FMA (Blackwell FFMA2): {d.x, d.y} = a * {w.x, w.y} + {d.x, d.y}, two IEEE fp32 FMAs in one issue slot.
 // ptxas folds the duplicated multiplicand into the scalar-broadcast operand form (FFMA2 Rd, Ra.F32, Rb.F32x2, Rc.F32x2).
+// Fully packed form: {d.x, d.y} += {a.x * b.x, a.y * b.y}.
+__device__ __forceinline__ void mapf_ffma2_pp(float2& d, const float2& a, const float2& b) {
+  unsigned long long A, B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(d.x), "f"(d.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(C) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(C));
+}
+
 __device__ __forceinline__ void mapf_ffma2(float2& d, float a, const float2& w) {
   unsigned long long A, B, C;
   asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a), "f"(a));

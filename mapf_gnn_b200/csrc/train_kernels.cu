@@ -110,6 +110,14 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
 // stores its 4 finished channels (100 contiguous floats of its row) straight from registers, so a CTA needs
 // (cin*25*33 + cout*cin*9) floats and three of them fit an SM.
 // ---------------------------------------------------------------------------------------------
+// 4-byte asynchronous global -> shared copy: no register staging, so a thread keeps its whole share of a tile in flight
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst_smem))), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 constexpr int kCtThreads = 128;
 constexpr int kCtPad = 33;
 
@@ -127,23 +135,18 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
   for (int i = tid; i < cout * cin * 9; i += kCtThreads) s_w[i] = __ldg(wpk + i);
   {
-    // staging: 8 independent global loads in flight per thread before the transposing stores
-    const int total = 32 * in_len;
-    for (int base = 0; base < total; base += kCtThreads * 8) {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int idx = base + k * kCtThreads + tid;
-        const int r = idx / in_len, i = idx - r * in_len;
-        v[k] = (idx < total && r < nb) ? __ldg(in + (int64_t(b0 + r) * N + n) * in_len + i) : 0.0f;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int idx = base + k * kCtThreads + tid;
-        const int r = idx / in_len, i = idx - r * in_len;
-        if (idx < total) s_in[i * kCtPad + r] = v[k];
+    // staging: every element is its own 4-byte cp.async (coalesced reads, transposing conflict-free writes), all of a
+    // thread's ~100 copies in flight at once
+    // (warp -> rows, lane -> elements: no index division in the loop)
+    for (int r = warp; r < 32; r += kCtThreads / 32) {
+      const float* src = in + (int64_t(b0 + r) * N + n) * in_len;
+      if (r < nb) {
+        for (int i = lane; i < in_len; i += 32) cp_async4(s_in + i * kCtPad + r, src + i);
+      } else {
+        for (int i = lane; i < in_len; i += 32) s_in[i * kCtPad + r] = 0.0f;
       }
     }
+    cp_async_wait_all();
   }
   __syncthreads();
   for (int cog = warp; cog < (cout >> 2); cog += kCtThreads / 32) {
@@ -424,52 +427,71 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ stats, int N, i
 }
 
 // dW[co][ci][tap] = sum_{rows, pixels} du[r][co][p] * in[r][ci][p + tap], db[co] = sum du
+// Persistent over tiles of 32 rows; thread = (co, ci) pair with its 9 tap sums in registers.  Rows are staged in PAIRS
+// ([16][len][2]) so that one LDS.64 fetches the same element of two rows and one packed FFMA2 advances the even-row
+// and the odd-row partial sum of a tap together: half the shared-memory wavefronts and half the FMA issue slots of the
+// scalar form.
 constexpr int kCwThreads = 256;
 constexpr int kCwRows = 32;
-constexpr int kCwSlots = 4;
 
-__global__ void __launch_bounds__(kCwThreads) conv_bwd_weight_kernel(const float* __restrict__ du,
-                                                                     const float* __restrict__ in, int cin, int cout,
-                                                                     int64_t rows, float* __restrict__ dw,
-                                                                     float* __restrict__ db) {
+template <int SLOTS>
+__global__ void __launch_bounds__(kCwThreads, SLOTS == 1 ? 2 : 1)
+conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ in, int cin, int cout, int64_t rows,
+                       float* __restrict__ dw, float* __restrict__ db) {
   extern __shared__ __align__(16) float s_cw[];
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
-  float* s_du = s_cw;                       // [32][out_len]
-  float* s_in = s_cw + kCwRows * out_len;   // [32][in_len]
+  float2* s_du = reinterpret_cast<float2*>(s_cw);                          // [16][out_len] (even row, odd row)
+  float2* s_in = reinterpret_cast<float2*>(s_cw) + (kCwRows / 2) * out_len;   // [16][in_len]
   const int tid = threadIdx.x;
   const int npairs = cin * cout;
   const bool small = npairs < kCwThreads;
   const int rstep = small ? kCwThreads / npairs : 1;
   const int rstart = small ? tid / npairs : 0;
   const bool active = small ? tid < npairs * rstep : true;
-  float acc[kCwSlots][9];
-  float accb[kCwSlots];
+  float2 acc[SLOTS][9];
+  float2 accb[SLOTS];
 #pragma unroll
-  for (int s = 0; s < kCwSlots; ++s) {
-    accb[s] = 0.0f;
+  for (int s = 0; s < SLOTS; ++s) {
+    accb[s] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[s][t] = 0.0f;
+    for (int t = 0; t < 9; ++t) acc[s][t] = make_float2(0.f, 0.f);
   }
+  auto stage = [&](const float* __restrict__ src, int len, int64_t r0, int nr, float2* dst) {
+    // element k of row 2 rp + h -> dst[rp][k].{x,y}: 4-byte cp.async each (coalesced reads), all in flight at once
+    // (warp -> rows, lane -> elements: no index division in the loop)
+    float* d1 = reinterpret_cast<float*>(dst);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < kCwRows; r += kCwThreads / 32) {
+      float* drow = d1 + int64_t(r >> 1) * len * 2 + (r & 1);
+      const float* srow = src + (r0 + r) * len;
+      if (r < nr) {
+        for (int k = lane; k < len; k += 32) cp_async4(drow + 2 * k, srow + k);
+      } else {
+        for (int k = lane; k < len; k += 32) drow[2 * k] = 0.0f;
+      }
+    }
+  };
   const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * kCwRows;
     const int nr = (rows - r0) < kCwRows ? int(rows - r0) : kCwRows;
     __syncthreads();
-    for (int idx = tid; idx < nr * out_len; idx += kCwThreads) s_du[idx] = __ldg(du + r0 * out_len + idx);
-    for (int idx = tid; idx < nr * in_len; idx += kCwThreads) s_in[idx] = __ldg(in + r0 * in_len + idx);
+    stage(du, out_len, r0, nr, s_du);
+    stage(in, in_len, r0, nr, s_in);
+    cp_async_wait_all();
     __syncthreads();
     if (!active) continue;
 #pragma unroll
-    for (int s = 0; s < kCwSlots; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       const int pp = small ? tid % npairs : tid + s * kCwThreads;
       if (pp >= npairs || (small && s > 0)) break;
       const int co = pp / cin, ci = pp - co * cin;
-      for (int r = rstart; r < nr; r += rstep) {
-        float d[kFovCells], v[kFovCells];
+      for (int rp = rstart; rp < kCwRows / 2; rp += rstep) {
+        float2 d[kFovCells], v[kFovCells];
 #pragma unroll
         for (int p = 0; p < kFovCells; ++p) {
-          d[p] = s_du[r * out_len + co * kFovCells + p];
-          v[p] = s_in[r * in_len + ci * kFovCells + p];
+          d[p] = s_du[rp * out_len + co * kFovCells + p];
+          v[p] = s_in[rp * in_len + ci * kFovCells + p];
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
@@ -481,24 +503,24 @@ __global__ void __launch_bounds__(kCwThreads) conv_bwd_weight_kernel(const float
               for (int x = 0; x < kFov; ++x) {
                 const int yy = y + ky - 1, xx = x + kx - 1;
                 if (yy >= 0 && yy < kFov && xx >= 0 && xx < kFov)
-                  acc[s][ky * 3 + kx] = fmaf(d[y * kFov + x], v[yy * kFov + xx], acc[s][ky * 3 + kx]);
+                  mapf_ffma2_pp(acc[s][ky * 3 + kx], d[y * kFov + x], v[yy * kFov + xx]);
               }
         if (ci == 0) {
 #pragma unroll
-          for (int p = 0; p < kFovCells; ++p) accb[s] += d[p];
+          for (int p = 0; p < kFovCells; ++p) { accb[s].x += d[p].x; accb[s].y += d[p].y; }
         }
       }
     }
   }
   if (!active) return;
 #pragma unroll
-  for (int s = 0; s < kCwSlots; ++s) {
+  for (int s = 0; s < SLOTS; ++s) {
     const int pp = small ? tid % npairs : tid + s * kCwThreads;
     if (pp >= npairs || (small && s > 0)) break;
     const int co = pp / cin, ci = pp - co * cin;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(dw + int64_t(pp) * 9 + t, acc[s][t]);
-    if (ci == 0 && db != nullptr) atomicAdd(db + co, accb[s]);
+    for (int t = 0; t < 9; ++t) atomicAdd(dw + int64_t(pp) * 9 + t, acc[s][t].x + acc[s][t].y);
+    if (ci == 0 && db != nullptr) atomicAdd(db + co, accb[s].x + accb[s].y);
   }
 }
 
@@ -801,7 +823,7 @@ int check_train(const mapf_net_params* p, int B, int N) {
   MAPF_REQUIRE(B > 0 && N > 0, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(N <= 64 && N <= 65535, MAPF_ERR_UNSUPPORTED);
   for (int l = 0; l < p->num_conv; ++l)
-    MAPF_REQUIRE(p->channels[l] * p->channels[l + 1] <= kCwSlots * kCwThreads, MAPF_ERR_UNSUPPORTED);
+    MAPF_REQUIRE(p->channels[l] * p->channels[l + 1] <= 4 * kCwThreads, MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(p->fc_out <= 256 && p->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
   return MAPF_OK;
 }
@@ -969,12 +991,19 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     {
       const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
       MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
-      if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel, size_t(smem), cache__); }())
-        return MAPF_ERR_CUDA;
+      MAPF_REQUIRE(cin * cout <= 4 * kCwThreads, MAPF_ERR_UNSUPPORTED);
       const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
       const int gridw = int(mapf_min64(ntiles, 2 * 148));
-      conv_bwd_weight_kernel<<<gridw, kCwThreads, smem, s>>>(da, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, rows,
-                                                            G.conv_w[l], G.conv_b[l]);
+      const float* lin = l == 0 ? a->states : ws + T.a[l - 1];
+      if (cin * cout <= kCwThreads) {
+        if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<1>, size_t(smem), cache__); }())
+          return MAPF_ERR_CUDA;
+        conv_bwd_weight_kernel<1><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, G.conv_w[l], G.conv_b[l]);
+      } else {
+        if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<4>, size_t(smem), cache__); }())
+          return MAPF_ERR_CUDA;
+        conv_bwd_weight_kernel<4><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, G.conv_w[l], G.conv_b[l]);
+      }
     }
     if (l > 0) {
       // data gradient = the same 3x3 convolution with mirrored, transposed filters

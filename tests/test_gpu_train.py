@@ -180,6 +180,10 @@ def test_cuda_graph_trainer_matches_eager(train_step):
             # the batch mean contains the conv bias, which random-walks by +-lr per step (noise gradients)
             assert np.abs(a.cpu().numpy() - b.cpu().numpy()).max() < 4 * 4 * 3e-4, k
         else:
-            # the two trainers differ only in the order of the atomic fp32/fp64 partial sums; Adam's m / sqrt(v)
-            # amplifies that noise for parameters with tiny gradients (seen up to 1.5e-4 after 4 steps)
-            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-4, k
+            # The two trainers differ only in the order of the atomic fp32/fp64 partial sums.  Adam's m / sqrt(v) turns
+            # that rounding noise into a +-lr step for the few elements whose gradient is at noise level (sign flip),
+            # so: all but a handful of elements agree to 1e-4, and no element is further apart than the 4 steps allow.
+            an, bn_ = a.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)
+            diff, scale = np.abs(an - bn_), max(np.abs(bn_).max(), 1e-12)
+            assert (diff > 1e-4 * scale).mean() < 5e-3, k
+            assert diff.max() <= 2 * 4 * 3e-4 + 1e-4 * scale, k
