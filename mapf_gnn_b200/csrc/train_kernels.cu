@@ -29,6 +29,7 @@ struct TrainLayout {
   int64_t u[MAPF_MAX_CONV], a[MAPF_MAX_CONV]; // pre-BN conv outputs, post BN+ReLU activations [rows][C*25]
   int64_t x, z, y;                            // [rows][F], [rows][KT], [rows][G]
   int64_t dy, dz, dx, da0, da1;
+  int64_t dwpart;                             // [grid <= 296][max cin*cout*9 + cmax] per-CTA weight-gradient partials
   int64_t total;
   int cmax;
 };
@@ -68,6 +69,12 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
   T.dx = take(rows * p.fc_out);
   T.da0 = take(rows * cmax * 25);
   T.da1 = take(rows * cmax * 25);
+  {
+    int64_t maxp = 0;
+    for (int l = 0; l < p.num_conv; ++l) maxp = max(maxp, int64_t(p.channels[l]) * p.channels[l + 1]);
+    const int64_t grid = mapf_min64((rows + 31) / 32, 2 * 148);
+    T.dwpart = take(grid * (maxp * 9 + cmax));
+  }
   T.total = off;
   return T;
 }
@@ -437,7 +444,7 @@ constexpr int kCwRows = 32;
 template <int SLOTS>
 __global__ void __launch_bounds__(kCwThreads, SLOTS == 1 ? 2 : 1)
 conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ in, int cin, int cout, int64_t rows,
-                       float* __restrict__ dw, float* __restrict__ db) {
+                       float* __restrict__ part) {
   extern __shared__ __align__(16) float s_cw[];
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
   float2* s_du = reinterpret_cast<float2*>(s_cw);                          // [16][out_len] (even row, odd row)
@@ -512,16 +519,54 @@ conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ i
       }
     }
   }
-  if (!active) return;
+  // Per-CTA partial sums go to part[blockIdx.x][npairs*9 + cout] (fixed order inside the CTA); a second kernel adds the
+  // CTAs in index order: no atomics (2 300 same-address atomics per filter tap cost more than the convolution itself
+  // when cin*cout is small) and a reproducible gradient.
+  float* mine = part + int64_t(blockIdx.x) * (npairs * 9 + cout);
+  if (small) {
+    float* s_red = s_cw;                       // [rstep][npairs][10]
+    __syncthreads();
+    if (active) {
+      float* dst = s_red + (int64_t(rstart) * npairs + tid % npairs) * 10;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) dst[t] = acc[0][t].x + acc[0][t].y;
+      dst[9] = accb[0].x + accb[0].y;
+    }
+    __syncthreads();
+    if (tid < npairs) {
+      float sum[10];
+#pragma unroll
+      for (int t = 0; t < 10; ++t) sum[t] = 0.0f;
+      for (int g = 0; g < rstep; ++g)
+#pragma unroll
+        for (int t = 0; t < 10; ++t) sum[t] += s_red[(int64_t(g) * npairs + tid) * 10 + t];
+      const int co = tid / cin, ci = tid - co * cin;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) mine[tid * 9 + t] = sum[t];
+      if (ci == 0) mine[npairs * 9 + co] = sum[9];
+    }
+    return;
+  }
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
-    const int pp = small ? tid % npairs : tid + s * kCwThreads;
-    if (pp >= npairs || (small && s > 0)) break;
+    const int pp = tid + s * kCwThreads;
+    if (pp >= npairs) break;
     const int co = pp / cin, ci = pp - co * cin;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(dw + int64_t(pp) * 9 + t, acc[s][t].x + acc[s][t].y);
-    if (ci == 0 && db != nullptr) atomicAdd(db + co, accb[s].x + accb[s].y);
+    for (int t = 0; t < 9; ++t) mine[pp * 9 + t] = acc[s][t].x + acc[s][t].y;
+    if (ci == 0) mine[npairs * 9 + co] = accb[s].x + accb[s].y;
   }
+}
+
+// dw[e] += sum over CTAs (in index order) of part[g][e]; the last `cout` entries are the bias gradient
+__global__ void conv_bwd_weight_reduce_kernel(const float* __restrict__ part, int grid, int nw, int cout,
+                                              float* __restrict__ dw, float* __restrict__ db) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nw + cout) return;
+  float sum = 0.0f;
+  for (int g = 0; g < grid; ++g) sum += part[int64_t(g) * (nw + cout) + e];
+  if (e < nw) dw[e] += sum;
+  else if (db != nullptr) db[e - nw] += sum;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -995,15 +1040,18 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
       const int gridw = int(mapf_min64(ntiles, 2 * 148));
       const float* lin = l == 0 ? a->states : ws + T.a[l - 1];
+      float* part = ws + T.dwpart;
       if (cin * cout <= kCwThreads) {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<1>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        conv_bwd_weight_kernel<1><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, G.conv_w[l], G.conv_b[l]);
+        conv_bwd_weight_kernel<1><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, part);
       } else {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<4>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        conv_bwd_weight_kernel<4><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, G.conv_w[l], G.conv_b[l]);
+        conv_bwd_weight_kernel<4><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, part);
       }
+      const int nw = cin * cout * 9;
+      conv_bwd_weight_reduce_kernel<<<(nw + cout + 127) / 128, 128, 0, s>>>(part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
     }
     if (l > 0) {
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
