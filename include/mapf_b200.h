@@ -221,7 +221,8 @@ typedef struct {
   const float* packed;
   float* workspace_x;
   float* workspace_z;     /* [B*N, (K+1)*F] floats: enables the tensor-core graph-filter path; NULL = fused FFMA kernel */
-  float* workspace_act;   /* [B*N, fc_in] floats: enables the tensor-core encoder FC; NULL = FC fused in the conv kernel */
+  float* workspace_act;   /* mapf_tc_presplit_a_size(B*N, fc_in) floats, 128-byte aligned: enables the tensor-core encoder
+                           * FC; NULL = FC fused in the conv kernel */
   float* logits;          /* [B,N,A] */
   int32_t* actions;       /* [B,N] or NULL */
 } mapf_policy_fwd_args;
@@ -356,6 +357,14 @@ int mapf_tc_pack_b(const float* b0, int32_t K0, const float* b1, int32_t K1, int
                    mapf_stream_t stream);
 int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
                  const float* bias, int32_t relu, mapf_stream_t stream);
+/* Encoder FC with the A operand pre-split by the conv kernel: mapf_encoder_conv_split_fwd writes the flattened conv
+ * output (framework_gnn.py:160-163) as TF32 hi / lo halves in the tensor-core tile order (mapf_tc_presplit_a_size
+ * floats), mapf_tc_fc_presplit computes relu(A W^T + b) (compressMLP, framework_gnn.py:93) from it with an all-TMA
+ * operand pipeline. */
+int64_t mapf_tc_presplit_a_size(int64_t M, int32_t K);
+int mapf_encoder_conv_split_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream);
+int mapf_tc_fc_presplit(int32_t M, int32_t N, int32_t K, const float* Ap, const float* Bp, float* C, int64_t ldc,
+                        const float* bias, int32_t relu, mapf_stream_t stream);
 int mapf_tc_mix_head(int32_t M, int32_t N, int32_t K, const float* Z, int64_t ldz, const float* Wp, const float* act_w,
                      const float* act_b, int32_t num_actions, float* logits, int32_t* actions, float* y,
                      mapf_stream_t stream);

@@ -167,13 +167,20 @@ __device__ __forceinline__ void conv3x3_relu_half(const float* __restrict__ in, 
 #define ENC_SYNC(phase) __syncthreads()
 #endif
 
-template <bool kFcSmem>
+// kMode 0: FC with the matrix resident in shared memory; 1: FC with the matrix read through L1 (it did not fit);
+// 2: no FC -- the flattened conv output leaves the kernel as the pre-split (TF32 hi | lo), pre-tiled A operand of the
+// tensor-core FC (mapf_tc_fc_presplit): x = Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4].
+constexpr int kSplitPs = 40;   // activation row pitch of the last layer in mode 2 (= 8 mod 32: conflict-free 8x4 reads)
+
+template <int kMode>
 __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims d, PackedLayout L, int64_t rows,
                                                                      int64_t nfull, int nhalf,
                                                                      const float* __restrict__ states,
                                                                      const float* __restrict__ packed,
                                                                      float* __restrict__ x) {
   extern __shared__ __align__(16) float s_enc[];
+  constexpr bool kFcSmem = kMode == 0, kSplit = kMode == 2;
+  constexpr int kLastPs = kSplit ? kSplitPs : kEncAgents;
   float* const s_w = s_enc;                     // packed prefix: conv filters/biases (+ FC matrix and bias)
   float* const s_b0 = s_enc + d.w_floats;
   float* const s_b1 = s_b0 + d.buf0_floats;
@@ -261,12 +268,13 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
     if (item < nfull) {
       // layer 0 reads the staging layout [agent][ci*25 + p]; later layers read [ci*25 + p][agent]
       conv3x3_relu_pair(s_st, kFovCells, 1, lane * kFovFloats, s_b1, s_w + L.conv_w[0], s_w + L.conv_b[0],
-                        d.channels[0], d.channels[1], warp, lane);
+                        d.channels[0], d.channels[1], warp, lane, d.num_conv == 1 ? kLastPs : kEncAgents);
       ENC_SYNC(1);
       prefetch(next_item(item));   // the staging buffer is free: the next images land during conv2 / conv3 / FC
       for (int l = 1; l < d.num_conv; ++l) {
         conv3x3_relu_pair(in1 ? s_b1 : s_b0, kFovCells * kEncAgents, kEncAgents, lane, in1 ? s_b0 : s_b1,
-                          s_w + L.conv_w[l], s_w + L.conv_b[l], d.channels[l], d.channels[l + 1], warp, lane);
+                          s_w + L.conv_w[l], s_w + L.conv_b[l], d.channels[l], d.channels[l + 1], warp, lane,
+                          l == d.num_conv - 1 ? kLastPs : kEncAgents);
         in1 = !in1;
         ENC_SYNC(1 + l);
       }
@@ -280,13 +288,47 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
         const float* src = l == 0 ? s_st : (in1 ? s_b1 : s_b0);
         float* dst = l == 0 ? s_b1 : (in1 ? s_b0 : s_b1);
         conv3x3_relu_half(src, l == 0 ? kFovCells : kFovCells * kHalf, l == 0 ? 1 : kHalf,
-                          l == 0 ? ag * kFovFloats : ag, l == 0 ? 0 : kHalf, dst, last ? kEncAgents : kHalf,
+                          l == 0 ? ag * kFovFloats : ag, l == 0 ? 0 : kHalf, dst, last ? kLastPs : kHalf,
                           last ? (1 << 30) : (d.channels[l + 1] + 1) >> 1, kHalf, s_w + L.conv_w[l], s_w + L.conv_b[l],
                           d.channels[l], d.channels[l + 1], warp, lane);
         if (l > 0) in1 = !in1;
         ENC_SYNC(1 + l);
       }
     }
+    if constexpr (kSplit) {
+      // flatten (C,H,W) -> TF32 hi / lo halves of the FC's A operand, 8 rows x 4 k core matrices: one warp store =
+      // one 128-byte core matrix; element (k, image) sits at act[k * 40 + image], so lane (r8, k4) reads bank 8 k4 + r8
+      const float* act = in1 ? s_b1 : s_b0;
+      const int nch = (d.fc_in + 7) >> 3;
+      float* base = x + (row0 >> 7) * int64_t(nch) * 2048;
+      const int rg0 = int(row0 & 127) >> 3;
+      // lane = (row group, row in group): it gathers the 4 k of one core-matrix row (4 conflict-free LDS: for a fixed
+      // k the warp reads 32 consecutive images) and stores them as one 16-byte piece each of the hi and the lo tile,
+      // so a warp instruction writes four whole 128-byte core matrices.  Full tile: one (chunk, k half) per warp
+      // step; half tile (two row groups): lanes 16-31 take the other k half of the same chunk.
+      const bool full_item = item < nfull;
+      const int r8 = lane & 7;
+      const int rgl = full_item ? lane >> 3 : (lane >> 3) & 1;
+      const int steps = full_item ? nch * 2 : nch;
+#pragma unroll 2
+      for (int u = warp; u < steps; u += kEncWarps) {
+        const int c = full_item ? u >> 1 : u;
+        const int kq = full_item ? u & 1 : lane >> 4;
+        const int k = c * 8 + kq * 4;
+        const float* src = act + k * kSplitPs + rgl * 8 + r8;
+        float4 v;
+        v.x = k + 0 < d.fc_in ? src[0] : 0.0f;
+        v.y = k + 1 < d.fc_in ? src[kSplitPs] : 0.0f;
+        v.z = k + 2 < d.fc_in ? src[2 * kSplitPs] : 0.0f;
+        v.w = k + 3 < d.fc_in ? src[3 * kSplitPs] : 0.0f;
+        float4 hi, lo;
+        tc::split4(v, hi, lo);
+        float* dst = base + int64_t(c) * 2048 + ((rg0 + rgl) * 2 + kq) * 32 + r8 * 4;
+        *reinterpret_cast<float4*>(dst) = hi;
+        *reinterpret_cast<float4*>(dst + 1024) = lo;
+      }
+      ENC_SYNC(4);   // the activation buffers are rewritten by the next item
+    } else {
     tc::mbar_wait(&s_wbar[1], 0);           // FC matrix resident
     const float* act = in1 ? s_b1 : s_b0;   // [fc_in][32]
     float* scratch = in1 ? s_b0 : s_b1;     // free buffer: split-K partials [128 threads][16]
@@ -361,6 +403,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
       }
       ENC_SYNC(5 + (jb >> 6) * 2);  // scratch / staging buffer is rewritten by the next block or tile
     }
+    }  // !kSplit
 #ifdef MAPF_ENC_DEBUG
     ++dbg_tile;
 #endif
@@ -495,13 +538,59 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (d.fc_in_smem) {
     static int cache_a[16] = {0};
-    if (!mapf_ensure_smem(encoder_fwd_kernel<true>, smem, cache_a)) return MAPF_ERR_CUDA;
-    encoder_fwd_kernel<true><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
+    if (!mapf_ensure_smem(encoder_fwd_kernel<0>, smem, cache_a)) return MAPF_ERR_CUDA;
+    encoder_fwd_kernel<0><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
   } else {
     static int cache_b[16] = {0};
-    if (!mapf_ensure_smem(encoder_fwd_kernel<false>, smem, cache_b)) return MAPF_ERR_CUDA;
-    encoder_fwd_kernel<false><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
+    if (!mapf_ensure_smem(encoder_fwd_kernel<1>, smem, cache_b)) return MAPF_ERR_CUDA;
+    encoder_fwd_kernel<1><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
   }
+  return mapf_launch_status();
+}
+
+// Conv stack of the encoder with the flattened output written as the pre-split A operand of mapf_tc_fc_presplit
+// (framework_gnn.py:160-163; the Linear + ReLU of :93 then runs on the tensor cores).  a->x must hold
+// mapf_tc_presplit_a_size(rows, fc_in) floats.
+extern "C" int mapf_encoder_conv_split_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream) {
+  const int st = mapf_check_params(p);
+  if (st != MAPF_OK) return st;
+  MAPF_REQUIRE(a && a->states && a->packed && a->x, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->rows > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(mapf_aligned(a->packed, 16) && mapf_aligned(a->x, 128) && mapf_aligned(a->states, 4), MAPF_ERR_ALIGN);
+  const PackedLayout L = mapf_packed_layout(*p);
+  EncoderDims d;
+  d.num_conv = p->num_conv;
+  for (int l = 0; l <= MAPF_MAX_CONV; ++l) d.channels[l] = l <= p->num_conv ? p->channels[l] : 0;
+  d.fc_in = p->fc_in;
+  d.fc_out = p->fc_out;
+  int b0 = kFovFloats, b1 = 0;
+  for (int l = 0; l < p->num_conv; ++l) {
+    const int pitch = l == p->num_conv - 1 ? kSplitPs : kEncAgents;
+    const int out = (kFovCells * p->channels[l + 1] * pitch + kEncAgents - 1) / kEncAgents;   // in 32-float rows
+    if (l & 1) b0 = max(b0, out); else b1 = max(b1, out);
+  }
+  d.buf0_floats = b0 * kEncAgents;
+  d.buf1_floats = b1 * kEncAgents;
+  d.fc_in_smem = 0;
+  d.w_floats = int(L.fc_wt);
+  const size_t smem = size_t(d.w_floats + d.buf0_floats + d.buf1_floats + kEncAgents * kFovFloats) * sizeof(float);
+  MAPF_REQUIRE(smem <= 227 * 1024 - 64, MAPF_ERR_UNSUPPORTED);
+  const int64_t ntiles = (a->rows + kEncAgents - 1) / kEncAgents;
+  const int sms = sm_count();
+  int64_t nfull = ntiles;
+  int nhalf = 0;
+  {
+    const int64_t rounds = ntiles / sms, rem = ntiles - rounds * sms;
+    if (rem > 0 && 2 * rem <= sms && !getenv("MAPF_B200_ENC_NO_HALF_TILES")) {
+      nfull = rounds * sms;
+      nhalf = int((a->rows - nfull * kEncAgents + kEncAgents / 2 - 1) / (kEncAgents / 2));
+    }
+  }
+  const int grid = int(nfull >= sms ? sms : (nfull > nhalf ? nfull : nhalf));
+  static int cache_c[16] = {0};
+  if (!mapf_ensure_smem(encoder_fwd_kernel<2>, smem, cache_c)) return MAPF_ERR_CUDA;
+  encoder_fwd_kernel<2><<<grid, kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(d, L, a->rows, nfull, nhalf,
+                                                                                         a->states, a->packed, a->x);
   return mapf_launch_status();
 }
 

@@ -177,12 +177,22 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
   const int64_t rows = int64_t(a->batch) * a->agents;
   int rc;
   if (a->workspace_act != nullptr && p->fc_out <= 128) {
-    // conv stack on FFMA -> act [rows, fc_in]; Linear + ReLU as a 3xTF32 tcgen05 GEMM
+    // conv stack on FFMA2 -> flattened activations; Linear + ReLU as a 3xTF32 tcgen05 GEMM.  Default: the conv kernel
+    // emits the GEMM's A operand pre-split and pre-tiled (all-TMA GEMM); MAPF_B200_FC_UNSPLIT=1 keeps the plain
+    // [rows, fc_in] hand-over with conversion warps in the GEMM (development switch).
     mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_act};
-    rc = mapf_encoder_conv_fwd(p, &e, stream);
-    if (rc != MAPF_OK) return rc;
-    rc = mapf_tc_gemm(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, p->fc_in, a->packed + L.tc_fc,
-                      a->workspace_x, p->fc_out, a->packed + L.fc_b, 1, stream);
+    static const bool unsplit = getenv("MAPF_B200_FC_UNSPLIT") != nullptr;
+    if (unsplit) {
+      rc = mapf_encoder_conv_fwd(p, &e, stream);
+      if (rc != MAPF_OK) return rc;
+      rc = mapf_tc_gemm(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, p->fc_in, a->packed + L.tc_fc,
+                        a->workspace_x, p->fc_out, a->packed + L.fc_b, 1, stream);
+    } else {
+      rc = mapf_encoder_conv_split_fwd(p, &e, stream);
+      if (rc != MAPF_OK) return rc;
+      rc = mapf_tc_fc_presplit(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, a->packed + L.tc_fc, a->workspace_x,
+                               p->fc_out, a->packed + L.fc_b, 1, stream);
+    }
   } else {
     mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_x};
     rc = mapf_encoder_fwd(p, &e, stream);

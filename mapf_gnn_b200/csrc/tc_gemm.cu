@@ -324,6 +324,136 @@ int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
   return mapf_launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Same GEMM with the A operand ALREADY split and tiled by its producer (the encoder's conv kernel writes
+// Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4]): no conversion warps, the whole operand pipeline is TMA.
+//   warp 0 lane 0 : per stage of kPsChunks 8-wide K chunks, one bulk copy for A (contiguous in Ap) and one for B
+//   warp 1 lane 0 : 3 tcgen05.mma per chunk (lo*hi, hi*lo, hi*hi), chunks alternate between two TMEM accumulators
+//   all 8 warps   : epilogue = bias, ReLU, transpose through shared memory, 128-byte row stores
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPsChunks = 2, kPsStages = 4;
+
+template <int NT>
+__global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
+  constexpr int kABytes = kTcM * 8 * 4, kBBytes = NT * 8 * 4;
+  constexpr int kStageA = kPsChunks * 2 * kABytes, kStageB = kPsChunks * 2 * kBBytes;
+  constexpr int kStageBytes = kStageA + kStageB;
+  constexpr uint32_t kCols = 2 * NT <= 128 ? 128 : 256;
+  extern __shared__ __align__(128) uint8_t s_tc[];
+  __shared__ __align__(8) uint64_t s_full[kPsStages], s_empty[kPsStages], s_done;
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[NT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * kTcM;
+  if (warp == 0) tc::tmem_alloc(&s_tmem, kCols);
+  if (tid == 0) {
+    for (int s = 0; s < kPsStages; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 1); }
+    tc::mbar_init(&s_done, 1);
+    tc::fence_mbar_init();
+  }
+  for (int i = tid; i < NT; i += kTcThreads) s_bias[i] = (g.bias != nullptr && i < g.N) ? __ldg(g.bias + i) : 0.0f;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const int nch = (g.K + 7) >> 3;
+  const int nsc = (nch + kPsChunks - 1) / kPsChunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const float* a_src = g.A + int64_t(blockIdx.x) * nch * (2 * kTcM * 8);
+      for (int sc = 0; sc < nsc; ++sc) {
+        const int s = sc % kPsStages;
+        const uint32_t ph = uint32_t(sc / kPsStages) & 1u;
+        tc::mbar_wait(&s_empty[s], ph ^ 1u);
+        const int c0 = sc * kPsChunks;
+        const int nc = nch - c0 < kPsChunks ? nch - c0 : kPsChunks;
+        uint8_t* st = s_tc + s * kStageBytes;
+        tc::mbar_expect_tx(&s_full[s], uint32_t(nc) * (2 * kABytes + 2 * kBBytes));
+        tc::bulk_g2s(st, a_src + int64_t(c0) * (2 * kTcM * 8), uint32_t(nc) * 2 * kABytes, &s_full[s]);
+        tc::bulk_g2s(st + kStageA, g.Bp + int64_t(c0) * (2 * NT * 8), uint32_t(nc) * 2 * kBBytes, &s_full[s]);
+        tc::mbar_arrive(&s_full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_tf32(kTcM, NT);
+      constexpr uint32_t sbo = 256, lbo = 128;
+      const uint32_t base = tc::smem_u32(s_tc);
+      for (int sc = 0; sc < nsc; ++sc) {
+        const int s = sc % kPsStages;
+        const uint32_t ph = uint32_t(sc / kPsStages) & 1u;
+        tc::mbar_wait(&s_full[s], ph);
+        tc::fence_after_sync();
+        const int c0 = sc * kPsChunks;
+        const int nc = nch - c0 < kPsChunks ? nch - c0 : kPsChunks;
+        const uint32_t sa = base + uint32_t(s) * kStageBytes, sb = sa + kStageA;
+        for (int ci = 0; ci < nc; ++ci) {
+          const int c = c0 + ci;
+          const uint32_t acc = tmem + uint32_t(c & 1) * NT;
+          const uint64_t dah = tc::smem_desc(sa + uint32_t(ci) * 2 * kABytes, lbo, sbo);
+          const uint64_t dal = tc::smem_desc(sa + uint32_t(ci) * 2 * kABytes + kABytes, lbo, sbo);
+          const uint64_t dbh = tc::smem_desc(sb + uint32_t(ci) * 2 * kBBytes, lbo, sbo);
+          const uint64_t dbl = tc::smem_desc(sb + uint32_t(ci) * 2 * kBBytes + kBBytes, lbo, sbo);
+          tc::mma_tf32(acc, dal, dbh, idesc, c >= 2);   // first touch of an accumulator overwrites; small terms first
+          tc::mma_tf32(acc, dah, dbl, idesc, true);
+          tc::mma_tf32(acc, dah, dbh, idesc, true);
+        }
+        tc::mma_commit(&s_empty[s]);
+      }
+      tc::mma_commit(&s_done);
+    }
+    __syncwarp();
+  }
+
+  {
+    tc::mbar_wait(&s_done, 0);
+    tc::fence_after_sync();
+    const int quad = warp & 3, half = warp >> 2;
+    constexpr int kHalfCols = NT / 2;
+    float* s_scr = reinterpret_cast<float*>(s_tc);
+    const bool two = nch > 1;
+#pragma unroll
+    for (int cbl = 0; cbl < kHalfCols; cbl += 32) {
+      const int cb = half * kHalfCols + cbl;
+      uint32_t r0[32], r1[32];
+      tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + cb, r0);
+      if (two) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + NT + cb, r1);
+      tc::tmem_ld_wait();
+      float* t = s_scr + warp * (32 * 33);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float o = __uint_as_float(r0[j]) + (two ? __uint_as_float(r1[j]) : 0.0f) + s_bias[cb + j];
+        if (g.relu) o = fmaxf(o, 0.0f);
+        t[lane * 33 + j] = o;
+      }
+      __syncwarp();
+      const int n = cb + lane;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int grow = m0 + quad * 32 + r;
+        if (grow < g.M && n < g.N) g.C[int64_t(grow) * g.ldc + n] = t[r * 33 + lane];
+      }
+      __syncwarp();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, kCols);
+}
+
+template <int NT>
+int launch_presplit(const TcGemmArgs& g, cudaStream_t s) {
+  constexpr size_t smem = size_t(kPsStages) * kPsChunks * (2 * kTcM * 8 * 4 + 2 * NT * 8 * 4);
+  static_assert(smem >= 8 * 32 * 33 * 4, "the epilogue transposes through the operand stages");
+  auto kernel = tc_presplit_kernel<NT>;
+  if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
+    return MAPF_ERR_CUDA;
+  kernel<<<(g.M + kTcM - 1) / kTcM, kTcThreads, smem, s>>>(g);
+  return mapf_launch_status();
+}
+
 }  // namespace
 
 // tile shapes: N <= 64 -> (NT 64, 4 accumulators); N <= 128 -> (NT 128, 2 accumulators); KC = 8 floats per stage
@@ -379,4 +509,27 @@ extern "C" int mapf_tc_mix_head(int32_t M, int32_t N, int32_t K, const float* Z,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (N <= 64) return launch_tc<64, kTcKC, 2, EPI_HEAD>(g, s);
   return launch_tc<128, kTcKC, 2, EPI_HEAD>(g, s);
+}
+
+// Floats of the pre-split A operand [ceil(M/128)][ceil(K/8)][hi|lo][128 x 8] that mapf_encoder_conv_split_fwd writes
+extern "C" int64_t mapf_tc_presplit_a_size(int64_t M, int32_t K) {
+  if (M <= 0 || K <= 0) return -1;
+  return ((M + kTcM - 1) / kTcM) * int64_t((K + 7) / 8) * (2 * kTcM * 8);
+}
+
+// C[M,N] = act(A B^T + bias) with A given pre-split / pre-tiled (Ap, see mapf_tc_presplit_a_size) and Bp from
+// mapf_tc_pack_b: the Linear + ReLU of the encoder (compressMLP, framework_gnn.py:93) behind the conv kernel.
+extern "C" int mapf_tc_fc_presplit(int32_t M, int32_t N, int32_t K, const float* Ap, const float* Bp, float* C,
+                                   int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream) {
+  MAPF_REQUIRE(Ap && Bp && C, MAPF_ERR_NULL);
+  MAPF_REQUIRE(M > 0 && N > 0 && K > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(N <= 128, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(Ap, 128) && mapf_aligned(Bp, 16), MAPF_ERR_ALIGN);
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = Ap; g.Bp = Bp;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (N <= 64) return launch_presplit<64>(g, s);
+  return launch_presplit<128>(g, s);
 }

@@ -94,7 +94,7 @@ def _policy_fwd(dims, message, states, gso, packed):
     a.batch, a.agents, a.message = B, N, int(message)
     a.states, a.packed, a.workspace_x = states.data_ptr(), packed.data_ptr(), work.data_ptr()
     if USE_TENSOR_CORES and USE_TENSOR_CORE_FC:
-        worka = torch.empty((B * N, p.fc_in), dtype=torch.float32, device=dev)
+        worka = torch.empty((lib.mapf_tc_presplit_a_size(B * N, p.fc_in),), dtype=torch.float32, device=dev)
         a.workspace_act = worka.data_ptr()
     if p.taps > 0:
         if gso is None:

@@ -96,6 +96,39 @@ def test_encoder_tile_schedules(rows):
     assert np.abs(x - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("rows", [1, 17, 129, 640, 2400, 4736 + 300, 4736 + 75 * 32 + 5])
+def test_presplit_tensor_core_fc_matches_oracle(rows):
+    """Conv kernel emitting the pre-split / pre-tiled A operand + all-TMA tcgen05 FC (mapf_encoder_conv_split_fwd,
+    mapf_tc_fc_presplit) against the oracle encoder, over full-tile, half-tile and ragged schedules."""
+    from mapf_gnn_b200 import _lib
+    from mapf_gnn_b200.ops import net_params
+    lib = _lib.load()
+    rng = np.random.default_rng(rows + 1)
+    states = torch.tensor(rng.integers(0, 4, size=(rows, 1, 2, 5, 5))).float()
+    states[:: 5] *= 0.61
+    params = oracle_params("gnn_k3")
+    with torch.no_grad():
+        ref = mo.encode_agents(params, states)[:, :, 0].numpy()
+    net = load_network("gnn_k3", num_agents=1).eval()
+    dims, packed = net.dims(), net.packed_weights()
+    p = net_params(dims)
+    st = states.cuda()
+    Ap = torch.full((lib.mapf_tc_presplit_a_size(rows, dims[6]),), float("nan"), device="cuda")
+    x = torch.empty((rows, dims[7]), device="cuda")
+    fcw = net.compressMLP[0].weight.detach().contiguous()
+    fcb = net.compressMLP[0].bias.detach().contiguous()
+    Bp = torch.empty((lib.mapf_tc_packed_b_size(dims[7], dims[6]),), device="cuda")
+    s = _lib.current_stream()
+    _lib.check(lib.mapf_tc_pack_b(fcw.data_ptr(), dims[6], None, 0, dims[7], Bp.data_ptr(), s), "pack")
+    ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
+    _lib.check(lib.mapf_encoder_conv_split_fwd(p, ea, s), "conv_split")
+    _lib.check(lib.mapf_tc_fc_presplit(rows, dims[7], dims[6], Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), dims[7],
+                                       fcb.data_ptr(), 1, s), "fc_presplit")
+    got = x.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) < REL
+
+
 def test_training_gso_convention_a_plus_i():
     """The data loader feeds A + I (data_loader.py:74); GCNLayer adds I again -> diagonal 2."""
     rng = np.random.default_rng(3)

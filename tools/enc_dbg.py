@@ -14,8 +14,16 @@ states = torch.randint(0, 4, (w["E"], w["N"], 2, 5, 5), device="cuda").float()
 dims, packed = net.dims(), net.packed_weights()
 dbg = torch.zeros(1024, dtype=torch.int64, device="cuda")
 lib.mapf_enc_set_debug(dbg.data_ptr())
+if os.environ.get("ENC_DBG_SPLIT"):
+    from mapf_gnn_b200.ops import net_params
+    p = net_params(dims); rows = w["E"] * w["N"]
+    Ap = torch.empty((lib.mapf_tc_presplit_a_size(rows, dims[6]),), device="cuda")
+    es = _lib.EncoderFwdArgs(rows, states.data_ptr(), packed.data_ptr(), Ap.data_ptr())
+    run = lambda: lib.mapf_encoder_conv_split_fwd(p, es, _lib.current_stream())
+else:
+    run = lambda: torch.ops.mapf.encoder_fwd(dims, states, packed)
 for _ in range(3):
-    dbg.zero_(); torch.ops.mapf.encoder_fwd(dims, states, packed); torch.cuda.synchronize()
+    dbg.zero_(); run(); torch.cuda.synchronize()
 d = dbg.cpu().numpy(); t0 = int(d[1023])
 a = d[:1024 - 0][:8 * 8 * 8 * 2].reshape(8, 8, 8, 2)     # tile, phase, warp, (arrive, leave)
 names = ["stage", "conv1", "conv2", "conv3", "fcA0", "fcB0", "fcA1", "fcB1"]

@@ -68,6 +68,19 @@ lib.mapf_tc_pack_b(fcw.data_ptr(), dims[6], None, 0, dims[7], Bp.data_ptr(), st)
 t_fc = timeit(lambda: lib.mapf_tc_gemm(rows, dims[7], dims[6], act.data_ptr(), dims[6], Bp.data_ptr(), xx.data_ptr(),
                                        dims[7], fcb.data_ptr(), 1, st))
 print(f"   conv-only {t_conv:.1f} us | tc FC gemm [{rows}x{dims[6]}]x[{dims[7]}] {t_fc:.1f} us")
+Ap = torch.empty((lib.mapf_tc_presplit_a_size(rows, dims[6]),), device="cuda")
+es = _lib.EncoderFwdArgs(rows, env.fov.data_ptr(), packed.data_ptr(), Ap.data_ptr())
+x2 = torch.empty((rows, dims[7]), device="cuda")
+t_convs = timeit(lambda: lib.mapf_encoder_conv_split_fwd(p, es, st))
+t_fcs = timeit(lambda: lib.mapf_tc_fc_presplit(rows, dims[7], dims[6], Ap.data_ptr(), Bp.data_ptr(), x2.data_ptr(), dims[7],
+                                                 fcb.data_ptr(), 1, st))
+t_both = timeit(lambda: (lib.mapf_encoder_conv_split_fwd(p, es, st),
+                         lib.mapf_tc_fc_presplit(rows, dims[7], dims[6], Ap.data_ptr(), Bp.data_ptr(), x2.data_ptr(),
+                                                 dims[7], fcb.data_ptr(), 1, st)))
+torch.cuda.synchronize()
+ref = torch.ops.mapf.encoder_fwd(dims, env.fov, packed)
+err = float((x2 - ref).abs().max() / ref.abs().max())
+print(f"   conv + pre-split A {t_convs:.1f} us | all-TMA tc FC {t_fcs:.1f} us | back to back {t_both:.1f} us | max rel diff vs fused FFMA encoder {err:.2e}")
 if dims[8] > 0:
     KT = (dims[8] + (1 if net.message else 0)) * dims[7]
     z = torch.empty((rows, KT), device="cuda")
