@@ -331,7 +331,7 @@ int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
 //   warp 1 lane 0 : 3 tcgen05.mma per chunk (lo*hi, hi*lo, hi*hi), chunks alternate between two TMEM accumulators
 //   all 8 warps   : epilogue = bias, ReLU, transpose through shared memory, 128-byte row stores
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kPsChunks = 2, kPsStages = 4;
+constexpr int kPsChunks = 4, kPsStages = 2;
 
 template <int NT>
 __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
