@@ -29,6 +29,7 @@ struct TrainLayout {
   int64_t u[MAPF_MAX_CONV], a[MAPF_MAX_CONV]; // pre-BN conv outputs, post BN+ReLU activations [rows][C*25]
   int64_t x, z, y;                            // [rows][F], [rows][KT], [rows][G]
   int64_t dy, dz, dx, da0, da1;
+  int64_t fcpk;                               // compressMLP weight, packed for the tensor-core GEMM (mapf_tc_pack_b)
   int64_t dwpart;                             // [grid <= 296][max cin*cout*9 + cmax] per-CTA weight-gradient partials
   int64_t total;
   int cmax;
@@ -75,6 +76,7 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
     const int64_t grid = mapf_min64((rows + 31) / 32, 2 * 148);
     T.dwpart = take(grid * (maxp * 9 + cmax));
   }
+  T.fcpk = take(p.fc_out <= 128 ? mapf_tc_b_floats(p.fc_out, p.fc_in) : 0);
   T.total = off;
   return T;
 }
@@ -558,15 +560,35 @@ conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ i
   }
 }
 
-// dw[e] += sum over CTAs (in index order) of part[g][e]; the last `cout` entries are the bias gradient
-__global__ void conv_bwd_weight_reduce_kernel(const float* __restrict__ part, int grid, int nw, int cout,
-                                              float* __restrict__ dw, float* __restrict__ db) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nw + cout) return;
-  float sum = 0.0f;
-  for (int g = 0; g < grid; ++g) sum += part[int64_t(g) * (nw + cout) + e];
-  if (e < nw) dw[e] += sum;
-  else if (db != nullptr) db[e - nw] += sum;
+// dw[e] += sum over CTAs of part[g][e] in a fixed order (the last `cout` entries are the bias gradient): a CTA owns 32
+// outputs, its 8 warps take the partials g = w, w + 8, ... (coalesced 128-byte rows), and the 8 warp sums meet in
+// shared memory in warp order.
+__global__ void __launch_bounds__(256) conv_bwd_weight_reduce_kernel(const float* __restrict__ part, int grid, int nw,
+                                                                     int cout, float* __restrict__ dw,
+                                                                     float* __restrict__ db) {
+  __shared__ float s_sum[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane, tot = nw + cout;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  if (e < tot) {
+    int g = warp;
+    for (; g + 24 < grid; g += 32) {
+      a0 += __ldg(part + int64_t(g) * tot + e);
+      a1 += __ldg(part + int64_t(g + 8) * tot + e);
+      a2 += __ldg(part + int64_t(g + 16) * tot + e);
+      a3 += __ldg(part + int64_t(g + 24) * tot + e);
+    }
+    for (; g < grid; g += 8) a0 += __ldg(part + int64_t(g) * tot + e);
+  }
+  s_sum[warp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0 && e < tot) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += s_sum[w][lane];
+    if (e < nw) dw[e] += sum;
+    else if (db != nullptr) db[e - nw] += sum;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -695,8 +717,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ i
   const int per = 256 / C;                  // row lanes per block pass
   const int c = tid % C, rl = tid / C;
   float s = 0.0f;
-  if (rl < per)
-    for (int64_t r = blockIdx.x * int64_t(per) + rl; r < rows; r += int64_t(gridDim.x) * per) s += __ldg(in + r * C + c);
+  if (rl < per) {
+    // 8 independent loads in flight per thread (a serial loop pays one L2 round trip per row)
+    const int64_t step = int64_t(gridDim.x) * per;
+    int64_t r = blockIdx.x * int64_t(per) + rl;
+    float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (; r + 7 * step < rows; r += 8 * step) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) part[q] += __ldg(in + (r + q * step) * C + c);
+    }
+    for (; r < rows; r += step) part[0] += __ldg(in + r * C + c);
+    s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+  }
   s_part[tid] = rl < per ? s : 0.0f;
   __syncthreads();
   if (tid < C) {
@@ -917,7 +949,13 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   MAPF_TRY(mapf_launch_status());
   const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
   // compressMLP: x = relu(a_L Wfc^T + b)
-  MAPF_TRY(gemm(s, int(rows), F, fin, ws + T.a[L - 1], fin, 1, p->fc_w, 1, fin, ws + T.x, F, p->fc_b, 1));
+  if (F <= 128 && (fin & 3) == 0 && getenv("MAPF_B200_TRAIN_FFMA_FC") == nullptr) {
+    // 3xTF32 tcgen05 GEMM on the current weights (re-packed every step: 100 KB)
+    MAPF_TRY(mapf_tc_pack_b(p->fc_w, fin, nullptr, 0, F, ws + T.fcpk, stream));
+    MAPF_TRY(mapf_tc_gemm(int32_t(rows), F, fin, ws + T.a[L - 1], fin, ws + T.fcpk, ws + T.x, F, p->fc_b, 1, stream));
+  } else {
+    MAPF_TRY(gemm(s, int(rows), F, fin, ws + T.a[L - 1], fin, 1, p->fc_w, 1, fin, ws + T.x, F, p->fc_b, 1));
+  }
   if (p->taps == 0) return gemm(s, int(rows), A, F, ws + T.x, F, 1, p->act_w, 1, F, a->logits, A, p->act_b, 0);
   mapf_graph_filter_fwd_args g{};
   g.batch = B; g.agents = N; g.in_dim = F; g.out_dim = p->node_dim; g.taps = p->taps;
@@ -1051,7 +1089,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
         conv_bwd_weight_kernel<4><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, part);
       }
       const int nw = cin * cout * 9;
-      conv_bwd_weight_reduce_kernel<<<(nw + cout + 127) / 128, 128, 0, s>>>(part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
+      conv_bwd_weight_reduce_kernel<<<(nw + cout + 31) / 32, 256, 0, s>>>(part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
     }
     if (l > 0) {
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
