@@ -30,3 +30,13 @@ def test_validation_order_draws_goals_independently():
 def test_too_small_board_raises_like_create_goals():
     with pytest.raises(ValueError):
         make_scenarios(np.random.default_rng(0), 4, 10, 3, 5)
+
+
+def test_round_aligned_group_sizes():
+    """Host logic of PipelinedHostRollout: groups whose encoder launches are whole rounds of the persistent kernel."""
+    from mapf_gnn_b200.rollout import PipelinedHostRollout as P
+    assert P.round_aligned_sizes(4096, 5, 2, 148) == [1894, 2202]          # 1894 * 5 = 9470 images = 2 rounds of 4736
+    assert P.round_aligned_sizes(90, 5, 3, 148) == [30, 30, 30]            # too small for a round: equal split
+    for E, N, G in [(4096, 5, 3), (8192, 64, 2), (4096, 20, 4), (7, 3, 7), (100000, 5, 8)]:
+        sizes = P.round_aligned_sizes(E, N, G, 148)
+        assert len(sizes) == G and sum(sizes) == E and min(sizes) >= 1
