@@ -33,6 +33,10 @@ struct EncoderDims {
   int buf1_floats;   // ping buffer 1: outputs of even layers
 };
 
+#ifdef MAPF_ENC_DEBUG
+__device__ long long* g_enc_dbg = nullptr;   // [tile][phase 0..7][warp][arrive, leave] clocks of block 0
+#endif
+
 // One 3x3 / stride 1 / zero-pad 1 convolution (BN folded) + ReLU over the tile's 32 images.
 // Input element (ci, p) of this lane's image is at in[ci*in_cs + p*in_ps + in_off]; out is
 // [Cout*25][32].  w is the packed [Cout/4][Cin][9][4] filter bank in shared memory.
@@ -49,6 +53,9 @@ __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, 
     }
     // float2 view: element [(cog*cin + ci)*9 + t]*2 + h with cog = pr/2, h = pr&1
     const float2* wp = reinterpret_cast<const float2*>(w) + (int64_t(pr >> 1) * cin * 9) * 2 + (pr & 1);
+#ifdef MAPF_ENC_DEBUG
+    const long long t_la = clock64();
+#endif
 #pragma unroll 2
     for (int ci = 0; ci < cin; ++ci) {
       float v[kFovCells];
@@ -72,17 +79,21 @@ __device__ __forceinline__ void conv3x3_relu_pair(const float* __restrict__ in, 
                 mapf_ffma2(acc[y * kFov + x], v[yy * kFov + xx], wv[ky * 3 + kx]);
             }
     }
+#ifdef MAPF_ENC_DEBUG
+    const long long t_lb = clock64();
+#endif
 #pragma unroll
     for (int p = 0; p < kFovCells; ++p) {
       out[((2 * pr) * kFovCells + p) * out_ps + lane] = fmaxf(acc[p].x, 0.0f);
       out[((2 * pr + 1) * kFovCells + p) * out_ps + lane] = fmaxf(acc[p].y, 0.0f);
     }
+#ifdef MAPF_ENC_DEBUG
+    if (g_enc_dbg && blockIdx.x == 0 && lane == 0 && cin > 2) {
+      g_enc_dbg[950 + warp * 3] = t_la; g_enc_dbg[951 + warp * 3] = t_lb; g_enc_dbg[952 + warp * 3] = clock64();
+    }
+#endif
   }
 }
-
-#ifdef MAPF_ENC_DEBUG
-__device__ long long* g_enc_dbg = nullptr;   // [tile][phase 0..7][warp][arrive, leave] clocks of block 0
-#endif
 
 // Same layer for a HALF tile of 16 agent images (the ragged last round of the persistent loop, see mapf_encoder_fwd):
 // lane = (agent = lane & 15, h = lane >> 4); the two half-warps split the INPUT channels of the warp's output pair,

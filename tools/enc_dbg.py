@@ -42,3 +42,5 @@ for tile in range(8):
 print("total", prev - t0, "first sync after start", int(a[0, 0, 0, 1]) - t0)
 h = d[900:924].reshape(8, 3)
 print("half-tile last layer, per warp: loop", (h[:, 1] - h[:, 0]).tolist(), "epilogue", (h[:, 2] - h[:, 1]).tolist(), "start spread", int(h[:, 0].max() - h[:, 0].min()))
+c = d[950:974].reshape(8, 3)
+print("full-tile conv (last 16->16 layer run), per warp: loop", (c[:, 1] - c[:, 0]).tolist(), "epilogue", (c[:, 2] - c[:, 1]).tolist(), "start spread", int(c[:, 0].max() - c[:, 0].min()), "end spread", int(c[:, 2].max() - c[:, 2].min()))
