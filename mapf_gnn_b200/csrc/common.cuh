@@ -37,6 +37,8 @@ struct PackedLayout {
   int64_t gf_wt;                  // [(K(+1))*F][G]
   int64_t tc_fc;                  // tensor-core B operand of the encoder FC (compressMLP.0.weight [F, fc_in])
   int64_t tc_gf;                  // tensor-core B operand of the mix: [W | W2] as chunked canonical TF32 hi/lo blocks
+  int64_t tc_conv;                // tensor-core B operands of the conv layers (enc_tc.cu), 0 floats when unsupported
+  int64_t tc_fc_pm;               // tensor-core B operand of the encoder FC with K ordered pixel-major (enc_tc.cu)
   int64_t act_w;                  // [A][G or F]
   int64_t act_b;                  // [A]
   int64_t total;
@@ -47,6 +49,14 @@ static inline __host__ __device__ int64_t mapf_round4(int64_t v) { return (v + 3
 // floats of a pre-tiled tensor-core B operand [N, K] (tc_gemm.cu: KC = 8, NT = 64 or 128, hi | lo per chunk)
 static inline __host__ __device__ int64_t mapf_tc_b_floats(int N, int K) {
   return int64_t((K + 7) / 8) * 2 * (N <= 64 ? 64 : 128) * 8;
+}
+
+// the tensor-core conv stack (enc_tc.cu) is built for 16-channel layers
+static inline __host__ __device__ bool mapf_enc_tc_dims_ok(const mapf_net_params& p) {
+  if (p.num_conv < 1 || p.num_conv > MAPF_MAX_CONV || p.fc_out > 128) return false;
+  for (int l = 1; l <= p.num_conv; ++l)
+    if (p.channels[l] != 16) return false;
+  return true;
 }
 
 static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net_params& p) {
@@ -68,6 +78,13 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
   if (p.fc_out <= 128) off += mapf_tc_b_floats(p.fc_out, p.fc_in);
   L.tc_gf = off;
   if (p.taps > 0 && p.node_dim <= 128) off += mapf_tc_b_floats(p.node_dim, (p.taps + 1) * p.fc_out);
+  L.tc_conv = off;
+  L.tc_fc_pm = off;
+  if (mapf_enc_tc_dims_ok(p)) {
+    for (int l = 0; l < p.num_conv; ++l) off += int64_t((p.channels[l] + 7) >> 3) * 2 * (144 * 8);
+    L.tc_fc_pm = off;
+    off += mapf_tc_b_floats(p.fc_out, p.fc_in);
+  }
   L.act_w = off;
   off += mapf_round4(int64_t(p.num_actions) * (p.taps > 0 ? p.node_dim : p.fc_out));
   L.act_b = off;

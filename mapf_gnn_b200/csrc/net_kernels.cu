@@ -11,6 +11,8 @@
 
 #include "common.cuh"
 
+int mapf_encoder_tc_pack(const mapf_net_params* p, float* packed, mapf_stream_t stream);   // enc_tc.cu
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -143,6 +145,10 @@ extern "C" int mapf_pack_weights(const mapf_net_params* p, float* packed, mapf_s
                                   packed + L.tc_gf, stream);
     if (rc != MAPF_OK) return rc;
   }
+  if (mapf_enc_tc_dims_ok(*p)) {
+    const int rc = mapf_encoder_tc_pack(p, packed, stream);
+    if (rc != MAPF_OK) return rc;
+  }
   return mapf_launch_status();
 }
 
@@ -182,7 +188,15 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
     // [rows, fc_in] hand-over with conversion warps in the GEMM (development switch).
     mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_act};
     static const bool unsplit = getenv("MAPF_B200_FC_UNSPLIT") != nullptr;
-    if (unsplit) {
+    static const bool ffma_conv = getenv("MAPF_B200_ENC_FFMA_CONV") != nullptr;
+    if (!ffma_conv && !unsplit && mapf_enc_tc_dims_ok(*p)) {
+      // conv stack on tcgen05 (activations as the A operand in tensor memory, enc_tc.cu) -> FC operand in pixel-major
+      // K order -> all-TMA tcgen05 FC against the matching B operand
+      rc = mapf_encoder_tc_conv_fwd(p, &e, stream);
+      if (rc != MAPF_OK) return rc;
+      rc = mapf_tc_fc_presplit(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, a->packed + L.tc_fc_pm,
+                               a->workspace_x, p->fc_out, a->packed + L.fc_b, 1, stream);
+    } else if (unsplit) {
       rc = mapf_encoder_conv_fwd(p, &e, stream);
       if (rc != MAPF_OK) return rc;
       rc = mapf_tc_gemm(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, p->fc_in, a->packed + L.tc_fc,

@@ -50,8 +50,9 @@ struct TcGemmArgs {
 };
 
 // B [N,K0] (+ [N,K1] appended along K) row-major fp32 -> chunked canonical hi / lo blocks
+// perm_c > 0: b0's K index is read pixel-major, k' = pixel*perm_c + c <- k = c*25 + pixel (FC behind enc_tc.cu)
 __global__ void tc_pack_b_kernel(const float* __restrict__ b0, int K0, const float* __restrict__ b1, int K1, int N,
-                                 int NT, int KC, float* __restrict__ out) {
+                                 int NT, int KC, float* __restrict__ out, int perm_c = 0) {
   const int K = K0 + K1;
   const int nchunks = (K + KC - 1) / KC;
   const int64_t per_chunk = int64_t(2) * NT * KC;
@@ -67,7 +68,10 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ b0, int K0, const flo
     const int kq = rest % (KC >> 2), rg = rest / (KC >> 2);
     const int row = rg * 8 + r8, k = c * KC + kq * 4 + k4i;
     float v = 0.0f;
-    if (row < N && k < K) v = k < K0 ? b0[int64_t(row) * K0 + k] : b1[int64_t(row) * K1 + (k - K0)];
+    if (row < N && k < K) {
+      if (perm_c > 0) v = b0[int64_t(row) * K0 + (k % perm_c) * kFovCells + k / perm_c];
+      else v = k < K0 ? b0[int64_t(row) * K0 + k] : b1[int64_t(row) * K1 + (k - K0)];
+    }
     float hi, lo;
     tc::split1(v, hi, lo);
     out[idx] = is_lo ? lo : hi;
@@ -474,6 +478,19 @@ extern "C" int mapf_tc_pack_b(const float* b0, int32_t K0, const float* b1, int3
   const int64_t total = mapf_tc_packed_b_size(N, K0 + K1);
   tc_pack_b_kernel<<<int((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(b0, K0, b1, K1, N, tc_nt(N),
                                                                                            kTcKC, out);
+  return mapf_launch_status();
+}
+
+// Same for the encoder FC matrix [N, 25*C] with its K index re-ordered pixel-major (the order in which enc_tc.cu
+// emits the flattened activations).
+extern "C" int mapf_tc_pack_b_pixel_major(const float* b, int32_t C, int32_t N, float* out, mapf_stream_t stream) {
+  MAPF_REQUIRE(b && out, MAPF_ERR_NULL);
+  MAPF_REQUIRE(N > 0 && N <= 128 && C > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(mapf_aligned(out, 16), MAPF_ERR_ALIGN);
+  const int K = C * kFovCells;
+  const int64_t total = mapf_tc_packed_b_size(N, K);
+  tc_pack_b_kernel<<<int((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(b, K, nullptr, 0, N, tc_nt(N),
+                                                                                           kTcKC, out, C);
   return mapf_launch_status();
 }
 
