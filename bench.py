@@ -65,8 +65,9 @@ def peaks():
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+        return {"hbm_gbs": float(p["hbm_gbs"]), "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)),
+                "tensor_tflops": float(p.get("bf16_tflops", 1590.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "tensor_tflops": 1590.0, "source": "fallback"}
 
 
 class ClockSampler:
@@ -234,15 +235,27 @@ def run_mine(args, w):
     units_all, units_nominal = float(t[1]), float(t[2])
     value = units_all / (dev_ms_max * 1e-3)
 
-    # ---- dominant kernel (encoder) timed alone, live, on the launching stream ----
+    # ---- dominant kernel timed alone, live, on the launching stream: the conv stack of the encoder, on the tensor cores
+    # (encoder_tc_kernel) for 16-channel networks, else inside the fused FFMA2 encoder kernel (encoder_fwd_kernel) ----
     dims = net.dims()
     packed = net.packed_weights()
+    from mapf_gnn_b200 import _lib as _mlib
+    tc_encoder = ro.worka is not None and _mlib.load().mapf_encoder_tc_supported(ro.params) == 1
+    if tc_encoder:
+        _ea = _mlib.EncoderFwdArgs(E * N, env.fov.data_ptr(), packed.data_ptr(), ro.worka.data_ptr())
+        _st = _mlib.current_stream()
+
+        def dominant():
+            _mlib.check(_mlib.load().mapf_encoder_tc_conv_fwd(ro.params, _ea, _st), "encoder_tc_conv_fwd")
+    else:
+        def dominant():
+            torch.ops.mapf.encoder_fwd(dims, env.fov, packed)
     enc_ms = []
     for i in range(3 + 10):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        torch.ops.mapf.encoder_fwd(dims, env.fov, packed)
+        dominant()
         b.record()
         b.synchronize()
         if i >= 3:
@@ -263,11 +276,17 @@ def run_mine(args, w):
     traffic = None
     try:       # ncu-measured DRAM bytes per launch of the dominant kernel (committed summary; null when not captured)
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch") if E == w["E"] else None
+            rec = json.load(fh).get(args.workload, {})
+            want = "encoder_tc_kernel" if tc_encoder else "encoder_fwd_kernel"
+            rec = rec.get(want, rec if rec.get("kernel") == want else {})
+            traffic = rec.get("dram_bytes_per_launch") if E == w["E"] else None
     except OSError:
         pass
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-    enc_tflops = E * N * w["enc_flops"] / (enc_ms * 1e-3) / 1e12
+    # algorithmic FLOPs of what the timed kernel computes: the whole encoder (296.0 kFLOP per agent) for the
+    # fused kernel, the conv stack alone (296.0 k minus the 2 x 400 x 64 FLOP of the Linear) for the tensor-core kernel
+    dom_flops = w["enc_flops"] - (2.0 * dims[6] * dims[7] if tc_encoder else 0.0)
+    enc_tflops = E * N * dom_flops / (enc_ms * 1e-3) / 1e12
     env_gbs = E * N * w["env_bytes"] / (env_ms * 1e-3) / 1e9
 
     # ---- end to end through the public API with HOST buffers (pinned), every step ----
@@ -314,7 +333,22 @@ def run_mine(args, w):
             cpu = {"value": v, "unit": "agent-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{args.cpu_episodes} episodes x {args.cpu_steps} steps of the same workload, "
                              f"{tot:.1f} s (python loop over single-episode numpy envs + batched torch-CPU forward)"}
-        launches_per_step = 3 if dims[8] > 0 else 3
+        # encoder conv stack, encoder FC, graph filter + head (or baseline head), env step
+        launches_per_step = 4 if tc_encoder else 3
+        if tc_encoder:
+            roof = {"bound": "tensor", "kernel": "encoder_tc_kernel", "achieved": enc_tflops,
+                    "peak": pk["tensor_tflops"], "unit": "TFLOP/s", "frac": enc_tflops / pk["tensor_tflops"],
+                    "traffic": traffic, "ms_per_launch": enc_ms, "share_of_step": enc_ms / (dev_ms_max / K),
+                    "peak_source": f"dense 16-bit tensor peak, cuBLAS burst ({pk['source']})",
+                    "algorithmic_flops_per_launch": E * N * dom_flops,
+                    "vs_fp32_ffma_peak": enc_tflops / fp32_peak,
+                    "note": "fp32-accurate conv stack = 3 fp16 MMAs per product (hi/lo split); the kernel is bound by "
+                            "the per-layer MMA issue/commit latency, not by tensor throughput (DESIGN.md 3.2)"}
+        else:
+            roof = {"bound": "fp32_ffma", "kernel": "encoder_fwd_kernel", "achieved": enc_tflops,
+                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": enc_tflops / fp32_peak, "traffic": traffic,
+                    "ms_per_launch": enc_ms, "share_of_step": enc_ms / (dev_ms_max / K),
+                    "peak_source": f"148 SM x 128 FFMA x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})"}
         line = {
             "metric": "agent-steps/sec (batched rollout)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
@@ -326,10 +360,7 @@ def run_mine(args, w):
                        "counted": "agent-steps of episodes not yet done (done episodes are frozen); "
                                   f"nominal E*N*K = {units_nominal:.0f}",
                        "wall_s_incl_flush": wall},
-            "roofline": {"bound": "fp32_ffma", "kernel": "encoder_fwd_kernel", "achieved": enc_tflops,
-                         "peak": fp32_peak, "unit": "TFLOP/s", "frac": enc_tflops / fp32_peak, "traffic": traffic,
-                         "ms_per_launch": enc_ms, "share_of_step": enc_ms / (dev_ms_max / K),
-                         "peak_source": f"148 SM x 128 FFMA x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})"},
+            "roofline": roof,
             "roofline_env": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": env_gbs, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": env_gbs / pk["hbm_gbs"], "ms_per_launch": env_ms,
                              "peak_source": pk["source"]},

@@ -81,7 +81,8 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
   L.tc_conv = off;
   L.tc_fc_pm = off;
   if (mapf_enc_tc_dims_ok(p)) {
-    for (int l = 0; l < p.num_conv; ++l) off += int64_t((3 * p.channels[l] + 7) >> 3) * 2 * (48 * 8);
+    off += 4;   // inverse filter scales
+    for (int l = 0; l < p.num_conv; ++l) off += int64_t((3 * p.channels[l] + 15) >> 4) * 2 * (48 * 8);
     L.tc_fc_pm = off;
     off += mapf_tc_b_floats(p.fc_out, p.fc_in);
   }

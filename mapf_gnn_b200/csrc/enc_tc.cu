@@ -7,21 +7,30 @@
 // i.e. the horizontal taps sit in K (the A operand holds the pixel and its left / right neighbour, zero at the image
 // border) and the filter rows sit in N; what is left for the epilogue is the vertical "col2im",
 //   out[pixel, co] = bias[co] + D[pixel, (1, co)] + D[pixel - 5, (0, co)] + D[pixel + 5, (2, co)].
-// The GEMM runs as 3xTF32 tcgen05.mma with the ACTIVATIONS AS THE A OPERAND IN TENSOR MEMORY (TS mode): lane = pixel and
-// warp = image, so every neighbour exchange is a warp shuffle (64 per thread and layer: 32 for the vertical sums, 32 for
-// the horizontal copies) and a layer's output never touches shared memory -- the epilogue threads read the 48 partial
-// sums of their pixel from TMEM (tcgen05.ld), add the neighbours' shares, apply bias and ReLU, split the result and its
-// two horizontal neighbours into TF32 hi / lo and write them straight back to TMEM (tcgen05.st) as the next layer's A
-// operand.  The B operand (BN-folded filters, hi | lo, canonical no-swizzle K-major tiles, 40 KB for three layers) stays
-// resident in shared memory; the tensor core reads only B from shared memory (1.5 KB per 24-cycle MMA).
+// The ACTIVATIONS ARE THE A OPERAND IN TENSOR MEMORY (TS mode): lane = pixel and warp = image, so every neighbour
+// exchange is a warp shuffle (64 per thread and layer) and a layer's output never touches shared memory -- the epilogue
+// threads read the 48 partial sums of their pixel from TMEM (tcgen05.ld), add the neighbours' shares, apply bias and
+// ReLU, and write the result and its two horizontal neighbours straight back to TMEM (tcgen05.st) as the next layer's A
+// operand.  The B operand (BN-folded filters) stays resident in shared memory (21 KB for three layers).
 //
-// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (25 pixels + 7 zero lanes).  A CTA holds three independent
-// warpgroups; each walks its own M tiles through all layers with its own 144 TMEM columns (D 48 | A hi 48 | A lo 48), its
-// own mbarrier and named barrier, started a third of a layer apart so that one group's MMAs run under the others'
-// epilogues.  The last layer's epilogue emits the flattened activations as the pre-split, pre-tiled A operand of the
-// encoder FC (mapf_tc_fc_presplit) with the K index ordered pixel-major (k = pixel * 16 + channel); the four images of a
-// tile meet in shared memory so that the global stores are whole 64-byte runs.  The FC's B operand is packed with the
-// same K permutation (PackedLayout::tc_fc_pm).
+// fp32 accuracy from 16-bit MMAs.  Dependent tcgen05.mma into one accumulator complete about 100 cycles apart however
+// small they are, so the number of MMAs per layer is what matters: kind::f16 covers K = 16 per instruction (TF32: 8)
+// and halves the A operand's TMEM columns.  Every operand is split into two fp16 numbers, x * 2^-e = hi + lo (11 + 11
+// significant bits, the same as the TF32 split of tc_gemm.cuh) and the layer is 3 products per K step, lo*hi + hi*lo +
+// hi*hi, accumulated in fp32 = 9 MMAs.  The power-of-two scales keep fp16's range out of the picture: the filters of a
+// layer share one static scale (largest |w| -> [2^9, 2^10), mapf_pack_weights), the activations of an image share a
+// dynamic one (largest activation of the image -> [2^9, 2^10), one warp max-reduction per layer); the product of the
+// two inverse scales rides on the multiplier of the epilogue's first FMA.  Entries far below their scale's maximum
+// are rounded at 2^-25 of it -- 2^-34 of the image's largest activation.
+//
+// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (25 pixels + 7 zero lanes).  A CTA holds four independent
+// warpgroups; each walks its own M tiles through all layers with its own 96 TMEM columns (D 48 | A hi 24 | A lo 24), its
+// own mbarrier and named barrier; one thread per group issues its MMAs, so the groups' accumulation chains interleave
+// in the tensor pipe.  The last layer's epilogue emits the flattened activations as the pre-split (TF32 hi | lo),
+// pre-tiled A operand of the encoder FC (mapf_tc_fc_presplit) with the K index ordered pixel-major (k = pixel * 16 +
+// channel); the four images of a tile meet in shared memory so that the global stores are whole 64-byte runs.  The FC's
+// B operand is packed with the same K permutation (PackedLayout::tc_fc_pm).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,28 +38,30 @@
 
 namespace {
 
-constexpr int kEtGroups = 3;                    // epilogue warpgroups per CTA
-constexpr int kEtThreads = 128 * kEtGroups + 32;   // + one warp whose lane 0 issues every tcgen05.mma
+constexpr int kEtGroups = 4;                    // warpgroups per CTA
+constexpr int kEtThreads = 128 * kEtGroups;
 constexpr int kEtCout = 16;                     // channels of every conv layer this kernel is built for
 constexpr int kEtN = 3 * kEtCout;               // GEMM N: (filter row, co)
-constexpr int kEtBlk = kEtN * 8;                // floats of one (K step, hi|lo) block of the B operand
-constexpr int kEtMaxK = 3 * kEtCout;            // widest A operand: (kx, ci)
-constexpr uint32_t kEtColAHi = kEtN, kEtColALo = kEtN + kEtMaxK, kEtSetCols = kEtN + 2 * kEtMaxK;   // 48 | 48 | 48
+constexpr int kEtBlk = kEtN * 16 / 2;           // floats (= pairs of halfs) of one (K step, hi|lo) block of the B operand
+constexpr int kEtHdr = 4;                       // floats in front of the B blocks: the layers' inverse filter scales
+constexpr uint32_t kEtColAHi = kEtN, kEtColALo = kEtN + 24, kEtSetCols = kEtN + 48;   // D 48 | A hi 24 | A lo 24
 constexpr int kEtOutPitch = 8 * 16 + 4;         // floats per pixel in the output staging buffer (8 runs x 64 B + 16 B)
 constexpr int kEtOutFloats = kFovCells * kEtOutPitch;
+static_assert(MAPF_MAX_CONV <= kEtHdr, "one inverse scale per layer");
 
 struct EncTcArgs {
   int num_conv;
   int cin[MAPF_MAX_CONV];
   int w_off[MAPF_MAX_CONV];       // float offset of the layer's B blocks inside the shared-memory weight image
   int64_t bias_off[MAPF_MAX_CONV];// float offset of the layer's folded bias inside `packed`
-  int w_floats;                   // floats of the B-operand image (all layers)
+  int w_floats;                   // floats of the weight image (header + all layers)
   int64_t rows;
   const float* states;
   const float* packed;            // whole packed buffer (biases)
   const float* wtc;               // packed + L.tc_conv
   float* ap;                      // pre-split FC operand out
   int nch;                        // 8-wide K chunks of the FC (fc_in / 8)
+  int skew;                       // start-up offset between the warpgroups, clocks
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -66,136 +77,129 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
+// zero 48 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_zero48(uint32_t taddr) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + 16u * i), "r"(0u)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// D[tmem] (+)= A[tmem] * B[smem]^T (TS mode): A = 128 lanes x 8 TF32 columns at a_tmem, issued by ONE thread
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                            bool accumulate) {
+// instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T (TS mode): A = 128 lanes x 8 columns (16 fp16, two per column) at a_tmem
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                           bool accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(uint32_t(accumulate))
       : "memory");
 }
 
-// TF32 hi / lo of v; hi rounded to nearest, lo = v - hi exact in fp32 (the tensor core drops its low 13 bits: a
-// relative 2^-21 of v, the size of the lo*lo term 3xTF32 drops anyway)
-__device__ __forceinline__ void split_fast(float v, uint32_t& hi, uint32_t& lo) {
-  const float h = tc::tf32_rn(v);
-  hi = __float_as_uint(h);
-  lo = __float_as_uint(v - h);
+// (a, b) -> fp16 pair hi (round to nearest) and fp16 pair lo = (a, b) - hi; a sits in the low half (lower K index)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 back = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// B operand of the conv GEMMs from the BN-folded filters of pack_weights_kernel ([Cout/4][Cin][9][4]):
-// per layer, per 8-wide K step: hi block | lo block, each [n/8][k/4][n%8][k%4] with n = ky*16 + co, k = kx*Cin + ci
+// power-of-two scale that brings a maximum magnitude `amax` into [2^9, 2^10), and its inverse
+__device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
+  int eb = int(__float_as_uint(amax) >> 23) & 0xFF;
+  eb = eb < 32 ? 32 : (eb > 240 ? 240 : eb);
+  scale = __uint_as_float(uint32_t(263 - eb) << 23);
+  inv = __uint_as_float(uint32_t(eb - 9) << 23);
+}
+
+// B operand of the conv GEMMs from the BN-folded filters of pack_weights_kernel ([Cout/4][Cin][9][4]); block l packs
+// layer l.  Region: [inverse filter scale of each layer (kEtHdr floats)] then per layer, per 16-wide K step: hi block |
+// lo block of fp16 pairs, each [n/8][k/8][n%8][k%8] with n = ky*16 + co, k = kx*Cin + ci (canonical no-swizzle K-major)
 __global__ void pack_tc_conv_kernel(mapf_net_params p, PackedLayout L, float* __restrict__ packed) {
-  int64_t base = 0;
-  for (int l = 0; l < p.num_conv; ++l) {
-    const int cin = p.channels[l], ks = (3 * cin + 7) >> 3;
-    const int64_t n = int64_t(ks) * 2 * kEtBlk;
-    for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < n; idx += int64_t(gridDim.x) * blockDim.x) {
-      int r = int(idx);
-      const int step = r / (2 * kEtBlk);
-      r -= step * 2 * kEtBlk;
-      const int is_lo = r >= kEtBlk;
-      if (is_lo) r -= kEtBlk;
-      const int k4i = r & 3, n8 = (r >> 2) & 7, kq = (r >> 5) & 1, ng = r >> 6;
-      const int nn = ng * 8 + n8, k = step * 8 + kq * 4 + k4i;
-      const int ky = nn / kEtCout, co = nn % kEtCout;
-      float v = 0.0f;
-      if (k < 3 * cin) {
-        const int kx = k / cin, ci = k - kx * cin;
-        v = packed[L.conv_w[l] + ((int64_t(co >> 2) * cin + ci) * 9 + ky * 3 + kx) * 4 + (co & 3)];
-      }
-      float hi, lo;
-      tc::split1(v, hi, lo);
-      packed[L.tc_conv + base + idx] = is_lo ? lo : hi;
+  __shared__ float s_red[256];
+  const int l = blockIdx.x;
+  const int cin = p.channels[l], nw = kEtCout * cin * 9;
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) m = fmaxf(m, fabsf(packed[L.conv_w[l] + i]));
+  s_red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) s_red[threadIdx.x] = fmaxf(s_red[threadIdx.x], s_red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  float scale, inv;
+  pow2_scale(s_red[0], scale, inv);
+  if (threadIdx.x == 0) packed[L.tc_conv + l] = inv;
+  int64_t base = kEtHdr;
+  for (int j = 0; j < l; ++j) base += int64_t((3 * p.channels[j] + 15) >> 4) * 2 * kEtBlk;
+  const int ks = (3 * cin + 15) >> 4;
+  __half* out = reinterpret_cast<__half*>(packed + L.tc_conv + base);
+  const int n = ks * 2 * kEtBlk * 2;   // halfs
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    int r = idx;
+    const int step = r / (4 * kEtBlk);
+    r -= step * 4 * kEtBlk;
+    const int is_lo = r >= 2 * kEtBlk;
+    if (is_lo) r -= 2 * kEtBlk;
+    const int k8i = r & 7, n8 = (r >> 3) & 7, kq = (r >> 6) & 1, ng = r >> 7;
+    const int nn = ng * 8 + n8, k = step * 16 + kq * 8 + k8i;
+    const int ky = nn / kEtCout, co = nn % kEtCout;
+    float v = 0.0f;
+    if (k < 3 * cin) {
+      const int kx = k / cin, ci = k - kx * cin;
+      v = packed[L.conv_w[l] + ((int64_t(co >> 2) * cin + ci) * 9 + ky * 3 + kx) * 4 + (co & 3)] * scale;
     }
-    base += n;
+    const __half hi = __float2half_rn(v);
+    out[idx] = is_lo ? __float2half_rn(v - __half2float(hi)) : hi;
   }
 }
 
 #ifdef MAPF_ENC_DEBUG
-__device__ long long* g_etc_dbg = nullptr;   // block 0: [layer iteration < 16][warp < 12][6 stamps]
+__device__ long long* g_etc_dbg = nullptr;   // block 0: [layer iteration < 16][warp < 16][10 stamps]
 #define ETC_STAMP(i)                                                                                   \
   do {                                                                                                 \
-    if (g_etc_dbg && blockIdx.x == 0 && lane == 0 && dbg_it < 16) g_etc_dbg[(dbg_it * 12 + warp) * 6 + (i)] = clock64(); \
+    if (g_etc_dbg && blockIdx.x == 0 && lane == 0 && dbg_it < 16) g_etc_dbg[(dbg_it * 16 + warp) * 10 + (i)] = clock64(); \
   } while (0)
 #else
 #define ETC_STAMP(i)
 #endif
 
 __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) {
-  extern __shared__ __align__(128) float s_w[];          // B-operand image of all layers, then the output staging buffers
+  extern __shared__ __align__(128) float s_w[];          // weight image (header + B blocks), then the output staging buffers
   __shared__ __align__(16) float s_bias[MAPF_MAX_CONV][kEtCout];
   __shared__ __align__(8) uint64_t s_bar[kEtGroups];     // MMAs of the group's current layer complete (tcgen05.commit)
-  __shared__ __align__(8) uint64_t s_ready[kEtGroups];   // the group's A operand is in TMEM and its D columns are free
   __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_lw[MAPF_MAX_CONV], s_lnm[MAPF_MAX_CONV];   // per layer: byte offset of its B blocks, MMA count
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, quad = warp & 3;
   float* const s_out = s_w + g.w_floats + wg * kEtOutFloats;
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
   if (tid == 0) {
-    for (int i = 0; i < kEtGroups; ++i) {
-      tc::mbar_init(&s_bar[i], 1);
-      tc::mbar_init(&s_ready[i], 4);     // one arrival per warp of the group
-    }
+    for (int i = 0; i < kEtGroups; ++i) tc::mbar_init(&s_bar[i], 4);   // one commit per warp of the group
     tc::fence_mbar_init();
   }
   for (int i = tid; i < (g.w_floats >> 2); i += kEtThreads)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(g.wtc) + i);
+  if (tid < g.num_conv) {   // (indexing the kernel-parameter arrays by a runtime layer number would go through local memory)
+    s_lw[tid] = uint32_t(kEtHdr + g.w_off[tid]) * 4u;
+    s_lnm[tid] = uint32_t(3 * ((3 * g.cin[tid] + 15) >> 4));
+  }
   if (tid < g.num_conv * kEtCout) s_bias[tid / kEtCout][tid % kEtCout] = __ldg(g.packed + g.bias_off[tid / kEtCout] + tid % kEtCout);
   tc::fence_proxy_async();      // the filters are read by the tensor core (async proxy)
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  constexpr uint32_t idesc = tc::idesc_tf32(128, kEtN);
-  const int64_t ntiles = (g.rows + 3) >> 2;
-  const int64_t stride = int64_t(gridDim.x) * kEtGroups;
-
-  if (wg == kEtGroups) {
-    // ===== MMA issuer: ONE thread issues the MMAs of all groups, group after group.  The tensor pipe runs them in
-    // issue order, so group 0's layer completes first and its epilogue runs under the MMAs of groups 1 and 2: the
-    // groups stay a third of a round apart instead of contending for the pipe (and then for the issue slots) in step.
-    if (lane == 0) {
-      const uint32_t w_base = tc::smem_u32(s_w);
-      uint32_t ph = 0;
-      for (int64_t t0 = int64_t(blockIdx.x) * kEtGroups; t0 < ntiles; t0 += stride) {
-        for (int l = 0; l < g.num_conv; ++l, ph ^= 1u) {
-          const uint32_t wl = w_base + uint32_t(g.w_off[l]) * 4u;
-          const int ksteps = (3 * g.cin[l] + 7) >> 3;
-          const uint64_t bh0 = tc::smem_desc(wl, 128, 256), bl0 = tc::smem_desc(wl + kEtBlk * 4, 128, 256);
-          for (int gi = 0; gi < kEtGroups; ++gi) {
-            if (t0 + gi >= ntiles) break;
-            const uint32_t tm = s_tmem + uint32_t(gi) * kEtSetCols;
-            tc::mbar_wait(&s_ready[gi], ph);
-            tc::fence_after_sync();
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t o = uint64_t(ks) * ((2 * kEtBlk * 4) >> 4);   // descriptor address field counts 16 bytes
-              const uint32_t ah = tm + kEtColAHi + uint32_t(ks) * 8, al = tm + kEtColALo + uint32_t(ks) * 8;
-              mma_tf32_ts(tm, al, bh0 + o, idesc, ks > 0);     // small terms first
-              mma_tf32_ts(tm, ah, bl0 + o, idesc, true);
-              mma_tf32_ts(tm, ah, bh0 + o, idesc, true);
-            }
-            tc::mma_commit(&s_bar[gi]);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
   const uint32_t tmem = s_tmem + uint32_t(wg) * kEtSetCols;             // this warpgroup's columns, lane 0
   const uint32_t tlane = tmem + (uint32_t(quad * 32) << 16);            // this warp's 32 lanes
   uint64_t* const bar = &s_bar[wg];
@@ -208,6 +212,11 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   const uint32_t v_ok = pix_ok ? 0xFFFFFFFFu : 0u;
   const uint32_t v_lf = (pix_ok && px > 0) ? 0xFFFFFFFFu : 0u, v_rt = (pix_ok && px < kFov - 1) ? 0xFFFFFFFFu : 0u;
 
+  constexpr uint32_t idesc = idesc_f16(128, kEtN);
+  const uint32_t w_base = tc::smem_u32(s_w);
+  const int64_t ntiles = (g.rows + 3) >> 2;
+  const int64_t stride = int64_t(gridDim.x) * kEtGroups;
+
   auto load_obs = [&](int64_t tile, float& v0, float& v1) {
     const int64_t img = tile * 4 + quad;
     v0 = 0.0f;
@@ -219,9 +228,11 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
     }
   };
   auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); };
-  // v of this pixel's left / right neighbour (zero outside the image)
-  auto left_of = [&](float v) { return __uint_as_float(__float_as_uint(__shfl_up_sync(0xffffffffu, v, 1)) & v_lf); };
-  auto right_of = [&](float v) { return __uint_as_float(__float_as_uint(__shfl_down_sync(0xffffffffu, v, 1)) & v_rt); };
+  // operand word of this pixel's left / right neighbour (zero outside the image)
+  auto left_of = [&](uint32_t w) { return __shfl_up_sync(0xffffffffu, w, 1) & v_lf; };
+  auto right_of = [&](uint32_t w) { return __shfl_down_sync(0xffffffffu, w, 1) & v_rt; };
+  // maximum over the warp of a non-negative float (its bit pattern orders like an unsigned integer): one REDUX
+  auto warp_max = [&](float m) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))); };
 
 #ifdef MAPF_ENC_DEBUG
   int dbg_it = 0;
@@ -229,17 +240,23 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   int64_t tile = int64_t(blockIdx.x) * kEtGroups + wg;
   float o0, o1;
   load_obs(tile, o0, o1);
+  tmem_zero48(tlane);
+  if (wg > 0) {   // start the groups a fraction of a layer apart: one group's MMA wait falls under the others' epilogues
+    const long long t0 = clock64();
+    while (clock64() - t0 < g.skew * wg) {}
+  }
   for (; tile < ntiles; tile += stride) {
-    // ---- layer-0 A operand: k = kx*2 + c, K padded to 8 ----
+    float inv_a;     // inverse of the scale of the A operand now in TMEM (one per image)
+    // ---- layer-0 A operand: k = kx*2 + c, K padded to 16 ----
     {
+      float sc;
+      pow2_scale(warp_max(fmaxf(fabsf(o0), fabsf(o1))), sc, inv_a);
       uint32_t hi[8], lo[8];
-      split_fast(left_of(o0), hi[0], lo[0]);
-      split_fast(left_of(o1), hi[1], lo[1]);
-      split_fast(o0, hi[2], lo[2]);
-      split_fast(o1, hi[3], lo[3]);
-      split_fast(right_of(o0), hi[4], lo[4]);
-      split_fast(right_of(o1), hi[5], lo[5]);
-      hi[6] = hi[7] = lo[6] = lo[7] = 0u;
+      split_h2(o0 * sc, o1 * sc, hi[1], lo[1]);
+      hi[0] = left_of(hi[1]);  lo[0] = left_of(lo[1]);
+      hi[2] = right_of(hi[1]); lo[2] = right_of(lo[1]);
+#pragma unroll
+      for (int i = 3; i < 8; ++i) hi[i] = lo[i] = 0u;
       tmem_st8(tlane + kEtColAHi, hi);
       tmem_st8(tlane + kEtColALo, lo);
     }
@@ -248,22 +265,41 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
 
     for (int l = 0; l < g.num_conv; ++l) {
       ETC_STAMP(0);
-      tmem_st_wait();                    // this lane's A row is in TMEM (and its reads of D are long done)
+      tmem_st_wait();
       tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s_ready[wg]);
+      wg_sync();                         // every lane's A row is in TMEM, every read of D is done
       ETC_STAMP(1);
+      if (lane == 0) {
+        // one thread issues an MMA about every 100 cycles however small it is, so the layer's MMAs are dealt over the
+        // group's four warps; D was zeroed by the previous epilogue, so every MMA accumulates and their order is free
+        tc::fence_after_sync();
+        ETC_STAMP(6);
+        const uint32_t wl = w_base + s_lw[l];
+        const int nm = int(s_lnm[l]);
+        for (int i = quad; i < nm; i += 4) {
+          const int ks = i / 3, ps = i - ks * 3;          // ps 0: lo*hi, 1: hi*lo, 2: hi*hi
+          const uint64_t bd = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + (ps == 1 ? kEtBlk * 4 : 0), 128, 256);
+          mma_f16_ts(tmem, tmem + (ps == 0 ? kEtColALo : kEtColAHi) + uint32_t(ks) * 8, bd, idesc, true);
+        }
+        ETC_STAMP(7);
+        tc::mma_commit(bar);
+        ETC_STAMP(8);
+      }
+      __syncwarp();
       tc::mbar_wait(bar, phase);
       phase ^= 1u;
       tc::fence_after_sync();
       ETC_STAMP(2);
 
-      // ---- epilogue: out[p][co] = bias[co] + D[p][(1,co)] + D[p-5][(0,co)] + D[p+5][(2,co)] ----
+      // ---- epilogue: out[p][co] = bias[co] + f * (D[p][(1,co)] + D[p-5][(0,co)] + D[p+5][(2,co)]) ----
       uint32_t r[3][kEtCout];
 #pragma unroll
       for (int u = 0; u < 3; ++u) tmem_ld16(tlane + uint32_t(u * kEtCout), r[u]);
       tc::tmem_ld_wait();
+      tmem_zero48(tlane);                // D is free again: the next layer's MMAs all accumulate
       ETC_STAMP(3);
+      const float f = inv_a * s_w[l];    // undo the activation scale of this image and the filter scale of this layer
+      const float f_up = m_up * f, f_dn = m_dn * f;
       float v[kEtCout];
       {
         const float4* b4 = reinterpret_cast<const float4*>(s_bias[l]);
@@ -273,31 +309,40 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
           v[4 * q] = b.x; v[4 * q + 1] = b.y; v[4 * q + 2] = b.z; v[4 * q + 3] = b.w;
         }
       }
+      float amax = 0.0f;
 #pragma unroll
       for (int c = 0; c < kEtCout; ++c) {
         const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kFov);
         const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kFov);
-        float a = v[c] + __uint_as_float(r[1][c]);
-        a = fmaf(up, m_up, a);
-        a = fmaf(dn, m_dn, a);
+        float a = fmaf(__uint_as_float(r[1][c]), f, v[c]);
+        a = fmaf(up, f_up, a);
+        a = fmaf(dn, f_dn, a);
         v[c] = __uint_as_float(__float_as_uint(fmaxf(a, 0.0f)) & v_ok);   // ReLU; lanes that are not pixels hold zero
+        amax = fmaxf(amax, v[c]);
       }
       ETC_STAMP(4);
       if (l + 1 < g.num_conv) {
-        // next layer's A operand: k = kx*16 + ci -> (left neighbour | this pixel | right neighbour), hi and lo
-        uint32_t h[kEtCout], o[kEtCout];
+        // next layer's A operand: k = kx*16 + ci -> (left neighbour | this pixel | right neighbour), fp16 hi and lo
+        float sc;
+        pow2_scale(warp_max(amax), sc, inv_a);
+        uint32_t h[8], o[8], t[8];
 #pragma unroll
-        for (int c = 0; c < kEtCout; ++c) split_fast(left_of(v[c]), h[c], o[c]);
-        tmem_st16(tlane + kEtColAHi, h);
-        tmem_st16(tlane + kEtColALo, o);
+        for (int c = 0; c < kEtCout; c += 2) split_h2(v[c] * sc, v[c + 1] * sc, h[c >> 1], o[c >> 1]);
+        tmem_st8(tlane + kEtColAHi + 8, h);
+        tmem_st8(tlane + kEtColALo + 8, o);
+        // the neighbours' operand words are the neighbours' own splits: shuffle the packed fp16 pairs
 #pragma unroll
-        for (int c = 0; c < kEtCout; ++c) split_fast(v[c], h[c], o[c]);
-        tmem_st16(tlane + kEtColAHi + kEtCout, h);
-        tmem_st16(tlane + kEtColALo + kEtCout, o);
+        for (int j = 0; j < 8; ++j) t[j] = left_of(h[j]);
+        tmem_st8(tlane + kEtColAHi, t);
 #pragma unroll
-        for (int c = 0; c < kEtCout; ++c) split_fast(right_of(v[c]), h[c], o[c]);
-        tmem_st16(tlane + kEtColAHi + 2 * kEtCout, h);
-        tmem_st16(tlane + kEtColALo + 2 * kEtCout, o);
+        for (int j = 0; j < 8; ++j) t[j] = left_of(o[j]);
+        tmem_st8(tlane + kEtColALo, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = right_of(h[j]);
+        tmem_st8(tlane + kEtColAHi + 16, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = right_of(o[j]);
+        tmem_st8(tlane + kEtColALo + 16, t);
       } else {
         // flattened activations, k = pixel*16 + c, as Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4]:
         // staged per pixel as 8 runs (chunk half, hi|lo, k quad) of 4 images x 16 bytes, then stored as 64-byte runs
@@ -316,8 +361,8 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
         const int wt = tid & 127;
 #pragma unroll
         for (int it = 0; it < (kFovCells * 32 + 127) / 128; ++it) {
-          const int f = it * 128 + wt;
-          const int p = f >> 5, run = (f >> 2) & 7, piece = f & 3;
+          const int fi = it * 128 + wt;
+          const int p = fi >> 5, run = (fi >> 2) & 7, piece = fi & 3;
           if (p < kFovCells && img0 + piece < g.rows) {
             const float4 val = *reinterpret_cast<const float4*>(s_out + p * kEtOutPitch + run * 16 + piece * 4);
             float* d = base + int64_t(2 * p + (run >> 2)) * 2048 + ((run >> 1) & 1) * 1024 + (run & 1) * 32 + piece * 4;
@@ -331,7 +376,6 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
 #endif
     }
   }
-  }  // epilogue groups
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(s_tmem, 512);
@@ -347,7 +391,7 @@ extern "C" int mapf_enc_tc_set_debug(long long* p) {
 
 // every conv layer 16 channels wide, input 2 planes, FC input 400 = 50 whole K chunks
 extern "C" int mapf_encoder_tc_supported(const mapf_net_params* p) {
-  static_assert(kEtCout == 16 && kEtBlk == 48 * 8, "mapf_packed_layout sizes the tc_conv region with these");
+  static_assert(kEtCout == 16 && kEtBlk == 48 * 8 && kEtHdr == 4, "mapf_packed_layout sizes the tc_conv region with these");
   if (mapf_check_params(p) != MAPF_OK) return 0;
   return mapf_enc_tc_dims_ok(*p) ? 1 : 0;
 }
@@ -355,7 +399,7 @@ extern "C" int mapf_encoder_tc_supported(const mapf_net_params* p) {
 // called by mapf_pack_weights behind pack_weights_kernel (same stream): needs the BN-folded filters in place
 int mapf_encoder_tc_pack(const mapf_net_params* p, float* packed, mapf_stream_t stream) {
   const PackedLayout L = mapf_packed_layout(*p);
-  pack_tc_conv_kernel<<<32, 256, 0, static_cast<cudaStream_t>(stream)>>>(*p, L, packed);
+  pack_tc_conv_kernel<<<p->num_conv, 256, 0, static_cast<cudaStream_t>(stream)>>>(*p, L, packed);
   const int rc = mapf_tc_pack_b_pixel_major(p->fc_w, p->channels[p->num_conv], p->fc_out, packed + L.tc_fc_pm, stream);
   if (rc != MAPF_OK) return rc;
   return mapf_launch_status();
@@ -376,9 +420,10 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
   for (int l = 0; l < p->num_conv; ++l) {
     g.cin[l] = p->channels[l];
     g.w_off[l] = off;
-    off += ((3 * p->channels[l] + 7) >> 3) * 2 * kEtBlk;
+    off += ((3 * p->channels[l] + 15) >> 4) * 2 * kEtBlk;
     g.bias_off[l] = L.conv_b[l];
   }
+  off += kEtHdr;
   g.w_floats = off;
   g.rows = a->rows;
   g.states = a->states;
@@ -386,6 +431,10 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
   g.wtc = a->packed + L.tc_conv;
   g.ap = a->x;
   g.nch = (p->fc_in + 7) >> 3;
+  {
+    const char* e = getenv("MAPF_B200_ETC_SKEW");   // development switch
+    g.skew = e ? atoi(e) : 1400;
+  }
   const size_t smem = size_t(off + kEtGroups * kEtOutFloats) * sizeof(float);
   MAPF_REQUIRE(smem <= 200 * 1024, MAPF_ERR_UNSUPPORTED);
   static int cache[16] = {0};

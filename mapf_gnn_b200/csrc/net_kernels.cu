@@ -187,8 +187,8 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
     // emits the GEMM's A operand pre-split and pre-tiled (all-TMA GEMM); MAPF_B200_FC_UNSPLIT=1 keeps the plain
     // [rows, fc_in] hand-over with conversion warps in the GEMM (development switch).
     mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_act};
-    static const bool unsplit = getenv("MAPF_B200_FC_UNSPLIT") != nullptr;
-    static const bool ffma_conv = getenv("MAPF_B200_ENC_FFMA_CONV") != nullptr;
+    const bool unsplit = getenv("MAPF_B200_FC_UNSPLIT") != nullptr;      // development switches, read per call
+    const bool ffma_conv = getenv("MAPF_B200_ENC_FFMA_CONV") != nullptr;
     if (!ffma_conv && !unsplit && mapf_enc_tc_dims_ok(*p)) {
       // conv stack on tcgen05 (activations as the A operand in tensor memory, enc_tc.cu) -> FC operand in pixel-major
       // K order -> all-TMA tcgen05 FC against the matching B operand

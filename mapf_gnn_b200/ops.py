@@ -21,9 +21,21 @@ _LIB = torch.library.Library("mapf", "DEF")
 
 # graph-filter mix on tcgen05 (3xTF32) when True; the fused fp32-FFMA kernel when False (development switch)
 USE_TENSOR_CORES = os.environ.get("MAPF_B200_TENSOR_CORES", "1") != "0"
-# encoder FC on tcgen05 as well (conv-only encoder kernel + tensor-core GEMM).  Off by default: at the benchmark
-# sizes the fused FFMA FC inside the persistent encoder kernel is as fast (see DESIGN.md 3.2 / profiles/)
+# encoder on tcgen05: the conv stack of 16-channel networks runs on the tensor cores (enc_tc.cu) with the FC behind it as
+# an all-TMA tcgen05 GEMM; other channel widths keep the fused FFMA2 encoder kernel.  MAPF_B200_TENSOR_CORE_ENCODER=0
+# forces the FFMA2 kernel; MAPF_B200_TENSOR_CORE_FC=1 hands the workspace to every network (development switch: FFMA2
+# conv kernel emitting the pre-split operand + tensor-core FC where the tensor-core conv stack does not apply).
+USE_TENSOR_CORE_ENCODER = os.environ.get("MAPF_B200_TENSOR_CORE_ENCODER", "1") != "0"
 USE_TENSOR_CORE_FC = os.environ.get("MAPF_B200_TENSOR_CORE_FC", "0") == "1"
+
+
+def wants_encoder_workspace(p) -> bool:
+    """True when mapf_policy_fwd should get ``workspace_act`` (the pre-split FC operand) for these dimensions."""
+    if not USE_TENSOR_CORES:
+        return False
+    if USE_TENSOR_CORE_FC:
+        return True
+    return USE_TENSOR_CORE_ENCODER and _lib.load().mapf_encoder_tc_supported(p) == 1
 
 _LIB.define("pack_weights(int[] dims, Tensor[] conv_w, Tensor[] conv_b, Tensor[] bn_gamma, Tensor[] bn_beta, "
             "Tensor[] bn_mean, Tensor[] bn_var, Tensor fc_w, Tensor fc_b, Tensor? gf_w, Tensor? gf_w2, "
@@ -93,7 +105,7 @@ def _policy_fwd(dims, message, states, gso, packed):
     a = _lib.PolicyFwdArgs()
     a.batch, a.agents, a.message = B, N, int(message)
     a.states, a.packed, a.workspace_x = states.data_ptr(), packed.data_ptr(), work.data_ptr()
-    if USE_TENSOR_CORES and USE_TENSOR_CORE_FC:
+    if wants_encoder_workspace(p):
         worka = torch.empty((lib.mapf_tc_presplit_a_size(B * N, p.fc_in),), dtype=torch.float32, device=dev)
         a.workspace_act = worka.data_ptr()
     if p.taps > 0:

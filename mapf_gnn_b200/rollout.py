@@ -37,7 +37,7 @@ class Rollout:
         self.work = torch.empty((E * N, dims[7]), dtype=torch.float32, device=dev)
         from . import ops
         self.worka = (torch.empty((self.lib.mapf_tc_presplit_a_size(E * N, dims[6]),), dtype=torch.float32, device=dev)
-                      if ops.USE_TENSOR_CORES and ops.USE_TENSOR_CORE_FC else None)
+                      if ops.wants_encoder_workspace(net_params(dims)) else None)
         self.workz = (torch.empty((E * N, (dims[8] + 1) * dims[7]), dtype=torch.float32, device=dev)
                       if dims[8] > 0 and ops.USE_TENSOR_CORES else None)
         self.params = net_params(dims)

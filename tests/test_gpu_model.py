@@ -129,6 +129,75 @@ def test_presplit_tensor_core_fc_matches_oracle(rows):
     assert rel_err(got, ref) < REL
 
 
+def _untile_presplit(Ap, rows, K):
+    """Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4] -> hi + lo as [rows, K]."""
+    nblk, nch = (rows + 127) // 128, (K + 7) // 8
+    a = Ap.cpu().numpy().reshape(nblk, nch, 2, 16, 2, 8, 4).transpose(2, 0, 3, 5, 1, 4, 6).reshape(2, nblk * 128, nch * 8)
+    return (a[0].astype(np.float64) + a[1])[:rows, :K]
+
+
+def _conv_stack_reference(params, states, depth):
+    import torch.nn.functional as F
+    h = states
+    for l in range(depth):
+        li = 3 * l
+        h = F.conv2d(h, params[f"convLayers.{li}.weight"], params[f"convLayers.{li}.bias"], padding=1)
+        bn = f"convLayers.{li + 1}"
+        h = F.relu(F.batch_norm(h, params[f"{bn}.running_mean"], params[f"{bn}.running_var"], params[f"{bn}.weight"],
+                                params[f"{bn}.bias"], False, 0.1, 1e-5))
+    return h.permute(0, 2, 3, 1).reshape(states.shape[0], -1).numpy()     # pixel-major (y, x, c)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+@pytest.mark.parametrize("rows", [1, 3, 4, 5, 127, 129, 1777, 4736 + 300])
+def test_tensor_core_conv_stack_matches_torch(rows, depth):
+    """enc_tc.cu: conv + BN + ReLU layers as tcgen05 GEMMs on fp16-split operands with per-image dynamic scales
+    (framework_gnn.py:55-71,160-163).  The emitted FC operand, re-assembled (hi + lo), must equal the torch-CPU conv stack
+    to fp32 accuracy for every tile raggedness and depth -- including all-zero images, huge, tiny, negative and
+    non-integer observations (the scale logic), which the FOV tensors of a rollout never contain."""
+    from mapf_gnn_b200 import _lib
+    from mapf_gnn_b200.ops import net_params
+    lib = _lib.load()
+    rng = np.random.default_rng(1000 * depth + rows)
+    states = torch.tensor(rng.integers(0, 4, size=(rows, 2, 5, 5))).float()
+    states[1::5] *= 0.61
+    states[2::7] = torch.randn_like(states[2::7])
+    states[3::11] = 0.0
+    states[4::13] *= 3.0e4
+    states[5::17] *= 1.0e-6
+    params = oracle_params("gnn_k3")
+    with torch.no_grad():
+        ref = _conv_stack_reference(params, states, depth)
+    net = load_network("gnn_k3", num_agents=1).eval()
+    g = net.param_groups()
+    d = lambda ts: [t.detach() for t in ts[:depth]]
+    dims = [depth, 2] + [16] * depth + [0] * (4 - depth) + [400, 64, 0, 0, 5]
+    packed = torch.ops.mapf.pack_weights(dims, d(g["conv_w"]), d(g["conv_b"]), d(g["bn_gamma"]), d(g["bn_beta"]),
+                                         d(g["bn_mean"]), d(g["bn_var"]), g["fc_w"].detach(), g["fc_b"].detach(), None,
+                                         None, torch.zeros(5, 64, device="cuda"), torch.zeros(5, device="cuda"))
+    p = net_params(dims)
+    assert lib.mapf_encoder_tc_supported(p) == 1
+    Ap = torch.full((lib.mapf_tc_presplit_a_size(rows, 400),), float("nan"), device="cuda")
+    st = states.cuda()
+    ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
+    _lib.check(lib.mapf_encoder_tc_conv_fwd(p, ea, _lib.current_stream()), "tc_conv")
+    got = _untile_presplit(Ap, rows, 400)
+    assert np.isfinite(got).all()
+    # per image: 1e-5 of the image's largest activation (the split keeps 22 bits relative to it)
+    scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
+    assert (np.abs(got - ref) / scale).max() < 1e-5
+
+
+def test_tensor_core_encoder_unsupported_widths_are_refused():
+    """The tensor-core conv stack is built for 16-channel layers; the baseline's 32-channel first layer must be
+    reported unsupported (the policy then keeps the FFMA2 encoder) instead of being mis-computed."""
+    from mapf_gnn_b200 import _lib
+    from mapf_gnn_b200.ops import net_params
+    lib = _lib.load()
+    assert lib.mapf_encoder_tc_supported(net_params(load_network("baseline").dims())) == 0
+    assert lib.mapf_encoder_tc_supported(net_params(load_network("gnn_k2").dims())) == 1
+
+
 def test_training_gso_convention_a_plus_i():
     """The data loader feeds A + I (data_loader.py:74); GCNLayer adds I again -> diagonal 2."""
     rng = np.random.default_rng(3)
@@ -287,7 +356,7 @@ def test_host_stepped_rollout_matches_device_rollout():
     assert torch.equal(env_a.fov, env_b.fov) and torch.equal(env_a.time, env_b.time)
 
 
-@pytest.mark.parametrize("path", ["fused_tc", "unfused_tc", "ffma", "tc_fc"])
+@pytest.mark.parametrize("path", ["fused_tc", "unfused_tc", "ffma", "tc_fc", "ffma_encoder"])
 @pytest.mark.parametrize("name,N", [("gnn_k3", 5), ("gnn_msg_k3", 20)])
 def test_every_policy_path_matches_oracle(monkeypatch, path, name, N):
     """The graph-filter / FC stage has several implementations (fused tcgen05 kernel, taps + tcgen05 GEMM, fused FFMA
@@ -297,8 +366,11 @@ def test_every_policy_path_matches_oracle(monkeypatch, path, name, N):
         monkeypatch.setenv("MAPF_B200_UNFUSED_GRAPH", "1")
     if path == "ffma":
         monkeypatch.setattr(ops, "USE_TENSOR_CORES", False)
-    if path == "tc_fc":
+    if path == "tc_fc":            # FFMA2 conv kernel emitting the pre-split operand + tensor-core FC
         monkeypatch.setattr(ops, "USE_TENSOR_CORE_FC", True)
+        monkeypatch.setenv("MAPF_B200_ENC_FFMA_CONV", "1")
+    if path == "ffma_encoder":     # fused FFMA2 encoder kernel (the default is the tensor-core conv stack)
+        monkeypatch.setattr(ops, "USE_TENSOR_CORE_ENCODER", False)
     rng = np.random.default_rng(17 + N)
     B = 70
     states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
