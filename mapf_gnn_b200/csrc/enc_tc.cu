@@ -38,7 +38,7 @@
 
 namespace {
 
-constexpr int kEtGroups = 4;                    // warpgroups per CTA
+constexpr int kEtGroups = 5;                    // warpgroups per CTA
 constexpr int kEtThreads = 128 * kEtGroups;
 constexpr int kEtCout = 16;                     // channels of every conv layer this kernel is built for
 constexpr int kEtN = 3 * kEtCout;               // GEMM N: (filter row, co)
@@ -76,15 +76,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
-}
-// zero 48 consecutive columns of this thread's lane
-__device__ __forceinline__ void tmem_zero48(uint32_t taddr) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + 16u * i), "r"(0u)
-        : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -165,10 +156,10 @@ __global__ void pack_tc_conv_kernel(mapf_net_params p, PackedLayout L, float* __
 }
 
 #ifdef MAPF_ENC_DEBUG
-__device__ long long* g_etc_dbg = nullptr;   // block 0: [layer iteration < 16][warp < 16][10 stamps]
+__device__ long long* g_etc_dbg = nullptr;   // block 0: [layer iteration < 16][warp < 20][10 stamps]
 #define ETC_STAMP(i)                                                                                   \
   do {                                                                                                 \
-    if (g_etc_dbg && blockIdx.x == 0 && lane == 0 && dbg_it < 16) g_etc_dbg[(dbg_it * 16 + warp) * 10 + (i)] = clock64(); \
+    if (g_etc_dbg && blockIdx.x == 0 && lane == 0 && dbg_it < 16) g_etc_dbg[(dbg_it * 20 + warp) * 10 + (i)] = clock64(); \
   } while (0)
 #else
 #define ETC_STAMP(i)
@@ -179,21 +170,21 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   __shared__ __align__(16) float s_bias[MAPF_MAX_CONV][kEtCout];
   __shared__ __align__(8) uint64_t s_bar[kEtGroups];     // MMAs of the group's current layer complete (tcgen05.commit)
   __shared__ uint32_t s_tmem;
-  __shared__ uint32_t s_lw[MAPF_MAX_CONV], s_lnm[MAPF_MAX_CONV];   // per layer: byte offset of its B blocks, MMA count
+  __shared__ uint32_t s_lw[MAPF_MAX_CONV], s_lnm[MAPF_MAX_CONV];   // per layer: byte offset of its B blocks, 16-wide K steps
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, quad = warp & 3;
   float* const s_out = s_w + g.w_floats + wg * kEtOutFloats;
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
   if (tid == 0) {
-    for (int i = 0; i < kEtGroups; ++i) tc::mbar_init(&s_bar[i], 4);   // one commit per warp of the group
+    for (int i = 0; i < kEtGroups; ++i) tc::mbar_init(&s_bar[i], 1);
     tc::fence_mbar_init();
   }
   for (int i = tid; i < (g.w_floats >> 2); i += kEtThreads)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(g.wtc) + i);
   if (tid < g.num_conv) {   // (indexing the kernel-parameter arrays by a runtime layer number would go through local memory)
     s_lw[tid] = uint32_t(kEtHdr + g.w_off[tid]) * 4u;
-    s_lnm[tid] = uint32_t(3 * ((3 * g.cin[tid] + 15) >> 4));
+    s_lnm[tid] = uint32_t((3 * g.cin[tid] + 15) >> 4);
   }
   if (tid < g.num_conv * kEtCout) s_bias[tid / kEtCout][tid % kEtCout] = __ldg(g.packed + g.bias_off[tid / kEtCout] + tid % kEtCout);
   tc::fence_proxy_async();      // the filters are read by the tensor core (async proxy)
@@ -240,7 +231,6 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   int64_t tile = int64_t(blockIdx.x) * kEtGroups + wg;
   float o0, o1;
   load_obs(tile, o0, o1);
-  tmem_zero48(tlane);
   if (wg > 0) {   // start the groups a fraction of a layer apart: one group's MMA wait falls under the others' epilogues
     const long long t0 = clock64();
     while (clock64() - t0 < g.skew * wg) {}
@@ -269,17 +259,22 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
       tc::fence_before_sync();
       wg_sync();                         // every lane's A row is in TMEM, every read of D is done
       ETC_STAMP(1);
-      if (lane == 0) {
-        // one thread issues an MMA about every 100 cycles however small it is, so the layer's MMAs are dealt over the
-        // group's four warps; D was zeroed by the previous epilogue, so every MMA accumulates and their order is free
+      if (quad == 0 && lane == 0) {
+        // ONE thread issues the layer's MMAs in a fixed order: the accumulation order -- and with it every bit of the
+        // result -- is the same on every run.  (Dealing the MMAs over the group's four warps shortens this phase by
+        // a quarter, one thread issues only about one MMA per 100 cycles, but the pipe then accumulates in arrival
+        // order and results differ in the last bit from run to run.)
         tc::fence_after_sync();
         ETC_STAMP(6);
         const uint32_t wl = w_base + s_lw[l];
-        const int nm = int(s_lnm[l]);
-        for (int i = quad; i < nm; i += 4) {
-          const int ks = i / 3, ps = i - ks * 3;          // ps 0: lo*hi, 1: hi*lo, 2: hi*hi
-          const uint64_t bd = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + (ps == 1 ? kEtBlk * 4 : 0), 128, 256);
-          mma_f16_ts(tmem, tmem + (ps == 0 ? kEtColALo : kEtColAHi) + uint32_t(ks) * 8, bd, idesc, true);
+        const int ksteps = int(s_lnm[l]);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t bh = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4), 128, 256);
+          const uint64_t bl = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + kEtBlk * 4, 128, 256);
+          const uint32_t ah = tmem + kEtColAHi + uint32_t(ks) * 8, al = tmem + kEtColALo + uint32_t(ks) * 8;
+          mma_f16_ts(tmem, al, bh, idesc, ks > 0);     // small terms first
+          mma_f16_ts(tmem, ah, bl, idesc, true);
+          mma_f16_ts(tmem, ah, bh, idesc, true);
         }
         ETC_STAMP(7);
         tc::mma_commit(bar);
@@ -296,7 +291,6 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
 #pragma unroll
       for (int u = 0; u < 3; ++u) tmem_ld16(tlane + uint32_t(u * kEtCout), r[u]);
       tc::tmem_ld_wait();
-      tmem_zero48(tlane);                // D is free again: the next layer's MMAs all accumulate
       ETC_STAMP(3);
       const float f = inv_a * s_w[l];    // undo the activation scale of this image and the filter scale of this layer
       const float f_up = m_up * f, f_dn = m_dn * f;

@@ -16,15 +16,15 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 20480
 st = torch.randint(0, 4, (rows, 2, 5, 5), device="cuda").float()
 Ap = torch.empty((lib.mapf_tc_presplit_a_size(rows, 400),), device="cuda")
 ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
-dbg = torch.zeros(16 * 16 * 10, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(16 * 20 * 10, dtype=torch.int64, device="cuda")
 lib.mapf_enc_tc_set_debug(dbg.data_ptr())
 for _ in range(3):
     dbg.zero_(); lib.mapf_encoder_tc_conv_fwd(p, ea, _lib.current_stream()); torch.cuda.synchronize()
-d = dbg.cpu().numpy().reshape(16, 16, 10)
+d = dbg.cpu().numpy().reshape(16, 20, 10)
 t0 = d[0, :, 0].min()
 names = ["top", "synced", "mma done", "ld0", "sums", "stored"]
 for it in range(16):
-    for wg in range(4):
+    for wg in range(5):
         w = d[it, wg * 4:(wg + 1) * 4]
         if w[0, 0] == 0:
             continue
