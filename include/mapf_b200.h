@@ -367,12 +367,17 @@ int mapf_tc_fc_presplit(int32_t M, int32_t N, int32_t K, const float* Ap, const 
                         const float* bias, int32_t relu, mapf_stream_t stream);
 /* Conv stack of the encoder on the tensor cores (framework_gnn.py:55-71,160-163 for 16-channel layers): each layer is
  * one 128 x 144 x Cin 3xTF32 GEMM per 4 agent images (all 9 taps at once, activations as the A operand in tensor
- * memory) followed by 9 shifted adds in the epilogue.  a->x receives the pre-split FC operand with its K index ordered
- * pixel-major; pair it with the B operand mapf_pack_weights builds for that order (mapf_tc_pack_b_pixel_major of
- * compressMLP.0.weight).  mapf_policy_fwd takes this path when workspace_act is given and the dimensions fit. */
+ * memory) followed by shifted adds in the epilogue.  a->x (mapf_tc_presplit_a_size floats) receives the FC operand
+ * fp16-split (x * 2^-e = hi + lo, one scale per image) with its K index ordered pixel-major, followed by the rows' inverse
+ * scales; mapf_tc_fc_presplit_f16 computes relu(A W^T + b) (compressMLP, framework_gnn.py:93) from it and the B operand
+ * mapf_tc_pack_b_f16_pixel_major builds from compressMLP.0.weight (mapf_pack_weights does this).  mapf_policy_fwd
+ * takes this path when workspace_act is given and the dimensions fit. */
 int mapf_encoder_tc_supported(const mapf_net_params* p);
 int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream);
-int mapf_tc_pack_b_pixel_major(const float* b, int32_t C, int32_t N, float* out, mapf_stream_t stream);
+int64_t mapf_tc_packed_b_f16_size(int32_t N, int32_t K);
+int mapf_tc_pack_b_f16_pixel_major(const float* b, int32_t C, int32_t N, float* out, mapf_stream_t stream);
+int mapf_tc_fc_presplit_f16(int32_t M, int32_t N, int32_t K, const float* Ap, const float* Bp, float* C, int64_t ldc,
+                            const float* bias, int32_t relu, mapf_stream_t stream);
 int mapf_tc_mix_head(int32_t M, int32_t N, int32_t K, const float* Z, int64_t ldz, const float* Wp, const float* act_w,
                      const float* act_b, int32_t num_actions, float* logits, int32_t* actions, float* y,
                      mapf_stream_t stream);

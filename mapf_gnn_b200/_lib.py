@@ -152,7 +152,10 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_encoder_tc_supported": (C.c_int, [C.POINTER(NetParams)]),
     "mapf_encoder_tc_conv_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(EncoderFwdArgs), C.c_void_p]),
-    "mapf_tc_pack_b_pixel_major": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mapf_tc_packed_b_f16_size": (C.c_int64, [C.c_int32, C.c_int32]),
+    "mapf_tc_pack_b_f16_pixel_major": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mapf_tc_fc_presplit_f16": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_tc_mix_head": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mapf_tc_graph_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

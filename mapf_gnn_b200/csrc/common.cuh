@@ -84,7 +84,7 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
     off += 4;   // inverse filter scales
     for (int l = 0; l < p.num_conv; ++l) off += int64_t((3 * p.channels[l] + 15) >> 4) * 2 * (48 * 8);
     L.tc_fc_pm = off;
-    off += mapf_tc_b_floats(p.fc_out, p.fc_in);
+    off += 4 + int64_t((p.fc_in + 15) / 16) * (p.fc_out <= 64 ? 64 : 128) * 16;   // fp16 hi|lo blocks + scale header
   }
   L.act_w = off;
   off += mapf_round4(int64_t(p.num_actions) * (p.taps > 0 ? p.node_dim : p.fc_out));

@@ -45,7 +45,7 @@ constexpr int kEtN = 3 * kEtCout;               // GEMM N: (filter row, co)
 constexpr int kEtBlk = kEtN * 16 / 2;           // floats (= pairs of halfs) of one (K step, hi|lo) block of the B operand
 constexpr int kEtHdr = 4;                       // floats in front of the B blocks: the layers' inverse filter scales
 constexpr uint32_t kEtColAHi = kEtN, kEtColALo = kEtN + 24, kEtSetCols = kEtN + 48;   // D 48 | A hi 24 | A lo 24
-constexpr int kEtOutPitch = 8 * 16 + 4;         // floats per pixel in the output staging buffer (8 runs x 64 B + 16 B)
+constexpr int kEtOutPitch = 4 * 16 + 4;         // words per pixel in the output staging buffer (4 runs x 64 B + 16 B)
 constexpr int kEtOutFloats = kFovCells * kEtOutPitch;
 static_assert(MAPF_MAX_CONV <= kEtHdr, "one inverse scale per layer");
 
@@ -60,7 +60,8 @@ struct EncTcArgs {
   const float* packed;            // whole packed buffer (biases)
   const float* wtc;               // packed + L.tc_conv
   float* ap;                      // pre-split FC operand out
-  int nch;                        // 8-wide K chunks of the FC (fc_in / 8)
+  float* row_inv;                 // inverse scale of every FC operand row out
+  int nch;                        // 16-wide K chunks of the FC (fc_in / 16)
   int skew;                       // start-up offset between the warpgroups, clocks
 };
 
@@ -79,10 +80,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate, both operands K-major
-__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
-  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
 // D[tmem] (+)= A[tmem] * B[smem]^T (TS mode): A = 128 lanes x 8 columns (16 fp16, two per column) at a_tmem
 __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                            bool accumulate) {
@@ -203,7 +200,7 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   const uint32_t v_ok = pix_ok ? 0xFFFFFFFFu : 0u;
   const uint32_t v_lf = (pix_ok && px > 0) ? 0xFFFFFFFFu : 0u, v_rt = (pix_ok && px < kFov - 1) ? 0xFFFFFFFFu : 0u;
 
-  constexpr uint32_t idesc = idesc_f16(128, kEtN);
+  constexpr uint32_t idesc = tc::idesc_f16(128, kEtN);
   const uint32_t w_base = tc::smem_u32(s_w);
   const int64_t ntiles = (g.rows + 3) >> 2;
   const int64_t stride = int64_t(gridDim.x) * kEtGroups;
@@ -338,28 +335,33 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
         for (int j = 0; j < 8; ++j) t[j] = right_of(o[j]);
         tmem_st8(tlane + kEtColALo + 16, t);
       } else {
-        // flattened activations, k = pixel*16 + c, as Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4]:
-        // staged per pixel as 8 runs (chunk half, hi|lo, k quad) of 4 images x 16 bytes, then stored as 64-byte runs
+        // flattened activations, k = pixel*16 + c, as the fp16-split A operand of the FC: Ap [row/128][k/16 = pixel]
+        // [hi|lo][(row%128)/8][(k%16)/8][row%8][k%8] with one power-of-two scale per image (its inverse goes to the row
+        // scale array behind the operand).  Staged per pixel as 4 runs (hi|lo, k half) of 4 images x 16 bytes, then
+        // stored as 64-byte runs.
+        float sc, inv_row;
+        pow2_scale(warp_max(amax), sc, inv_row);
         if (pix_ok) {
-          float* dst = s_out + lane * kEtOutPitch + quad * 4;
+          uint32_t h[8], o[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 hi4, lo4;
-            tc::split4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi4, lo4);
-            *reinterpret_cast<float4*>(dst + (((q >> 1) * 2 + 0) * 2 + (q & 1)) * 16) = hi4;
-            *reinterpret_cast<float4*>(dst + (((q >> 1) * 2 + 1) * 2 + (q & 1)) * 16) = lo4;
-          }
+          for (int c = 0; c < kEtCout; c += 2) split_h2(v[c] * sc, v[c + 1] * sc, h[c >> 1], o[c >> 1]);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(s_out) + lane * kEtOutPitch + quad * 4;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+          *reinterpret_cast<uint4*>(dst + 32) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dst + 48) = make_uint4(o[4], o[5], o[6], o[7]);
         }
+        if (lane == 0 && img0 + quad < g.rows) g.row_inv[img0 + quad] = inv_row;
         wg_sync();
         float* const base = g.ap + (img0 >> 7) * int64_t(g.nch) * 2048 + ((img0 & 127) >> 3) * 64 + (img0 & 7) * 4;
         const int wt = tid & 127;
 #pragma unroll
-        for (int it = 0; it < (kFovCells * 32 + 127) / 128; ++it) {
+        for (int it = 0; it < (kFovCells * 16 + 127) / 128; ++it) {
           const int fi = it * 128 + wt;
-          const int p = fi >> 5, run = (fi >> 2) & 7, piece = fi & 3;
+          const int p = fi >> 4, run = (fi >> 2) & 3, piece = fi & 3;     // run = (hi|lo, k half)
           if (p < kFovCells && img0 + piece < g.rows) {
             const float4 val = *reinterpret_cast<const float4*>(s_out + p * kEtOutPitch + run * 16 + piece * 4);
-            float* d = base + int64_t(2 * p + (run >> 2)) * 2048 + ((run >> 1) & 1) * 1024 + (run & 1) * 32 + piece * 4;
+            float* d = base + int64_t(p) * 2048 + (run >> 1) * 1024 + (run & 1) * 32 + piece * 4;
             *reinterpret_cast<float4*>(d) = val;
           }
         }
@@ -394,7 +396,7 @@ extern "C" int mapf_encoder_tc_supported(const mapf_net_params* p) {
 int mapf_encoder_tc_pack(const mapf_net_params* p, float* packed, mapf_stream_t stream) {
   const PackedLayout L = mapf_packed_layout(*p);
   pack_tc_conv_kernel<<<p->num_conv, 256, 0, static_cast<cudaStream_t>(stream)>>>(*p, L, packed);
-  const int rc = mapf_tc_pack_b_pixel_major(p->fc_w, p->channels[p->num_conv], p->fc_out, packed + L.tc_fc_pm, stream);
+  const int rc = mapf_tc_pack_b_f16_pixel_major(p->fc_w, p->channels[p->num_conv], p->fc_out, packed + L.tc_fc_pm, stream);
   if (rc != MAPF_OK) return rc;
   return mapf_launch_status();
 }
@@ -424,7 +426,8 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
   g.packed = a->packed;
   g.wtc = a->packed + L.tc_conv;
   g.ap = a->x;
-  g.nch = (p->fc_in + 7) >> 3;
+  g.nch = (p->fc_in + 15) >> 4;
+  g.row_inv = a->x + ((a->rows + 127) >> 7) * int64_t(g.nch) * 2048;
   {
     const char* e = getenv("MAPF_B200_ETC_SKEW");   // development switch
     g.skew = e ? atoi(e) : 1400;

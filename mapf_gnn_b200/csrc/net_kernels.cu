@@ -194,8 +194,8 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
       // K order -> all-TMA tcgen05 FC against the matching B operand
       rc = mapf_encoder_tc_conv_fwd(p, &e, stream);
       if (rc != MAPF_OK) return rc;
-      rc = mapf_tc_fc_presplit(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, a->packed + L.tc_fc_pm,
-                               a->workspace_x, p->fc_out, a->packed + L.fc_b, 1, stream);
+      rc = mapf_tc_fc_presplit_f16(int32_t(rows), p->fc_out, p->fc_in, a->workspace_act, a->packed + L.tc_fc_pm,
+                                   a->workspace_x, p->fc_out, a->packed + L.fc_b, 1, stream);
     } else if (unsplit) {
       rc = mapf_encoder_conv_fwd(p, &e, stream);
       if (rc != MAPF_OK) return rc;

@@ -21,6 +21,8 @@
 //                          global stores are 128-byte coalesced; EPI_HEAD needs one exchange between the two halves
 // The tensor core's fp32 accumulation loses a little precision per accumulate, so consecutive chunks rotate over
 // NACC independent TMEM accumulators that are summed in registers in the epilogue.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -47,12 +49,14 @@ struct TcGemmArgs {
   float* logits;       // [M, A]
   int32_t* actions;    // [M] or NULL
   float* y;            // optional [M, N] post-ReLU features or NULL
+  // fp16-split presplit GEMM
+  const float* row_scale;   // [M] inverse scale of each A row
+  const float* b_hdr;       // [0] inverse scale of B
 };
 
 // B [N,K0] (+ [N,K1] appended along K) row-major fp32 -> chunked canonical hi / lo blocks
-// perm_c > 0: b0's K index is read pixel-major, k' = pixel*perm_c + c <- k = c*25 + pixel (FC behind enc_tc.cu)
 __global__ void tc_pack_b_kernel(const float* __restrict__ b0, int K0, const float* __restrict__ b1, int K1, int N,
-                                 int NT, int KC, float* __restrict__ out, int perm_c = 0) {
+                                 int NT, int KC, float* __restrict__ out) {
   const int K = K0 + K1;
   const int nchunks = (K + KC - 1) / KC;
   const int64_t per_chunk = int64_t(2) * NT * KC;
@@ -68,13 +72,42 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ b0, int K0, const flo
     const int kq = rest % (KC >> 2), rg = rest / (KC >> 2);
     const int row = rg * 8 + r8, k = c * KC + kq * 4 + k4i;
     float v = 0.0f;
-    if (row < N && k < K) {
-      if (perm_c > 0) v = b0[int64_t(row) * K0 + (k % perm_c) * kFovCells + k / perm_c];
-      else v = k < K0 ? b0[int64_t(row) * K0 + k] : b1[int64_t(row) * K1 + (k - K0)];
-    }
+    if (row < N && k < K) v = k < K0 ? b0[int64_t(row) * K0 + k] : b1[int64_t(row) * K1 + (k - K0)];
     float hi, lo;
     tc::split1(v, hi, lo);
     out[idx] = is_lo ? lo : hi;
+  }
+}
+
+// fp16-split, scaled, pixel-major B operand (see mapf_tc_pack_b_f16_pixel_major); one block
+__global__ void tc_pack_b_f16_kernel(const float* __restrict__ b, int C, int N, int NT, float* __restrict__ out) {
+  __shared__ float s_red[1024];
+  const int K = C * kFovCells;
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) m = fmaxf(m, fabsf(b[i]));
+  s_red[threadIdx.x] = m;
+  __syncthreads();
+  for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+    if (threadIdx.x < st) s_red[threadIdx.x] = fmaxf(s_red[threadIdx.x], s_red[threadIdx.x + st]);
+    __syncthreads();
+  }
+  int eb = int(__float_as_uint(s_red[0]) >> 23) & 0xFF;
+  eb = eb < 32 ? 32 : (eb > 240 ? 240 : eb);
+  const float scale = __uint_as_float(uint32_t(263 - eb) << 23);
+  if (threadIdx.x < 4) out[threadIdx.x] = threadIdx.x == 0 ? __uint_as_float(uint32_t(eb - 9) << 23) : 0.0f;
+  __half* o = reinterpret_cast<__half*>(out + 4);
+  const int nch = (K + 15) >> 4, per_chunk = 2 * NT * 16;
+  for (int idx = threadIdx.x; idx < nch * per_chunk; idx += blockDim.x) {
+    const int c = idx / per_chunk;
+    int r = idx - c * per_chunk;
+    const int is_lo = r >= NT * 16;
+    if (is_lo) r -= NT * 16;
+    const int k8i = r & 7, n8 = (r >> 3) & 7, kq = (r >> 6) & 1, ng = r >> 7;
+    const int row = ng * 8 + n8, k = c * 16 + kq * 8 + k8i;
+    float v = 0.0f;
+    if (row < N && k < K) v = b[int64_t(row) * K + (k % C) * kFovCells + k / C] * scale;
+    const __half hi = __float2half_rn(v);
+    o[idx] = is_lo ? __float2half_rn(v - __half2float(hi)) : hi;
   }
 }
 
@@ -331,18 +364,19 @@ int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------
 // Same GEMM with the A operand ALREADY split and tiled by its producer (the encoder's conv kernel writes
 // Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4]): no conversion warps, the whole operand pipeline is TMA.
-//   warp 0 lane 0 : per stage of kPsChunks 8-wide K chunks, one bulk copy for A (contiguous in Ap) and one for B
-//   warp 1 lane 0 : 3 tcgen05.mma per chunk (lo*hi, hi*lo, hi*hi), chunks alternate between two TMEM accumulators
+//   warp 0 lane 0   : per stage of kPsChunks 8-wide K chunks, one bulk copy for A (contiguous in Ap) and one for B
+//   warps 1-4 lane 0: warp w issues the 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) of chunk w-1 of every stage into its own
+//                     TMEM accumulator (four issuers: a thread issues about one MMA per 100 cycles)
 //   all 8 warps   : epilogue = bias, ReLU, transpose through shared memory, 128-byte row stores
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPsChunks = 4, kPsStages = 2;
 
-template <int NT>
+template <int NT, bool F16>
 __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
   constexpr int kABytes = kTcM * 8 * 4, kBBytes = NT * 8 * 4;
   constexpr int kStageA = kPsChunks * 2 * kABytes, kStageB = kPsChunks * 2 * kBBytes;
   constexpr int kStageBytes = kStageA + kStageB;
-  constexpr uint32_t kCols = 2 * NT <= 128 ? 128 : 256;
+  constexpr uint32_t kCols = kPsChunks * NT <= 256 ? 256 : 512;
   extern __shared__ __align__(128) uint8_t s_tc[];
   __shared__ __align__(8) uint64_t s_full[kPsStages], s_empty[kPsStages], s_done;
   __shared__ uint32_t s_tmem;
@@ -351,8 +385,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
   const int m0 = blockIdx.x * kTcM;
   if (warp == 0) tc::tmem_alloc(&s_tmem, kCols);
   if (tid == 0) {
-    for (int s = 0; s < kPsStages; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], 1); }
-    tc::mbar_init(&s_done, 1);
+    for (int s = 0; s < kPsStages; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_empty[s], kPsChunks); }
+    tc::mbar_init(&s_done, kPsChunks);
     tc::fence_mbar_init();
   }
   for (int i = tid; i < NT; i += kTcThreads) s_bias[i] = (g.bias != nullptr && i < g.N) ? __ldg(g.bias + i) : 0.0f;
@@ -360,12 +394,12 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
-  const int nch = (g.K + 7) >> 3;
+  const int nch = F16 ? (g.K + 15) >> 4 : (g.K + 7) >> 3;   // a chunk is 32 bytes of K per row: 8 TF32 or 16 fp16
   const int nsc = (nch + kPsChunks - 1) / kPsChunks;
 
   if (warp == 0) {
     if (lane == 0) {
-      const float* a_src = g.A + int64_t(blockIdx.x) * nch * (2 * kTcM * 8);
+      const float* a_src = g.A + int64_t(blockIdx.x) * nch * (2 * kTcM * 8);   // (same bytes per chunk in both modes)
       for (int sc = 0; sc < nsc; ++sc) {
         const int s = sc % kPsStages;
         const uint32_t ph = uint32_t(sc / kPsStages) & 1u;
@@ -380,29 +414,36 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp <= kPsChunks) {
+    // issuer warp w (1..4) owns chunk w-1 of every stage and TMEM accumulator w-1: one thread issues only about one MMA
+    // per 100 cycles, four issue in parallel; each accumulator is filled by one thread in a fixed order (reproducible)
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_tf32(kTcM, NT);
+      constexpr uint32_t idesc = F16 ? tc::idesc_f16(kTcM, NT) : tc::idesc_tf32(kTcM, NT);
       constexpr uint32_t sbo = 256, lbo = 128;
       const uint32_t base = tc::smem_u32(s_tc);
+      const int ci = warp - 1;
+      const uint32_t acc = tmem + uint32_t(ci) * NT;
       for (int sc = 0; sc < nsc; ++sc) {
         const int s = sc % kPsStages;
         const uint32_t ph = uint32_t(sc / kPsStages) & 1u;
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
-        const int c0 = sc * kPsChunks;
-        const int nc = nch - c0 < kPsChunks ? nch - c0 : kPsChunks;
-        const uint32_t sa = base + uint32_t(s) * kStageBytes, sb = sa + kStageA;
-        for (int ci = 0; ci < nc; ++ci) {
-          const int c = c0 + ci;
-          const uint32_t acc = tmem + uint32_t(c & 1) * NT;
+        const int c = sc * kPsChunks + ci;
+        if (c < nch) {
+          const uint32_t sa = base + uint32_t(s) * kStageBytes, sb = sa + kStageA;
           const uint64_t dah = tc::smem_desc(sa + uint32_t(ci) * 2 * kABytes, lbo, sbo);
           const uint64_t dal = tc::smem_desc(sa + uint32_t(ci) * 2 * kABytes + kABytes, lbo, sbo);
           const uint64_t dbh = tc::smem_desc(sb + uint32_t(ci) * 2 * kBBytes, lbo, sbo);
           const uint64_t dbl = tc::smem_desc(sb + uint32_t(ci) * 2 * kBBytes + kBBytes, lbo, sbo);
-          tc::mma_tf32(acc, dal, dbh, idesc, c >= 2);   // first touch of an accumulator overwrites; small terms first
-          tc::mma_tf32(acc, dah, dbl, idesc, true);
-          tc::mma_tf32(acc, dah, dbh, idesc, true);
+          if (F16) {
+            tc::mma_f16(acc, dal, dbh, idesc, sc > 0);
+            tc::mma_f16(acc, dah, dbl, idesc, true);
+            tc::mma_f16(acc, dah, dbh, idesc, true);
+          } else {
+            tc::mma_tf32(acc, dal, dbh, idesc, sc > 0);   // first touch of an accumulator overwrites; small terms first
+            tc::mma_tf32(acc, dah, dbl, idesc, true);
+            tc::mma_tf32(acc, dah, dbh, idesc, true);
+          }
         }
         tc::mma_commit(&s_empty[s]);
       }
@@ -417,18 +458,33 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
     const int quad = warp & 3, half = warp >> 2;
     constexpr int kHalfCols = NT / 2;
     float* s_scr = reinterpret_cast<float*>(s_tc);
-    const bool two = nch > 1;
+    const int nacc = nch < kPsChunks ? nch : kPsChunks;   // accumulators that were written
 #pragma unroll
     for (int cbl = 0; cbl < kHalfCols; cbl += 32) {
       const int cb = half * kHalfCols + cbl;
       uint32_t r0[32], r1[32];
+      float v[32];
       tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + cb, r0);
-      if (two) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + NT + cb, r1);
+      if (nacc > 1) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + NT + cb, r1);
       tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + (nacc > 1 ? __uint_as_float(r1[j]) : 0.0f);
+      if (nacc > 2) {
+        tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + 2 * NT + cb, r0);
+        if (nacc > 3) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + 3 * NT + cb, r1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r0[j]) + (nacc > 3 ? __uint_as_float(r1[j]) : 0.0f);
+      }
       float* t = s_scr + warp * (32 * 33);
+      float rs = 1.0f;   // fp16-split operands: undo the row's and the matrix' power-of-two scales
+      if (F16) {
+        const int row = m0 + quad * 32 + lane;
+        rs = (row < g.M ? __ldg(g.row_scale + row) : 0.0f) * __ldg(g.b_hdr);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float o = __uint_as_float(r0[j]) + (two ? __uint_as_float(r1[j]) : 0.0f) + s_bias[cb + j];
+        float o = fmaf(v[j], rs, s_bias[cb + j]);
         if (g.relu) o = fmaxf(o, 0.0f);
         t[lane * 33 + j] = o;
       }
@@ -447,11 +503,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
   if (warp == 0) tc::tmem_dealloc(tmem, kCols);
 }
 
-template <int NT>
+template <int NT, bool F16>
 int launch_presplit(const TcGemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = size_t(kPsStages) * kPsChunks * (2 * kTcM * 8 * 4 + 2 * NT * 8 * 4);
   static_assert(smem >= 8 * 32 * 33 * 4, "the epilogue transposes through the operand stages");
-  auto kernel = tc_presplit_kernel<NT>;
+  auto kernel = tc_presplit_kernel<NT, F16>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   kernel<<<(g.M + kTcM - 1) / kTcM, kTcThreads, smem, s>>>(g);
@@ -481,17 +537,41 @@ extern "C" int mapf_tc_pack_b(const float* b0, int32_t K0, const float* b1, int3
   return mapf_launch_status();
 }
 
-// Same for the encoder FC matrix [N, 25*C] with its K index re-ordered pixel-major (the order in which enc_tc.cu
-// emits the flattened activations).
-extern "C" int mapf_tc_pack_b_pixel_major(const float* b, int32_t C, int32_t N, float* out, mapf_stream_t stream) {
+// Encoder FC matrix [N, 25*C] for the fp16-split GEMM behind enc_tc.cu: K index re-ordered pixel-major (k' = pixel*C + c
+// <- k = c*25 + pixel, the order in which the conv kernel emits the flattened activations), scaled by a power of two
+// that brings the largest |w| into [2^9, 2^10), split into fp16 hi / lo.  out = [inverse scale, 0, 0, 0] then per
+// 16-wide K chunk: hi block | lo block, each [n/8][k/8][n%8][k%8] (canonical no-swizzle K-major, NT rows).
+extern "C" int64_t mapf_tc_packed_b_f16_size(int32_t N, int32_t K) {
+  if (N <= 0 || N > 128 || K <= 0) return -1;
+  return 4 + int64_t((K + 15) / 16) * tc_nt(N) * 16;
+}
+
+extern "C" int mapf_tc_pack_b_f16_pixel_major(const float* b, int32_t C, int32_t N, float* out, mapf_stream_t stream) {
   MAPF_REQUIRE(b && out, MAPF_ERR_NULL);
   MAPF_REQUIRE(N > 0 && N <= 128 && C > 0, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(mapf_aligned(out, 16), MAPF_ERR_ALIGN);
-  const int K = C * kFovCells;
-  const int64_t total = mapf_tc_packed_b_size(N, K);
-  tc_pack_b_kernel<<<int((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(b, K, nullptr, 0, N, tc_nt(N),
-                                                                                           kTcKC, out, C);
+  tc_pack_b_f16_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(b, C, N, tc_nt(N), out);
   return mapf_launch_status();
+}
+
+// C[M,N] = act(A B^T + bias) with both operands fp16-split: Ap = the conv kernel's output [row/128][k/16][hi|lo]
+// [(row%128)/8][(k%16)/8][row%8][k%8] (fp16) followed, at float offset ceil(M/128)*ceil(K/16)*2048, by the inverse scale
+// of every row; Bp from mapf_tc_pack_b_f16_pixel_major.
+extern "C" int mapf_tc_fc_presplit_f16(int32_t M, int32_t N, int32_t K, const float* Ap, const float* Bp, float* C,
+                                       int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream) {
+  MAPF_REQUIRE(Ap && Bp && C, MAPF_ERR_NULL);
+  MAPF_REQUIRE(M > 0 && N > 0 && K > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(N <= 128, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(Ap, 128) && mapf_aligned(Bp, 16), MAPF_ERR_ALIGN);
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = Ap; g.Bp = Bp + 4;
+  g.row_scale = Ap + int64_t((M + kTcM - 1) / kTcM) * ((K + 15) / 16) * 2048;
+  g.b_hdr = Bp;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (N <= 64) return launch_presplit<64, true>(g, s);
+  return launch_presplit<128, true>(g, s);
 }
 
 // C[M,N] = act(A[M,K] B^T + bias): fp32 in / out, 3xTF32 on the tensor cores; Bp from mapf_tc_pack_b.
@@ -547,6 +627,6 @@ extern "C" int mapf_tc_fc_presplit(int32_t M, int32_t N, int32_t K, const float*
   g.A = Ap; g.Bp = Bp;
   g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (N <= 64) return launch_presplit<64>(g, s);
-  return launch_presplit<128>(g, s);
+  if (N <= 64) return launch_presplit<64, false>(g, s);
+  return launch_presplit<128, false>(g, s);
 }

@@ -54,7 +54,7 @@ def test_packed_size_matches_layout():
     dims = [3, 2, 16, 16, 16, 0, 400, 64, 3, 128, 5]
     n = lib.mapf_packed_weights_size(net_params(dims))
     expect = (288 + 16) + (2304 + 16) * 2 + 400 * 64 + 64 + 4 * 64 * 128 + 50 * 2 * 64 * 8 + 32 * 2 * 128 * 8 + 5 * 128 + 8
-    expect += 4 + (1 + 3 + 3) * 2 * 48 * 8 + 50 * 2 * 64 * 8   # tensor-core conv B operands + pixel-major FC operand
+    expect += 4 + (1 + 3 + 3) * 2 * 48 * 8 + 4 + 25 * 64 * 16   # tensor-core conv B operands + pixel-major FC operand
     assert n == expect
 
 

@@ -129,11 +129,15 @@ def test_presplit_tensor_core_fc_matches_oracle(rows):
     assert rel_err(got, ref) < REL
 
 
-def _untile_presplit(Ap, rows, K):
-    """Ap [row/128][k/8][hi|lo][(row%128)/8][(k%8)/4][row%8][k%4] -> hi + lo as [rows, K]."""
-    nblk, nch = (rows + 127) // 128, (K + 7) // 8
-    a = Ap.cpu().numpy().reshape(nblk, nch, 2, 16, 2, 8, 4).transpose(2, 0, 3, 5, 1, 4, 6).reshape(2, nblk * 128, nch * 8)
-    return (a[0].astype(np.float64) + a[1])[:rows, :K]
+def _untile_presplit_f16(Ap, rows, K):
+    """enc_tc.cu output: fp16 hi|lo tiles [row/128][k/16][hi|lo][(row%128)/8][(k%16)/8][row%8][k%8] followed by the
+    rows' inverse scales -> (hi + lo) * inverse scale as [rows, K] float64."""
+    nblk, nch = (rows + 127) // 128, (K + 15) // 16
+    words = nblk * nch * 2048
+    h = Ap[:words].view(torch.float16).cpu().numpy().astype(np.float64)
+    a = h.reshape(nblk, nch, 2, 16, 2, 8, 8).transpose(2, 0, 3, 5, 1, 4, 6).reshape(2, nblk * 128, nch * 16)
+    inv = Ap[words:words + rows].cpu().numpy().astype(np.float64)
+    return (a[0] + a[1])[:rows, :K] * inv[:, None]
 
 
 def _conv_stack_reference(params, states, depth):
@@ -152,7 +156,7 @@ def _conv_stack_reference(params, states, depth):
 @pytest.mark.parametrize("rows", [1, 3, 4, 5, 127, 129, 1777, 4736 + 300])
 def test_tensor_core_conv_stack_matches_torch(rows, depth):
     """enc_tc.cu: conv + BN + ReLU layers as tcgen05 GEMMs on fp16-split operands with per-image dynamic scales
-    (framework_gnn.py:55-71,160-163).  The emitted FC operand, re-assembled (hi + lo), must equal the torch-CPU conv stack
+    (framework_gnn.py:55-71,160-163).  The emitted FC operand, re-assembled ((hi + lo) / scale), must equal the torch-CPU conv stack
     to fp32 accuracy for every tile raggedness and depth -- including all-zero images, huge, tiny, negative and
     non-integer observations (the scale logic), which the FOV tensors of a rollout never contain."""
     from mapf_gnn_b200 import _lib
@@ -181,11 +185,44 @@ def test_tensor_core_conv_stack_matches_torch(rows, depth):
     st = states.cuda()
     ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
     _lib.check(lib.mapf_encoder_tc_conv_fwd(p, ea, _lib.current_stream()), "tc_conv")
-    got = _untile_presplit(Ap, rows, 400)
+    got = _untile_presplit_f16(Ap, rows, 400)
     assert np.isfinite(got).all()
     # per image: 1e-5 of the image's largest activation (the split keeps 22 bits relative to it)
     scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
     assert (np.abs(got - ref) / scale).max() < 1e-5
+
+
+@pytest.mark.parametrize("rows", [1, 5, 128, 131, 2400, 4736 + 300])
+def test_tensor_core_encoder_matches_oracle(rows):
+    """Conv stack on the tensor cores + fp16-split FC (mapf_encoder_tc_conv_fwd, mapf_tc_pack_b_f16_pixel_major,
+    mapf_tc_fc_presplit_f16) against the oracle encoder (framework_gnn.py:156-166), through the C ABI."""
+    from mapf_gnn_b200 import _lib
+    from mapf_gnn_b200.ops import net_params
+    lib = _lib.load()
+    rng = np.random.default_rng(rows + 7)
+    states = torch.tensor(rng.integers(0, 4, size=(rows, 1, 2, 5, 5))).float()
+    states[:: 5] *= 0.61
+    params = oracle_params("gnn_k3")
+    with torch.no_grad():
+        ref = mo.encode_agents(params, states)[:, :, 0].numpy()
+    net = load_network("gnn_k3", num_agents=1).eval()
+    dims, packed = net.dims(), net.packed_weights()
+    p = net_params(dims)
+    st = states.cuda()
+    Ap = torch.full((lib.mapf_tc_presplit_a_size(rows, dims[6]),), float("nan"), device="cuda")
+    x = torch.empty((rows, dims[7]), device="cuda")
+    fcw = net.compressMLP[0].weight.detach().contiguous()
+    fcb = net.compressMLP[0].bias.detach().contiguous()
+    Bp = torch.empty((lib.mapf_tc_packed_b_f16_size(dims[7], dims[6]),), device="cuda")
+    s = _lib.current_stream()
+    _lib.check(lib.mapf_tc_pack_b_f16_pixel_major(fcw.data_ptr(), 16, dims[7], Bp.data_ptr(), s), "pack")
+    ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
+    _lib.check(lib.mapf_encoder_tc_conv_fwd(p, ea, s), "tc_conv")
+    _lib.check(lib.mapf_tc_fc_presplit_f16(rows, dims[7], dims[6], Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), dims[7],
+                                           fcb.data_ptr(), 1, s), "fc_f16")
+    got = x.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) < 1e-5
 
 
 def test_tensor_core_encoder_unsupported_widths_are_refused():

@@ -22,9 +22,12 @@ d = lambda ts: [t.detach() for t in ts]
 
 
 def untile(Ap, rows, K):
-    nblk, nch = (rows + 127) // 128, (K + 7) // 8
-    a = Ap.cpu().numpy().reshape(nblk, nch, 2, 16, 2, 8, 4).transpose(2, 0, 3, 5, 1, 4, 6).reshape(2, nblk * 128, nch * 8)
-    return (a[0] + a[1])[:rows, :K], a[0][:rows, :K], a[1][:rows, :K]
+    nblk, nch = (rows + 127) // 128, (K + 15) // 16
+    words = nblk * nch * 2048
+    h = Ap[:words].view(torch.float16).cpu().numpy().astype(np.float64)
+    a = h.reshape(nblk, nch, 2, 16, 2, 8, 8).transpose(2, 0, 3, 5, 1, 4, 6).reshape(2, nblk * 128, nch * 16)
+    inv = Ap[words:words + rows].cpu().numpy().astype(np.float64)[:, None]
+    return ((a[0] + a[1])[:rows, :K] * inv), (a[0][:rows, :K] * inv), (a[1][:rows, :K] * inv)
 
 
 def conv_ref(states, depth):
@@ -85,14 +88,14 @@ dims, packed = net.dims(), net.packed_weights()
 p = net_params(dims)
 st = states.cuda()
 Ap = torch.empty((lib.mapf_tc_presplit_a_size(rows, 400),), device="cuda")
-Bp = torch.empty((lib.mapf_tc_packed_b_size(64, 400),), device="cuda")
+Bp = torch.empty((lib.mapf_tc_packed_b_f16_size(64, 400),), device="cuda")
 fcw, fcb = g["fc_w"].detach().contiguous(), g["fc_b"].detach().contiguous()
 s = _lib.current_stream()
-_lib.check(lib.mapf_tc_pack_b_pixel_major(fcw.data_ptr(), 16, 64, Bp.data_ptr(), s), "pack pm")
+_lib.check(lib.mapf_tc_pack_b_f16_pixel_major(fcw.data_ptr(), 16, 64, Bp.data_ptr(), s), "pack pm")
 x = torch.empty((rows, 64), device="cuda")
 ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
 _lib.check(lib.mapf_encoder_tc_conv_fwd(p, ea, s), "tc_conv")
-_lib.check(lib.mapf_tc_fc_presplit(rows, 64, 400, Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), 64, fcb.data_ptr(), 1, s), "fc")
+_lib.check(lib.mapf_tc_fc_presplit_f16(rows, 64, 400, Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), 64, fcb.data_ptr(), 1, s), "fc")
 torch.cuda.synchronize()
 got = x.cpu().numpy()
 print(f"full encoder rows {rows}: rel err {np.abs(got - ref).max() / np.abs(ref).max():.3e}")
@@ -119,8 +122,8 @@ for rows in (20480, 81920):
     ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
     ex = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), x.data_ptr())
     t_conv = timeit(lambda: lib.mapf_encoder_tc_conv_fwd(p, ea, s))
-    t_fc = timeit(lambda: lib.mapf_tc_fc_presplit(rows, 64, 400, Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), 64, fcb.data_ptr(), 1, s))
+    t_fc = timeit(lambda: lib.mapf_tc_fc_presplit_f16(rows, 64, 400, Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), 64, fcb.data_ptr(), 1, s))
     t_both = timeit(lambda: (lib.mapf_encoder_tc_conv_fwd(p, ea, s),
-                             lib.mapf_tc_fc_presplit(rows, 64, 400, Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), 64, fcb.data_ptr(), 1, s)))
+                             lib.mapf_tc_fc_presplit_f16(rows, 64, 400, Ap.data_ptr(), Bp.data_ptr(), x.data_ptr(), 64, fcb.data_ptr(), 1, s)))
     t_old = timeit(lambda: lib.mapf_encoder_fwd(p, ex, s))
     print(f"rows {rows}: tc conv {t_conv:.1f} us | presplit FC {t_fc:.1f} us | both {t_both:.1f} us | FFMA2 encoder {t_old:.1f} us")
