@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "mapf_b200.h"
 
@@ -121,6 +122,37 @@ static inline bool mapf_ensure_smem(F func, size_t bytes, int* cache /* [16] zer
   if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) != cudaSuccess) return false;
   cache[slot] = int(bytes);
   return true;
+}
+
+// Programmatic dependent launch: the kernels of a rollout step (encoder conv stack -> encoder FC -> graph filter + head ->
+// env step -> next step's encoder ...) are launched with programmatic stream serialization, so a kernel's CTAs may become
+// resident -- and run their prologue: barrier init, TMEM allocation, weights into shared memory -- while the previous
+// kernel drains.  Every kernel calls mapf_pdl_wait() before its first access to memory another kernel of the chain
+// writes or reads (it returns once ALL earlier kernels have completed and flushed), and mapf_pdl_launch() to let its own
+// successor start early.  Without the launch attribute both are no-ops.  MAPF_B200_NO_PDL=1 switches the attribute off.
+__device__ __forceinline__ void mapf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mapf_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool mapf_pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) cached = getenv("MAPF_B200_NO_PDL") == nullptr ? 1 : 0;
+  return cached == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static inline void mapf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mapf_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through mapf_launch_status()
 }
 
 // Packed fp32 FMA (Blackwell FFMA2): {d.x, d.y} = a * {w.x, w.y} + {d.x, d.y}, two IEEE fp32 FMAs in one issue slot.

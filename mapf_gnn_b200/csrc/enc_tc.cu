@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
 #endif
   int64_t tile = int64_t(blockIdx.x) * kEtGroups + wg;
   float o0, o1;
+  mapf_pdl_wait();      // everything above touched only the packed weights; the observations come from the env kernel
+  mapf_pdl_launch();
   load_obs(tile, o0, o1);
   if (wg > 0) {   // start the groups a fraction of a layer apart: one group's MMA wait falls under the others' epilogues
     const long long t0 = clock64();
@@ -441,6 +443,6 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
   const int64_t ntiles = (a->rows + 3) >> 2;
   const int64_t want = (ntiles + kEtGroups - 1) / kEtGroups;
   const int grid = int(want < sms ? want : sms);
-  encoder_tc_kernel<<<grid, kEtThreads, smem, static_cast<cudaStream_t>(stream)>>>(g);
+  mapf_launch_pdl(encoder_tc_kernel, dim3(grid), dim3(kEtThreads), smem, static_cast<cudaStream_t>(stream), g);
   return mapf_launch_status();
 }

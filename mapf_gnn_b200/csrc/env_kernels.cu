@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
   const int N = a.agents, H = a.board, stride = a.cell_stride;
   const bool agent = (el < nep) && (lane < N);
 
+  mapf_pdl_wait();      // boards, positions and actions come from the kernels in front
+  mapf_pdl_launch();
   {  // stage this CTA's boards (contiguous, 16-byte aligned by construction)
     const uint4* src = reinterpret_cast<const uint4*>(a.cells + int64_t(e0) * stride);
     uint4* dst = reinterpret_cast<uint4*>(s_cells);
@@ -203,7 +205,7 @@ int launch_env_step(const mapf_env_step_args& a, cudaStream_t s) {
       return MAPF_ERR_CUDA;
   }
   const int grid = (a.episodes + EPB - 1) / EPB;
-  env_step_kernel<LANES><<<grid, kEnvThreads, smem, s>>>(a);
+  mapf_launch_pdl(env_step_kernel<LANES>, dim3(grid), dim3(kEnvThreads), smem, s, a);
   return mapf_launch_status();
 }
 

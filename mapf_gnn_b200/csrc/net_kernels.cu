@@ -72,6 +72,12 @@ __global__ void pack_weights_kernel(mapf_net_params p, PackedLayout L, float* __
   }
 }
 
+// Ends every weight packing.  The step kernels read the packed weights BEFORE their griddepcontrol.wait (weights into
+// shared memory under the previous kernel's tail); that is safe because a programmatically launched kernel can only start
+// once the kernel right in front of it has started everywhere -- and this normally launched no-op starts only after the
+// packing kernels have completed and flushed.
+__global__ void pack_fence_kernel() {}
+
 __global__ void pack_graph_weights_kernel(const float* __restrict__ w, const float* __restrict__ w2, int F, int K,
                                           int G, float* __restrict__ wt) {
   const int KF = K * F;
@@ -149,6 +155,7 @@ extern "C" int mapf_pack_weights(const mapf_net_params* p, float* packed, mapf_s
     const int rc = mapf_encoder_tc_pack(p, packed, stream);
     if (rc != MAPF_OK) return rc;
   }
+  pack_fence_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>();
   return mapf_launch_status();
 }
 

@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
+  mapf_pdl_wait();      // the A operand (and its row scales) come from the conv kernel in front
+  mapf_pdl_launch();
   const int nch = F16 ? (g.K + 15) >> 4 : (g.K + 7) >> 3;   // a chunk is 32 bytes of K per row: 8 TF32 or 16 fp16
   const int nsc = (nch + kPsChunks - 1) / kPsChunks;
 
@@ -510,7 +512,7 @@ int launch_presplit(const TcGemmArgs& g, cudaStream_t s) {
   auto kernel = tc_presplit_kernel<NT, F16>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
-  kernel<<<(g.M + kTcM - 1) / kTcM, kTcThreads, smem, s>>>(g);
+  mapf_launch_pdl(kernel, dim3((g.M + kTcM - 1) / kTcM), dim3(kTcThreads), smem, s, g);
   return mapf_launch_status();
 }
 

@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     s_head[i] = n < g.G ? __ldg(g.act_w + int64_t(q) * g.G + n) : 0.0f;
   }
   if (tid < g.num_actions) s_head[kMaxActions * kTgNT + tid] = __ldg(g.act_b + tid);
+  mapf_pdl_wait();      // adjacency and node features come from the kernels in front
+  mapf_pdl_launch();
   // ---- graph shift operator of the tile's episodes ----
   for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
     const int el = idx / (N * N), rem = idx - el * N * N;
@@ -319,6 +321,6 @@ extern "C" int mapf_tc_graph_head(int32_t batch, int32_t agents, int32_t in_dim,
   MAPF_REQUIRE(smem <= 227 * 1024, MAPF_ERR_UNSUPPORTED);
   static int cache[16] = {0};
   if (!mapf_ensure_smem(tc_graph_kernel, smem, cache)) return MAPF_ERR_CUDA;
-  tc_graph_kernel<<<ntiles, kTgThreads, smem, static_cast<cudaStream_t>(stream)>>>(g, epc);
+  mapf_launch_pdl(tc_graph_kernel, dim3(ntiles), dim3(kTgThreads), smem, static_cast<cudaStream_t>(stream), g, epc);
   return mapf_launch_status();
 }
