@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
   const int N = a.agents, H = a.board, stride = a.cell_stride;
   const bool agent = (el < nep) && (lane < N);
 
-  mapf_pdl_wait();      // boards, positions and actions come from the kernels in front
-  mapf_pdl_launch();
+  // do_move & 4 (mapf_rollout): boards, positions, goals and done flags were last written before the policy kernels in
+  // front of this launch started, only the actions come from the kernel right in front -- stage the state while it drains
+  const bool old_state = (a.do_move & 4) != 0;
+  if (!old_state) { mapf_pdl_wait(); mapf_pdl_launch(); }
   {  // stage this CTA's boards (contiguous, 16-byte aligned by construction)
     const uint4* src = reinterpret_cast<const uint4*>(a.cells + int64_t(e0) * stride);
     uint4* dst = reinterpret_cast<uint4*>(s_cells);
@@ -64,8 +66,9 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
     const int2 p = reinterpret_cast<const int2*>(a.pos)[int64_t(e) * N + lane];
     const int2 g = __ldg(reinterpret_cast<const int2*>(a.goal) + int64_t(e) * N + lane);
     ox = p.x; oy = p.y; gx = g.x; gy = g.y;
-    moving = a.do_move && (!a.done[e] || (a.do_move & 2));   // do_move & 2: keep stepping finished episodes
+    moving = (a.do_move & 3) && (!a.done[e] || (a.do_move & 2));   // do_move & 2: keep stepping finished episodes
   }
+  if (old_state) { mapf_pdl_wait(); mapf_pdl_launch(); }
   __syncthreads();
 
   uint8_t* cells = s_cells + el * stride;
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_arg
     }
   }
 
-  if (a.do_move && tid < nep) {  // time += 1; done = checkAllInGoal() (:195-197)
+  if ((a.do_move & 3) && tid < nep) {  // time += 1; done = checkAllInGoal() (:195-197)
     const int ee = e0 + tid;
     if (!a.done[ee] || (a.do_move & 2)) {
       a.time[ee] += 1;
@@ -232,7 +235,7 @@ extern "C" int mapf_env_reset(const mapf_env_reset_args* a, mapf_stream_t stream
 extern "C" int mapf_env_step(const mapf_env_step_args* a, mapf_stream_t stream) {
   MAPF_REQUIRE(a != nullptr, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->pos && a->goal && a->cells && a->time && a->done, MAPF_ERR_NULL);
-  MAPF_REQUIRE(!a->do_move || a->actions, MAPF_ERR_NULL);
+  MAPF_REQUIRE(!(a->do_move & 3) || a->actions, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->episodes > 0 && a->agents > 0 && a->board > 0 && a->d2_limit >= 0, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(a->cell_stride >= a->board * a->board && (a->cell_stride & 15) == 0, MAPF_ERR_ALIGN);
   MAPF_REQUIRE(mapf_aligned(a->cells, 16) && mapf_aligned(a->pos, 8) && mapf_aligned(a->goal, 8), MAPF_ERR_ALIGN);

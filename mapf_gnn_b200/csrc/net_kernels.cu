@@ -12,6 +12,10 @@
 #include "common.cuh"
 
 int mapf_encoder_tc_pack(const mapf_net_params* p, float* packed, mapf_stream_t stream);   // enc_tc.cu
+int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
+                          int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
+                          const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
+                          int gso_is_old, mapf_stream_t stream);                             // tc_graph.cu
 
 namespace {
 
@@ -245,9 +249,10 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
   if (a->agents <= 32 && mapf_tc_graph_supported(a->agents, p->fc_out, p->node_dim, p->taps) &&
       getenv("MAPF_B200_UNFUSED_GRAPH") == nullptr) {
     // fused tensor-core path: S, hops, 3xTF32 tcgen05 mix, ReLU, head, argmax in one kernel
-    return mapf_tc_graph_head(a->batch, a->agents, p->fc_out, p->node_dim, p->taps, a->message ? 0 : 1,
-                              a->message ? 1 : 0, a->workspace_x, a->gso, a->packed + L.tc_gf, a->packed + L.act_w,
-                              a->packed + L.act_b, p->num_actions, a->logits, a->actions, stream);
+    // gso is an input of this launch sequence: complete before the encoder kernels above were launched
+    return mapf_tc_graph_head_ex(a->batch, a->agents, p->fc_out, p->node_dim, p->taps, a->message ? 0 : 1,
+                                 a->message ? 1 : 0, a->workspace_x, a->gso, a->packed + L.tc_gf, a->packed + L.act_w,
+                                 a->packed + L.act_b, p->num_actions, a->logits, a->actions, 1, stream);
   }
   // two-kernel tensor-core path: filter taps -> Z (tiny kernel), then 3xTF32 tcgen05 mix + ReLU + head + argmax
   g.z = a->workspace_z;
@@ -268,7 +273,7 @@ extern "C" int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a
     int rc = mapf_policy_fwd(p, &a->policy, stream);
     if (rc != MAPF_OK) return rc;
     mapf_env_step_args e = a->env;
-    e.do_move = 1;
+    e.do_move = 1 | 4;   // 4: boards / positions are older than the policy kernels in front (see env_step_kernel)
     rc = mapf_env_step(&e, stream);
     if (rc != MAPF_OK) return rc;
   }

@@ -38,6 +38,7 @@ struct TcGraphArgs {
   const float* act_b;   // [A]
   float* logits;        // [B*N, A]
   int32_t* actions;     // [B*N] or NULL
+  int gso_is_old;       // 1: gso was complete before the kernel IN FRONT of this one started (read it before the grid wait)
 };
 
 __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int epc) {
@@ -68,8 +69,10 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     s_head[i] = n < g.G ? __ldg(g.act_w + int64_t(q) * g.G + n) : 0.0f;
   }
   if (tid < g.num_actions) s_head[kMaxActions * kTgNT + tid] = __ldg(g.act_b + tid);
-  mapf_pdl_wait();      // adjacency and node features come from the kernels in front
-  mapf_pdl_launch();
+  // Inside mapf_policy_fwd the adjacency is an input of the whole launch sequence -- complete before the encoder kernels in
+  // front of this one started -- so the shift operator is built while the encoder FC still runs; the node features come
+  // from that FC and are read behind the grid wait.
+  if (!g.gso_is_old) { mapf_pdl_wait(); mapf_pdl_launch(); }
   // ---- graph shift operator of the tile's episodes ----
   for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
     const int el = idx / (N * N), rem = idx - el * N * N;
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     const int i = rem / N, j = rem - i * N;
     sm[idx] = (dinv[el * N + i] * sm[idx]) * dinv[el * N + j];
   }
+  if (g.gso_is_old) { mapf_pdl_wait(); mapf_pdl_launch(); }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -304,16 +308,30 @@ extern "C" int mapf_tc_graph_supported(int32_t agents, int32_t in_dim, int32_t o
 }
 
 // Whole graph-filter + head tail of Network.forward from agent-major x [B*N, F] and gso [B,N,N]; Wp = packed [W | W2].
+int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
+                          int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
+                          const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
+                          int gso_is_old, mapf_stream_t stream);
+
 extern "C" int mapf_tc_graph_head(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
                                   int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso,
                                   const float* Wp, const float* act_w, const float* act_b, int32_t num_actions,
                                   float* logits, int32_t* actions, mapf_stream_t stream) {
+  return mapf_tc_graph_head_ex(batch, agents, in_dim, out_dim, taps, add_self_loop, has_skip, x, gso, Wp, act_w, act_b,
+                               num_actions, logits, actions, 0, stream);
+}
+
+// gso_is_old = 1 (mapf_policy_fwd behind its encoder kernels): see TcGraphArgs
+int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
+                          int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
+                          const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
+                          int gso_is_old, mapf_stream_t stream) {
   MAPF_REQUIRE(x && gso && Wp && act_w && act_b && logits, MAPF_ERR_NULL);
   MAPF_REQUIRE(batch > 0 && num_actions > 0 && num_actions <= kMaxActions, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(mapf_tc_graph_supported(agents, in_dim, out_dim, taps), MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(mapf_aligned(x, 16) && mapf_aligned(Wp, 16), MAPF_ERR_ALIGN);
   TcGraphArgs g{batch, agents, in_dim, taps, out_dim, has_skip ? 1 : 0, add_self_loop ? 1 : 0, num_actions,
-                x, gso, Wp, act_w, act_b, logits, actions};
+                x, gso, Wp, act_w, act_b, logits, actions, gso_is_old};
   const int epc = kTgM / agents;
   const int ntiles = (batch + epc - 1) / epc;
   const size_t smem = size_t(kTgProd) * kTgStageBytes + sizeof(float) * (size_t(kTgProd) * kTgM * 8 +
