@@ -460,7 +460,7 @@ def main():
     ap.add_argument("--cpu-episodes", type=int, default=4096)
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=2,
+    ap.add_argument("--e2e-groups", type=int, default=4,
                     help="independent episode groups whose host round trips overlap in the end-to-end measurement")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-train-graph", action="store_true", help="do not replay the training step as a CUDA graph")
