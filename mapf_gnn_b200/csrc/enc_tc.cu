@@ -6,7 +6,7 @@
 //   D[pixel, (ky, co)] = sum_{kx, ci} act[pixel + kx - 1, ci] * W[co, ci, ky, kx]        128 x 48 x 48
 // i.e. the horizontal taps sit in K (the A operand holds the pixel and its left / right neighbour, zero at the image
 // border) and the filter rows sit in N; what is left for the epilogue is the vertical "col2im",
-//   out[pixel, co] = bias[co] + D[pixel, (1, co)] + D[pixel - 5, (0, co)] + D[pixel + 5, (2, co)].
+//   out[pixel, co] = bias[co] + D[pixel, (1, co)] + D[pixel above, (0, co)] + D[pixel below, (2, co)].
 // The ACTIVATIONS ARE THE A OPERAND IN TENSOR MEMORY (TS mode): lane = pixel and warp = image, so every neighbour
 // exchange is a warp shuffle (64 per thread and layer) and a layer's output never touches shared memory -- the epilogue
 // threads read the 48 partial sums of their pixel from TMEM (tcgen05.ld), add the neighbours' shares, apply bias and
@@ -23,7 +23,7 @@
 // two inverse scales rides on the multiplier of the epilogue's first FMA.  Entries far below their scale's maximum
 // are rounded at 2^-25 of it -- 2^-34 of the image's largest activation.
 //
-// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (25 pixels + 7 zero lanes).  A CTA holds four independent
+// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (5 rows of 5 pixels, one zero lane between rows).  A CTA holds four independent
 // warpgroups; each walks its own M tiles through all layers with its own 96 TMEM columns (D 48 | A hi 24 | A lo 24), its
 // own mbarrier and named barrier; one thread per group issues its MMAs, so the groups' accumulation chains interleave
 // in the tensor pipe.  The last layer's epilogue emits the flattened activations as the pre-split (TF32 hi | lo),
@@ -193,12 +193,14 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   uint64_t* const bar = &s_bar[wg];
   uint32_t phase = 0;
 
-  // lane = pixel (y, x) of this warp's image
-  const int py = lane / kFov, px = lane - py * kFov;
-  const bool pix_ok = lane < kFovCells;
+  // lanes of a warp = one image, rows six lanes apart: lane 1 + 6y + x holds pixel (y, x); lanes 0, 6, 12, 18, 24, 30, 31 hold
+  // zeros, so the left / right neighbour of a border pixel is a zero lane and the horizontal exchange needs no masks
+  const int py = (lane + 5) / 6 - 1, px = lane - 1 - 6 * py;             // lane 0 -> py = -1... guarded by pix_ok
+  const bool pix_ok = lane >= 1 && lane <= 29 && px >= 0 && px < kFov;
+  const int pidx = pix_ok ? py * kFov + px : 0;
   const float m_up = (pix_ok && py > 0) ? 1.0f : 0.0f, m_dn = (pix_ok && py < kFov - 1) ? 1.0f : 0.0f;
   const uint32_t v_ok = pix_ok ? 0xFFFFFFFFu : 0u;
-  const uint32_t v_lf = (pix_ok && px > 0) ? 0xFFFFFFFFu : 0u, v_rt = (pix_ok && px < kFov - 1) ? 0xFFFFFFFFu : 0u;
+  constexpr int kRow = kFov + 1;                                         // lanes between vertically adjacent pixels
 
   constexpr uint32_t idesc = tc::idesc_f16(128, kEtN);
   const uint32_t w_base = tc::smem_u32(s_w);
@@ -210,15 +212,16 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
     v0 = 0.0f;
     v1 = 0.0f;
     if (tile < ntiles && img < g.rows && pix_ok) {
-      const float* s = g.states + img * kFovFloats + lane;
+      const float* s = g.states + img * kFovFloats + pidx;
       v0 = __ldg(s);
       v1 = __ldg(s + kFovCells);
     }
   };
   auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); };
-  // operand word of this pixel's left / right neighbour (zero outside the image)
-  auto left_of = [&](uint32_t w) { return __shfl_up_sync(0xffffffffu, w, 1) & v_lf; };
-  auto right_of = [&](uint32_t w) { return __shfl_down_sync(0xffffffffu, w, 1) & v_rt; };
+  // operand word of this pixel's left / right neighbour: the neighbouring lane (a zero lane outside the image; lanes 0
+  // and 31, whose shuffle source does not exist, get their own zero back)
+  auto left_of = [&](uint32_t w) { return __shfl_up_sync(0xffffffffu, w, 1); };
+  auto right_of = [&](uint32_t w) { return __shfl_down_sync(0xffffffffu, w, 1); };
   // maximum over the warp of a non-negative float (its bit pattern orders like an unsigned integer): one REDUX
   auto warp_max = [&](float m) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))); };
 
@@ -305,8 +308,8 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
       float amax = 0.0f;
 #pragma unroll
       for (int c = 0; c < kEtCout; ++c) {
-        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kFov);
-        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kFov);
+        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow);
+        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kRow);
         float a = fmaf(__uint_as_float(r[1][c]), f, v[c]);
         a = fmaf(up, f_up, a);
         a = fmaf(dn, f_dn, a);
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
           uint32_t h[8], o[8];
 #pragma unroll
           for (int c = 0; c < kEtCout; c += 2) split_h2(v[c] * sc, v[c + 1] * sc, h[c >> 1], o[c >> 1]);
-          uint32_t* dst = reinterpret_cast<uint32_t*>(s_out) + lane * kEtOutPitch + quad * 4;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(s_out) + pidx * kEtOutPitch + quad * 4;
           *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
           *reinterpret_cast<uint4*>(dst + 32) = make_uint4(o[0], o[1], o[2], o[3]);
