@@ -98,6 +98,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // filters -> [Cout'/4][Cin'][9][4].  flip = 0: plain regrouping of w [Cout][Cin][9].  flip = 1: the
 // data-gradient filter bank, Cout' = Cin (padded to 4), Cin' = Cout, tap mirrored.
 __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int flip, float* __restrict__ out) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int co2 = flip ? int(r4(cin)) : cout, ci2 = flip ? cout : cin;
   const int total = co2 * ci2 * 9;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
                                                                 const float* __restrict__ bias,
                                                                 float* __restrict__ out, double* __restrict__ stats,
                                                                 int stat_c) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   extern __shared__ __align__(16) float s_ct[];
   float* s_w = s_ct;                                 // [cout/4][cin][9][4]
   float* s_in = s_ct + ((cout * cin * 9 + 3) & ~3);  // [cin*25][33]
@@ -233,6 +237,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
                                    float momentum, float* __restrict__ meaninv, float* running_mean,
                                    float* running_var, int64_t* batches, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ scale_shift) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     float rm = running_mean ? running_mean[c] : 0.0f, rv = running_var ? running_var[c] : 0.0f;
@@ -259,6 +265,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
 
 __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ scale_shift, int N, int C,
                                 int64_t planes, float* __restrict__ a) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   // coalesced, one element per thread and iteration; the (slot, channel) coefficients come from a tiny L1-resident table
   const int64_t total = planes * kFovCells;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
@@ -272,6 +280,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __rest
 // 128-bit variant for C*25 % 4 == 0 (a row's C*25 floats are 16-byte aligned, so a float4 never leaves its row)
 __global__ void bn_apply4_kernel(const float4* __restrict__ u, const float* __restrict__ scale_shift, int N, int C,
                                  int64_t rows, float4* __restrict__ a) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const uint32_t row4 = uint32_t(C * kFovCells) >> 2;
   const int64_t total = rows * row4;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
@@ -291,6 +301,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ u,
                                                             const float* __restrict__ meaninv, int B, int N, int C,
                                                             int stat_c, double* __restrict__ stats) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y, b0 = blockIdx.x * 32;
   const int nb = min(32, B - b0);
@@ -317,6 +329,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 __global__ void bn_bwd_coef_kernel(const double* __restrict__ stats, const float* __restrict__ meaninv,
                                    const float* __restrict__ gamma, int N, int C, int stat_c, double count,
                                    float* __restrict__ coef) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
@@ -330,6 +344,8 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ stats, const float
 __global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ a, const float* __restrict__ u,
                                     const float* __restrict__ meaninv, const float* __restrict__ coef, int N, int C,
                                     int64_t planes) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int64_t total = planes * kFovCells;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const uint32_t pl = uint32_t(idx / kFovCells);
@@ -345,6 +361,8 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restr
 __global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __restrict__ a, const float4* __restrict__ u,
                                      const float* __restrict__ meaninv, const float* __restrict__ coef, int N, int C,
                                      int64_t rows) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const uint32_t row4 = uint32_t(C * kFovCells) >> 2;
   const int64_t total = rows * row4;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
@@ -373,6 +391,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __res
                                                              const float4* __restrict__ u,
                                                              const float* __restrict__ meaninv, int B, int N, int C,
                                                              int stat_c, double* __restrict__ stats) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   __shared__ float s_sum[64 * 2];
   const int n = blockIdx.y, b0 = blockIdx.x * 32;
   const int nb = min(32, B - b0);
@@ -424,6 +444,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __res
 
 __global__ void bn_param_grads_kernel(const double* __restrict__ stats, int N, int C, int stat_c,
                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double g = 0.0, b = 0.0;
@@ -447,6 +469,8 @@ template <int SLOTS>
 __global__ void __launch_bounds__(kCwThreads, SLOTS == 1 ? 2 : 1)
 conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ in, int cin, int cout, int64_t rows,
                        float* __restrict__ part) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   extern __shared__ __align__(16) float s_cw[];
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
   float2* s_du = reinterpret_cast<float2*>(s_cw);                          // [16][out_len] (even row, odd row)
@@ -566,6 +590,8 @@ conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ i
 __global__ void __launch_bounds__(256) conv_bwd_weight_reduce_kernel(const float* __restrict__ part, int grid, int nw,
                                                                      int cout, float* __restrict__ dw,
                                                                      float* __restrict__ db) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   __shared__ float s_sum[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane, tot = nw + cout;
@@ -610,6 +636,8 @@ constexpr int kGemmTM = 128, kGemmTN = 64, kGemmK = 16, kGemmThreads = 256;
 // 128 x 64 tile, 8 x 4 outputs per thread kept as FFMA2 pairs along n, global -> register prefetch of the next K slab
 // while the current one is multiplied out of shared memory.
 __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   __shared__ __align__(16) float As[kGemmK][kGemmTM + 4];
   __shared__ __align__(16) float Bs[kGemmK][kGemmTN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -698,7 +726,7 @@ int gemm(cudaStream_t s, int M, int N, int K, const float* A, int64_t sam, int64
          int64_t ldmask = 0, int splits = 1) {
   GemmArgs g{M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, mask, ldmask, relu, splits};
   dim3 grid((N + kGemmTN - 1) / kGemmTN, (M + kGemmTM - 1) / kGemmTM, splits);
-  sgemm_kernel<<<grid, kGemmThreads, 0, s>>>(g);
+  mapf_launch_pdl(sgemm_kernel, dim3(grid), dim3(kGemmThreads), 0, s, g);
   return mapf_launch_status();
 }
 
@@ -712,6 +740,8 @@ int splits_for(int64_t rows, int tiles) {
 // out[c] = sum_r in[r][c]   (C <= 256)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, int64_t rows, int C,
                                                      float* __restrict__ out) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   __shared__ float s_part[256];
   const int tid = threadIdx.x;
   const int per = 256 / C;                  // row lanes per block pass
@@ -748,6 +778,8 @@ __global__ void __launch_bounds__(128) recurrence_bwd_kernel(const float* __rest
                                                              const float* __restrict__ x, int N, int F, int K,
                                                              int has_skip, int add_self_loop, float* __restrict__ dx,
                                                              int64_t dx_sb, int64_t dx_sn, int64_t dx_sf) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   extern __shared__ __align__(16) float s_rb[];
   const int KT = (K + has_skip) * F;
   float* sm = s_rb;                 // [N][N]
@@ -796,6 +828,8 @@ __global__ void __launch_bounds__(128) recurrence_bwd_kernel(const float* __rest
 
 // [B,C,N] -> [B*N, C]
 __global__ void bcn_to_rows_kernel(const float* __restrict__ in, int B, int C, int N, float* __restrict__ out) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int64_t total = int64_t(B) * C * N;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -811,6 +845,8 @@ __global__ void bcn_to_rows_kernel(const float* __restrict__ in, int B, int C, i
 // loss and optimiser
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ce_loss_kernel(mapf_ce_loss_args a) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   const int A = a.num_actions;
   float loss = 0.0f;
@@ -838,6 +874,8 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(mapf_ce_loss_args a) {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out,
                                                     int32_t* step_dev) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   if (step_dev != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;   // read by the next kernel
   double s = 0.0;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
@@ -854,6 +892,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, float bc1, float bc2_sqrt) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
   if (a.step_dev != nullptr) {   // device-resident step count (CUDA-graph replay): bias corrections computed here
     const double t = double(*a.step_dev);
     bc1 = float(1.0 - pow(double(a.beta1), t));
@@ -884,7 +924,7 @@ int launch_conv_train(cudaStream_t s, const float* in, int cin, int cout, int B,
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_train_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   dim3 grid((B + 31) / 32, N);
-  conv_train_kernel<<<grid, kCtThreads, smem, s>>>(in, cin, cout, B, N, wpk, bias, out, stats, stat_c);
+  mapf_launch_pdl(conv_train_kernel, dim3(grid), dim3(kCtThreads), smem, s, in, cin, cout, B, N, wpk, bias, out, stats, stat_c);
   return mapf_launch_status();
 }
 
@@ -930,20 +970,20 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   for (int l = 0; l < L; ++l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
     MAPF_REQUIRE(p->conv_w[l] && p->conv_b[l] && p->bn_gamma[l] && p->bn_beta[l], MAPF_ERR_NULL);
-    pack_conv_kernel<<<(cout * cin * 9 + 255) / 256, 256, 0, s>>>(p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
+    mapf_launch_pdl(pack_conv_kernel, dim3((cout * cin * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
     double* st = stat + int64_t(l) * N * T.cmax * 2;
     MAPF_TRY(launch_conv_train(s, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, B, N, ws + T.convpk[l],
                                p->conv_b[l], ws + T.u[l], st, T.cmax));
-    bn_finalize_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
+    mapf_launch_pdl(bn_finalize_kernel, dim3((cout + 63) / 64), dim3(64), 0, s, st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
                                                       const_cast<float*>(p->bn_mean[l]),
                                                       const_cast<float*>(p->bn_var[l]), a->bn_batches[l], p->bn_gamma[l],
                                                       p->bn_beta[l], ws + T.scsh[l]);
     const int64_t planes = rows * cout;
     if ((cout * kFovCells) % 4 == 0)
-      bn_apply4_kernel<<<unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16)), 256, 0, s>>>(
+      mapf_launch_pdl(bn_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s, 
           reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.scsh[l], N, cout, rows, reinterpret_cast<float4*>(ws + T.a[l]));
     else
-      bn_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(ws + T.u[l], ws + T.scsh[l], N,
+      mapf_launch_pdl(bn_apply_kernel, dim3(unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16))), dim3(256), 0, s, ws + T.u[l], ws + T.scsh[l], N,
                                                                                         cout, planes, ws + T.a[l]);
   }
   MAPF_TRY(mapf_launch_status());
@@ -1015,7 +1055,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   const int row_splits = splits_for(rows, 4);
   const float* head_act = K > 0 ? ws + T.y : ws + T.x;
   // actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0]
-  colsum_kernel<<<int(mapf_min64((rows + 255) / 256, 296)), 256, 0, s>>>(a->dlogits, rows, A, G.act_b);
+  mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, a->dlogits, rows, A, G.act_b);
   MAPF_TRY(gemm(s, A, head_in, int(rows), a->dlogits, 1, A, head_act, head_in, 1, G.act_w, head_in, nullptr, 0, nullptr,
                 0, splits_for(rows, (head_in + 63) / 64)));
   if (K > 0) {
@@ -1035,13 +1075,13 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
     if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(recurrence_bwd_kernel, size_t(smem), cache__); }())
       return MAPF_ERR_CUDA;
-    recurrence_bwd_kernel<<<B, 128, smem, s>>>(ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
+    mapf_launch_pdl(recurrence_bwd_kernel, dim3(B), dim3(128), smem, s, ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
                                                a->message ? 0 : 1, ws + T.dx, int64_t(N) * F, F, 1);
   } else {
     MAPF_TRY(gemm(s, int(rows), F, A, a->dlogits, A, 1, p->act_w, F, 1, ws + T.dx, F, nullptr, 0, ws + T.x, F));
   }
   // compressMLP backward
-  colsum_kernel<<<int(mapf_min64((rows + 255) / 256, 296)), 256, 0, s>>>(ws + T.dx, rows, F, G.fc_b);
+  mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, ws + T.dx, rows, F, G.fc_b);
   MAPF_TRY(gemm(s, F, fin, int(rows), ws + T.dx, 1, F, ws + T.a[L - 1], fin, 1, G.fc_w, fin, nullptr, 0, nullptr, 0,
                 splits_for(rows, ((F + 127) / 128) * ((fin + 63) / 64))));
   float* da = ws + T.da0;
@@ -1055,22 +1095,22 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     dim3 grid((B + 31) / 32, N);
     const bool vec4 = (cout * kFovCells) % 4 == 0 && cout * kFovCells / 4 <= 256 && cout <= 64;
     if (vec4)
-      bn_bwd_reduce4_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]),
+      mapf_launch_pdl(bn_bwd_reduce4_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]),
                                                  reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.meaninv[l], B, N, cout,
                                                  T.cmax, st);
     else
-      bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
-    bn_bwd_coef_kernel<<<(N * cout + 127) / 128, 128, 0, s>>>(st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
+      mapf_launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
+    mapf_launch_pdl(bn_bwd_coef_kernel, dim3((N * cout + 127) / 128), dim3(128), 0, s, st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
                                                              ws + T.coef[l]);
     const int64_t planes = rows * cout;
     if ((cout * kFovCells) % 4 == 0)
-      bn_bwd_apply4_kernel<<<unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16)), 256, 0, s>>>(
+      mapf_launch_pdl(bn_bwd_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s, 
           reinterpret_cast<float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]), reinterpret_cast<const float4*>(ws + T.u[l]),
           ws + T.meaninv[l], ws + T.coef[l], N, cout, rows);
     else
-      bn_bwd_apply_kernel<<<unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16)), 256, 0, s>>>(
+      mapf_launch_pdl(bn_bwd_apply_kernel, dim3(unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16))), dim3(256), 0, s, 
           da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
-    bn_param_grads_kernel<<<(cout + 63) / 64, 64, 0, s>>>(st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
+    mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, s, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
       const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
       MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
@@ -1082,19 +1122,19 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       if (cin * cout <= kCwThreads) {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<1>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        conv_bwd_weight_kernel<1><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, part);
+        mapf_launch_pdl(conv_bwd_weight_kernel<1>, dim3(gridw), dim3(kCwThreads), smem, s, da, lin, cin, cout, rows, part);
       } else {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<4>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        conv_bwd_weight_kernel<4><<<gridw, kCwThreads, smem, s>>>(da, lin, cin, cout, rows, part);
+        mapf_launch_pdl(conv_bwd_weight_kernel<4>, dim3(gridw), dim3(kCwThreads), smem, s, da, lin, cin, cout, rows, part);
       }
       const int nw = cin * cout * 9;
-      conv_bwd_weight_reduce_kernel<<<(nw + cout + 31) / 32, 256, 0, s>>>(part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
+      mapf_launch_pdl(conv_bwd_weight_reduce_kernel, dim3((nw + cout + 31) / 32), dim3(256), 0, s, part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
     }
     if (l > 0) {
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
       const int cin_pad = int(r4(cin));
-      pack_conv_kernel<<<(cin_pad * cout * 9 + 255) / 256, 256, 0, s>>>(p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
+      mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
       MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
       MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
       float* t = da; da = da_next; da_next = t;
@@ -1109,7 +1149,7 @@ extern "C" int mapf_ce_loss(const mapf_ce_loss_args* a, mapf_stream_t stream) {
   MAPF_REQUIRE(a->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(a->loss, 0, sizeof(float), s) != cudaSuccess) return MAPF_ERR_CUDA;
-  ce_loss_kernel<<<unsigned((a->rows + 255) / 256), 256, 0, s>>>(*a);
+  mapf_launch_pdl(ce_loss_kernel, dim3(unsigned((a->rows + 255) / 256)), dim3(256), 0, s, *a);
   return mapf_launch_status();
 }
 
@@ -1119,10 +1159,10 @@ extern "C" int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(a->scratch, 0, sizeof(double), s) != cudaSuccess) return MAPF_ERR_CUDA;
   const int blocks = int(mapf_min64((a->n + 255) / 256, 148));
-  sumsq_kernel<<<blocks, 256, 0, s>>>(a->grads, a->n, a->scratch, a->step_dev);
+  mapf_launch_pdl(sumsq_kernel, dim3(blocks), dim3(256), 0, s, a->grads, a->n, a->scratch, a->step_dev);
   const double bc1 = 1.0 - pow(double(a->beta1), double(a->step));
   const double bc2 = 1.0 - pow(double(a->beta2), double(a->step));
-  clip_adam_kernel<<<blocks, 256, 0, s>>>(*a, float(bc1), float(sqrt(bc2)));
+  mapf_launch_pdl(clip_adam_kernel, dim3(blocks), dim3(256), 0, s, *a, float(bc1), float(sqrt(bc2)));
   return mapf_launch_status();
 }
 
@@ -1146,7 +1186,7 @@ extern "C" int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_s
   float* dyr = dz + r4(rows * KT);
   // recompute the filter taps z with the forward kernel
   MAPF_TRY(mapf_pack_graph_weights(a->w, a->w2, F, K, G, wt, stream));
-  bcn_to_rows_kernel<<<unsigned(mapf_min64((rows * G + 255) / 256, 148 * 16)), 256, 0, s>>>(a->dy, B, G, N, dyr);
+  mapf_launch_pdl(bcn_to_rows_kernel, dim3(unsigned(mapf_min64((rows * G + 255) / 256, 148 * 16))), dim3(256), 0, s, a->dy, B, G, N, dyr);
   mapf_graph_filter_fwd_args g{};
   g.batch = B; g.agents = N; g.in_dim = F; g.out_dim = G; g.taps = K;
   g.add_self_loop = a->add_self_loop; g.has_skip = skip; g.relu = 0; g.num_actions = 0;
@@ -1169,7 +1209,7 @@ extern "C" int mapf_graph_filter_bwd(const mapf_graph_filter_bwd_args* a, mapf_s
   MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(recurrence_bwd_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
-  recurrence_bwd_kernel<<<B, 128, smem, s>>>(dz, a->gso, nullptr, N, F, K, skip, a->add_self_loop, a->dx, int64_t(F) * N,
+  mapf_launch_pdl(recurrence_bwd_kernel, dim3(B), dim3(128), smem, s, dz, a->gso, nullptr, N, F, K, skip, a->add_self_loop, a->dx, int64_t(F) * N,
                                              1, N);
   return mapf_launch_status();
 }
