@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
   const bool pix_ok = lane >= 1 && lane <= 29 && px >= 0 && px < kFov;
   const int pidx = pix_ok ? py * kFov + px : 0;
   const float m_up = (pix_ok && py > 0) ? 1.0f : 0.0f, m_dn = (pix_ok && py < kFov - 1) ? 1.0f : 0.0f;
-  const uint32_t v_ok = pix_ok ? 0xFFFFFFFFu : 0u;
   constexpr int kRow = kFov + 1;                                         // lanes between vertically adjacent pixels
 
   constexpr uint32_t idesc = tc::idesc_f16(128, kEtN);
@@ -313,14 +312,16 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
         float a = fmaf(__uint_as_float(r[1][c]), f, v[c]);
         a = fmaf(up, f_up, a);
         a = fmaf(dn, f_dn, a);
-        v[c] = __uint_as_float(__float_as_uint(fmaxf(a, 0.0f)) & v_ok);   // ReLU; lanes that are not pixels hold zero
+        v[c] = fmaxf(a, 0.0f);                                          // ReLU
         amax = fmaxf(amax, v[c]);
       }
+      amax = pix_ok ? amax : 0.0f;   // lanes that are not pixels hold finite garbage: they are zeroed by their scale below
       ETC_STAMP(4);
       if (l + 1 < g.num_conv) {
         // next layer's A operand: k = kx*16 + ci -> (left neighbour | this pixel | right neighbour), fp16 hi and lo
         float sc;
         pow2_scale(warp_max(amax), sc, inv_a);
+        sc = pix_ok ? sc : 0.0f;     // zero rows for the lanes between the image rows
         uint32_t h[8], o[8], t[8];
 #pragma unroll
         for (int c = 0; c < kEtCout; c += 2) split_h2(v[c] * sc, v[c + 1] * sc, h[c >> 1], o[c >> 1]);
