@@ -206,6 +206,11 @@ def run_mine(args, w):
     active = torch.zeros(K, dtype=torch.int64, device=dev)
     for i in range(W):
         ro.run(1)
+    # the timed step is ONE CUDA-graph replay of the step's launch sequence (same kernels, same order): the host then
+    # issues one launch per step and cannot open gaps between the kernels when 8 ranks share the box's cores
+    step_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(step_graph):
+        ro.run(1)
     env.reset()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -218,7 +223,7 @@ def run_mine(args, w):
         active[i] = E - env.done.sum()
         flush.zero_()
         ev0[i].record()
-        ro.run(1)
+        step_graph.replay()
         ev1[i].record()
     barrier()
     wall = time.perf_counter() - t_wall0
@@ -356,7 +361,8 @@ def run_mine(args, w):
             "config": {"workload": f"{args.workload}: {w['desc']}", "episodes_per_gpu": E, "agents": N, "board": H,
                        "obstacles": w["M"], "weights": f"tests/golden/weights_{w['model']}.npz",
                        "l2": "flushed between steps (256 MiB memset outside the event pairs)",
-                       "timing": "cuda events per step on the launching stream, max over ranks",
+                       "timing": "cuda events per step on the launching stream, max over ranks; a step = one CUDA-graph "
+                                 "replay of the rollout step's kernel sequence",
                        "counted": "agent-steps of episodes not yet done (done episodes are frozen); "
                                   f"nominal E*N*K = {units_nominal:.0f}",
                        "wall_s_incl_flush": wall},
