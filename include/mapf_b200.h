@@ -89,6 +89,9 @@ int mapf_make_scenarios(int32_t episodes, int32_t agents, int32_t board, int32_t
  * Episodes whose done flag is already set are frozen (callers of the reference `break`,
  * evaluate.py:251): no move, no time increment, observation recomputed.  do_move == 3 steps finished episodes too
  * (the reference env itself never freezes; data_generation/record.py:78-88 keeps stepping).
+ * do_move bit 2 (value 4) is a scheduling hint set by mapf_rollout: boards / positions / goals / done flags were last
+ * written BEFORE the kernels launched in front of this call started (only `actions` comes from the kernel right in
+ * front), so the kernel may stage them before its grid-dependency wait.  Never set it when that is not guaranteed.
  * d2_limit: smallest integer d2 with sqrt((double)d2) >= sensing_range. */
 typedef struct {
   int32_t episodes, agents, board;
