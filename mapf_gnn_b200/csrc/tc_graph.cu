@@ -69,6 +69,14 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     s_head[i] = n < g.G ? __ldg(g.act_w + int64_t(q) * g.G + n) : 0.0f;
   }
   if (tid < g.num_actions) s_head[kMaxActions * kTgNT + tid] = __ldg(g.act_b + tid);
+  __syncthreads();      // the mbarriers are initialised
+  if (warp < kTgProd && lane == 0) {
+    // the B chunk of every producer's first emit (tap 0, slice = warp) is packed weights: fetch it now, under the shift
+    // operator build (and, inside mapf_policy_fwd, under the encoder FC that runs in front of this kernel)
+    tc::mbar_expect_tx(&s_full[warp], 2 * kTgBBytes);
+    tc::bulk_g2s(s_tg + warp * kTgStageBytes + 2 * kTgABytes, g.Bp + int64_t(warp) * (2 * kTgNT * 8), 2 * kTgBBytes,
+                 &s_full[warp]);
+  }
   // Inside mapf_policy_fwd the adjacency is an input of the whole launch sequence -- complete before the encoder kernels in
   // front of this one started -- so the shift operator is built while the encoder FC still runs; the node features come
   // from that FC and are read behind the grid wait.
@@ -124,7 +132,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     auto emit = [&](int c, const float (*v)[8]) {
       tc::mbar_wait(&s_empty[p], (ne & 1) ^ 1);
       ++ne;
-      if (lane == 0) {
+      if (lane == 0 && ne > 1) {          // (the first emit's B chunk was fetched in the prologue)
         tc::mbar_expect_tx(&s_full[p], 2 * kTgBBytes);
         tc::bulk_g2s(b_hi, g.Bp + int64_t(c) * (2 * kTgNT * 8), 2 * kTgBBytes, &s_full[p]);
       }
@@ -142,20 +150,30 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
       tc::fence_proxy_async();
       tc::mbar_arrive(&s_full[p]);
     };
+    // x[:, 8j..8j+8) of this lane's four rows; the next slice is loaded while the current one is emitted
+    auto load_slice = [&](int j, float4 (&lo4)[4], float4 (&hi4)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        lo4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hi4[i] = lo4[i];
+        if (rlive[i] && j < slices) {
+          const float4* src = reinterpret_cast<const float4*>(g.x + (row0 + rr[i]) * F + 8 * j);
+          lo4[i] = __ldg(src);
+          hi4[i] = __ldg(src + 1);
+        }
+      }
+    };
+    float4 nlo[4], nhi[4];
+    load_slice(p, nlo, nhi);
     for (int si = 0; si < per_warp; ++si) {
       const int j = p + kTgProd * si;
       float xv[4][8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (rlive[i]) {
-          const float4* src = reinterpret_cast<const float4*>(g.x + (row0 + rr[i]) * F + 8 * j);
-          v0 = __ldg(src);
-          v1 = __ldg(src + 1);
-        }
-        xv[i][0] = v0.x; xv[i][1] = v0.y; xv[i][2] = v0.z; xv[i][3] = v0.w;
-        xv[i][4] = v1.x; xv[i][5] = v1.y; xv[i][6] = v1.z; xv[i][7] = v1.w;
+        xv[i][0] = nlo[i].x; xv[i][1] = nlo[i].y; xv[i][2] = nlo[i].z; xv[i][3] = nlo[i].w;
+        xv[i][4] = nhi[i].x; xv[i][5] = nhi[i].y; xv[i][6] = nhi[i].z; xv[i][7] = nhi[i].w;
       }
+      load_slice(si + 1 < per_warp ? j + kTgProd : slices, nlo, nhi);
       for (int k = 0; k < K; ++k) {
         if (k > 0) {
           // x_k[row j] = sum_i S[i][j] x_{k-1}[row i] over the rows of the same episode (held by other lanes)
