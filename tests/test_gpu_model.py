@@ -187,6 +187,9 @@ def test_tensor_core_conv_stack_matches_torch(rows, depth):
     _lib.check(lib.mapf_encoder_tc_conv_fwd(p, ea, _lib.current_stream()), "tc_conv")
     got = _untile_presplit_f16(Ap, rows, 400)
     assert np.isfinite(got).all()
+    # bounds canary: behind the operand tiles and the row scales the NaN fill of the workspace must be untouched
+    used = ((rows + 127) // 128) * 25 * 2048 + rows
+    assert bool(torch.isnan(Ap[used:]).all())
     # per image: 1e-5 of the image's largest activation (the split keeps 22 bits relative to it)
     scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
     assert (np.abs(got - ref) / scale).max() < 1e-5
@@ -210,7 +213,8 @@ def test_tensor_core_encoder_matches_oracle(rows):
     p = net_params(dims)
     st = states.cuda()
     Ap = torch.full((lib.mapf_tc_presplit_a_size(rows, dims[6]),), float("nan"), device="cuda")
-    x = torch.empty((rows, dims[7]), device="cuda")
+    xg = torch.full((rows + 8, dims[7]), float("nan"), device="cuda")     # 8 canary rows behind the output
+    x = xg[:rows]
     fcw = net.compressMLP[0].weight.detach().contiguous()
     fcb = net.compressMLP[0].bias.detach().contiguous()
     Bp = torch.empty((lib.mapf_tc_packed_b_f16_size(dims[7], dims[6]),), device="cuda")
@@ -222,6 +226,7 @@ def test_tensor_core_encoder_matches_oracle(rows):
                                            fcb.data_ptr(), 1, s), "fc_f16")
     got = x.cpu().numpy()
     assert np.isfinite(got).all()
+    assert bool(torch.isnan(xg[rows:]).all())
     assert rel_err(got, ref) < 1e-5
 
 
