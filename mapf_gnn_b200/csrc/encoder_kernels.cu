@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
   }
   __syncthreads();   // barrier words initialised before anyone polls them
 
+  mapf_pdl_wait();      // the weight copies above touch only the packed buffer; the observations come from the env kernel
+  mapf_pdl_launch();
   float* const s_st = s_b1 + d.buf1_floats;     // [32][50] image staging, filled by cp.async one item ahead
 
   // Work items of this CTA: full tiles b, b + G, ... (< nfull) of 32 agent images, then half tile b (< nhalf) of 16.
@@ -550,11 +552,11 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   if (d.fc_in_smem) {
     static int cache_a[16] = {0};
     if (!mapf_ensure_smem(encoder_fwd_kernel<0>, smem, cache_a)) return MAPF_ERR_CUDA;
-    encoder_fwd_kernel<0><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
+    mapf_launch_pdl(encoder_fwd_kernel<0>, dim3(grid), dim3(kEncThreads), smem, s, d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
   } else {
     static int cache_b[16] = {0};
     if (!mapf_ensure_smem(encoder_fwd_kernel<1>, smem, cache_b)) return MAPF_ERR_CUDA;
-    encoder_fwd_kernel<1><<<grid, kEncThreads, smem, s>>>(d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
+    mapf_launch_pdl(encoder_fwd_kernel<1>, dim3(grid), dim3(kEncThreads), smem, s, d, L, a->rows, nfull, nhalf, a->states, a->packed, a->x);
   }
   return mapf_launch_status();
 }
@@ -600,8 +602,8 @@ extern "C" int mapf_encoder_conv_split_fwd(const mapf_net_params* p, const mapf_
   const int grid = int(nfull >= sms ? sms : (nfull > nhalf ? nfull : nhalf));
   static int cache_c[16] = {0};
   if (!mapf_ensure_smem(encoder_fwd_kernel<2>, smem, cache_c)) return MAPF_ERR_CUDA;
-  encoder_fwd_kernel<2><<<grid, kEncThreads, smem, static_cast<cudaStream_t>(stream)>>>(d, L, a->rows, nfull, nhalf,
-                                                                                         a->states, a->packed, a->x);
+  mapf_launch_pdl(encoder_fwd_kernel<2>, dim3(grid), dim3(kEncThreads), smem, static_cast<cudaStream_t>(stream), d, L,
+                  a->rows, nfull, nhalf, a->states, a->packed, a->x);
   return mapf_launch_status();
 }
 

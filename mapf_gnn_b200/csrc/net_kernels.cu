@@ -98,6 +98,8 @@ __global__ void pack_graph_weights_kernel(const float* __restrict__ w, const flo
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_fwd_kernel(mapf_head_fwd_args a) {
   extern __shared__ __align__(16) float s_head[];  // [32 rows][D + 1]
+  mapf_pdl_wait();
+  mapf_pdl_launch();
   const int D = a.in_dim, A = a.num_actions;
   const int64_t row0 = int64_t(blockIdx.x) * 32;
   const int nrows = (a.rows - row0) < 32 ? int(a.rows - row0) : 32;
@@ -181,7 +183,7 @@ extern "C" int mapf_head_fwd(const mapf_head_fwd_args* a, mapf_stream_t stream) 
   if (smem > 40 * 1024 &&
       [&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(head_fwd_kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
-  head_fwd_kernel<<<unsigned((a->rows + 31) / 32), 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  mapf_launch_pdl(head_fwd_kernel, dim3(unsigned((a->rows + 31) / 32)), dim3(256), smem, static_cast<cudaStream_t>(stream), *a);
   return mapf_launch_status();
 }
 
