@@ -52,12 +52,13 @@ static inline __host__ __device__ int64_t mapf_tc_b_floats(int N, int K) {
   return int64_t((K + 7) / 8) * 2 * (N <= 64 ? 64 : 128) * 8;
 }
 
-// the tensor-core conv stack (enc_tc.cu) is built for 16-channel layers
+// the tensor-core conv stack (enc_tc.cu) is built for a first layer of 16 or 32 channels and 16-channel layers behind it
 static inline __host__ __device__ bool mapf_enc_tc_dims_ok(const mapf_net_params& p) {
   if (p.num_conv < 1 || p.num_conv > MAPF_MAX_CONV || p.fc_out > 128) return false;
-  for (int l = 1; l <= p.num_conv; ++l)
+  if (p.channels[1] != 16 && p.channels[1] != 32) return false;
+  for (int l = 2; l <= p.num_conv; ++l)
     if (p.channels[l] != 16) return false;
-  return true;
+  return p.channels[p.num_conv] == 16;
 }
 
 static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net_params& p) {
@@ -83,7 +84,8 @@ static inline __host__ __device__ PackedLayout mapf_packed_layout(const mapf_net
   L.tc_fc_pm = off;
   if (mapf_enc_tc_dims_ok(p)) {
     off += 4;   // inverse filter scales
-    for (int l = 0; l < p.num_conv; ++l) off += int64_t((3 * p.channels[l] + 15) >> 4) * 2 * (48 * 8);
+    for (int l = 0; l < p.num_conv; ++l)
+      off += int64_t(p.channels[l + 1] / 16) * ((3 * p.channels[l] + 15) >> 4) * 2 * (48 * 8);
     L.tc_fc_pm = off;
     off += 4 + int64_t((p.fc_in + 15) / 16) * (p.fc_out <= 64 ? 64 : 128) * 16;   // fp16 hi|lo blocks + scale header
   }

@@ -38,15 +38,23 @@
 
 namespace {
 
-constexpr int kEtGroups = 5;                    // warpgroups per CTA
-constexpr int kEtThreads = 128 * kEtGroups;
-constexpr int kEtCout = 16;                     // channels of every conv layer this kernel is built for
+constexpr int kEtCout = 16;                     // channels per GEMM: a 32-channel first layer is two of them
 constexpr int kEtN = 3 * kEtCout;               // GEMM N: (filter row, co)
 constexpr int kEtBlk = kEtN * 16 / 2;           // floats (= pairs of halfs) of one (K step, hi|lo) block of the B operand
 constexpr int kEtHdr = 4;                       // floats in front of the B blocks: the layers' inverse filter scales
-constexpr uint32_t kEtColAHi = kEtN, kEtColALo = kEtN + 24, kEtSetCols = kEtN + 48;   // D 48 | A hi 24 | A lo 24
+constexpr uint32_t kEtColAHi = kEtN;            // TMEM columns of a set: D 48 | A hi 24*C1/16 | A lo 24*C1/16
 constexpr int kEtOutPitch = 4 * 16 + 4;         // words per pixel in the output staging buffer (4 runs x 64 B + 16 B)
 constexpr int kEtOutFloats = kFovCells * kEtOutPitch;
+constexpr int kEtMaxC = 32;                     // widest layer (the first one of the baseline network)
+// C1 = channels of the first layer (16: the GNN networks, 32: the baseline); every later layer has 16.  The operand of
+// layer 1 has 3*C1 K entries, so a set needs 96 or 144 TMEM columns and a CTA holds five or three warpgroups.
+template <int C1> struct EtCfg {
+  static constexpr int kGroups = C1 == 16 ? 5 : 3;
+  static constexpr int kThreads = 128 * kGroups;
+  static constexpr uint32_t kAW = 24 * (C1 / 16);
+  static constexpr uint32_t kColALo = kEtColAHi + kAW;
+  static constexpr uint32_t kSetCols = kEtColAHi + 2 * kAW;
+};
 static_assert(MAPF_MAX_CONV <= kEtHdr, "one inverse scale per layer");
 
 struct EncTcArgs {
@@ -116,7 +124,7 @@ __device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv)
 __global__ void pack_tc_conv_kernel(mapf_net_params p, PackedLayout L, float* __restrict__ packed) {
   __shared__ float s_red[256];
   const int l = blockIdx.x;
-  const int cin = p.channels[l], nw = kEtCout * cin * 9;
+  const int cin = p.channels[l], cout = p.channels[l + 1], nw = cout * cin * 9;
   float m = 0.0f;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) m = fmaxf(m, fabsf(packed[L.conv_w[l] + i]));
   s_red[threadIdx.x] = m;
@@ -129,19 +137,21 @@ __global__ void pack_tc_conv_kernel(mapf_net_params p, PackedLayout L, float* __
   pow2_scale(s_red[0], scale, inv);
   if (threadIdx.x == 0) packed[L.tc_conv + l] = inv;
   int64_t base = kEtHdr;
-  for (int j = 0; j < l; ++j) base += int64_t((3 * p.channels[j] + 15) >> 4) * 2 * kEtBlk;
+  for (int j = 0; j < l; ++j) base += int64_t(p.channels[j + 1] / kEtCout) * ((3 * p.channels[j] + 15) >> 4) * 2 * kEtBlk;
   const int ks = (3 * cin + 15) >> 4;
   __half* out = reinterpret_cast<__half*>(packed + L.tc_conv + base);
-  const int n = ks * 2 * kEtBlk * 2;   // halfs
+  const int per_half = ks * 2 * kEtBlk * 2;            // halfs of one 16-channel output group: [K step][hi|lo][48 x 16]
+  const int n = (cout / kEtCout) * per_half;
   for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    int r = idx;
+    const int grp = idx / per_half;
+    int r = idx - grp * per_half;
     const int step = r / (4 * kEtBlk);
     r -= step * 4 * kEtBlk;
     const int is_lo = r >= 2 * kEtBlk;
     if (is_lo) r -= 2 * kEtBlk;
     const int k8i = r & 7, n8 = (r >> 3) & 7, kq = (r >> 6) & 1, ng = r >> 7;
     const int nn = ng * 8 + n8, k = step * 16 + kq * 8 + k8i;
-    const int ky = nn / kEtCout, co = nn % kEtCout;
+    const int ky = nn / kEtCout, co = grp * kEtCout + nn % kEtCout;
     float v = 0.0f;
     if (k < 3 * cin) {
       const int kx = k / cin, ci = k - kx * cin;
@@ -162,9 +172,12 @@ __device__ long long* g_etc_dbg = nullptr;   // block 0: [layer iteration < 16][
 #define ETC_STAMP(i)
 #endif
 
-__global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) {
+template <int C1>
+__global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncTcArgs g) {
+  constexpr int kEtGroups = EtCfg<C1>::kGroups, kEtThreads = EtCfg<C1>::kThreads;
+  constexpr uint32_t kEtColALo = EtCfg<C1>::kColALo, kEtSetCols = EtCfg<C1>::kSetCols;
   extern __shared__ __align__(128) float s_w[];          // weight image (header + B blocks), then the output staging buffers
-  __shared__ __align__(16) float s_bias[MAPF_MAX_CONV][kEtCout];
+  __shared__ __align__(16) float s_bias[MAPF_MAX_CONV][kEtMaxC];
   __shared__ __align__(8) uint64_t s_bar[kEtGroups];     // MMAs of the group's current layer complete (tcgen05.commit)
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_lw[MAPF_MAX_CONV], s_lnm[MAPF_MAX_CONV];   // per layer: byte offset of its B blocks, 16-wide K steps
@@ -183,7 +196,10 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
     s_lw[tid] = uint32_t(kEtHdr + g.w_off[tid]) * 4u;
     s_lnm[tid] = uint32_t((3 * g.cin[tid] + 15) >> 4);
   }
-  if (tid < g.num_conv * kEtCout) s_bias[tid / kEtCout][tid % kEtCout] = __ldg(g.packed + g.bias_off[tid / kEtCout] + tid % kEtCout);
+  if (tid < g.num_conv * kEtMaxC) {
+    const int l = tid / kEtMaxC, c = tid % kEtMaxC;
+    s_bias[l][c] = c < (l == 0 ? C1 : kEtCout) ? __ldg(g.packed + g.bias_off[l] + c) : 0.0f;
+  }
   tc::fence_proxy_async();      // the filters are read by the tensor core (async proxy)
   tc::fence_before_sync();
   __syncthreads();
@@ -254,7 +270,14 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
     load_obs(tile + stride, o0, o1);     // next tile's pixels arrive while this one is computed
     const int64_t img0 = tile * 4;
 
-    for (int l = 0; l < g.num_conv; ++l) {
+    // MMA rounds of a tile: layer 0 once per group of 16 output channels (twice for the 32-channel first layer of the
+    // baseline network: the second round re-uses D after the first round's partial sums have been read), then one per layer
+    constexpr int kHalves = C1 / kEtCout;
+    float v0[kEtCout];            // C1 == 32: the first 16 channels of layer 0, kept while the second round runs
+    float amax0 = 0.0f;
+    for (int rd = 0; rd < g.num_conv + kHalves - 1; ++rd) {
+      const int l = rd < kHalves ? 0 : rd - (kHalves - 1);
+      const int half = rd < kHalves ? rd : 0;
       ETC_STAMP(0);
       tmem_st_wait();
       tc::fence_before_sync();
@@ -267,8 +290,8 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
         // order and results differ in the last bit from run to run.)
         tc::fence_after_sync();
         ETC_STAMP(6);
-        const uint32_t wl = w_base + s_lw[l];
         const int ksteps = int(s_lnm[l]);
+        const uint32_t wl = w_base + s_lw[l] + uint32_t(half * ksteps) * (2 * kEtBlk * 4);
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t bh = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4), 128, 256);
           const uint64_t bl = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + kEtBlk * 4, 128, 256);
@@ -297,7 +320,7 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
       const float f_up = m_up * f, f_dn = m_dn * f;
       float v[kEtCout];
       {
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias[l]);
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias[l] + half * kEtCout);
 #pragma unroll
         for (int q = 0; q < kEtCout / 4; ++q) {
           const float4 b = b4[q];
@@ -317,29 +340,45 @@ __global__ void __launch_bounds__(kEtThreads, 1) encoder_tc_kernel(EncTcArgs g) 
       }
       amax = pix_ok ? amax : 0.0f;   // lanes that are not pixels hold finite garbage: they are zeroed by their scale below
       ETC_STAMP(4);
-      if (l + 1 < g.num_conv) {
-        // next layer's A operand: k = kx*16 + ci -> (left neighbour | this pixel | right neighbour), fp16 hi and lo
+      if (kHalves == 2 && rd == 0) {
+        // first half of the 32-channel layer: keep it in registers, the operand is written when both halves are known
+#pragma unroll
+        for (int c = 0; c < kEtCout; ++c) v0[c] = v[c];
+        amax0 = amax;
+      } else if (l + 1 < g.num_conv) {
+        // next layer's A operand: k = kx*C + ci -> (left neighbour | this pixel | right neighbour), fp16 hi and lo
+        constexpr int kW = kEtCout / 2;                 // operand words (fp16 pairs) per 16 channels
+        const bool wide = kHalves == 2 && l == 0;       // this layer has 32 output channels (v0 | v)
+        const int nw = wide ? 2 * kW : kW;              // words per copy
         float sc;
-        pow2_scale(warp_max(amax), sc, inv_a);
+        pow2_scale(warp_max(wide ? fmaxf(amax, amax0) : amax), sc, inv_a);
         sc = pix_ok ? sc : 0.0f;     // zero rows for the lanes between the image rows
-        uint32_t h[8], o[8], t[8];
+        uint32_t h[kW], o[kW], t[kW];
 #pragma unroll
-        for (int c = 0; c < kEtCout; c += 2) split_h2(v[c] * sc, v[c + 1] * sc, h[c >> 1], o[c >> 1]);
-        tmem_st8(tlane + kEtColAHi + 8, h);
-        tmem_st8(tlane + kEtColALo + 8, o);
-        // the neighbours' operand words are the neighbours' own splits: shuffle the packed fp16 pairs
+        for (int part = 0; part < kHalves; ++part) {
+          if (part == 1 && !wide) break;
+          const int cb = wide ? part * kW : 0;          // first operand word of this group of 16 channels
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = left_of(h[j]);
-        tmem_st8(tlane + kEtColAHi, t);
+          for (int c = 0; c < kEtCout; c += 2) {
+            const float a0 = (wide && part == 0) ? v0[c] : v[c], a1 = (wide && part == 0) ? v0[c + 1] : v[c + 1];
+            split_h2(a0 * sc, a1 * sc, h[c >> 1], o[c >> 1]);
+          }
+          tmem_st8(tlane + kEtColAHi + nw + cb, h);
+          tmem_st8(tlane + kEtColALo + nw + cb, o);
+          // the neighbours' operand words are the neighbours' own splits: shuffle the packed fp16 pairs
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = left_of(o[j]);
-        tmem_st8(tlane + kEtColALo, t);
+          for (int j = 0; j < kW; ++j) t[j] = left_of(h[j]);
+          tmem_st8(tlane + kEtColAHi + cb, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = right_of(h[j]);
-        tmem_st8(tlane + kEtColAHi + 16, t);
+          for (int j = 0; j < kW; ++j) t[j] = left_of(o[j]);
+          tmem_st8(tlane + kEtColALo + cb, t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = right_of(o[j]);
-        tmem_st8(tlane + kEtColALo + 16, t);
+          for (int j = 0; j < kW; ++j) t[j] = right_of(h[j]);
+          tmem_st8(tlane + kEtColAHi + 2 * nw + cb, t);
+#pragma unroll
+          for (int j = 0; j < kW; ++j) t[j] = right_of(o[j]);
+          tmem_st8(tlane + kEtColALo + 2 * nw + cb, t);
+        }
       } else {
         // flattened activations, k = pixel*16 + c, as the fp16-split A operand of the FC: Ap [row/128][k/16 = pixel]
         // [hi|lo][(row%128)/8][(k%16)/8][row%8][k%8] with one power-of-two scale per image (its inverse goes to the row
@@ -391,9 +430,10 @@ extern "C" int mapf_enc_tc_set_debug(long long* p) {
 }
 #endif
 
-// every conv layer 16 channels wide, input 2 planes, FC input 400 = 50 whole K chunks
+// first conv layer 16 or 32 channels wide, every later one 16, input 2 planes, FC input 400 = 25 whole K chunks
 extern "C" int mapf_encoder_tc_supported(const mapf_net_params* p) {
-  static_assert(kEtCout == 16 && kEtBlk == 48 * 8 && kEtHdr == 4, "mapf_packed_layout sizes the tc_conv region with these");
+  static_assert(kEtCout == 16 && kEtBlk == 48 * 8 && kEtHdr == 4 && kEtMaxC == 32,
+                "mapf_packed_layout / mapf_enc_tc_dims_ok size the tc_conv region with these");
   if (mapf_check_params(p) != MAPF_OK) return 0;
   return mapf_enc_tc_dims_ok(*p) ? 1 : 0;
 }
@@ -422,7 +462,7 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
   for (int l = 0; l < p->num_conv; ++l) {
     g.cin[l] = p->channels[l];
     g.w_off[l] = off;
-    off += ((3 * p->channels[l] + 15) >> 4) * 2 * kEtBlk;
+    off += (p->channels[l + 1] / kEtCout) * ((3 * p->channels[l] + 15) >> 4) * 2 * kEtBlk;
     g.bias_off[l] = L.conv_b[l];
   }
   off += kEtHdr;
@@ -438,15 +478,22 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
     const char* e = getenv("MAPF_B200_ETC_SKEW");   // development switch
     g.skew = e ? atoi(e) : 1400;
   }
-  const size_t smem = size_t(off + kEtGroups * kEtOutFloats) * sizeof(float);
-  MAPF_REQUIRE(smem <= 200 * 1024, MAPF_ERR_UNSUPPORTED);
-  static int cache[16] = {0};
-  if (!mapf_ensure_smem(encoder_tc_kernel, smem, cache)) return MAPF_ERR_CUDA;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (a->rows + 3) >> 2;
-  const int64_t want = (ntiles + kEtGroups - 1) / kEtGroups;
-  const int grid = int(want < sms ? want : sms);
-  mapf_launch_pdl(encoder_tc_kernel, dim3(grid), dim3(kEtThreads), smem, static_cast<cudaStream_t>(stream), g);
+  auto launch = [&](auto cfg, auto kernel, int* cache) -> int {
+    constexpr int kGroups = decltype(cfg)::kGroups, kThreads = decltype(cfg)::kThreads;
+    const size_t smem = size_t(off + kGroups * kEtOutFloats) * sizeof(float);
+    if (smem > 200 * 1024) return MAPF_ERR_UNSUPPORTED;
+    if (!mapf_ensure_smem(kernel, smem, cache)) return MAPF_ERR_CUDA;
+    const int64_t want = (ntiles + kGroups - 1) / kGroups;
+    const int grid = int(want < sms ? want : sms);
+    mapf_launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), g);
+    return MAPF_OK;
+  };
+  static int cache16[16] = {0}, cache32[16] = {0};
+  const int rc = p->channels[1] == 16 ? launch(EtCfg<16>{}, encoder_tc_kernel<16>, cache16)
+                                      : launch(EtCfg<32>{}, encoder_tc_kernel<32>, cache32);
+  if (rc != MAPF_OK) return rc;
   return mapf_launch_status();
 }

@@ -195,11 +195,13 @@ class PipelinedHostRollout:
             raise ValueError("groups must be in [1, episodes]")
         if group_sizes is None:
             sms = torch.cuda.get_device_properties(torch.device(device)).multi_processor_count
-            # images one CTA of the encoder takes per round: 5 warpgroups x 4 images on the tensor-core conv stack
+            # images one CTA of the encoder takes per round: 5 (or 3) warpgroups x 4 images on the tensor-core conv stack
             # (enc_tc.cu), one 32-image tile in the FFMA2 kernel
             from . import ops
-            tile = 20 if ops.wants_encoder_workspace(net_params(net.dims())) and \
-                _lib.load().mapf_encoder_tc_supported(net_params(net.dims())) == 1 else 32
+            tile = 32
+            if ops.wants_encoder_workspace(net_params(net.dims())) and \
+                    _lib.load().mapf_encoder_tc_supported(net_params(net.dims())) == 1:
+                tile = 20 if net.dims()[2] == 16 else 12      # 3 warpgroups when the first layer has 32 channels
             group_sizes = self.round_aligned_sizes(E, goals.shape[1], groups, sms, tile)
         if len(group_sizes) != groups or sum(group_sizes) != E or min(group_sizes) < 1:
             raise ValueError("group_sizes must be positive and sum to the number of episodes")

@@ -85,14 +85,16 @@ def test_state_dict_layout_matches_shipped_weights():
 
 def test_tensor_core_encoder_selection_is_host_logic():
     """Which encoder mapf_policy_fwd gets a workspace for is decided on the host from the channel widths (no GPU call):
-    16-channel networks -> tensor-core conv stack, the baseline's 32-channel first layer -> FFMA2 kernel."""
+    a first layer of 16 or 32 channels with 16-channel layers behind it -> tensor-core conv stack, else FFMA2 kernel."""
     from mapf_gnn_b200 import _lib, ops
     from mapf_gnn_b200.ops import net_params
     lib = _lib.load()
     gnn = net_params([3, 2, 16, 16, 16, 0, 400, 64, 3, 128, 5])
     base = net_params([3, 2, 32, 16, 16, 0, 400, 64, 0, 0, 5])
-    assert lib.mapf_encoder_tc_supported(gnn) == 1 and lib.mapf_encoder_tc_supported(base) == 0
+    other = net_params([3, 2, 16, 32, 16, 0, 400, 64, 0, 0, 5])
+    assert lib.mapf_encoder_tc_supported(gnn) == 1 and lib.mapf_encoder_tc_supported(base) == 1
+    assert lib.mapf_encoder_tc_supported(other) == 0
     assert ops.wants_encoder_workspace(gnn) == (ops.USE_TENSOR_CORES and (ops.USE_TENSOR_CORE_ENCODER or ops.USE_TENSOR_CORE_FC))
-    assert ops.wants_encoder_workspace(base) == (ops.USE_TENSOR_CORES and ops.USE_TENSOR_CORE_FC)
+    assert ops.wants_encoder_workspace(other) == (ops.USE_TENSOR_CORES and ops.USE_TENSOR_CORE_FC)
     assert lib.mapf_tc_packed_b_f16_size(64, 400) == 4 + 25 * 64 * 16
     assert lib.mapf_tc_packed_b_f16_size(200, 400) == -1

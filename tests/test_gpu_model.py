@@ -230,14 +230,53 @@ def test_tensor_core_encoder_matches_oracle(rows):
     assert rel_err(got, ref) < 1e-5
 
 
-def test_tensor_core_encoder_unsupported_widths_are_refused():
-    """The tensor-core conv stack is built for 16-channel layers; the baseline's 32-channel first layer must be
-    reported unsupported (the policy then keeps the FFMA2 encoder) instead of being mis-computed."""
+@pytest.mark.parametrize("depth", [2, 3])
+@pytest.mark.parametrize("rows", [1, 7, 12, 13, 131, 1777 + 5])
+def test_tensor_core_conv_stack_baseline_widths(rows, depth):
+    """The baseline network's conv stack (first layer 2 -> 32 channels, framework_baseline.py): layer 0 runs as two
+    16-channel GEMM rounds, layer 1 contracts over 3 x 32 operand entries, three warpgroups per CTA."""
     from mapf_gnn_b200 import _lib
     from mapf_gnn_b200.ops import net_params
     lib = _lib.load()
-    assert lib.mapf_encoder_tc_supported(net_params(load_network("baseline").dims())) == 0
+    rng = np.random.default_rng(77 * depth + rows)
+    states = torch.tensor(rng.integers(0, 4, size=(rows, 2, 5, 5))).float()
+    states[1::5] *= 0.61
+    states[2::7] = torch.randn_like(states[2::7])
+    states[3::11] = 0.0
+    params = oracle_params("baseline")
+    with torch.no_grad():
+        ref = _conv_stack_reference(params, states, depth)
+    net = load_network("baseline", num_agents=1).eval()
+    g = net.param_groups()
+    d = lambda ts: [t.detach() for t in ts[:depth]]
+    dims = [depth, 2, 32] + [16] * (depth - 1) + [0] * (4 - depth) + [400, 64, 0, 0, 5]
+    packed = torch.ops.mapf.pack_weights(dims, d(g["conv_w"]), d(g["conv_b"]), d(g["bn_gamma"]), d(g["bn_beta"]),
+                                         d(g["bn_mean"]), d(g["bn_var"]), g["fc_w"].detach(), g["fc_b"].detach(), None,
+                                         None, torch.zeros(5, 64, device="cuda"), torch.zeros(5, device="cuda"))
+    p = net_params(dims)
+    assert lib.mapf_encoder_tc_supported(p) == 1
+    Ap = torch.full((lib.mapf_tc_presplit_a_size(rows, 400),), float("nan"), device="cuda")
+    st = states.cuda()
+    ea = _lib.EncoderFwdArgs(rows, st.data_ptr(), packed.data_ptr(), Ap.data_ptr())
+    _lib.check(lib.mapf_encoder_tc_conv_fwd(p, ea, _lib.current_stream()), "tc_conv")
+    got = _untile_presplit_f16(Ap, rows, 400)
+    assert np.isfinite(got).all()
+    used = ((rows + 127) // 128) * 25 * 2048 + rows
+    assert bool(torch.isnan(Ap[used:]).all())
+    scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
+    assert (np.abs(got - ref) / scale).max() < 1e-5
+
+
+def test_tensor_core_encoder_width_support():
+    """The tensor-core conv stack takes a first layer of 16 or 32 channels with 16-channel layers behind it; anything
+    else must be reported unsupported (the policy then keeps the FFMA2 encoder) instead of being mis-computed."""
+    from mapf_gnn_b200 import _lib
+    from mapf_gnn_b200.ops import net_params
+    lib = _lib.load()
+    assert lib.mapf_encoder_tc_supported(net_params(load_network("baseline").dims())) == 1
     assert lib.mapf_encoder_tc_supported(net_params(load_network("gnn_k2").dims())) == 1
+    assert lib.mapf_encoder_tc_supported(net_params([3, 2, 16, 32, 16, 0, 400, 64, 0, 0, 5])) == 0
+    assert lib.mapf_encoder_tc_supported(net_params([1, 2, 32, 0, 0, 0, 800, 64, 0, 0, 5])) == 0
 
 
 def test_training_gso_convention_a_plus_i():
