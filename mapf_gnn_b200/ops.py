@@ -21,8 +21,8 @@ _LIB = torch.library.Library("mapf", "DEF")
 
 # graph-filter mix on tcgen05 (3xTF32) when True; the fused fp32-FFMA kernel when False (development switch)
 USE_TENSOR_CORES = os.environ.get("MAPF_B200_TENSOR_CORES", "1") != "0"
-# encoder on tcgen05: the conv stack of 16-channel networks runs on the tensor cores (enc_tc.cu) with the FC behind it as
-# an all-TMA tcgen05 GEMM; other channel widths keep the fused FFMA2 encoder kernel.  MAPF_B200_TENSOR_CORE_ENCODER=0
+# encoder on tcgen05: the conv stack (first layer 16 or 32 channels, 16-channel layers behind it) runs on the tensor cores
+# (enc_tc.cu) with the FC behind it as an all-TMA tcgen05 GEMM; other channel widths keep the fused FFMA2 encoder kernel.  MAPF_B200_TENSOR_CORE_ENCODER=0
 # forces the FFMA2 kernel; MAPF_B200_TENSOR_CORE_FC=1 hands the workspace to every network (development switch: FFMA2
 # conv kernel emitting the pre-split operand + tensor-core FC where the tensor-core conv stack does not apply).
 USE_TENSOR_CORE_ENCODER = os.environ.get("MAPF_B200_TENSOR_CORE_ENCODER", "1") != "0"
