@@ -23,10 +23,14 @@
 // two inverse scales rides on the multiplier of the epilogue's first FMA.  Entries far below their scale's maximum
 // are rounded at 2^-25 of it -- 2^-34 of the image's largest activation.
 //
-// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (5 rows of 5 pixels, one zero lane between rows).  A CTA holds four independent
+// The baseline network's first layer has 32 channels (framework_baseline.py): encoder_tc_kernel<32> runs it as two 16-channel
+// GEMM rounds on the same operand, gives the 32 outputs one scale and a 3 x 32-entry operand (144 TMEM columns per set,
+// three warpgroups instead of five); layer 1 then contracts over six K steps.
+//
+// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (5 rows of 5 pixels, one zero lane between rows).  A CTA holds five independent
 // warpgroups; each walks its own M tiles through all layers with its own 96 TMEM columns (D 48 | A hi 24 | A lo 24), its
-// own mbarrier and named barrier; one thread per group issues its MMAs, so the groups' accumulation chains interleave
-// in the tensor pipe.  The last layer's epilogue emits the flattened activations as the pre-split (TF32 hi | lo),
+// own mbarrier and named barrier; one thread per group issues its MMAs in a fixed order (reproducible results), so the
+// groups' accumulation chains interleave in the tensor pipe.  The last layer's epilogue emits the flattened activations as the pre-split (TF32 hi | lo),
 // pre-tiled A operand of the encoder FC (mapf_tc_fc_presplit) with the K index ordered pixel-major (k = pixel * 16 +
 // channel); the four images of a tile meet in shared memory so that the global stores are whole 64-byte runs.  The FC's
 // B operand is packed with the same K permutation (PackedLayout::tc_fc_pm).
