@@ -279,6 +279,40 @@ def test_tensor_core_encoder_width_support():
     assert lib.mapf_encoder_tc_supported(net_params([1, 2, 32, 0, 0, 0, 800, 64, 0, 0, 5])) == 0
 
 
+def test_programmatic_dependent_launch_does_not_change_results(tmp_path):
+    """The step kernels are chained by programmatic dependent launch (griddepcontrol); with the launch attribute switched
+    off (MAPF_B200_NO_PDL=1, read once per process -> a subprocess) a rollout must give bit-identical logits, actions and
+    positions: the early prologues may only touch data that is older than the kernel in front."""
+    import os, subprocess, sys, textwrap
+    script = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+        import mapf_gnn_b200 as m
+        from helpers import load_network, model_config
+        out = {}
+        for name, N in (("gnn_k3", 5), ("baseline", 5), ("gnn_msg_k3", 20)):
+            rng = np.random.default_rng(5)
+            starts, goals, obst = m.make_scenarios(rng, 64, N, 14, 6)
+            env = m.BatchedGraphEnv(model_config(name, N, board_size=[14, 14]), goals, starts, obst, sensing_range=5)
+            ro = m.Rollout(load_network(name, num_agents=N).eval(), env)
+            ro.run(7)
+            torch.cuda.synchronize()
+            out[name + "/logits"] = ro.logits.cpu().numpy(); out[name + "/pos"] = env.pos.cpu().numpy()
+            out[name + "/actions"] = ro.actions.cpu().numpy()
+        np.savez(sys.argv[2], **out)
+    """)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, extra in (("pdl", {}), ("nopdl", {"MAPF_B200_NO_PDL": "1"})):
+        path = str(tmp_path / f"{tag}.npz")
+        env = dict(os.environ, **extra)
+        env.pop("MAPF_B200_NO_PDL", None) if not extra else None
+        subprocess.run([sys.executable, "-c", script, root, path], check=True, env=env, timeout=300)
+        res[tag] = np.load(path)
+    for k in res["pdl"].files:
+        assert np.array_equal(res["pdl"][k], res["nopdl"][k]), k
+
+
 def test_training_gso_convention_a_plus_i():
     """The data loader feeds A + I (data_loader.py:74); GCNLayer adds I again -> diagonal 2."""
     rng = np.random.default_rng(3)
