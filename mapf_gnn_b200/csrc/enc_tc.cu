@@ -478,10 +478,6 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
   g.ap = a->x;
   g.nch = (p->fc_in + 15) >> 4;
   g.row_inv = a->x + ((a->rows + 127) >> 7) * int64_t(g.nch) * 2048;
-  {
-    const char* e = getenv("MAPF_B200_ETC_SKEW");   // development switch
-    g.skew = e ? atoi(e) : 1400;
-  }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (a->rows + 3) >> 2;
@@ -492,6 +488,11 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
     if (!mapf_ensure_smem(kernel, smem, cache)) return MAPF_ERR_CUDA;
     const int64_t want = (ntiles + kGroups - 1) / kGroups;
     const int grid = int(want < sms ? want : sms);
+    // start-up offset between the warpgroups: about a fifth of a layer for a long launch, less when every group sees
+    // only a tile or two (measured optimum 400 / 700 / 1000 / 1400 clocks at 1 / 2 / 4 / 7 tiles per group)
+    const int64_t rounds = (ntiles + int64_t(grid) * kGroups - 1) / (int64_t(grid) * kGroups);
+    const char* e = getenv("MAPF_B200_ETC_SKEW");   // development switch
+    g.skew = e ? atoi(e) : int(rounds >= 6 ? 1400 : 300 + 200 * rounds);
     mapf_launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), g);
     return MAPF_OK;
   };
