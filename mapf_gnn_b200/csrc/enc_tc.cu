@@ -13,27 +13,30 @@
 // ReLU, and write the result and its two horizontal neighbours straight back to TMEM (tcgen05.st) as the next layer's A
 // operand.  The B operand (BN-folded filters) stays resident in shared memory (21 KB for three layers).
 //
-// fp32 accuracy from 16-bit MMAs.  Dependent tcgen05.mma into one accumulator complete about 100 cycles apart however
-// small they are, so the number of MMAs per layer is what matters: kind::f16 covers K = 16 per instruction (TF32: 8)
-// and halves the A operand's TMEM columns.  Every operand is split into two fp16 numbers, x * 2^-e = hi + lo (11 + 11
-// significant bits, the same as the TF32 split of tc_gemm.cuh) and the layer is 3 products per K step, lo*hi + hi*lo +
-// hi*hi, accumulated in fp32 = 9 MMAs.  The power-of-two scales keep fp16's range out of the picture: the filters of a
-// layer share one static scale (largest |w| -> [2^9, 2^10), mapf_pack_weights), the activations of an image share a
-// dynamic one (largest activation of the image -> [2^9, 2^10), one warp max-reduction per layer); the product of the
-// two inverse scales rides on the multiplier of the epilogue's first FMA.  Entries far below their scale's maximum
-// are rounded at 2^-25 of it -- 2^-34 of the image's largest activation.
+// fp32 accuracy from 16-bit MMAs.  One thread issues a tcgen05.mma only about every 100 cycles however small the MMA is,
+// so the number of MMAs per layer is what matters: kind::f16 covers K = 16 per instruction (TF32: 8) and halves the A
+// operand's TMEM columns.  Every operand is split into two fp16 numbers, x * 2^-e = hi + lo (11 + 11 significant bits,
+// the same as the TF32 split of tc_gemm.cuh) and the layer is 3 products per K step, lo*hi + hi*lo + hi*hi, accumulated
+// in fp32 = 9 MMAs.  The power-of-two scales keep fp16's range out of the picture: the filters of a layer share one
+// static scale (largest |w| -> [2^9, 2^10), mapf_pack_weights), the activations of an image share a dynamic one
+// (largest activation of the image -> [2^9, 2^10), one warp max-reduction per layer); the product of the two inverse
+// scales rides on the multiplier of the epilogue's first FMA.  Entries far below their scale's maximum are rounded at
+// 2^-25 of it -- 2^-34 of the image's largest activation.
 //
-// The baseline network's first layer has 32 channels (framework_baseline.py): encoder_tc_kernel<32> runs it as two 16-channel
-// GEMM rounds on the same operand, gives the 32 outputs one scale and a 3 x 32-entry operand (144 TMEM columns per set,
-// three warpgroups instead of five); layer 1 then contracts over six K steps.
+// The baseline network's first layer has 32 channels (framework_baseline.py): encoder_tc_kernel<32> runs it as two
+// 16-channel GEMM rounds on the same operand, gives the 32 outputs one scale and a 3 x 32-entry operand (144 TMEM
+// columns per set, three warpgroups instead of five); layer 1 then contracts over six K steps.
 //
-// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (5 rows of 5 pixels, one zero lane between rows).  A CTA holds five independent
-// warpgroups; each walks its own M tiles through all layers with its own 96 TMEM columns (D 48 | A hi 24 | A lo 24), its
-// own mbarrier and named barrier; one thread per group issues its MMAs in a fixed order (reproducible results), so the
-// groups' accumulation chains interleave in the tensor pipe.  The last layer's epilogue emits the flattened activations as the pre-split (TF32 hi | lo),
-// pre-tiled A operand of the encoder FC (mapf_tc_fc_presplit) with the K index ordered pixel-major (k = pixel * 16 +
-// channel); the four images of a tile meet in shared memory so that the global stores are whole 64-byte runs.  The FC's
-// B operand is packed with the same K permutation (PackedLayout::tc_fc_pm).
+// One M tile = 128 TMEM lanes = 4 agent images x 32 lanes (5 rows of 5 pixels, one zero lane between rows, so the
+// horizontal exchange needs no border masks).  A CTA holds five independent warpgroups; each walks its own M tiles
+// through all layers with its own 96 TMEM columns (D 48 | A hi 24 | A lo 24), its own mbarrier and named barrier; one
+// thread per group issues its MMAs in a fixed order (reproducible results), and the groups start a fraction of a layer
+// apart so that one group's MMA round trip falls under the others' epilogues.  The last layer's epilogue emits the
+// flattened activations as the fp16-split, pre-tiled A operand of the encoder FC (mapf_tc_fc_presplit_f16: one scale per
+// image, its inverse stored behind the operand) with the K index ordered pixel-major (k = pixel * 16 + channel); the
+// four images of a tile meet in shared memory so that the global stores are whole 64-byte runs.  The FC's B operand is
+// packed with the same K permutation (PackedLayout::tc_fc_pm).  The kernel is launched with programmatic stream
+// serialization: everything in front of mapf_pdl_wait() touches only the packed weights.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
