@@ -41,14 +41,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep until the phase flips, do not poll
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep until the phase flips, do not poll
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a tensor-core pipeline bug must never hang the GPU.  On timeout the kernel traps (the launch
 // then reports an error instead of spinning forever).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+  for (uint32_t spin = 0; spin < (1u << 20); ++spin)   // each try sleeps at most 20 us: a dead pipeline traps within ~20 s
     if (mbar_try_wait(bar, parity)) return;
   asm volatile("trap;");
 }
