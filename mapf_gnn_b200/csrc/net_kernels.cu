@@ -15,7 +15,8 @@ int mapf_encoder_tc_pack(const mapf_net_params* p, float* packed, mapf_stream_t 
 int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
                           int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
                           const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
-                          int gso_is_old, mapf_stream_t stream);                             // tc_graph.cu
+                          int gso_is_old, const mapf_env_step_args* env, mapf_stream_t stream);   // tc_graph.cu
+int mapf_tc_graph_env_fusable(int32_t agents, int32_t cell_stride);                          // tc_graph.cu
 
 namespace {
 
@@ -187,7 +188,17 @@ extern "C" int mapf_head_fwd(const mapf_head_fwd_args* a, mapf_stream_t stream) 
   return mapf_launch_status();
 }
 
+// env != NULL (mapf_rollout): when the fused tensor-core graph kernel runs and the shapes allow it, the environment step of
+// the same episodes is executed in that kernel's tail and *env_done is set; the caller launches mapf_env_step otherwise.
+static int policy_fwd_impl(const mapf_net_params* p, const mapf_policy_fwd_args* a, const mapf_env_step_args* env,
+                           int* env_done, mapf_stream_t stream);
+
 extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_args* a, mapf_stream_t stream) {
+  return policy_fwd_impl(p, a, nullptr, nullptr, stream);
+}
+
+static int policy_fwd_impl(const mapf_net_params* p, const mapf_policy_fwd_args* a, const mapf_env_step_args* env,
+                           int* env_done, mapf_stream_t stream) {
   const int st = mapf_check_params(p);
   if (st != MAPF_OK) return st;
   MAPF_REQUIRE(a && a->states && a->packed && a->workspace_x && a->logits, MAPF_ERR_NULL);
@@ -252,9 +263,21 @@ extern "C" int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_a
       getenv("MAPF_B200_UNFUSED_GRAPH") == nullptr) {
     // fused tensor-core path: S, hops, 3xTF32 tcgen05 mix, ReLU, head, argmax in one kernel
     // gso is an input of this launch sequence: complete before the encoder kernels above were launched
-    return mapf_tc_graph_head_ex(a->batch, a->agents, p->fc_out, p->node_dim, p->taps, a->message ? 0 : 1,
-                                 a->message ? 1 : 0, a->workspace_x, a->gso, a->packed + L.tc_gf, a->packed + L.act_w,
-                                 a->packed + L.act_b, p->num_actions, a->logits, a->actions, 1, stream);
+    // Fusing the env step into the graph kernel's tail saves a launch and its prologue: worth it for small launches
+    // (a host-stepped episode group: end to end 1.78e8 -> 1.87e8 agent-steps/s at C2a), not for a full resident batch, where
+    // the separate env kernel's many small CTAs finish sooner (2.32e8 against 2.28e8 fused).  MAPF_B200_FUSED_ENV=0 / 1
+    // forces either.
+    const char* fe = getenv("MAPF_B200_FUSED_ENV");
+    const bool want_fused = fe != nullptr ? fe[0] == '1' : rows <= 12288;
+    const bool fuse_env = want_fused && env != nullptr && a->actions != nullptr && env->actions == a->actions &&
+                          env->episodes == a->batch && env->agents == a->agents &&
+                          mapf_tc_graph_env_fusable(a->agents, env->cell_stride);
+    rc = mapf_tc_graph_head_ex(a->batch, a->agents, p->fc_out, p->node_dim, p->taps, a->message ? 0 : 1,
+                               a->message ? 1 : 0, a->workspace_x, a->gso, a->packed + L.tc_gf, a->packed + L.act_w,
+                               a->packed + L.act_b, p->num_actions, a->logits, a->actions, 1, fuse_env ? env : nullptr,
+                               stream);
+    if (rc == MAPF_OK && fuse_env) *env_done = 1;
+    return rc;
   }
   // two-kernel tensor-core path: filter taps -> Z (tiny kernel), then 3xTF32 tcgen05 mix + ReLU + head + argmax
   g.z = a->workspace_z;
@@ -272,12 +295,15 @@ extern "C" int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a
   MAPF_REQUIRE(a->env.fov == a->policy.states && (p->taps == 0 || a->env.adj == a->policy.gso), MAPF_ERR_SHAPE);
   MAPF_REQUIRE(a->env.episodes == a->policy.batch && a->env.agents == a->policy.agents, MAPF_ERR_SHAPE);
   for (int t = 0; t < a->steps; ++t) {
-    int rc = mapf_policy_fwd(p, &a->policy, stream);
-    if (rc != MAPF_OK) return rc;
     mapf_env_step_args e = a->env;
     e.do_move = 1 | 4;   // 4: boards / positions are older than the policy kernels in front (see env_step_kernel)
-    rc = mapf_env_step(&e, stream);
+    int env_done = 0;    // set when the env step ran in the tail of the fused graph kernel
+    int rc = policy_fwd_impl(p, &a->policy, &e, &env_done, stream);
     if (rc != MAPF_OK) return rc;
+    if (!env_done) {
+      rc = mapf_env_step(&e, stream);
+      if (rc != MAPF_OK) return rc;
+    }
   }
   return MAPF_OK;
 }

@@ -17,6 +17,7 @@
 //                          (lo*hi, hi*lo, hi*hi), commit to `empty`.
 //   all warps  epilogue  : tcgen05.ld, ReLU, 5-way head, exchange of the two column halves, first-max argmax.
 #include "common.cuh"
+#include "env_step.cuh"
 #include "tc_gemm.cuh"
 
 namespace {
@@ -39,8 +40,14 @@ struct TcGraphArgs {
   float* logits;        // [B*N, A]
   int32_t* actions;     // [B*N] or NULL
   int gso_is_old;       // 1: gso was complete before the kernel IN FRONT of this one started (read it before the grid wait)
+  mapf_env_step_args env;   // ENVL > 0: the environment step of the tile's episodes runs in the tail of this kernel
 };
 
+// ENVL = 0: graph filter + head only.  ENVL = 8 / 16 / 32 (mapf_rollout): LANES of the fused environment step -- the CTA
+// that chose the actions of its episodes also moves them and writes their next observation (env_step.cuh), so a rollout
+// step is three kernels; the boards / positions are staged in the prologue, ahead of the grid wait (they were last written
+// two kernels back).
+template <int ENVL>
 __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int epc) {
   extern __shared__ __align__(128) uint8_t s_tg[];
   __shared__ __align__(8) uint64_t s_full[kTgProd], s_empty[kTgProd], s_done;
@@ -51,6 +58,11 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   float* scratch = reinterpret_cast<float*>(s_tg + kTgProd * kTgStageBytes);  // [4 warps][128][8]
   float* sm = scratch + kTgProd * kTgM * 8;                                   // [epc][N][N]
   float* dinv = sm + ((epc * N * N + 3) & ~3);                                // [128]
+  // fused env step: [128] actions | per-thread arrays | boards of the tile's episodes
+  constexpr int kEL = ENVL > 0 ? ENVL : 8;
+  int32_t* s_act = reinterpret_cast<int32_t*>(dinv + kTgM);
+  EnvShared<kEL, kTgThreads>& s_env = *reinterpret_cast<EnvShared<kEL, kTgThreads>*>(s_act + kTgM);
+  uint8_t* s_boards = reinterpret_cast<uint8_t*>(&s_env) + ((sizeof(EnvShared<kEL, kTgThreads>) + 15) & ~size_t(15));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int e0 = blockIdx.x * epc;
@@ -80,6 +92,8 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   // Inside mapf_policy_fwd the adjacency is an input of the whole launch sequence -- complete before the encoder kernels in
   // front of this one started -- so the shift operator is built while the encoder FC still runs; the node features come
   // from that FC and are read behind the grid wait.
+  EnvAgent env_ag{};
+  if (ENVL > 0) env_ag = env_step_stage<kEL, kTgThreads>(g.env, e0, nep, tid, s_boards, s_env);
   if (!g.gso_is_old) { mapf_pdl_wait(); mapf_pdl_launch(); }
   // ---- graph shift operator of the tile's episodes ----
   for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
@@ -310,11 +324,13 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
         }
       }
       if (g.actions != nullptr) g.actions[row0 + row] = arg;
+      if (ENVL > 0) s_act[row] = arg;
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  if (ENVL > 0) env_step_finish<kEL, kTgThreads>(g.env, e0, nep, tid, s_boards, s_env, env_ag, s_act);
 }
 
 }  // namespace
@@ -329,21 +345,33 @@ extern "C" int mapf_tc_graph_supported(int32_t agents, int32_t in_dim, int32_t o
 int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
                           int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
                           const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
-                          int gso_is_old, mapf_stream_t stream);
+                          int gso_is_old, const mapf_env_step_args* env, mapf_stream_t stream);
 
 extern "C" int mapf_tc_graph_head(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
                                   int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso,
                                   const float* Wp, const float* act_w, const float* act_b, int32_t num_actions,
                                   float* logits, int32_t* actions, mapf_stream_t stream) {
   return mapf_tc_graph_head_ex(batch, agents, in_dim, out_dim, taps, add_self_loop, has_skip, x, gso, Wp, act_w, act_b,
-                               num_actions, logits, actions, 0, stream);
+                               num_actions, logits, actions, 0, nullptr, stream);
 }
 
-// gso_is_old = 1 (mapf_policy_fwd behind its encoder kernels): see TcGraphArgs
+// 1 if the environment step of `agents`-agent episodes on boards of `cell_stride` bytes can run in the tail of the graph
+// kernel: an episode's LANES times the episodes of a 128-row tile must fit the CTA's 256 threads
+int mapf_tc_graph_env_fusable(int32_t agents, int32_t cell_stride) {
+  // measured: small teams gain (one launch less), at N = 20 the separate env kernel with its many small CTAs is faster
+  // than 6 episodes per 256-thread CTA in the graph kernel's tail (336 -> 345 us per C3 step)
+  if (agents < 1 || agents > 8) return 0;
+  const int lanes = agents <= 8 ? 8 : agents <= 16 ? 16 : 32;
+  const int epc = kTgM / agents;
+  return epc * lanes <= kTgThreads && size_t(epc) * cell_stride <= 64 * 1024;
+}
+
+// gso_is_old = 1 (mapf_policy_fwd behind its encoder kernels): see TcGraphArgs.  env != NULL (mapf_rollout): the env step
+// of the same episodes is fused into the kernel (caller checked mapf_tc_graph_env_fusable; needs actions != NULL).
 int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim, int32_t taps,
                           int32_t add_self_loop, int32_t has_skip, const float* x, const float* gso, const float* Wp,
                           const float* act_w, const float* act_b, int32_t num_actions, float* logits, int32_t* actions,
-                          int gso_is_old, mapf_stream_t stream) {
+                          int gso_is_old, const mapf_env_step_args* env, mapf_stream_t stream) {
   MAPF_REQUIRE(x && gso && Wp && act_w && act_b && logits, MAPF_ERR_NULL);
   MAPF_REQUIRE(batch > 0 && num_actions > 0 && num_actions <= kMaxActions, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(mapf_tc_graph_supported(agents, in_dim, out_dim, taps), MAPF_ERR_UNSUPPORTED);
@@ -352,11 +380,26 @@ int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t
                 x, gso, Wp, act_w, act_b, logits, actions, gso_is_old};
   const int epc = kTgM / agents;
   const int ntiles = (batch + epc - 1) / epc;
-  const size_t smem = size_t(kTgProd) * kTgStageBytes + sizeof(float) * (size_t(kTgProd) * kTgM * 8 +
-                      ((size_t(epc) * agents * agents + 3) & ~size_t(3)) + kTgM);
+  size_t smem = size_t(kTgProd) * kTgStageBytes + sizeof(float) * (size_t(kTgProd) * kTgM * 8 +
+                ((size_t(epc) * agents * agents + 3) & ~size_t(3)) + kTgM);
+  int envl = 0;
+  if (env != nullptr) {
+    MAPF_REQUIRE(actions != nullptr && env->episodes == batch && env->agents == agents, MAPF_ERR_SHAPE);
+    MAPF_REQUIRE(mapf_tc_graph_env_fusable(agents, env->cell_stride) && gso_is_old, MAPF_ERR_UNSUPPORTED);
+    envl = agents <= 8 ? 8 : agents <= 16 ? 16 : 32;
+    g.env = *env;
+    smem += sizeof(int32_t) * kTgM + 4096 /* EnvShared (3.7 KB at most), rounded up */ + size_t(epc) * env->cell_stride;
+  }
   MAPF_REQUIRE(smem <= 227 * 1024, MAPF_ERR_UNSUPPORTED);
-  static int cache[16] = {0};
-  if (!mapf_ensure_smem(tc_graph_kernel, smem, cache)) return MAPF_ERR_CUDA;
-  mapf_launch_pdl(tc_graph_kernel, dim3(ntiles), dim3(kTgThreads), smem, static_cast<cudaStream_t>(stream), g, epc);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto launch = [&](auto kernel, int* cache) -> int {
+    if (!mapf_ensure_smem(kernel, smem, cache)) return MAPF_ERR_CUDA;
+    mapf_launch_pdl(kernel, dim3(ntiles), dim3(kTgThreads), smem, s, g, epc);
+    return MAPF_OK;
+  };
+  static int c0[16] = {0}, c8[16] = {0}, c16[16] = {0}, c32[16] = {0};
+  const int rc = envl == 0 ? launch(tc_graph_kernel<0>, c0) : envl == 8 ? launch(tc_graph_kernel<8>, c8)
+               : envl == 16 ? launch(tc_graph_kernel<16>, c16) : launch(tc_graph_kernel<32>, c32);
+  if (rc != MAPF_OK) return rc;
   return mapf_launch_status();
 }
