@@ -113,34 +113,91 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def config_of(name, w, episodes):
+    """The `config` object of the JSON line: the same for both arms (the driver compares them)."""
+    return {"workload": f"{name}: {w['desc']}", "episodes_per_gpu": episodes, "agents": w["N"], "board": w["H"],
+            "obstacles": w["M"], "sensing_range": w["r"], "weights": f"tests/golden/weights_{w['model']}.npz"}
+
+
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference (R2 protocol of SURVEY 8d: python loop over reference-style
-# single-episode envs + one batched torch-CPU forward using every host thread)
+# CPU arm.  Nothing below imports mapf_gnn_b200 (the reference arm must not map the product's library).
+# With the unmodified reference staged under oracle/_ref (oracle/stage_ref.py) the reference's own GraphEnv and Network
+# classes are timed (kind "reference"); without it the numpy / torch-CPU port in oracle/ (kind "port").
+#   R2 (SURVEY 8d, the stronger baseline, the one the >= 100x target is quoted against): python loop over E
+#       single-episode GraphEnv.step (benchmarks/benchmark_performance.py:84-95) + ONE batched model forward per step
+#       on every host thread.
+#   R1: the literal evaluate.py:223-241 loop -- one GraphEnv and one B = 1 model call per episode-step.
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_steps(w, episodes, steps, warmup, seed=0):
+def _cpu_setup(w, episodes, seed):
     import torch
-    from mapf_gnn_b200.scenarios import make_scenarios
     from oracle import env_oracle as eo
-    from oracle import model_oracle as mo
+    from oracle import ref_loader
     rng = np.random.default_rng(seed)
     N, H = w["N"], w["H"]
-    starts, goals, obst = make_scenarios(rng, episodes, N, H, w["M"])
-    params = {k: torch.from_numpy(v) for k, v in load_weights(w["model"]).items()}
+    starts, goals, obst = eo.make_scenarios(rng, episodes, N, H, w["M"])
+    weights = {k: torch.from_numpy(v) for k, v in load_weights(w["model"]).items()}
+    if ref_loader.available():
+        cfg = dict(model_config(w), device="cpu")
+        ns = ref_loader.load()
+        net = ref_loader.build_network(cfg)
+        net.load_state_dict(weights)
+        net.eval()
+        envs = [ns.GraphEnv(cfg, goal=goals[e].astype(np.int64), starting_positions=starts[e].astype(np.int64).copy(),
+                            obstacles=obst[e].astype(np.int64), sensing_range=w["r"]) for e in range(episodes)]
+        obs = [env.reset() for env in envs]
+        emb = envs[0].getEmbedding()
+        is_gnn = cfg["net_type"] == "gnn"
+
+        def forward(states, gso):
+            return net(states, gso) if is_gnn else net(states)
+
+        def step(e, act):
+            return envs[e].step(act, emb)[0]
+        return "reference", obs, forward, step
+    from oracle import model_oracle as mo
     envs = [eo.EnvOracle(N, H, goals[e], starts[e], obst[e], sensing_range=w["r"]) for e in range(episodes)]
-    obs = [e.observe() for e in envs]
+    obs = [env.observe() for env in envs]
+    return "port", obs, (lambda states, gso: mo.forward(weights, states, gso)), (lambda e, act: envs[e].step(act)[0])
+
+
+def cpu_rollout_r2(w, episodes, steps, warmup, seed=0):
+    import torch
+    kind, obs, forward, step = _cpu_setup(w, episodes, seed)
     total = 0.0
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         states = torch.tensor(np.stack([o["fov"] for o in obs])).float()
         gso = torch.tensor(np.stack([o["adj_matrix"] for o in obs])).float()
         with torch.no_grad():
-            logits = mo.forward(params, states, gso)
-        acts = mo.greedy_actions(logits)
-        obs = [envs[e].step(acts[e])[0] for e in range(episodes)]
+            logits = forward(states, gso)
+        acts = np.argmax(logits.numpy(), axis=2)
+        obs = [step(e, acts[e]) for e in range(episodes)]
         dt = time.perf_counter() - t0
         if it >= warmup:
             total += dt
-    return episodes * N * steps / total, total
+    return {"value": episodes * w["N"] * steps / total, "seconds": total, "kind": kind}
+
+
+def cpu_rollout_r1(w, episodes, steps, seed=0):
+    import torch
+    kind, obs, forward, step = _cpu_setup(w, episodes, seed)
+    t0 = time.perf_counter()
+    for e in range(episodes):
+        o = obs[e]
+        for _ in range(steps):
+            fov = torch.tensor(o["fov"]).float().unsqueeze(0)
+            gso = torch.tensor(o["adj_matrix"]).float().unsqueeze(0)
+            with torch.no_grad():
+                action = forward(fov, gso).squeeze(0).numpy()
+            o = step(e, np.argmax(action, axis=1))
+    total = time.perf_counter() - t0
+    return {"value": episodes * w["N"] * steps / total, "seconds": total, "kind": kind}
+
+
+_PROTOCOL = {"reference": "the unmodified reference classes staged under oracle/_ref (GraphEnv.step per episode in a python "
+                          "loop + one batched Network.forward per step; SURVEY 8d protocol R2)",
+             "port": "oracle/ port of the reference (python loop over single-episode numpy envs + batched torch-CPU "
+                     "forward; oracle/_ref not staged on this box)"}
 
 
 def run_reference(args, w):
@@ -150,17 +207,23 @@ def run_reference(args, w):
         return
     torch.set_num_threads(os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1; the CPU arm may use every core
     episodes = args.ref_episodes
-    value, total = cpu_reference_steps(w, episodes, args.steps, args.warmup)
+    r2 = cpu_rollout_r2(w, episodes, args.steps, args.warmup)
+    r1 = cpu_rollout_r1(w, max(1, min(32, episodes)), min(args.steps, 8))
     cores = torch.get_num_threads()
+    value = r2["value"]
     line = {
         "impl": "reference", "metric": "agent-steps/sec (batched rollout)", "value": value, "unit": "agent-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r2["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "episodes_per_step": episodes, "agents": w["N"],
-                   "board": w["H"]},
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{episodes} episodes x {args.steps} steps of the same workload "
-                                   f"(python loop over single-episode numpy envs + batched torch-CPU forward)"},
+        "config": config_of(args.workload, w, args.episodes or w["E"]),
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": r2["kind"],
+                         "sample": f"{episodes} episodes x {args.steps} steps of the workload per timed run "
+                                   f"(throughput is per agent-step, independent of the episode count): "
+                                   + _PROTOCOL[r2["kind"]],
+                         "r1_literal_evaluate_loop": {"value": r1["value"], "unit": "agent-steps/s",
+                                                      "sample": "B = 1 model call per episode-step, evaluate.py:223-241",
+                                                      "seconds": r1["seconds"]}},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,19 +233,44 @@ def run_reference(args, w):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_mine(args, w):
+def _time_alone(fn, flush, reps=10, warm=3):
+    """Mean CUDA-event time (ms) of one launch sequence issued alone on the current stream, L2 flushed before each."""
+    import torch
+    ms = []
+    for i in range(warm + reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        if i >= warm:
+            ms.append(a.elapsed_time(b))
+    return float(np.mean(ms))
+
+
+def _traffic(name, kernel, full_size):
+    """ncu-measured DRAM bytes per launch of `kernel` on workload `name` (committed summary; None when not captured)."""
+    if not full_size:
+        return None
+    for fn in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as fh:
+                rec = json.load(fh).get(name, {})
+        except OSError:
+            continue
+        rec = rec.get(kernel, rec if rec.get("kernel") == kernel else {})
+        if rec.get("dram_bytes_per_launch") is not None:
+            return rec["dram_bytes_per_launch"]
+    return None
+
+
+def measure_workload(m, name, w, args, dev, rank, world, barrier, flush, K, W):
+    """Device-timed rollout steps of one workload + its kernels timed alone.  Returns the numbers and the live objects."""
     import torch
     import torch.distributed as dist
-    import mapf_gnn_b200 as m
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    from mapf_gnn_b200 import _lib as _mlib
+    lib = _mlib.load()
     E, N, H = args.episodes or w["E"], w["N"], w["H"]
     rng = np.random.default_rng(1000 + rank)
     starts, goals, obst = m.make_scenarios(rng, E, N, H, w["M"])
@@ -192,15 +280,7 @@ def run_mine(args, w):
     net = net.to(dev).eval()
     env = m.BatchedGraphEnv(cfg, goals, starts, obst, sensing_range=w["r"], device=dev)
     ro = m.Rollout(net, env)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    K, W = args.steps, args.warmup
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     active = torch.zeros(K, dtype=torch.int64, device=dev)
@@ -213,9 +293,6 @@ def run_mine(args, w):
         ro.run(1)
     env.reset()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     t_wall0 = time.perf_counter()
     for i in range(K):
         if i % EPISODE_LEN == 0 and i > 0:
@@ -239,60 +316,145 @@ def run_mine(args, w):
         dev_ms_max = dev_ms
     units_all, units_nominal = float(t[1]), float(t[2])
     value = units_all / (dev_ms_max * 1e-3)
-
-    # ---- dominant kernel timed alone, live, on the launching stream: the conv stack of the encoder, on the tensor cores
-    # (encoder_tc_kernel) for 16-channel networks, else inside the fused FFMA2 encoder kernel (encoder_fwd_kernel) ----
+    ms_step = dev_ms_max / K
+    pk = peaks()
+    full = E == w["E"]
+    rows = E * N
     dims = net.dims()
     packed = net.packed_weights()
-    from mapf_gnn_b200 import _lib as _mlib
-    tc_encoder = ro.worka is not None and _mlib.load().mapf_encoder_tc_supported(ro.params) == 1
-    if tc_encoder:
-        _ea = _mlib.EncoderFwdArgs(E * N, env.fov.data_ptr(), packed.data_ptr(), ro.worka.data_ptr())
-        _st = _mlib.current_stream()
+    st = _mlib.current_stream()
 
-        def dominant():
-            _mlib.check(_mlib.load().mapf_encoder_tc_conv_fwd(ro.params, _ea, _st), "encoder_tc_conv_fwd")
+    # ---- dominant kernel timed alone, live, on the launching stream: the conv stack of the encoder, on the tensor cores
+    # (encoder_tc_kernel) where the dimensions fit, else inside the fused FFMA2 encoder kernel (encoder_fwd_kernel) ----
+    tc_encoder = ro.worka is not None and lib.mapf_encoder_tc_supported(ro.params) == 1
+    if tc_encoder:
+        ea = _mlib.EncoderFwdArgs(rows, env.fov.data_ptr(), packed.data_ptr(), ro.worka.data_ptr())
+        enc_ms = _time_alone(lambda: _mlib.check(lib.mapf_encoder_tc_conv_fwd(ro.params, ea, st), "enc_tc"), flush)
     else:
-        def dominant():
-            torch.ops.mapf.encoder_fwd(dims, env.fov, packed)
-    enc_ms = []
-    for i in range(3 + 10):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        dominant()
-        b.record()
-        b.synchronize()
-        if i >= 3:
-            enc_ms.append(a.elapsed_time(b))
-    enc_ms = float(np.mean(enc_ms))
-    env_ms = []
-    for i in range(3 + 10):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        env.observe()
-        b.record()
-        b.synchronize()
-        if i >= 3:
-            env_ms.append(a.elapsed_time(b))
-    env_ms = float(np.mean(env_ms))
-    pk = peaks()
-    traffic = None
-    try:       # ncu-measured DRAM bytes per launch of the dominant kernel (committed summary; null when not captured)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            rec = json.load(fh).get(args.workload, {})
-            want = "encoder_tc_kernel" if tc_encoder else "encoder_fwd_kernel"
-            rec = rec.get(want, rec if rec.get("kernel") == want else {})
-            traffic = rec.get("dram_bytes_per_launch") if E == w["E"] else None
-    except OSError:
-        pass
+        enc_ms = _time_alone(lambda: torch.ops.mapf.encoder_fwd(dims, env.fov, packed), flush)
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     # algorithmic FLOPs of what the timed kernel computes: the whole encoder (296.0 kFLOP per agent) for the
-    # fused kernel, the conv stack alone (296.0 k minus the 2 x 400 x 64 FLOP of the Linear) for the tensor-core kernel
-    dom_flops = w["enc_flops"] - (2.0 * dims[6] * dims[7] if tc_encoder else 0.0)
-    enc_tflops = E * N * dom_flops / (enc_ms * 1e-3) / 1e12
-    env_gbs = E * N * w["env_bytes"] / (env_ms * 1e-3) / 1e9
+    # fused kernels, the conv stack alone (296.0 k minus the 2 x 400 x 64 FLOP of the Linear) when the FC is a second kernel
+    fc_separate = tc_encoder and not ENC_TC_FUSED_FC
+    dom_flops = w["enc_flops"] - (2.0 * dims[6] * dims[7] if fc_separate else 0.0)
+    enc_tflops = rows * dom_flops / (enc_ms * 1e-3) / 1e12
+    if tc_encoder:
+        roof = {"bound": "tensor", "kernel": "encoder_tc_kernel", "achieved": enc_tflops, "peak": pk["tensor_tflops"],
+                "unit": "TFLOP/s", "frac": enc_tflops / pk["tensor_tflops"],
+                "traffic": _traffic(name, "encoder_tc_kernel", full), "ms_per_launch": enc_ms,
+                "share_of_step": enc_ms / ms_step,
+                "peak_source": f"dense 16-bit tensor peak, cuBLAS burst ({pk['source']})",
+                "algorithmic_flops_per_launch": rows * dom_flops, "vs_fp32_ffma_peak": enc_tflops / fp32_peak,
+                "note": "fp32-accurate conv stack = 3 fp16 MMAs per product (hi/lo split) on 25 of 32 lanes; the kernel "
+                        "is bound by the per-layer MMA issue/commit latency, not by tensor throughput (DESIGN.md 3.2)"}
+    else:
+        roof = {"bound": "fp32_ffma", "kernel": "encoder_fwd_kernel", "achieved": enc_tflops, "peak": fp32_peak,
+                "unit": "TFLOP/s", "frac": enc_tflops / fp32_peak, "traffic": _traffic(name, "encoder_fwd_kernel", full),
+                "ms_per_launch": enc_ms, "share_of_step": enc_ms / ms_step,
+                "peak_source": f"148 SM x 128 FFMA x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})"}
+
+    # ---- environment step kernel alone (FOV + adjacency: HBM-bound; SURVEY 8d bytes per agent-step) ----
+    env_ms = _time_alone(lambda: env.observe(), flush)
+    env_gbs = rows * w["env_bytes"] / (env_ms * 1e-3) / 1e9
+    roof_env = {"bound": "hbm", "kernel": "env_step_kernel", "achieved": env_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": env_gbs / pk["hbm_gbs"], "ms_per_launch": env_ms, "share_of_step": env_ms / ms_step,
+                "traffic": _traffic(name, "env_step_kernel", full),
+                "algorithmic_bytes_per_launch": rows * w["env_bytes"], "peak_source": pk["source"]}
+
+    # ---- graph-filter stage alone (S, hops, mix, ReLU, head, argmax) ----
+    roof_graph = None
+    if dims[8] > 0:
+        F, K_, G = dims[7], dims[8], dims[9]
+        skip = 1 if net.message else 0
+        KT = (K_ + skip) * F
+        gf = net.GFL[0]
+        Wt = gf.W.detach().contiguous()
+        W2 = gf.W2.detach().contiguous() if net.message else None
+        Wp = torch.empty((lib.mapf_tc_packed_b_size(G, KT),), device=dev)
+        _mlib.check(lib.mapf_tc_pack_b(Wt.data_ptr(), K_ * F, None if W2 is None else W2.data_ptr(), F if skip else 0, G,
+                                       Wp.data_ptr(), st), "tc_pack_b")
+        aw = net.actionMLP[0].weight.detach().contiguous()
+        ab = net.actionMLP[0].bias.detach().contiguous()
+        lg = torch.empty((rows, 5), device=dev)
+        ac = torch.empty((rows,), dtype=torch.int32, device=dev)
+        x = ro.work
+        # SURVEY 8d per agent: shift 2(K-1)FN + mix 2KFG (+ skip 2FG) + head 2*G*5 FLOP; fused bytes 4F + 4N in, 24 out
+        g_flops = 2.0 * (K_ - 1) * F * N + 2.0 * KT * G + 2.0 * G * 5
+        fused = N <= 32 and lib.mapf_tc_graph_supported(N, F, G, K_) == 1
+        if fused:
+            fn = lambda: _mlib.check(lib.mapf_tc_graph_head(E, N, F, G, K_, 0 if skip else 1, skip, x.data_ptr(),
+                                                           env.adj_matrix.data_ptr(), Wp.data_ptr(), aw.data_ptr(),
+                                                           ab.data_ptr(), 5, lg.data_ptr(), ac.data_ptr(), st), "tc_graph")
+            g_ms = _time_alone(fn, flush)
+            g_bytes = rows * (4 * F + 4 * N + 24)
+            tfl = rows * g_flops / (g_ms * 1e-3) / 1e12
+            roof_graph = {"bound": "tensor", "kernel": "tc_graph_kernel", "achieved": tfl, "peak": pk["tensor_tflops"],
+                          "unit": "TFLOP/s", "frac": tfl / pk["tensor_tflops"], "ms_per_launch": g_ms,
+                          "share_of_step": g_ms / ms_step, "algorithmic_flops_per_launch": rows * g_flops,
+                          "hbm_gbs": g_bytes / (g_ms * 1e-3) / 1e9, "hbm_frac": g_bytes / (g_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                          "algorithmic_bytes_per_launch": g_bytes, "traffic": _traffic(name, "tc_graph_kernel", full),
+                          "note": "fused S + hops + 3xTF32 mix + head: the taps never touch HBM, so the stage is bound by "
+                                  "its per-CTA latency chain, not by HBM (SURVEY 8d: fused it turns compute-bound)"}
+        else:
+            z = ro.workz
+            ga = _mlib.GraphFilterFwdArgs()
+            ga.batch, ga.agents, ga.in_dim, ga.out_dim, ga.taps = E, N, F, G, K_
+            ga.add_self_loop, ga.has_skip = 0 if skip else 1, skip
+            ga.x, ga.x_sb, ga.x_sn, ga.x_sf = x.data_ptr(), N * F, F, 1
+            ga.gso, ga.z = env.adj_matrix.data_ptr(), z.data_ptr()
+            taps_ms = _time_alone(lambda: _mlib.check(lib.mapf_graph_taps(ga, st), "graph_taps"), flush)
+            mix_ms = _time_alone(lambda: _mlib.check(lib.mapf_tc_mix_head(rows, G, KT, z.data_ptr(), KT, Wp.data_ptr(),
+                                                                         aw.data_ptr(), ab.data_ptr(), 5, lg.data_ptr(),
+                                                                         ac.data_ptr(), None, st), "tc_mix_head"), flush)
+            t_bytes = rows * (4 * F + 4 * N + 4 * KT)        # SURVEY 8d recurrence kernel: read X, A; write Z
+            gbs = t_bytes / (taps_ms * 1e-3) / 1e9
+            roof_graph = {"bound": "hbm", "kernel": "graph_taps_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
+                          "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "ms_per_launch": taps_ms,
+                          "share_of_step": taps_ms / ms_step, "algorithmic_bytes_per_launch": t_bytes,
+                          "traffic": _traffic(name, "graph_taps_kernel", full),
+                          "mix_head": {"kernel": "tc_gemm_kernel<EPI_HEAD>", "ms_per_launch": mix_ms,
+                                       "tflops": rows * (2.0 * KT * G + 2.0 * G * 5) / (mix_ms * 1e-3) / 1e12}}
+    launches = (2 if fc_separate else 1) + (0 if dims[8] == 0 else (1 if (N <= 32) else 2)) + (1 if dims[8] == 0 else 0) + 1
+    res = {"value": value, "ms_per_step": ms_step, "units_nominal": units_nominal, "wall": wall,
+           "roofline": roof, "roofline_env": roof_env, "roofline_graph": roof_graph, "launches_per_step": launches}
+    live = {"net": net, "env": env, "ro": ro, "cfg": cfg, "goals": goals, "starts": starts, "obst": obst, "E": E}
+    return res, live
+
+
+ENC_TC_FUSED_FC = False   # set by run_mine from the library (True once the conv kernel carries the FC in its tail)
+
+
+def run_mine(args, w):
+    import torch
+    import torch.distributed as dist
+    import mapf_gnn_b200 as m
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mapf_gnn_b200 import _lib as _mlib
+    global ENC_TC_FUSED_FC
+    ENC_TC_FUSED_FC = bool(getattr(_mlib, "ENC_TC_FUSED_FC", False))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    N = w["N"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res, live = measure_workload(m, args.workload, w, args, dev, rank, world, barrier, flush, K, W)
+    net, env, cfg, E = live["net"], live["env"], live["cfg"], live["E"]
+    goals, starts, obst = live["goals"], live["starts"], live["obst"]
 
     # ---- end to end through the public API with HOST buffers (pinned), every step ----
     # Per step: the state (positions) is uploaded from pinned host memory, the step runs, and actions, new positions
@@ -327,57 +489,63 @@ def run_mine(args, w):
     e2e_value = float(u[0]) / float(t[0])
     # the sampler ran through the device-timed steps, the per-kernel timings and the end-to-end loop
     clocks = sampler.stop() if rank == 0 else None
+    h2d, d2h = pl.h2d_bytes, pl.d2h_bytes
+    del pl
 
     train = None if args.no_train else run_train(args, w, env, dev, rank, world, barrier)
+    del live, env, net
+
+    # ---- the other BASELINE configs, compact: same protocol (flushed L2, one graph replay per step), fewer steps ----
+    others = {}
+    if not args.no_other_workloads and args.workload == "c2a" and not args.episodes:
+        for name in args.other_workloads:
+            ow = WORKLOADS[name]
+            r, lv = measure_workload(m, name, ow, args, dev, rank, world, barrier, flush, args.other_steps, max(3, W))
+            del lv
+            torch.cuda.empty_cache()
+            others[name] = {"config": config_of(name, ow, ow["E"]), "value": r["value"], "unit": "agent-steps/s",
+                            "ms_per_step": r["ms_per_step"], "steps": args.other_steps, "n_gpus": world,
+                            "roofline": {k: r["roofline"][k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac",
+                                                                        "ms_per_launch", "share_of_step")},
+                            "roofline_env": {k: r["roofline_env"][k] for k in ("achieved", "peak", "unit", "frac",
+                                                                                "ms_per_launch")},
+                            "roofline_graph": None if r["roofline_graph"] is None else
+                            {k: v for k, v in r["roofline_graph"].items() if k != "note"}}
 
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            v, tot = cpu_reference_steps(w, args.cpu_episodes, args.cpu_steps, 1)
-            cpu = {"value": v, "unit": "agent-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            r2 = cpu_rollout_r2(w, args.cpu_episodes, args.cpu_steps, 1)
+            cpu = {"value": r2["value"], "unit": "agent-steps/s", "cores": torch.get_num_threads(), "kind": r2["kind"],
                    "sample": f"{args.cpu_episodes} episodes x {args.cpu_steps} steps of the same workload, "
-                             f"{tot:.1f} s (python loop over single-episode numpy envs + batched torch-CPU forward)"}
-        # encoder conv stack, encoder FC, graph filter + head (or baseline head), env step
-        launches_per_step = 4 if tc_encoder else 3
-        if tc_encoder:
-            roof = {"bound": "tensor", "kernel": "encoder_tc_kernel", "achieved": enc_tflops,
-                    "peak": pk["tensor_tflops"], "unit": "TFLOP/s", "frac": enc_tflops / pk["tensor_tflops"],
-                    "traffic": traffic, "ms_per_launch": enc_ms, "share_of_step": enc_ms / (dev_ms_max / K),
-                    "peak_source": f"dense 16-bit tensor peak, cuBLAS burst ({pk['source']})",
-                    "algorithmic_flops_per_launch": E * N * dom_flops,
-                    "vs_fp32_ffma_peak": enc_tflops / fp32_peak,
-                    "note": "fp32-accurate conv stack = 3 fp16 MMAs per product (hi/lo split); the kernel is bound by "
-                            "the per-layer MMA issue/commit latency, not by tensor throughput (DESIGN.md 3.2)"}
-        else:
-            roof = {"bound": "fp32_ffma", "kernel": "encoder_fwd_kernel", "achieved": enc_tflops,
-                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": enc_tflops / fp32_peak, "traffic": traffic,
-                    "ms_per_launch": enc_ms, "share_of_step": enc_ms / (dev_ms_max / K),
-                    "peak_source": f"148 SM x 128 FFMA x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})"}
+                             f"{r2['seconds']:.1f} s: " + _PROTOCOL[r2["kind"]]}
         line = {
-            "metric": "agent-steps/sec (batched rollout)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "metric": "agent-steps/sec (batched rollout)", "value": res["value"], "unit": "agent-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "episodes_per_gpu": E, "agents": N, "board": H,
-                       "obstacles": w["M"], "weights": f"tests/golden/weights_{w['model']}.npz",
-                       "l2": "flushed between steps (256 MiB memset outside the event pairs)",
-                       "timing": "cuda events per step on the launching stream, max over ranks; a step = one CUDA-graph "
-                                 "replay of the rollout step's kernel sequence",
-                       "counted": "agent-steps of episodes not yet done (done episodes are frozen); "
-                                  f"nominal E*N*K = {units_nominal:.0f}",
-                       "wall_s_incl_flush": wall},
-            "roofline": roof,
-            "roofline_env": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": env_gbs, "peak": pk["hbm_gbs"],
-                             "unit": "GB/s", "frac": env_gbs / pk["hbm_gbs"], "ms_per_launch": env_ms,
-                             "peak_source": pk["source"]},
+            "config": config_of(args.workload, w, E),
+            "measurement": {"l2": "flushed between steps (256 MiB memset outside the event pairs)",
+                            "timing": "cuda events per step on the launching stream, max over ranks; a step = one "
+                                      "CUDA-graph replay of the rollout step's kernel sequence",
+                            "counted": "agent-steps of episodes not yet done (done episodes are frozen); "
+                                       f"nominal E*N*K = {res['units_nominal']:.0f}",
+                            "wall_s_incl_flush": res["wall"]},
+            "roofline": res["roofline"],
+            "roofline_env": res["roofline_env"],
+            "roofline_graph": res["roofline_graph"],
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": pl.h2d_bytes,
-                    "d2h_bytes_per_step": pl.d2h_bytes, "steps": ke, "groups": G,
-                    "api": "PipelinedHostRollout: per group and step pinned upload, CUDA-graph replay, pinned download, "
-                           "event wait; the groups' host round trips overlap each other's kernels"},
-            "gpu_launches": K * launches_per_step,
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": ke, "groups": G,
+                    "api": "PipelinedHostRollout: per group and step pinned upload of the state (agent POSITIONS only: "
+                           "boards, goals and weights are resident, observations are produced on the device), CUDA-graph "
+                           "replay, pinned download of actions + new positions + done flags, event wait; the groups' "
+                           "host round trips overlap each other's kernels.  This is not the reference caller protocol "
+                           "of shipping fov / gso tensors per step (evaluate.py:225-226)"},
+            "gpu_launches": K * res["launches_per_step"],
             "clocks": clocks,
             "train": train,
+            "workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -463,11 +631,15 @@ def main():
     ap.add_argument("--workload", default="c2a", choices=sorted(WORKLOADS))
     ap.add_argument("--episodes", type=int, default=0, help="episodes per GPU (default: the workload's)")
     ap.add_argument("--ref-episodes", type=int, default=512, help="episodes per step of the --impl reference arm")
-    ap.add_argument("--cpu-episodes", type=int, default=4096)
+    ap.add_argument("--cpu-episodes", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=4,
                     help="independent episode groups whose host round trips overlap in the end-to-end measurement")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the compact lines of the other BASELINE configs (key `workloads`)")
+    ap.add_argument("--other-workloads", nargs="*", default=["c1", "c2b", "c3", "c5"], choices=sorted(WORKLOADS))
+    ap.add_argument("--other-steps", type=int, default=32)
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-train-graph", action="store_true", help="do not replay the training step as a CUDA graph")
     ap.add_argument("--train-batches", type=int, nargs="*", default=[128, 1024, 8192])

@@ -6,7 +6,8 @@
  *   - takes one plain-C argument struct of DEVICE pointers + int sizes and a cudaStream_t,
  *   - is asynchronous on that stream, never allocates, never synchronises, never throws,
  *   - keeps no global mutable state apart from an idempotent per-device cache of "dynamic shared memory already
- *     granted" flags (re-entrant; thread-safe per stream),
+ *     granted" flags (re-entrant; thread-safe per stream) and never reads the process environment: development
+ *     switches are explicit `flags` fields of the argument structs,
  *   - returns MAPF_OK (0) or a negative mapf_status code; mapf_last_error_string(code)
  *     gives the message.  All buffers are caller-owned.
  *
@@ -106,8 +107,24 @@ typedef struct {
   uint8_t* done;          /* [E] in/out */
   float* fov;             /* [E,N,2,5,5] out (may be NULL) */
   float* adj;             /* [E,N,N] out (may be NULL) */
+  int32_t episodes_per_cta; /* work decomposition: 0 = chosen by the library; else 1 .. 128 / next_pow2(N).  Results are
+                             * identical for every value (tests sweep it). */
 } mapf_env_step_args;
 int mapf_env_step(const mapf_env_step_args* a, mapf_stream_t stream);
+
+/* The single rules of GraphEnv._updatePositions on caller-supplied candidate positions, for callers (and the
+ * reference's tests/test_env.py:97-121,164-194) that poke them one at a time.  stages, applied in the reference's order:
+ * bit 0 check_collision_obstacle (env_graph_gridv1.py:303-313: a candidate inside the obstacle set reverts to pos_temp),
+ * bit 1 check_boundary (:267-271: clamp to the board), bit 2 check_collisions (:282-301: every member of a shared cell
+ * reverts to pos_temp, single pass).  The board is not touched (updateBoard :273-275 is part of mapf_env_step). */
+typedef struct {
+  int32_t episodes, agents, board, cell_stride;
+  int32_t stages;
+  int32_t* pos;            /* [E,N,2] in/out: candidate positions (positionX / positionY) */
+  const int32_t* pos_temp; /* [E,N,2] positions to revert to (positionX_temp / positionY_temp) */
+  const uint8_t* cells;    /* [E,cell_stride] (obstacle-set flag); may be NULL when bit 0 is clear */
+} mapf_env_rules_args;
+int mapf_env_apply_rules(const mapf_env_rules_args* a, mapf_stream_t stream);
 
 /* GraphEnv.computeMetrics (env_graph_gridv1.py:138-154,168-172): per episode
  * success = (#agents on own goal)/N, flow_time = time if all on goal else N*max_time. */
@@ -228,7 +245,15 @@ typedef struct {
                            * FC; NULL = FC fused in the conv kernel */
   float* logits;          /* [B,N,A] */
   int32_t* actions;       /* [B,N] or NULL */
+  int32_t flags;          /* 0 = the library's choices; development switches MAPF_POLICY_* below (every combination gives
+                           * the same logits within the stated tolerance and the same actions; tests sweep them) */
 } mapf_policy_fwd_args;
+#define MAPF_POLICY_FFMA_CONV 1      /* conv stack on the FFMA2 kernel even where the tensor-core stack applies */
+#define MAPF_POLICY_FC_UNSPLIT 2     /* plain [rows, fc_in] hand-over to the encoder FC (conversion warps in the GEMM) */
+#define MAPF_POLICY_UNFUSED_GRAPH 4  /* graph filter as taps kernel + tensor-core mix instead of the fused kernel */
+#define MAPF_POLICY_FUSED_ENV_ON 8   /* mapf_rollout: always run the env step in the tail of the graph kernel */
+#define MAPF_POLICY_FUSED_ENV_OFF 16 /* mapf_rollout: never */
+#define MAPF_POLICY_NO_PDL 32        /* launch the call's kernels without programmatic stream serialization */
 int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_args* a, mapf_stream_t stream);
 
 /* `steps` iterations of the rollout protocol of evaluate.py:223-241 for E resident episodes,
@@ -279,7 +304,10 @@ typedef struct {
   float* workspace;          /* mapf_train_workspace_size floats, 16-byte aligned */
   float* logits;             /* [B,N,A] out */
   int64_t* bn_batches[MAPF_MAX_CONV];
+  int32_t flags;             /* development switches MAPF_TRAIN_* below; 0 = tensor-core FC and graph mix */
 } mapf_train_fwd_args;
+#define MAPF_TRAIN_FFMA_FC 1     /* compressMLP forward on the FFMA GEMM */
+#define MAPF_TRAIN_FFMA_GRAPH 2  /* graph filter forward on the fused FFMA kernel */
 int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream);
 
 /* Backward of the above from d(loss)/d(logits); must follow mapf_train_forward on the same

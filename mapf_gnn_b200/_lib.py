@@ -12,6 +12,10 @@ import os
 from . import _build
 
 MAX_CONV = 4
+# mapf_policy_fwd_args.flags / mapf_train_fwd_args.flags (include/mapf_b200.h)
+POLICY_FFMA_CONV, POLICY_FC_UNSPLIT, POLICY_UNFUSED_GRAPH, POLICY_FUSED_ENV_ON, POLICY_FUSED_ENV_OFF, POLICY_NO_PDL = \
+    1, 2, 4, 8, 16, 32
+TRAIN_FFMA_FC, TRAIN_FFMA_GRAPH = 1, 2
 c_f32p = C.c_void_p      # device pointers travel as integers
 c_i32p = C.c_void_p
 c_u8p = C.c_void_p
@@ -28,7 +32,13 @@ class EnvStepArgs(C.Structure):
     _fields_ = [("episodes", C.c_int32), ("agents", C.c_int32), ("board", C.c_int32), ("cell_stride", C.c_int32),
                 ("d2_limit", C.c_int32), ("do_move", C.c_int32),
                 ("pos", c_i32p), ("goal", c_i32p), ("actions", c_i32p), ("cells", c_u8p),
-                ("time", c_i32p), ("done", c_u8p), ("fov", c_f32p), ("adj", c_f32p)]
+                ("time", c_i32p), ("done", c_u8p), ("fov", c_f32p), ("adj", c_f32p),
+                ("episodes_per_cta", C.c_int32)]
+
+
+class EnvRulesArgs(C.Structure):
+    _fields_ = [("episodes", C.c_int32), ("agents", C.c_int32), ("board", C.c_int32), ("cell_stride", C.c_int32),
+                ("stages", C.c_int32), ("pos", c_i32p), ("pos_temp", c_i32p), ("cells", c_u8p)]
 
 
 class EnvMetricsArgs(C.Structure):
@@ -69,7 +79,8 @@ class HeadFwdArgs(C.Structure):
 class PolicyFwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32),
                 ("states", c_f32p), ("gso", c_f32p), ("packed", c_f32p), ("workspace_x", c_f32p),
-                ("workspace_z", c_f32p), ("workspace_act", c_f32p), ("logits", c_f32p), ("actions", c_i32p)]
+                ("workspace_z", c_f32p), ("workspace_act", c_f32p), ("logits", c_f32p), ("actions", c_i32p),
+                ("flags", C.c_int32)]
 
 
 class NetGrads(C.Structure):
@@ -82,7 +93,7 @@ class NetGrads(C.Structure):
 class TrainFwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32), ("momentum", C.c_float),
                 ("states", c_f32p), ("gso", c_f32p), ("workspace", c_f32p), ("logits", c_f32p),
-                ("bn_batches", C.c_void_p * MAX_CONV)]
+                ("bn_batches", C.c_void_p * MAX_CONV), ("flags", C.c_int32)]
 
 
 class TrainBwdArgs(C.Structure):
@@ -124,6 +135,7 @@ _SIGNATURES = {
     "mapf_env_reset": (C.c_int, [C.POINTER(EnvResetArgs), C.c_void_p]),
     "mapf_env_step": (C.c_int, [C.POINTER(EnvStepArgs), C.c_void_p]),
     "mapf_env_metrics": (C.c_int, [C.POINTER(EnvMetricsArgs), C.c_void_p]),
+    "mapf_env_apply_rules": (C.c_int, [C.POINTER(EnvRulesArgs), C.c_void_p]),
     "mapf_packed_weights_size": (C.c_int64, [C.POINTER(NetParams)]),
     "mapf_pack_weights": (C.c_int, [C.POINTER(NetParams), C.c_void_p, C.c_void_p]),
     "mapf_pack_graph_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

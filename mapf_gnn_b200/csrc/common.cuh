@@ -131,15 +131,47 @@ static inline bool mapf_ensure_smem(F func, size_t bytes, int* cache /* [16] zer
 // resident -- and run their prologue: barrier init, TMEM allocation, weights into shared memory -- while the previous
 // kernel drains.  Every kernel calls mapf_pdl_wait() before its first access to memory another kernel of the chain
 // writes or reads (it returns once ALL earlier kernels have completed and flushed), and mapf_pdl_launch() to let its own
-// successor start early.  Without the launch attribute both are no-ops.  MAPF_B200_NO_PDL=1 switches the attribute off.
+// successor start early.  Without the launch attribute both are no-ops (mapf_policy_fwd_args.flags & MAPF_POLICY_NO_PDL).
 __device__ __forceinline__ void mapf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void mapf_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-static inline bool mapf_pdl_enabled() {
-  static int cached = -1;
-  if (cached < 0) cached = getenv("MAPF_B200_NO_PDL") == nullptr ? 1 : 0;
-  return cached == 1;
+// Data written by an EARLIER KERNEL of a programmatically launched chain must not be read through the non-coherent path
+// (__ldg / ld.global.nc): ptxas treats such a load as a read of immutable memory and may schedule it ABOVE
+// griddepcontrol.wait, i.e. before the producing kernel has finished (found in round 2: the env kernel read the previous
+// step's actions).  mapf_ld_dep is an ordinary coherent load; `asm volatile` keeps it behind the wait, no memory clobber
+// so that independent loads can still be batched ahead of shared-memory stores.  Weights (packed long before, behind
+// pack_fence_kernel) keep __ldg.
+__device__ __forceinline__ float mapf_ld_dep(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
+__device__ __forceinline__ float4 mapf_ld_dep(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 mapf_ld_dep(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int mapf_ld_dep(const int* p) {
+  int v;
+  asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// Per-thread, per-call launch option: the entry points that take a `flags` field (mapf_policy_fwd, mapf_rollout) switch
+// programmatic launches off for the duration of the call when MAPF_POLICY_NO_PDL is set.  Thread-local and restored on
+// return: the library stays re-entrant and keeps no process-wide mutable state.
+inline thread_local int mapf_tl_no_pdl = 0;
+struct MapfPdlScope {
+  int saved;
+  explicit MapfPdlScope(bool no_pdl) : saved(mapf_tl_no_pdl) { if (no_pdl) mapf_tl_no_pdl = 1; }
+  ~MapfPdlScope() { mapf_tl_no_pdl = saved; }
+};
+static inline bool mapf_pdl_enabled() { return mapf_tl_no_pdl == 0; }
 
 template <typename... KArgs, typename... Args>
 static inline void mapf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

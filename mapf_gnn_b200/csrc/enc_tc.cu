@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
     v1 = 0.0f;
     if (tile < ntiles && img < g.rows && pix_ok) {
       const float* s = g.states + img * kFovFloats + pidx;
-      v0 = __ldg(s);
-      v1 = __ldg(s + kFovCells);
+      v0 = mapf_ld_dep(s);            // written by the env kernel in front: not __ldg (common.cuh)
+      v1 = mapf_ld_dep(s + kFovCells);
     }
   };
   auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); };
@@ -494,8 +494,7 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
     // start-up offset between the warpgroups: about a fifth of a layer for a long launch, less when every group sees
     // only a tile or two (measured optimum 400 / 700 / 1000 / 1400 clocks at 1 / 2 / 4 / 7 tiles per group)
     const int64_t rounds = (ntiles + int64_t(grid) * kGroups - 1) / (int64_t(grid) * kGroups);
-    const char* e = getenv("MAPF_B200_ETC_SKEW");   // development switch
-    g.skew = e ? atoi(e) : int(rounds >= 6 ? 1400 : 300 + 200 * rounds);
+    g.skew = int(rounds >= 6 ? 1400 : 300 + 200 * rounds);
     mapf_launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), g);
     return MAPF_OK;
   };

@@ -255,9 +255,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_fwd_kernel(EncoderDims
           const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_st + 4 * q));
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + 4 * q));
         }
-        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_st[i] = __ldg(src + i);
+        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_st[i] = mapf_ld_dep(src + i);
       } else {
-        for (int i = tid; i < nfl; i += kEncThreads) s_st[i] = __ldg(src + i);
+        for (int i = tid; i < nfl; i += kEncThreads) s_st[i] = mapf_ld_dep(src + i);
       }
       for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) s_st[i] = 0.0f;
     }
@@ -453,10 +453,10 @@ __global__ void __launch_bounds__(kEncThreads * NG, 1) encoder_conv_kernel(Encod
       if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const int nq = nfl >> 2;
         for (int q = tid; q < nq; q += kEncThreads)
-          reinterpret_cast<float4*>(s_b0)[q] = __ldg(reinterpret_cast<const float4*>(src) + q);
-        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+          reinterpret_cast<float4*>(s_b0)[q] = mapf_ld_dep(reinterpret_cast<const float4*>(src) + q);
+        for (int i = (nq << 2) + tid; i < nfl; i += kEncThreads) s_b0[i] = mapf_ld_dep(src + i);
       } else {
-        for (int i = tid; i < nfl; i += kEncThreads) s_b0[i] = __ldg(src + i);
+        for (int i = tid; i < nfl; i += kEncThreads) s_b0[i] = mapf_ld_dep(src + i);
       }
       for (int i = nfl + tid; i < kEncAgents * kFovFloats; i += kEncThreads) s_b0[i] = 0.0f;
     }
@@ -542,7 +542,7 @@ extern "C" int mapf_encoder_fwd(const mapf_net_params* p, const mapf_encoder_fwd
   int nhalf = 0;
   {
     const int64_t rounds = ntiles / sms, rem = ntiles - rounds * sms;
-    if (rem > 0 && 2 * rem <= sms && !getenv("MAPF_B200_ENC_NO_HALF_TILES")) {
+    if (rem > 0 && 2 * rem <= sms) {
       nfull = rounds * sms;
       nhalf = int((a->rows - nfull * kEncAgents + kEncAgents / 2 - 1) / (kEncAgents / 2));
     }
@@ -594,7 +594,7 @@ extern "C" int mapf_encoder_conv_split_fwd(const mapf_net_params* p, const mapf_
   int nhalf = 0;
   {
     const int64_t rounds = ntiles / sms, rem = ntiles - rounds * sms;
-    if (rem > 0 && 2 * rem <= sms && !getenv("MAPF_B200_ENC_NO_HALF_TILES")) {
+    if (rem > 0 && 2 * rem <= sms) {
       nfull = rounds * sms;
       nhalf = int((a->rows - nfull * kEncAgents + kEncAgents / 2 - 1) / (kEncAgents / 2));
     }
@@ -635,8 +635,7 @@ extern "C" int mapf_encoder_conv_fwd(const mapf_net_params* p, const mapf_encode
   const size_t gbytes = size_t(d.buf0_floats + d.buf1_floats) * sizeof(float);
   const size_t limit = 227 * 1024;
   MAPF_REQUIRE(wbytes + gbytes <= limit, MAPF_ERR_UNSUPPORTED);
-  const char* force = getenv("MAPF_B200_ENC_GROUPS");   // development switch; one group measured faster
-  const int ng = (force && force[0] == '2' && wbytes + 2 * gbytes <= limit) ? 2 : 1;
+  const int ng = 1;   // two independent 256-thread groups per CTA measured slower (worse tile quantisation)
   const size_t smem = wbytes + ng * gbytes;
   const int64_t ntiles = (a->rows + kEncAgents - 1) / kEncAgents;
   const int64_t want = (ntiles + ng - 1) / ng;

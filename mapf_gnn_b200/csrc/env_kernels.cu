@@ -2,13 +2,14 @@
 // New B200-first design of the semantics of the reference's single-episode numpy GraphEnv
 // (grid/env_graph_gridv1.py; exact rules restated in SURVEY.md 8a A1-A4).
 //
-// Work decomposition: one CTA of 128 threads owns EPB = 128/LANES consecutive episodes, LANES =
+// Work decomposition: one CTA of 128 threads owns up to 128/LANES consecutive episodes, LANES =
 // next power of two >= N lanes per episode.  The episodes' board cells are staged into shared
 // memory with 128-bit coalesced loads, all integer logic (move, obstacle revert, clamp, single-pass
 // collision revert, closest-4 threshold) runs on shared memory, and the two observation tensors of
-// the CTA's episodes -- contiguous ranges of fov[E,N,2,5,5] and adj[E,N,N] -- are written back
-// cooperatively with 128-bit coalesced stores.  HBM traffic per agent-step is the algorithmic
-// minimum: pos + goal + H*H/N board bytes in, 200 B FOV + 4N B adjacency + the 2 changed cells out.
+// the CTA's episodes -- contiguous ranges of fov[E,N,2,5,5] and adj[E,N,N] -- are assembled in a
+// shared-memory staging area and leave as one TMA bulk store each (env_step.cuh).  HBM traffic per
+// agent-step is the algorithmic minimum: pos + goal + H*H/N board bytes in, 200 B FOV + 4N B
+// adjacency + the 2 changed cells out.
 #include <limits.h>
 
 #include "common.cuh"
@@ -34,20 +35,21 @@ __global__ void env_reset_kernel(mapf_env_reset_args a) {
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_args a) {
-  constexpr int EPB = kEnvThreads / LANES;
-  extern __shared__ __align__(16) uint8_t s_cells[];
+__global__ void __launch_bounds__(kEnvThreads) env_step_kernel(mapf_env_step_args a, int epb) {
+  extern __shared__ __align__(16) uint8_t s_env_dyn[];   // [epb boards | staging of the CTA's adj and fov slices]
   __shared__ EnvShared<LANES, kEnvThreads> sh;
+  uint8_t* s_cells = s_env_dyn;
+  float* s_out = reinterpret_cast<float*>(s_env_dyn + size_t(epb) * a.cell_stride);
   const int tid = threadIdx.x;
-  const int e0 = blockIdx.x * EPB;
-  const int nep = min(EPB, a.episodes - e0);
+  const int e0 = blockIdx.x * epb;
+  const int nep = min(epb, a.episodes - e0);
   // do_move & 4 (mapf_rollout): boards, positions, goals and done flags were last written before the policy kernels in
   // front of this launch started, only the actions come from the kernel right in front -- stage the state while it drains
   const bool old_state = (a.do_move & 4) != 0;
   if (!old_state) { mapf_pdl_wait(); mapf_pdl_launch(); }
   const EnvAgent ag = env_step_stage<LANES, kEnvThreads>(a, e0, nep, tid, s_cells, sh);
   if (old_state) { mapf_pdl_wait(); mapf_pdl_launch(); }
-  env_step_finish<LANES, kEnvThreads>(a, e0, nep, tid, s_cells, sh, ag, nullptr);
+  env_step_finish<LANES, kEnvThreads>(a, e0, nep, tid, s_cells, sh, ag, nullptr, s_out);
 }
 
 __global__ void env_metrics_kernel(mapf_env_metrics_args a) {
@@ -63,17 +65,56 @@ __global__ void env_metrics_kernel(mapf_env_metrics_args a) {
   a.flow_time[e] = (hit == a.agents) ? a.time[e] : a.agents * a.max_time;
 }
 
+// Episodes per CTA: LANES lanes per episode do the per-agent rules, all 128 threads write the observations.  Few episodes
+// per CTA keep every SM busy at small E (C2a: 4096 episodes -> 1024 CTAs instead of 256) and the staging area small at
+// large N; a multiple of 4 for odd N keeps the CTA's output slices 16-byte aligned (bulk stores).
+// The single rules of _updatePositions on caller-supplied candidate positions (the reference's tests and callers poke
+// them one at a time): bit 0 check_collision_obstacle (:303-313), bit 1 check_boundary (:267-271), bit 2 check_collisions
+// (:282-301), applied in the reference's order.  One CTA per episode, one thread per agent.
+__global__ void __launch_bounds__(128) env_rules_kernel(mapf_env_rules_args a) {
+  __shared__ int s_x[128], s_y[128];
+  const int e = blockIdx.x, i = threadIdx.x, N = a.agents, H = a.board;
+  const bool agent = i < N;
+  int2 p = make_int2(kEnvFarAway, kEnvFarAway), t = p;
+  if (agent) {
+    p = reinterpret_cast<const int2*>(a.pos)[int64_t(e) * N + i];
+    t = reinterpret_cast<const int2*>(a.pos_temp)[int64_t(e) * N + i];
+    if ((a.stages & 1) && p.x >= 0 && p.x < H && p.y >= 0 && p.y < H &&
+        (a.cells[int64_t(e) * a.cell_stride + p.y * H + p.x] & kObstacleFlag))
+      p = t;
+    if (a.stages & 2) { p.x = min(max(p.x, 0), H - 1); p.y = min(max(p.y, 0), H - 1); }
+  }
+  if (a.stages & 4) {
+    s_x[i] = p.x; s_y[i] = p.y;
+    __syncthreads();
+    int cnt = 0;
+    for (int j = 0; j < N; ++j) cnt += (s_x[j] == p.x) & (s_y[j] == p.y);
+    if (agent && cnt > 1) p = t;
+  }
+  if (agent) reinterpret_cast<int2*>(a.pos)[int64_t(e) * N + i] = p;
+}
+
 template <int LANES>
 int launch_env_step(const mapf_env_step_args& a, cudaStream_t s) {
   constexpr int EPB = kEnvThreads / LANES;
-  const size_t smem = size_t(EPB) * a.cell_stride;
+  const auto smem_of = [&](int epb) {
+    return size_t(epb) * a.cell_stride + sizeof(float) * size_t(env_stage_floats(epb, a.agents));
+  };
+  int epb = a.episodes_per_cta;
+  if (epb <= 0) {
+    const int align = (a.agents & 1) ? 4 : 1;
+    epb = EPB;
+    while (epb > 1 && epb / 2 >= align && ((a.episodes + epb - 1) / epb < 148 * 8 || smem_of(epb) > 36 * 1024)) epb >>= 1;
+  }
+  MAPF_REQUIRE(epb >= 1 && epb <= EPB, MAPF_ERR_UNSUPPORTED);
+  const size_t smem = smem_of(epb);
   if (smem > 200 * 1024) return MAPF_ERR_UNSUPPORTED;
   if (smem > 40 * 1024) {
     if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(env_step_kernel<LANES>, size_t(smem), cache__); }())
       return MAPF_ERR_CUDA;
   }
-  const int grid = (a.episodes + EPB - 1) / EPB;
-  mapf_launch_pdl(env_step_kernel<LANES>, dim3(grid), dim3(kEnvThreads), smem, s, a);
+  const int grid = (a.episodes + epb - 1) / epb;
+  mapf_launch_pdl(env_step_kernel<LANES>, dim3(grid), dim3(kEnvThreads), smem, s, a, epb);
   return mapf_launch_status();
 }
 
@@ -113,6 +154,16 @@ extern "C" int mapf_env_step(const mapf_env_step_args* a, mapf_stream_t stream) 
   if (n <= 64) return launch_env_step<64>(*a, s);
   if (n <= 128) return launch_env_step<128>(*a, s);
   return MAPF_ERR_UNSUPPORTED;
+}
+
+extern "C" int mapf_env_apply_rules(const mapf_env_rules_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a != nullptr && a->pos && a->pos_temp, MAPF_ERR_NULL);
+  MAPF_REQUIRE(!(a->stages & 1) || a->cells, MAPF_ERR_NULL);
+  MAPF_REQUIRE(a->episodes > 0 && a->agents > 0 && a->board > 0 && (a->stages & ~7) == 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(a->agents <= 128, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(a->pos, 8) && mapf_aligned(a->pos_temp, 8), MAPF_ERR_ALIGN);
+  env_rules_kernel<<<a->episodes, 128, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  return mapf_launch_status();
 }
 
 extern "C" int mapf_env_metrics(const mapf_env_metrics_args* a, mapf_stream_t stream) {

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(TM * 4) graph_filter_kernel(mapf_graph_filter_
   for (int idx = tid; idx < nep * N * N; idx += NT) {
     const int el = idx / (N * N), rem = idx - el * N * N;
     const int i = rem / N, j = rem - i * N;
-    float v = __ldg(a.gso + int64_t(e0 + el) * N * N + rem);
+    float v = mapf_ld_dep(a.gso + int64_t(e0 + el) * N * N + rem);
     if (a.add_self_loop && i == j) v += 1.0f;
     sm[idx] = v;
   }
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TM * 4) graph_filter_kernel(mapf_graph_filter_
     const int f4 = F >> 2;
     for (int idx = tid; idx < TM * f4; idx += NT) {
       const int row = idx / f4, c = (idx - row * f4) << 2;
-      const float4 v = row < rows_used ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = row < rows_used ? mapf_ld_dep(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
       zt[(c + 0) * ZS + row] = v.x;
       zt[(c + 1) * ZS + row] = v.y;
       zt[(c + 2) * ZS + row] = v.z;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(TM * 4) graph_filter_kernel(mapf_graph_filter_
       float v = 0.0f;
       if (row < rows_used) {
         const int el = row / N, n = row - el * N;
-        v = __ldg(a.x + int64_t(e0 + el) * a.x_sb + int64_t(n) * a.x_sn + int64_t(f) * a.x_sf);
+        v = mapf_ld_dep(a.x + int64_t(e0 + el) * a.x_sb + int64_t(n) * a.x_sn + int64_t(f) * a.x_sf);
       }
       zt[f * ZS + row] = v;
     }
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(TZ * 4) graph_taps_kernel(mapf_graph_filter_fw
   for (int idx = tid; idx < nep * N * N; idx += NT) {
     const int el = idx / (N * N), rem = idx - el * N * N;
     const int i = rem / N, j = rem - i * N;
-    float v = __ldg(a.gso + int64_t(e0 + el) * N * N + rem);
+    float v = mapf_ld_dep(a.gso + int64_t(e0 + el) * N * N + rem);
     if (a.add_self_loop && i == j) v += 1.0f;
     sm[idx] = v;
   }
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(TZ * 4) graph_taps_kernel(mapf_graph_filter_fw
     const int f4 = F >> 2;
     for (int idx = tid; idx < rows_used * f4; idx += NT) {
       const int row = idx / f4, c = (idx - row * f4) << 2;
-      *reinterpret_cast<float4*>(z + row * ZR + c) = __ldg(src + idx);
+      *reinterpret_cast<float4*>(z + row * ZR + c) = mapf_ld_dep(src + idx);
     }
   }
   __syncthreads();

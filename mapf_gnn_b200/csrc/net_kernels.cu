@@ -7,8 +7,6 @@
 // 8a A5-A9); the decomposition below is new.  All arithmetic is fp32 FFMA: the action argmax must be
 // bit-exact against fp32 logits whose top-2 margin goes down to 3e-5, which rules out
 // TF32/BF16 tensor-core inputs without error-compensating splits.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 int mapf_encoder_tc_pack(const mapf_net_params* p, float* packed, mapf_stream_t stream);   // enc_tc.cu
@@ -106,7 +104,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(mapf_head_fwd_args a) {
   const int nrows = (a.rows - row0) < 32 ? int(a.rows - row0) : 32;
   for (int idx = threadIdx.x; idx < nrows * D; idx += blockDim.x) {
     const int r = idx / D, c = idx - r * D;
-    s_head[r * (D + 1) + c] = __ldg(a.x + row0 * D + idx);
+    s_head[r * (D + 1) + c] = mapf_ld_dep(a.x + row0 * D + idx);
   }
   __shared__ float s_logit[32][kMaxActions];
   __syncthreads();
@@ -203,6 +201,7 @@ static int policy_fwd_impl(const mapf_net_params* p, const mapf_policy_fwd_args*
   if (st != MAPF_OK) return st;
   MAPF_REQUIRE(a && a->states && a->packed && a->workspace_x && a->logits, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->batch > 0 && a->agents > 0, MAPF_ERR_SHAPE);
+  const MapfPdlScope pdl_scope((a->flags & MAPF_POLICY_NO_PDL) != 0);
   const PackedLayout L = mapf_packed_layout(*p);
   const int64_t rows = int64_t(a->batch) * a->agents;
   int rc;
@@ -211,8 +210,8 @@ static int policy_fwd_impl(const mapf_net_params* p, const mapf_policy_fwd_args*
     // emits the GEMM's A operand pre-split and pre-tiled (all-TMA GEMM); MAPF_B200_FC_UNSPLIT=1 keeps the plain
     // [rows, fc_in] hand-over with conversion warps in the GEMM (development switch).
     mapf_encoder_fwd_args e{rows, a->states, a->packed, a->workspace_act};
-    const bool unsplit = getenv("MAPF_B200_FC_UNSPLIT") != nullptr;      // development switches, read per call
-    const bool ffma_conv = getenv("MAPF_B200_ENC_FFMA_CONV") != nullptr;
+    const bool unsplit = (a->flags & MAPF_POLICY_FC_UNSPLIT) != 0;      // development switches of the caller
+    const bool ffma_conv = (a->flags & MAPF_POLICY_FFMA_CONV) != 0;
     if (!ffma_conv && !unsplit && mapf_enc_tc_dims_ok(*p)) {
       // conv stack on tcgen05 (activations as the A operand in tensor memory, enc_tc.cu) -> FC operand in pixel-major
       // K order -> all-TMA tcgen05 FC against the matching B operand
@@ -260,15 +259,15 @@ static int policy_fwd_impl(const mapf_net_params* p, const mapf_policy_fwd_args*
   // The fused kernel runs the hops inside its 4 producer warps: right for small teams, too serial for N = 64 where the
   // hops are 37 % of the MACs (measured: C5 987 us unfused vs 1415 us fused; C2a 24.7 vs 18.5 us).
   if (a->agents <= 32 && mapf_tc_graph_supported(a->agents, p->fc_out, p->node_dim, p->taps) &&
-      getenv("MAPF_B200_UNFUSED_GRAPH") == nullptr) {
+      !(a->flags & MAPF_POLICY_UNFUSED_GRAPH)) {
     // fused tensor-core path: S, hops, 3xTF32 tcgen05 mix, ReLU, head, argmax in one kernel
     // gso is an input of this launch sequence: complete before the encoder kernels above were launched
     // Fusing the env step into the graph kernel's tail saves a launch and its prologue: worth it for small launches
     // (a host-stepped episode group: end to end 1.78e8 -> 1.87e8 agent-steps/s at C2a), not for a full resident batch, where
-    // the separate env kernel's many small CTAs finish sooner (2.32e8 against 2.28e8 fused).  MAPF_B200_FUSED_ENV=0 / 1
-    // forces either.
-    const char* fe = getenv("MAPF_B200_FUSED_ENV");
-    const bool want_fused = fe != nullptr ? fe[0] == '1' : rows <= 12288;
+    // the separate env kernel's many small CTAs finish sooner (2.32e8 against 2.28e8 fused).  MAPF_POLICY_FUSED_ENV_ON / _OFF
+    // force either.
+    const bool want_fused = (a->flags & MAPF_POLICY_FUSED_ENV_ON) ? true
+                            : (a->flags & MAPF_POLICY_FUSED_ENV_OFF) ? false : rows <= 12288;
     const bool fuse_env = want_fused && env != nullptr && a->actions != nullptr && env->actions == a->actions &&
                           env->episodes == a->batch && env->agents == a->agents &&
                           mapf_tc_graph_env_fusable(a->agents, env->cell_stride);
@@ -294,6 +293,7 @@ extern "C" int mapf_rollout(const mapf_net_params* p, const mapf_rollout_args* a
   MAPF_REQUIRE(a->policy.actions != nullptr && a->env.actions == a->policy.actions, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->env.fov == a->policy.states && (p->taps == 0 || a->env.adj == a->policy.gso), MAPF_ERR_SHAPE);
   MAPF_REQUIRE(a->env.episodes == a->policy.batch && a->env.agents == a->policy.agents, MAPF_ERR_SHAPE);
+  const MapfPdlScope pdl_scope((a->policy.flags & MAPF_POLICY_NO_PDL) != 0);   // covers the env step launches too
   for (int t = 0; t < a->steps; ++t) {
     mapf_env_step_args e = a->env;
     e.do_move = 1 | 4;   // 4: boards / positions are older than the policy kernels in front (see env_step_kernel)

@@ -169,11 +169,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
         if (c < nchunks && grow < g.M) {
           const float* p = g.A + int64_t(grow) * g.lda;
           if (gk + 3 < g.K) {
-            v[it] = __ldg(reinterpret_cast<const float4*>(p + gk));
+            v[it] = mapf_ld_dep(reinterpret_cast<const float4*>(p + gk));
           } else {
-            if (gk + 0 < g.K) v[it].x = __ldg(p + gk + 0);
-            if (gk + 1 < g.K) v[it].y = __ldg(p + gk + 1);
-            if (gk + 2 < g.K) v[it].z = __ldg(p + gk + 2);
+            if (gk + 0 < g.K) v[it].x = mapf_ld_dep(p + gk + 0);
+            if (gk + 1 < g.K) v[it].y = mapf_ld_dep(p + gk + 1);
+            if (gk + 2 < g.K) v[it].z = mapf_ld_dep(p + gk + 2);
           }
         }
       }
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
       float rs = 1.0f;   // fp16-split operands: undo the row's and the matrix' power-of-two scales
       if (F16) {
         const int row = m0 + quad * 32 + lane;
-        rs = (row < g.M ? __ldg(g.row_scale + row) : 0.0f) * __ldg(g.b_hdr);
+        rs = (row < g.M ? mapf_ld_dep(g.row_scale + row) : 0.0f) * __ldg(g.b_hdr);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
     const int el = idx / (N * N), rem = idx - el * N * N;
     const int i = rem / N, j = rem - i * N;
-    float v = __ldg(g.gso + int64_t(e0 + el) * N * N + rem);
+    float v = mapf_ld_dep(g.gso + int64_t(e0 + el) * N * N + rem);
     if (g.add_self_loop && i == j) v += 1.0f;
     sm[idx] = v;
   }
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
         hi4[i] = lo4[i];
         if (rlive[i] && j < slices) {
           const float4* src = reinterpret_cast<const float4*>(g.x + (row0 + rr[i]) * F + 8 * j);
-          lo4[i] = __ldg(src);
-          hi4[i] = __ldg(src + 1);
+          lo4[i] = mapf_ld_dep(src);
+          hi4[i] = mapf_ld_dep(src + 1);
         }
       }
     };
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
             float v = 0.0f;
             if (rlive[i]) {
               const int q = rjl[i] * F + 8 * j + f;
-              v = __ldg(g.x + (row0 + rep[i] * N + (q % N)) * F + (q / N));
+              v = mapf_ld_dep(g.x + (row0 + rep[i] * N + (q % N)) * F + (q / N));
             }
             sv[i][f] = v;
           }
@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
-  if (ENVL > 0) env_step_finish<kEL, kTgThreads>(g.env, e0, nep, tid, s_boards, s_env, env_ag, s_act);
+  // the operand stages are idle now (every MMA has completed): they stage the observations on their way out
+  if (ENVL > 0)
+    env_step_finish<kEL, kTgThreads>(g.env, e0, nep, tid, s_boards, s_env, env_ag, s_act, reinterpret_cast<float*>(stages));
 }
 
 }  // namespace
@@ -363,7 +365,8 @@ int mapf_tc_graph_env_fusable(int32_t agents, int32_t cell_stride) {
   if (agents < 1 || agents > 8) return 0;
   const int lanes = agents <= 8 ? 8 : agents <= 16 ? 16 : 32;
   const int epc = kTgM / agents;
-  return epc * lanes <= kTgThreads && size_t(epc) * cell_stride <= 64 * 1024;
+  return epc * lanes <= kTgThreads && size_t(epc) * cell_stride <= 64 * 1024 &&
+         size_t(env_stage_floats(epc, agents)) * sizeof(float) <= size_t(kTgProd) * kTgStageBytes;
 }
 
 // gso_is_old = 1 (mapf_policy_fwd behind its encoder kernels): see TcGraphArgs.  env != NULL (mapf_rollout): the env step
@@ -388,7 +391,7 @@ int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t
     MAPF_REQUIRE(mapf_tc_graph_env_fusable(agents, env->cell_stride) && gso_is_old, MAPF_ERR_UNSUPPORTED);
     envl = agents <= 8 ? 8 : agents <= 16 ? 16 : 32;
     g.env = *env;
-    smem += sizeof(int32_t) * kTgM + 4096 /* EnvShared (3.7 KB at most), rounded up */ + size_t(epc) * env->cell_stride;
+    smem += sizeof(int32_t) * kTgM + ((sizeof(EnvShared<8, kTgThreads>) + 15) & ~size_t(15)) + size_t(epc) * env->cell_stride;
   }
   MAPF_REQUIRE(smem <= 227 * 1024, MAPF_ERR_UNSUPPORTED);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
   const int n = blockIdx.y, b0 = blockIdx.x * 32;
   const int nb = min(32, B - b0);
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
-  for (int i = tid; i < cout * cin * 9; i += kCtThreads) s_w[i] = __ldg(wpk + i);
+  for (int i = tid; i < cout * cin * 9; i += kCtThreads) s_w[i] = mapf_ld_dep(wpk + i);
   {
     // staging: every element is its own 4-byte cp.async (coalesced reads, transposing conflict-free writes), all of a
     // thread's ~100 copies in flight at once
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kCtThreads) conv_train_kernel(const float* __r
     float2 acc[2][kFovCells];   // channel pairs (4cog, 4cog+1), (4cog+2, 4cog+3): one FFMA2 each per tap
     {
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias) + cog);
+      if (bias != nullptr) b = mapf_ld_dep(reinterpret_cast<const float4*>(bias) + cog);
 #pragma unroll
       for (int p = 0; p < kFovCells; ++p) { acc[0][p] = make_float2(b.x, b.y); acc[1][p] = make_float2(b.z, b.w); }
     }
@@ -272,7 +272,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __rest
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const uint32_t pl = uint32_t(idx / kFovCells);
     const uint32_t c = pl % uint32_t(C), n = (pl / uint32_t(C)) % uint32_t(N);
-    const float2 ws = __ldg(reinterpret_cast<const float2*>(scale_shift) + (n * C + c));
+    const float2 ws = mapf_ld_dep(reinterpret_cast<const float2*>(scale_shift) + (n * C + c));
     a[idx] = fmaxf(fmaf(u[idx], ws.x, ws.y), 0.0f);
   }
 }
@@ -289,8 +289,8 @@ __global__ void bn_apply4_kernel(const float4* __restrict__ u, const float* __re
     const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
     const float2* tab = reinterpret_cast<const float2*>(scale_shift) + n * C;
     const float4 v = u[idx];
-    const float2 w0 = __ldg(tab + o / kFovCells), w1 = __ldg(tab + (o + 1) / kFovCells);
-    const float2 w2 = __ldg(tab + (o + 2) / kFovCells), w3 = __ldg(tab + (o + 3) / kFovCells);
+    const float2 w0 = mapf_ld_dep(tab + o / kFovCells), w1 = mapf_ld_dep(tab + (o + 1) / kFovCells);
+    const float2 w2 = mapf_ld_dep(tab + (o + 2) / kFovCells), w3 = mapf_ld_dep(tab + (o + 3) / kFovCells);
     a[idx] = make_float4(fmaxf(fmaf(v.x, w0.x, w0.y), 0.0f), fmaxf(fmaf(v.y, w1.x, w1.y), 0.0f),
                          fmaxf(fmaf(v.z, w2.x, w2.y), 0.0f), fmaxf(fmaf(v.w, w3.x, w3.y), 0.0f));
   }
@@ -350,8 +350,8 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restr
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const uint32_t pl = uint32_t(idx / kFovCells);
     const uint32_t c = pl % uint32_t(C), n = (pl / uint32_t(C)) % uint32_t(N);
-    const float2 mi = __ldg(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
-    const float4 k = __ldg(reinterpret_cast<const float4*>(coef) + (n * C + c));
+    const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
+    const float4 k = mapf_ld_dep(reinterpret_cast<const float4*>(coef) + (n * C + c));
     const float dy = a[idx] > 0.0f ? da[idx] : 0.0f;
     const float xhat = (u[idx] - mi.x) * mi.y;
     da[idx] = k.x * (dy - k.y - xhat * k.z);
@@ -374,8 +374,8 @@ __global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t c = (o + j) / kFovCells;
-      const float2 mi = __ldg(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
-      const float4 k = __ldg(reinterpret_cast<const float4*>(coef) + (n * C + c));
+      const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
+      const float4 k = mapf_ld_dep(reinterpret_cast<const float4*>(coef) + (n * C + c));
       const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
       const float xhat = (uu[j] - mi.x) * mi.y;
       r[j] = k.x * (dy - k.y - xhat * k.z);
@@ -599,12 +599,12 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_reduce_kernel(const float
   if (e < tot) {
     int g = warp;
     for (; g + 24 < grid; g += 32) {
-      a0 += __ldg(part + int64_t(g) * tot + e);
-      a1 += __ldg(part + int64_t(g + 8) * tot + e);
-      a2 += __ldg(part + int64_t(g + 16) * tot + e);
-      a3 += __ldg(part + int64_t(g + 24) * tot + e);
+      a0 += mapf_ld_dep(part + int64_t(g) * tot + e);
+      a1 += mapf_ld_dep(part + int64_t(g + 8) * tot + e);
+      a2 += mapf_ld_dep(part + int64_t(g + 16) * tot + e);
+      a3 += mapf_ld_dep(part + int64_t(g + 24) * tot + e);
     }
-    for (; g < grid; g += 8) a0 += __ldg(part + int64_t(g) * tot + e);
+    for (; g < grid; g += 8) a0 += mapf_ld_dep(part + int64_t(g) * tot + e);
   }
   s_sum[warp][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
       int m, k;
       if (a_kfast) { m = e >> 4; k = e & 15; } else { m = e & 127; k = e >> 7; }
       const int gm = m0 + m, gk = k0 + k;
-      ra[i] = (gm < g.M && gk < kend) ? __ldg(g.A + gm * g.sam + gk * g.sak) : 0.0f;
+      ra[i] = (gm < g.M && gk < kend) ? mapf_ld_dep(g.A + gm * g.sam + gk * g.sak) : 0.0f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
       int n, kb;
       if (b_nfast) { n = e & 63; kb = e >> 6; } else { n = e >> 4; kb = e & 15; }
       const int gn = n0 + n, gkb = k0 + kb;
-      rb[i] = (gn < g.N && gkb < kend) ? __ldg(g.B + gkb * g.sbk + gn * g.sbn) : 0.0f;
+      rb[i] = (gn < g.N && gkb < kend) ? mapf_ld_dep(g.B + gkb * g.sbk + gn * g.sbn) : 0.0f;
     }
   };
   auto stash = [&]() {
@@ -712,9 +712,9 @@ __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
       if (g.splits > 1) {
         atomicAdd(g.C + m * g.ldc + n, v);
       } else {
-        if (g.bias) v += __ldg(g.bias + n);
+        if (g.bias) v += mapf_ld_dep(g.bias + n);
         if (g.relu) v = fmaxf(v, 0.0f);
-        if (g.mask) v = __ldg(g.mask + m * g.ldmask + n) > 0.0f ? v : 0.0f;
+        if (g.mask) v = mapf_ld_dep(g.mask + m * g.ldmask + n) > 0.0f ? v : 0.0f;
         g.C[m * g.ldc + n] = v;
       }
     }
@@ -754,9 +754,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ i
     float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (; r + 7 * step < rows; r += 8 * step) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) part[q] += __ldg(in + (r + q * step) * C + c);
+      for (int q = 0; q < 8; ++q) part[q] += mapf_ld_dep(in + (r + q * step) * C + c);
     }
-    for (; r < rows; r += step) part[0] += __ldg(in + r * C + c);
+    for (; r < rows; r += step) part[0] += mapf_ld_dep(in + r * C + c);
     s = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
   }
   s_part[tid] = rl < per ? s : 0.0f;
@@ -788,11 +788,11 @@ __global__ void __launch_bounds__(128) recurrence_bwd_kernel(const float* __rest
   const int tid = threadIdx.x, e = blockIdx.x;
   for (int idx = tid; idx < N * N; idx += 128) {
     const int i = idx / N, j = idx - i * N;
-    float v = __ldg(gso + int64_t(e) * N * N + idx);
+    float v = mapf_ld_dep(gso + int64_t(e) * N * N + idx);
     if (add_self_loop && i == j) v += 1.0f;
     sm[idx] = v;
   }
-  for (int idx = tid; idx < N * KT; idx += 128) d[idx] = __ldg(dz + int64_t(e) * N * KT + idx);
+  for (int idx = tid; idx < N * KT; idx += 128) d[idx] = mapf_ld_dep(dz + int64_t(e) * N * KT + idx);
   __syncthreads();
   if (tid < N) {
     float deg = 0.0f;
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(128) recurrence_bwd_kernel(const float* __rest
       const int q = f * N + i;  // X[b,f,n] sits at flat f*N+n = n'*F + f' of the reshaped [N,F] view
       v += d[(q / F) * KT + K * F + (q % F)];
     }
-    if (x != nullptr && !(__ldg(x + (int64_t(e) * N + i) * F + f) > 0.0f)) v = 0.0f;
+    if (x != nullptr && !(mapf_ld_dep(x + (int64_t(e) * N + i) * F + f) > 0.0f)) v = 0.0f;
     dx[int64_t(e) * dx_sb + int64_t(i) * dx_sn + int64_t(f) * dx_sf] = v;
   }
 }
@@ -837,7 +837,7 @@ __global__ void bcn_to_rows_kernel(const float* __restrict__ in, int B, int C, i
     const int64_t r = idx / C;
     const int n = int(r % N);
     const int64_t b = r / N;
-    out[idx] = __ldg(in + (b * C + c) * N + n);
+    out[idx] = mapf_ld_dep(in + (b * C + c) * N + n);
   }
 }
 
@@ -989,7 +989,7 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   MAPF_TRY(mapf_launch_status());
   const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
   // compressMLP: x = relu(a_L Wfc^T + b)
-  if (F <= 128 && (fin & 3) == 0 && getenv("MAPF_B200_TRAIN_FFMA_FC") == nullptr) {
+  if (F <= 128 && (fin & 3) == 0 && !(a->flags & MAPF_TRAIN_FFMA_FC)) {
     // 3xTF32 tcgen05 GEMM on the current weights (re-packed every step: 100 KB)
     MAPF_TRY(mapf_tc_pack_b(p->fc_w, fin, nullptr, 0, F, ws + T.fcpk, stream));
     MAPF_TRY(mapf_tc_gemm(int32_t(rows), F, fin, ws + T.a[L - 1], fin, ws + T.fcpk, ws + T.x, F, p->fc_b, 1, stream));
@@ -1012,7 +1012,7 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   g.logits = a->logits; g.actions = nullptr;
   const int KT = (p->taps + (a->message ? 1 : 0)) * F;
   const bool tensor_path = N <= 64 && p->node_dim <= 128 && (p->node_dim & 15) == 0 && (F & 3) == 0 &&
-                           mapf_aligned(p->act_w, 16) && getenv("MAPF_B200_TRAIN_FFMA_GRAPH") == nullptr;
+                           mapf_aligned(p->act_w, 16) && !(a->flags & MAPF_TRAIN_FFMA_GRAPH);
   if (tensor_path) {
     // filter taps Z (saved for the weight gradient) + 3xTF32 tcgen05 mix with relu(Y) stored for the backward pass
     MAPF_TRY(mapf_tc_pack_b(p->gf_w, p->taps * F, a->message ? p->gf_w2 : nullptr, a->message ? F : 0, p->node_dim,

@@ -56,6 +56,7 @@ class BatchedGraphEnv:
         self.max_time = int(config["max_time"])
         self.sensing_range = sensing_range
         self.d2_limit = d2_limit_from_range(sensing_range)
+        self.episodes_per_cta = 0        # work decomposition of the step kernel: 0 = the library's choice
         goals = torch.as_tensor(np.asarray(goals)) if not torch.is_tensor(goals) else goals
         if goals.dim() != 3 or goals.shape[1] != self.nb_agents or goals.shape[2] != 2:
             raise ValueError(f"goals must be [E,{self.nb_agents},2], got {tuple(goals.shape)}")
@@ -102,6 +103,7 @@ class BatchedGraphEnv:
         a.pos, a.goal, a.actions = _lib.ptr(self.pos), _lib.ptr(self.goal), _lib.ptr(actions)
         a.cells, a.time, a.done = _lib.ptr(self.cells), _lib.ptr(self.time), _lib.ptr(self.done)
         a.fov, a.adj = _lib.ptr(self.fov), _lib.ptr(self.adj_matrix)
+        a.episodes_per_cta = self.episodes_per_cta
         return a
 
     # -- reference: GraphEnv.getObservations, env_graph_gridv1.py:97-106 ------------------------
@@ -187,22 +189,78 @@ class GraphEnv:
         self.positionX_temp, self.positionY_temp = self.positionX.copy(), self.positionY.copy()
         return self.getObservations()
 
-    def _pull(self):
-        pos = self._env.pos[0].cpu().numpy()
-        self.positionX, self.positionY = pos[:, 0].copy(), pos[:, 1].copy()
+    def _pull(self, positions=True):
+        if positions:
+            pos = self._env.pos[0].cpu().numpy()
+            self.positionX, self.positionY = pos[:, 0].copy(), pos[:, 1].copy()
         self.board = self._env.board()[0].cpu().numpy().astype(np.float64)
         self.adj_matrix = self._env.adj_matrix[0].cpu().numpy().astype(np.float64)
         self.distance_matrix = self.adj_matrix
         self._fov = self._env.fov[0].cpu().numpy().astype(np.float64)
         self.time = int(self._env.time[0].item())
 
+    # ``positionX / positionY / positionX_temp / positionY_temp`` are host-writable like the reference's attributes
+    # (tests/test_env.py:97-121,164-194 poke them): every kernel call below first uploads the host values.
+    def _host_pos(self, x, y):
+        return torch.from_numpy(np.stack([np.asarray(x).reshape(-1), np.asarray(y).reshape(-1)], axis=1)
+                                .astype(np.int32)).reshape(1, self.nb_agents, 2)
+
+    def _push(self):
+        self._env.pos.copy_(self._host_pos(self.positionX, self.positionY))
+
+    def _apply_rules(self, stages):
+        env = self._env
+        self._push()
+        temp = self._host_pos(self.positionX_temp, self.positionY_temp).to(env.device)
+        a = _lib.EnvRulesArgs()
+        a.episodes, a.agents, a.board, a.cell_stride, a.stages = 1, self.nb_agents, self.board_size, env.cell_stride, stages
+        a.pos, a.pos_temp, a.cells = _lib.ptr(env.pos), _lib.ptr(temp), _lib.ptr(env.cells)
+        with torch.cuda.device(env.device):
+            _lib.check(env.lib.mapf_env_apply_rules(a, _lib.current_stream()), "env_apply_rules")
+        pos = env.pos[0].cpu().numpy()
+        self.positionX, self.positionY = pos[:, 0].copy(), pos[:, 1].copy()
+
+    def check_collision_obstacle(self):
+        """env_graph_gridv1.py:303-313: candidates inside the obstacle set revert to positionX/Y_temp."""
+        self._apply_rules(1)
+
+    def check_boundary(self):
+        """env_graph_gridv1.py:267-271: clamp to the board."""
+        self._apply_rules(2)
+
+    def check_collisions(self):
+        """env_graph_gridv1.py:282-301: every member of a shared cell reverts to positionX/Y_temp (single pass)."""
+        self._apply_rules(4)
+
+    def check_goals(self):
+        """env_graph_gridv1.py:161-166 is a value no-op (agents at their goal are not frozen)."""
+
+    def updateBoard(self):
+        """env_graph_gridv1.py:273-275 on the device board: old cells <- 0, new cells <- 1 (obstacle-set flag kept)."""
+        env, H = self._env, self.board_size
+        old = torch.as_tensor(np.asarray(self.positionY_temp).reshape(-1) * H + np.asarray(self.positionX_temp).reshape(-1),
+                              device=env.device, dtype=torch.long)
+        new = torch.as_tensor(np.asarray(self.positionY).reshape(-1) * H + np.asarray(self.positionX).reshape(-1),
+                              device=env.device, dtype=torch.long)
+        env.cells[0, old] &= 0x80
+        env.cells[0, new] = (env.cells[0, new] & 0x80) | 1
+        self.board = env.board()[0].cpu().numpy().astype(np.float64)
+
+    def _computeDistance(self):
+        """env_graph_gridv1.py:117-136 (+ _computeClosest :174-181) for the current host positions."""
+        self._push()
+        self._env.observe()
+        self._pull(positions=False)
+
     def getObservations(self):
-        board = self.board.copy()
-        board[self.goal[:, 1], self.goal[:, 0]] += 4          # updateBoardGoal :277-280
-        return {"board": board, "fov": self._fov, "adj_matrix": self.adj_matrix, "distances": self.distance_matrix,
-                "embeddings": self.embedding}
+        return {"board": self._board_with_goals(), "fov": self.preprocessObs(), "adj_matrix": self.adj_matrix,
+                "distances": self.distance_matrix, "embeddings": self.embedding}
 
     def preprocessObs(self):
+        """env_graph_gridv1.py:248-265 for the current host positions and the current board."""
+        self._push()
+        self._env.observe()
+        self._fov = self._env.fov[0].cpu().numpy().astype(np.float64)
         return self._fov
 
     def getGraph(self):
@@ -215,19 +273,32 @@ class GraphEnv:
         return np.array([self.positionX, self.positionY]).T
 
     def step(self, actions, emb=None):
+        """env_graph_gridv1.py:183-198.  Like the reference, the env itself never freezes: agents keep moving and the
+        clock keeps running after all of them reached their goals (only the callers stop, evaluate.py:251)."""
         if emb is not None:
             self.embedding = emb
-        self.positionX_temp, self.positionY_temp = self.positionX.copy(), self.positionY.copy()
-        self._env.step(np.asarray(actions).reshape(1, self.nb_agents))
+        self._push()
+        self.positionX_temp, self.positionY_temp = np.array(self.positionX).copy(), np.array(self.positionY).copy()
+        self._env.step(np.asarray(actions).reshape(1, self.nb_agents), freeze_done=False)
         self._pull()
-        return self.getObservations(), {}, self.checkAllInGoal(), {}
+        obs = {"board": self._board_with_goals(), "fov": self._fov, "adj_matrix": self.adj_matrix,
+               "distances": self.distance_matrix, "embeddings": self.embedding}
+        return obs, {}, self.checkAllInGoal(), {}
+
+    def _board_with_goals(self):
+        board = self.board.copy()
+        board[self.goal[:, 1], self.goal[:, 0]] += 4          # updateBoardGoal :277-280
+        return board
 
     def checkAllInGoal(self):
         return bool(np.array_equal(self.getPositions(), self.goal))
 
     def computeMetrics(self):
+        self._push()
         success, flow = self._env.computeMetrics()
-        return float(success[0].item()), int(flow[0].item())
+        # the kernel's fp32 ratio -> the reference's float64 ratio of the same integer count (tests compare == 0.4)
+        hits = int(round(float(success[0].item()) * self.nb_agents))
+        return hits / self.nb_agents, int(flow[0].item())
 
     def computeFlowTime(self):
         return self.computeMetrics()[1]

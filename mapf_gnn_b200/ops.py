@@ -29,6 +29,31 @@ USE_TENSOR_CORE_ENCODER = os.environ.get("MAPF_B200_TENSOR_CORE_ENCODER", "1") !
 USE_TENSOR_CORE_FC = os.environ.get("MAPF_B200_TENSOR_CORE_FC", "0") == "1"
 
 
+def policy_flags() -> int:
+    """Development switches of the policy launch sequence.  They live HERE (the library never reads the environment)
+    and are read per call: MAPF_B200_ENC_FFMA_CONV / FC_UNSPLIT / UNFUSED_GRAPH / NO_PDL = 1, MAPF_B200_FUSED_ENV = 0|1."""
+    env = os.environ
+    f = 0
+    if env.get("MAPF_B200_ENC_FFMA_CONV"):
+        f |= _lib.POLICY_FFMA_CONV
+    if env.get("MAPF_B200_FC_UNSPLIT"):
+        f |= _lib.POLICY_FC_UNSPLIT
+    if env.get("MAPF_B200_UNFUSED_GRAPH"):
+        f |= _lib.POLICY_UNFUSED_GRAPH
+    if env.get("MAPF_B200_NO_PDL"):
+        f |= _lib.POLICY_NO_PDL
+    fe = env.get("MAPF_B200_FUSED_ENV")
+    if fe:
+        f |= _lib.POLICY_FUSED_ENV_ON if fe[0] == "1" else _lib.POLICY_FUSED_ENV_OFF
+    return f
+
+
+def train_flags() -> int:
+    env = os.environ
+    return (_lib.TRAIN_FFMA_FC if env.get("MAPF_B200_TRAIN_FFMA_FC") else 0) | \
+           (_lib.TRAIN_FFMA_GRAPH if env.get("MAPF_B200_TRAIN_FFMA_GRAPH") else 0)
+
+
 def wants_encoder_workspace(p) -> bool:
     """True when mapf_policy_fwd should get ``workspace_act`` (the pre-split FC operand) for these dimensions."""
     if not USE_TENSOR_CORES:
@@ -119,6 +144,7 @@ def _policy_fwd(dims, message, states, gso, packed):
             workz = torch.empty((B * N, (p.taps + 1) * p.fc_out), dtype=torch.float32, device=dev)
             a.workspace_z = workz.data_ptr()
     a.logits, a.actions = logits.data_ptr(), actions.data_ptr()
+    a.flags = policy_flags()
     with torch.cuda.device(dev):
         _lib.check(lib.mapf_policy_fwd(p, a, _stream()), "policy_fwd")
     return logits, actions

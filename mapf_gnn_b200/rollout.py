@@ -53,6 +53,8 @@ class Rollout:
         p.workspace_z = None if self.workz is None else self.workz.data_ptr()
         p.workspace_act = None if self.worka is None else self.worka.data_ptr()
         p.logits, p.actions = self.logits.data_ptr(), self.actions.data_ptr()
+        from . import ops
+        p.flags = ops.policy_flags()
         a.steps = int(steps)
         return a
 

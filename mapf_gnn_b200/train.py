@@ -74,6 +74,8 @@ def _forward(net, states, gso, ws):
     bns = [m for m in net.convLayers if isinstance(m, torch.nn.BatchNorm2d)]
     for l, bn in enumerate(bns):
         a.bn_batches[l] = bn.num_batches_tracked.data_ptr()
+    from . import ops
+    a.flags = ops.train_flags()
     with torch.cuda.device(states.device):
         _lib.check(lib.mapf_train_forward(p, a, _stream()), "train_forward")
     net._weights_epoch = getattr(net, "_weights_epoch", 0) + 1   # running stats changed behind torch's back

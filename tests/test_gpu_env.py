@@ -177,3 +177,101 @@ def test_device_scenarios_drive_a_rollout():
     for e in range(50):
         ob = orc[e].observe()
         assert np.array_equal(env.fov[e].cpu().numpy(), ob["fov"].astype(np.float32))
+
+
+@pytest.mark.parametrize("E,N,H,M,r", [(67, 5, 18, 5, 6), (41, 20, 32, 40, 6), (9, 64, 64, 200, 6), (13, 33, 24, 20, 5),
+                                       (5, 100, 40, 30, 5), (130, 2, 6, 3, 3)])
+def test_step_decomposition_independent(E, N, H, M, r):
+    """mapf_env_step_args.episodes_per_cta only changes the work decomposition (and whether a CTA's output slices are
+    16-byte aligned, i.e. leave as TMA bulk stores or as the scalar copy): every value gives the oracle's result, and
+    nothing is written behind the observation tensors (NaN canaries)."""
+    import mapf_gnn_b200 as m
+    rng = np.random.default_rng(100 + N)
+    starts, goals, obst = eo.make_scenarios(rng, E, N, H, M)
+    lanes = 8
+    while lanes < N:
+        lanes *= 2
+    actions = rng.integers(0, 5, size=(3, E, N))
+    oracles = [eo.EnvOracle(N, H, goals[e], starts[e], obst[e], sensing_range=r) for e in range(E)]
+    ref = []
+    for t in range(3):
+        ref.append([oracles[e].step(actions[t][e])[0] for e in range(E)])
+    for epb in sorted({0, 1, 2, 3, 4, 5, 128 // lanes}):
+        if epb > 128 // lanes:
+            continue
+        env = m.BatchedGraphEnv(_cfg(N, H), goals, starts, obst, sensing_range=r)
+        env.episodes_per_cta = epb
+        fbuf = torch.full((E * N * 50 + 256,), float("nan"), device="cuda")
+        abuf = torch.full((E * N * N + 256,), float("nan"), device="cuda")
+        env.fov = fbuf[:E * N * 50].view(E, N, 2, 5, 5)
+        env.adj_matrix = abuf[:E * N * N].view(E, N, N)
+        for t in range(3):
+            env.step(actions[t], freeze_done=False)
+            fov, adj = env.fov.cpu().numpy(), env.adj_matrix.cpu().numpy()
+            for e in range(E):
+                assert np.array_equal(fov[e], ref[t][e]["fov"].astype(np.float32)), (epb, t, e)
+                assert np.array_equal(adj[e], ref[t][e]["adj_matrix"].astype(np.float32)), (epb, t, e)
+        assert torch.isnan(fbuf[E * N * 50:]).all() and torch.isnan(abuf[E * N * N:]).all(), epb
+    env = m.BatchedGraphEnv(_cfg(N, H), goals, starts, obst, sensing_range=r)
+    env.episodes_per_cta = 128 // lanes + 1
+    with pytest.raises(RuntimeError):
+        env.observe()
+
+
+def test_facade_keeps_stepping_after_done(env_cases):
+    """The reference GraphEnv never freezes itself (env_graph_gridv1.py:183-198: only its callers break on done): the
+    facade must follow the golden trace THROUGH and PAST the step at which all agents are on their goals."""
+    import mapf_gnn_b200 as m
+    c = env_cases["goalrun_3a_8"]
+    n, h, mm, T, max_time = (int(v) for v in c["meta"])
+    env = m.GraphEnv(_cfg(n, h, max_time), goal=c["goals"], starting_positions=c["starts"].copy(),
+                     obstacles=c["obstacles"] if mm else None, sensing_range=float(c["range"][0]))
+    first = int(np.argmax(c["done"]))
+    assert first + 1 < T, "the golden case must continue after done"
+    for t in range(T):
+        obs, _, done, _ = env.step(c["actions"][t], None)
+        assert np.array_equal(env.getPositions(), c["pos"][t + 1]), t
+        assert np.array_equal(obs["fov"], c["fov"][t + 1]), t
+        assert np.array_equal(obs["adj_matrix"], c["adj"][t + 1]), t
+        assert done == bool(c["done"][t]), t
+        assert env.time == t + 1
+
+
+def test_facade_rule_methods_and_writable_positions():
+    """check_collision_obstacle / check_boundary / check_collisions / _computeDistance / computeMetrics on host-written
+    positionX / positionY (the attributes tests/test_env.py:97-121,164-194 poke), against the oracle's closed forms."""
+    import mapf_gnn_b200 as m
+    rng = np.random.default_rng(11)
+    N, H = 12, 9
+    obstacles = np.array([[2, 3], [4, 4], [6, 1], [0, 8]])
+    goals = eo.make_scenarios(rng, 1, N, H, 0)[1][0]
+    env = m.GraphEnv(_cfg(N, H), goal=goals, starting_positions=eo.make_scenarios(rng, 1, N, H, 0)[0][0],
+                     obstacles=obstacles, sensing_range=4)
+    obst_set = set(map(tuple, obstacles.tolist()))
+    for trial in range(20):
+        temp = rng.integers(0, H, size=(N, 2))
+        cand = temp + rng.integers(-2, 3, size=(N, 2))
+        if trial % 3 == 0:
+            cand[: N // 2] = cand[0]                      # many agents in one cell
+        # obstacle rule
+        env.positionX_temp, env.positionY_temp = temp[:, 0].copy(), temp[:, 1].copy()
+        env.positionX, env.positionY = cand[:, 0].copy(), cand[:, 1].copy()
+        env.check_collision_obstacle()
+        want = np.array([temp[i] if tuple(cand[i]) in obst_set else cand[i] for i in range(N)])
+        assert np.array_equal(env.getPositions(), want)
+        # boundary rule
+        env.check_boundary()
+        want = np.clip(want, 0, H - 1)
+        assert np.array_equal(env.getPositions(), want)
+        # collision rule: every member of a shared cell reverts (single pass)
+        env.check_collisions()
+        keys = [tuple(p) for p in want]
+        want2 = np.array([temp[i] if keys.count(keys[i]) > 1 else want[i] for i in range(N)])
+        assert np.array_equal(env.getPositions(), want2)
+        # adjacency of the host-written positions
+        env._computeDistance()
+        adj = eo.adjacency_closed_form(want2, eo.d2_limit_from_range(4))
+        assert np.array_equal(env.adj_matrix, adj.astype(np.float64))
+        assert env.distance_matrix is env.adj_matrix
+        sr, _ = env.computeMetrics()
+        assert abs(sr - float(np.mean(np.all(want2 == goals, axis=1)))) < 1e-7

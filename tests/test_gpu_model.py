@@ -279,38 +279,30 @@ def test_tensor_core_encoder_width_support():
     assert lib.mapf_encoder_tc_supported(net_params([1, 2, 32, 0, 0, 0, 800, 64, 0, 0, 5])) == 0
 
 
-def test_programmatic_dependent_launch_does_not_change_results(tmp_path):
+def test_programmatic_dependent_launch_does_not_change_results(monkeypatch):
     """The step kernels are chained by programmatic dependent launch (griddepcontrol); with the launch attribute switched
-    off (MAPF_B200_NO_PDL=1, read once per process -> a subprocess) a rollout must give bit-identical logits, actions and
-    positions: the early prologues may only touch data that is older than the kernel in front."""
-    import os, subprocess, sys, textwrap
-    script = textwrap.dedent("""
-        import sys, numpy as np, torch
-        sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
-        import mapf_gnn_b200 as m
-        from helpers import load_network, model_config
-        out = {}
-        for name, N in (("gnn_k3", 5), ("baseline", 5), ("gnn_msg_k3", 20)):
-            rng = np.random.default_rng(5)
-            starts, goals, obst = m.make_scenarios(rng, 64, N, 14, 6)
-            env = m.BatchedGraphEnv(model_config(name, N, board_size=[14, 14]), goals, starts, obst, sensing_range=5)
-            ro = m.Rollout(load_network(name, num_agents=N).eval(), env)
-            ro.run(7)
-            torch.cuda.synchronize()
-            out[name + "/logits"] = ro.logits.cpu().numpy(); out[name + "/pos"] = env.pos.cpu().numpy()
-            out[name + "/actions"] = ro.actions.cpu().numpy()
-        np.savez(sys.argv[2], **out)
-    """)
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = {}
-    for tag, extra in (("pdl", {}), ("nopdl", {"MAPF_B200_NO_PDL": "1"})):
-        path = str(tmp_path / f"{tag}.npz")
-        env = dict(os.environ, **extra)
-        env.pop("MAPF_B200_NO_PDL", None) if not extra else None
-        subprocess.run([sys.executable, "-c", script, root, path], check=True, env=env, timeout=300)
-        res[tag] = np.load(path)
-    for k in res["pdl"].files:
-        assert np.array_equal(res["pdl"][k], res["nopdl"][k]), k
+    off (mapf_policy_fwd_args.flags & MAPF_POLICY_NO_PDL; the Python layer maps MAPF_B200_NO_PDL=1 to it per call) a
+    rollout must give bit-identical logits, actions and positions: the early prologues may only touch data that is
+    older than the kernel in front."""
+    import mapf_gnn_b200 as m
+
+    def run(name, N):
+        rng = np.random.default_rng(5)
+        starts, goals, obst = m.make_scenarios(rng, 64, N, 14, 6)
+        env = m.BatchedGraphEnv(model_config(name, N, board_size=[14, 14]), goals, starts, obst, sensing_range=5)
+        ro = m.Rollout(load_network(name, num_agents=N).eval(), env)
+        ro.run(7)
+        torch.cuda.synchronize()
+        return {"logits": ro.logits.cpu().numpy(), "pos": env.pos.cpu().numpy(), "actions": ro.actions.cpu().numpy(),
+                "fov": env.fov.cpu().numpy(), "adj": env.adj_matrix.cpu().numpy()}
+
+    for name, N in (("gnn_k3", 5), ("baseline", 5), ("gnn_msg_k3", 20)):
+        monkeypatch.delenv("MAPF_B200_NO_PDL", raising=False)
+        a = run(name, N)
+        monkeypatch.setenv("MAPF_B200_NO_PDL", "1")
+        b = run(name, N)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (name, k)
 
 
 def test_training_gso_convention_a_plus_i():
@@ -340,19 +332,29 @@ def test_weights_repack_after_update():
     assert torch.allclose(b, a + 1.0, atol=1e-5)
 
 
-def test_rollout_matches_teacher_forced_oracle():
+# name, E, N, H, M, T, seed: gnn_k3 at the C1 shape, the baseline at the C2b shape, the message-passing network at the C3
+# shape (N = 20: separate env kernel behind the fused graph kernel), K = 4 at N = 64 (taps + mix kernels, C5 shape)
+ROLLOUT_CASES = [("gnn_k3", 48, 5, 18, 5, 12, 0), ("baseline", 48, 5, 28, 8, 12, 1), ("gnn_k2", 48, 5, 28, 8, 12, 1),
+                 ("gnn_msg_k3", 24, 20, 32, 40, 10, 2), ("gnn_k4_seed4", 6, 64, 64, 200, 5, 4)]
+
+
+@pytest.mark.parametrize("no_pdl", [False, True])
+@pytest.mark.parametrize("name,E,N,H,M,T,seed", ROLLOUT_CASES)
+def test_rollout_matches_teacher_forced_oracle(name, E, N, H, M, T, seed, no_pdl, monkeypatch):
     """Full on-device rollout (policy -> argmax -> env step) vs oracle env + oracle model, teacher-forced:
     the oracle follows the device's actions; device actions must equal the oracle's argmax wherever the
-    oracle's margin is above the fp32 noise floor, and states must stay bit-identical."""
+    oracle's margin is above the fp32 noise floor, and states must stay bit-identical.  Every network family at its
+    BASELINE shape, with and without programmatic dependent launch (mapf_policy_fwd_args.flags & MAPF_POLICY_NO_PDL)."""
     import mapf_gnn_b200 as m
-    E, N, H, M, T = 48, 5, 18, 5, 12
-    rng = np.random.default_rng(0)
+    if no_pdl:
+        monkeypatch.setenv("MAPF_B200_NO_PDL", "1")
+    rng = np.random.default_rng(seed)
     starts, goals, obst = eo.make_scenarios(rng, E, N, H, M)
-    cfg = model_config("gnn_k3", N, board_size=[H, H])
+    cfg = model_config(name, N, board_size=[H, H])
     env = m.BatchedGraphEnv(cfg, goals, starts, obst, sensing_range=6)
-    net = load_network("gnn_k3").eval()
+    net = load_network(name, num_agents=N).eval()
     ro = m.Rollout(net, env)
-    params = oracle_params("gnn_k3")
+    params = oracle_params(name)
     oracles = [eo.EnvOracle(N, H, goals[e], starts[e], obst[e], sensing_range=6) for e in range(E)]
     obs = [o.observe() for o in oracles]
     alive = np.ones(E, dtype=bool)
@@ -366,12 +368,14 @@ def test_rollout_matches_teacher_forced_oracle():
             ref = mo.forward(params, states, gso).numpy()
         assert rel_err(ro.logits.cpu().numpy()[alive], ref[alive]) < REL
         flips += _check_actions(acts[alive], ref[alive])
-        pos = env.pos.cpu().numpy()
+        pos, fov, adj = env.pos.cpu().numpy(), env.fov.cpu().numpy(), env.adj_matrix.cpu().numpy()
         for e in range(E):
             if not alive[e]:
                 continue
             obs[e], d = oracles[e].step(acts[e])
-            assert np.array_equal(pos[e], oracles[e].positions)
+            assert np.array_equal(pos[e], oracles[e].positions), (t, e)
+            assert np.array_equal(fov[e], obs[e]["fov"].astype(np.float32)), (t, e)
+            assert np.array_equal(adj[e], obs[e]["adj_matrix"].astype(np.float32)), (t, e)
             alive[e] = not d
         assert np.array_equal(env.done.cpu().numpy().astype(bool), ~alive)
     assert flips <= 2
