@@ -553,10 +553,33 @@ def run_mine(args, w):
 
 
 def cpu_train_steps(model, states, gso, targets, steps):
-    """train.py:82-100 on the host through the oracle port: train-mode forward, CE, backward, clip, Adam."""
+    """train.py:82-100 on the host: train-mode forward, CrossEntropyLoss, backward, clip_grad_norm_(1.0), Adam(3e-4,
+    weight_decay 1e-4) -- with the unmodified reference Network when it is staged (oracle/_ref), else the oracle port."""
     import torch
+    from oracle import ref_loader
+    weights = {k: torch.from_numpy(v) for k, v in load_weights(model).items()}
+    if ref_loader.available():
+        cfg = dict(model_config(dict(model=model, N=int(states.shape[1]), H=18)), device="cpu")
+        net = ref_loader.build_network(cfg)
+        net.load_state_dict(weights)
+        net.train()
+        opt = torch.optim.Adam(net.parameters(), lr=3e-4, weight_decay=1e-4)
+        crit = torch.nn.CrossEntropyLoss()
+        is_gnn = cfg["net_type"] == "gnn"
+        total = 0.0
+        for it in range(steps + 1):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            out = net(states, gso) if is_gnn else net(states)
+            loss = crit(out.reshape(-1, 5), targets.long().reshape(-1))
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+            opt.step()
+            if it > 0:
+                total += time.perf_counter() - t0
+        return states.shape[0] * steps / total, "reference"
     from oracle import model_oracle as mo
-    params = {k: torch.from_numpy(v) for k, v in load_weights(model).items()}
+    params = weights
     keys = mo.trainable_keys(params)
     m = {k: torch.zeros_like(params[k]) for k in keys}
     v = {k: torch.zeros_like(params[k]) for k in keys}
@@ -568,7 +591,7 @@ def cpu_train_steps(model, states, gso, targets, steps):
         params = dict(params, **newp, **{k: t.detach() for k, t in bn.items()})
         if it > 0:
             total += time.perf_counter() - t0
-    return states.shape[0] * steps / total
+    return states.shape[0] * steps / total, "port"
 
 
 def run_train(args, w, env, dev, rank, world, barrier):
@@ -591,7 +614,9 @@ def run_train(args, w, env, dev, rank, world, barrier):
         net = m.build_network(cfg)
         net.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights(model).items()})
         net = net.to(dev).train()
-        trainer = tr.Trainer(net, use_graph=(world == 1 and not args.no_train_graph))
+        trainer = tr.Trainer(net, use_graph=False, peer_allreduce=False if args.nccl_allreduce else None)
+        # the step replays as ONE CUDA graph; with several ranks that needs the peer-memory all-reduce (no NCCL call inside)
+        trainer.use_graph = (not args.no_train_graph) and (world == 1 or trainer.peer is not None)
         reps = (B + env.episodes - 1) // env.episodes
         states = env.fov.repeat(reps, 1, 1, 1, 1)[:B].contiguous()
         gso = (env.adj_matrix + eye).repeat(reps, 1, 1)[:B].contiguous()
@@ -613,11 +638,15 @@ def run_train(args, w, env, dev, rank, world, barrier):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
         entry = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms / steps, "cuda_graph": trainer.use_graph,
+                 "allreduce": None if world == 1 else ("peer-memory one-shot, fused with the gradient norm"
+                                                       if trainer.peer is not None else "nccl"),
                  "samples_per_s": B * world * steps / (ms * 1e-3), "loss": float(loss.item())}
         if rank == 0 and world == 1 and not args.no_cpu_baseline and B <= 1024:
-            entry["cpu_samples_per_s"] = cpu_train_steps(model, states.cpu(), gso.cpu(), targets.cpu().long(), 3)
+            entry["cpu_samples_per_s"], entry["cpu_kind"] = cpu_train_steps(model, states.cpu(), gso.cpu(),
+                                                                            targets.cpu().long(), 3)
         results.append(entry)
-    return {"metric": "train samples/sec (forward + CE + backward + clip + Adam" + (" + NCCL all-reduce)" if world > 1
+        trainer.close()
+    return {"metric": "train samples/sec (forward + CE + backward + clip + Adam" + (" + gradient all-reduce)" if world > 1
                                                                                     else ")"),
             "model": model, "agents": N, "results": results}
 
@@ -642,6 +671,8 @@ def main():
     ap.add_argument("--other-steps", type=int, default=32)
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-train-graph", action="store_true", help="do not replay the training step as a CUDA graph")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="training: NCCL all-reduce of the flat gradient instead of the fused peer-memory kernel")
     ap.add_argument("--train-batches", type=int, nargs="*", default=[128, 1024, 8192])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -354,6 +354,28 @@ typedef struct {
 } mapf_clip_adam_args;
 int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream);
 
+/* Multi-GPU training step (the reference is single-process, train.py:96-100 is the step body this extends):
+ * one-shot all-reduce (mean) of the flat gradient over NVLink PEER MEMORY fused with the gradient-norm reduction, followed
+ * by the same clip + Adam kernel as mapf_clip_adam -- two launches, no NCCL call, capturable in a CUDA graph.
+ * Every rank passes peer-mapped pointers to all ranks' published gradient buffers of this step and to all ranks' flag
+ * blocks (int32[16], zero-initialised: [0..7] arrival epochs written by the peers, [8] the owner's epoch counter).  The
+ * caller alternates between two gradient buffers per rank from step to step (see train_kernels.cu).  a->grads receives
+ * the averaged gradient (then scaled by the clip coefficient, as in mapf_clip_adam).  A peer that never arrives traps the
+ * kernel after ~10 s instead of hanging the GPU. */
+typedef struct {
+  int32_t world, rank;          /* world <= 8 */
+  const float* peer_grads[8];   /* [world] a->n floats each, 16-byte aligned; [rank] = this rank's own buffer */
+  int32_t* peer_flags[8];       /* [world] flag blocks; [rank] = this rank's own */
+} mapf_peer_reduce_args;
+int mapf_peer_reduce_clip_adam(const mapf_peer_reduce_args* r, const mapf_clip_adam_args* a, mapf_stream_t stream);
+/* Peer-mapped device memory by CUDA IPC -- the only entry points that allocate: mapf_peer_alloc returns zeroed device
+ * memory and its 64-byte IPC handle (to be sent to the other ranks, e.g. with an all-gather); mapf_peer_open maps another
+ * process' handle into this process (peer access enabled lazily); close / free undo them. */
+int mapf_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle);
+int mapf_peer_open(const uint8_t* handle, void** ptr);
+int mapf_peer_close(void* ptr);
+int mapf_peer_free(void* ptr);
+
 /* Backward of the standalone GCNLayer / MessagePassingLayer (gnn.py:72-126,178-235) in the reference
  * layouts: x [B,F,N], dy [B,G,N] -> dx [B,F,N], dw [F,K,G], dw2 [F,G] (w2/dw2 NULL for GCNLayer).
  * workspace: mapf_graph_filter_bwd_workspace_size(B, N, F, G, K, has_skip) floats. */

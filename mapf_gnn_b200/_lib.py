@@ -114,6 +114,10 @@ class ClipAdamArgs(C.Structure):
                 ("grad_norm", c_f32p), ("scratch", C.c_void_p), ("step_dev", C.c_void_p), ("lr_dev", C.c_void_p)]
 
 
+class PeerReduceArgs(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("peer_grads", C.c_void_p * 8), ("peer_flags", C.c_void_p * 8)]
+
+
 class GraphFilterBwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
                 ("taps", C.c_int32), ("add_self_loop", C.c_int32),
@@ -151,6 +155,11 @@ _SIGNATURES = {
     "mapf_train_backward": (C.c_int, [C.POINTER(NetParams), C.POINTER(TrainBwdArgs), C.c_void_p]),
     "mapf_ce_loss": (C.c_int, [C.POINTER(CeLossArgs), C.c_void_p]),
     "mapf_clip_adam": (C.c_int, [C.POINTER(ClipAdamArgs), C.c_void_p]),
+    "mapf_peer_reduce_clip_adam": (C.c_int, [C.POINTER(PeerReduceArgs), C.POINTER(ClipAdamArgs), C.c_void_p]),
+    "mapf_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "mapf_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mapf_peer_close": (C.c_int, [C.c_void_p]),
+    "mapf_peer_free": (C.c_int, [C.c_void_p]),
     "mapf_graph_filter_bwd_workspace_size": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                           C.c_int32]),
     "mapf_graph_filter_bwd": (C.c_int, [C.POINTER(GraphFilterBwdArgs), C.c_void_p]),

@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
   const uint32_t tlane = tmem + (uint32_t(quad * 32) << 16);            // this warp's 32 lanes
   uint64_t* const bar = &s_bar[wg];
   uint32_t phase = 0;
+  // warp-uniform copies for the MMA-issuing warp (lane 0's values, which ptxas can keep in uniform registers)
+  const bool issuer_warp = __shfl_sync(0xffffffffu, quad, 0) == 0;
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
   // lanes of a warp = one image, rows six lanes apart: lane 1 + 6y + x holds pixel (y, x); lanes 0, 6, 12, 18, 24, 30, 31 hold
   // zeros, so the left / right neighbour of a border pixel is a zero lane and the horizontal exchange needs no masks
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
   constexpr int kRow = kFov + 1;                                         // lanes between vertically adjacent pixels
 
   constexpr uint32_t idesc = tc::idesc_f16(128, kEtN);
-  const uint32_t w_base = tc::smem_u32(s_w);
+  const uint32_t w_base_u = __shfl_sync(0xffffffffu, tc::smem_u32(s_w), 0);
   const int64_t ntiles = (g.rows + 3) >> 2;
   const int64_t stride = int64_t(gridDim.x) * kEtGroups;
 
@@ -290,26 +293,29 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
       tc::fence_before_sync();
       wg_sync();                         // every lane's A row is in TMEM, every read of D is done
       ETC_STAMP(1);
-      if (quad == 0 && lane == 0) {
+      if (issuer_warp) {
         // ONE thread issues the layer's MMAs in a fixed order: the accumulation order -- and with it every bit of the
         // result -- is the same on every run.  (Dealing the MMAs over the group's four warps shortens this phase by
-        // a quarter, one thread issues only about one MMA per 100 cycles, but the pipe then accumulates in arrival
-        // order and results differ in the last bit from run to run.)
+        // a quarter, but the pipe then accumulates in arrival order and results differ in the last bit from run to run.)
+        // The whole warp enters this (warp-uniform) branch and elect.sync picks the issuing lane: every operand below is
+        // then a uniform-register value and ptxas emits plain UTCHMMAs -- behind a divergent `lane == 0` branch it wraps
+        // each MMA in an ELECT / R2UR.BROADCAST loop that costs ~100 clocks per instruction.
         tc::fence_after_sync();
         ETC_STAMP(6);
         const int ksteps = int(s_lnm[l]);
-        const uint32_t wl = w_base + s_lw[l] + uint32_t(half * ksteps) * (2 * kEtBlk * 4);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t bh = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4), 128, 256);
-          const uint64_t bl = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + kEtBlk * 4, 128, 256);
-          const uint32_t ah = tmem + kEtColAHi + uint32_t(ks) * 8, al = tmem + kEtColALo + uint32_t(ks) * 8;
-          mma_f16_ts(tmem, al, bh, idesc, ks > 0);     // small terms first
-          mma_f16_ts(tmem, ah, bl, idesc, true);
-          mma_f16_ts(tmem, ah, bh, idesc, true);
+        const uint32_t wl = w_base_u + s_lw[l] + uint32_t(half * ksteps) * (2 * kEtBlk * 4);
+        if (tc::elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t bh = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4), 128, 256);
+            const uint64_t bl = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + kEtBlk * 4, 128, 256);
+            const uint32_t ah = tmem_u + kEtColAHi + uint32_t(ks) * 8, al = tmem_u + kEtColALo + uint32_t(ks) * 8;
+            mma_f16_ts(tmem_u, al, bh, idesc, ks > 0);     // small terms first
+            mma_f16_ts(tmem_u, ah, bl, idesc, true);
+            mma_f16_ts(tmem_u, ah, bh, idesc, true);
+          }
+          tc::mma_commit(bar);
         }
         ETC_STAMP(7);
-        tc::mma_commit(bar);
-        ETC_STAMP(8);
       }
       __syncwarp();
       tc::mbar_wait(bar, phase);

@@ -27,6 +27,19 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync): the branch it guards stays warp-uniform for ptxas
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -891,9 +891,85 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
-__global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, float bc1, float bc2_sqrt) {
+// One-shot gradient all-reduce over NVLink peer memory, fused with the gradient-norm reduction (47.8 k - 64.2 k
+// floats, pure latency).  Every rank publishes its flat gradient in a peer-mapped buffer; this kernel (same launch on every
+// rank, no NCCL call, capturable in a CUDA graph) signals "my gradient of epoch e is complete" into every peer's flag
+// array, waits for all peers' signals, then every CTA sums its slice of ALL ranks' buffers in rank order (identical
+// bits on every rank), scales by 1 / world, writes the averaged gradient to the local buffer clip_adam_kernel reads and
+// accumulates its squared norm.  Two gradient buffers alternate by step parity: a rank that races ahead writes the other
+// buffer, and cannot reach the step after that before every peer has signalled the next epoch, i.e. finished reading.
+struct PeerReduceArgs {
+  int world, rank;
+  int64_t n;                 // floats, multiple of 4
+  const float* grads[8];     // peer-mapped gradient buffers of this step's parity ([rank] = own)
+  int32_t* flags[8];         // peer-mapped flag blocks: int32[8] arrival epochs + [8] = the owner's epoch counter
+  float* out;                // local averaged gradient
+  double* sumsq;
+  int32_t* step_dev;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {   // never from a stale L1 line
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) peer_reduce_sumsq_kernel(PeerReduceArgs a) {
+  mapf_pdl_wait();   // the backward kernels in front have completed: the local gradient is final
+  mapf_pdl_launch();
+  int32_t* const mine = a.flags[a.rank];
+  const int epoch = ld_acquire_sys(mine + 8) + 1;   // incremented by the clip_adam kernel behind this one
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0 && a.step_dev != nullptr) *a.step_dev += 1;   // read by the next kernel
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(a.flags[threadIdx.x] + a.rank, epoch);
+    }
+  }
+  if (threadIdx.x < a.world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine + threadIdx.x) < epoch) {
+      __nanosleep(64);
+      if (clock64() - t0 > 20000000000LL) asm volatile("trap;");   // ~10 s: a missing peer must not hang the GPU
+    }
+  }
+  __syncthreads();
+  const float inv = 1.0f / float(a.world);
+  double s = 0.0;
+  for (int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 4; i < a.n; i += int64_t(gridDim.x) * blockDim.x * 4) {
+    float4 acc = ld_peer_v4(a.grads[0] + i);
+    for (int r = 1; r < a.world; ++r) {
+      const float4 v = ld_peer_v4(a.grads[r] + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    *reinterpret_cast<float4*>(a.out + i) = acc;
+    s += double(acc.x) * acc.x + double(acc.y) * acc.y + double(acc.z) * acc.z + double(acc.w) * acc.w;
+  }
+  s = warp_sum(s);
+  __shared__ double s_s[8];
+  if ((threadIdx.x & 31) == 0) s_s[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_s[w];
+    atomicAdd(a.sumsq, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, float bc1, float bc2_sqrt,
+                                                        int32_t* epoch_inc) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
   mapf_pdl_launch();
+  if (epoch_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *epoch_inc += 1;   // peer all-reduce epoch
   if (a.step_dev != nullptr) {   // device-resident step count (CUDA-graph replay): bias corrections computed here
     const double t = double(*a.step_dev);
     bc1 = float(1.0 - pow(double(a.beta1), t));
@@ -1162,8 +1238,66 @@ extern "C" int mapf_clip_adam(const mapf_clip_adam_args* a, mapf_stream_t stream
   mapf_launch_pdl(sumsq_kernel, dim3(blocks), dim3(256), 0, s, a->grads, a->n, a->scratch, a->step_dev);
   const double bc1 = 1.0 - pow(double(a->beta1), double(a->step));
   const double bc2 = 1.0 - pow(double(a->beta2), double(a->step));
-  mapf_launch_pdl(clip_adam_kernel, dim3(blocks), dim3(256), 0, s, *a, float(bc1), float(sqrt(bc2)));
+  mapf_launch_pdl(clip_adam_kernel, dim3(blocks), dim3(256), 0, s, *a, float(bc1), float(sqrt(bc2)),
+                  static_cast<int32_t*>(nullptr));
   return mapf_launch_status();
+}
+
+extern "C" int mapf_peer_reduce_clip_adam(const mapf_peer_reduce_args* r, const mapf_clip_adam_args* a,
+                                          mapf_stream_t stream) {
+  MAPF_REQUIRE(r && a && a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->grad_norm && a->scratch, MAPF_ERR_NULL);
+  MAPF_REQUIRE(r->world >= 1 && r->world <= 8 && r->rank >= 0 && r->rank < r->world, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(a->n > 0 && (a->n & 3) == 0 && (a->step >= 1 || a->step_dev != nullptr), MAPF_ERR_SHAPE);
+  PeerReduceArgs k{};
+  k.world = r->world; k.rank = r->rank; k.n = a->n;
+  for (int i = 0; i < r->world; ++i) {
+    MAPF_REQUIRE(r->peer_grads[i] && r->peer_flags[i], MAPF_ERR_NULL);
+    MAPF_REQUIRE(mapf_aligned(r->peer_grads[i], 16), MAPF_ERR_ALIGN);
+    k.grads[i] = r->peer_grads[i];
+    k.flags[i] = r->peer_flags[i];
+  }
+  MAPF_REQUIRE(mapf_aligned(a->grads, 16), MAPF_ERR_ALIGN);
+  k.out = a->grads; k.sumsq = a->scratch; k.step_dev = a->step_dev;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(a->scratch, 0, sizeof(double), s) != cudaSuccess) return MAPF_ERR_CUDA;
+  const int blocks = int(mapf_min64((a->n / 4 + 255) / 256, 148));
+  mapf_launch_pdl(peer_reduce_sumsq_kernel, dim3(blocks), dim3(256), 0, s, k);
+  const double bc1 = 1.0 - pow(double(a->beta1), double(a->step));
+  const double bc2 = 1.0 - pow(double(a->beta2), double(a->step));
+  const int ablocks = int(mapf_min64((a->n + 255) / 256, 148));
+  mapf_launch_pdl(clip_adam_kernel, dim3(ablocks), dim3(256), 0, s, *a, float(bc1), float(sqrt(bc2)),
+                  r->peer_flags[r->rank] + 8);
+  return mapf_launch_status();
+}
+
+// Peer-mapped device buffers (CUDA IPC): the only entry points of the library that allocate.
+extern "C" int mapf_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle) {
+  MAPF_REQUIRE(ptr && handle, MAPF_ERR_NULL);
+  MAPF_REQUIRE(bytes > 0, MAPF_ERR_SHAPE);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  void* p = nullptr;
+  if (cudaMalloc(&p, size_t(bytes)) != cudaSuccess) { (void)cudaGetLastError(); return MAPF_ERR_CUDA; }
+  if (cudaMemset(p, 0, size_t(bytes)) != cudaSuccess) { (void)cudaGetLastError(); cudaFree(p); return MAPF_ERR_CUDA; }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { (void)cudaGetLastError(); cudaFree(p); return MAPF_ERR_CUDA; }
+  memcpy(handle, &h, 64);
+  *ptr = p;
+  return MAPF_OK;
+}
+extern "C" int mapf_peer_open(const uint8_t* handle, void** ptr) {
+  MAPF_REQUIRE(ptr && handle, MAPF_ERR_NULL);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  if (cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); return MAPF_ERR_CUDA; }
+  return MAPF_OK;
+}
+extern "C" int mapf_peer_close(void* ptr) {
+  if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) { (void)cudaGetLastError(); return MAPF_ERR_CUDA; }
+  return MAPF_OK;
+}
+extern "C" int mapf_peer_free(void* ptr) {
+  if (ptr && cudaFree(ptr) != cudaSuccess) { (void)cudaGetLastError(); return MAPF_ERR_CUDA; }
+  return MAPF_OK;
 }
 
 extern "C" int64_t mapf_graph_filter_bwd_workspace_size(int32_t batch, int32_t agents, int32_t in_dim, int32_t out_dim,

@@ -75,6 +75,21 @@ _LIB.define("env_step(Tensor(a!) pos, Tensor goal, Tensor? actions, Tensor(b!) c
             "Tensor(d!) done, Tensor(e!) fov, Tensor(f!) adj, int board, int d2_limit, bool do_move) -> ()")
 
 
+# training step (train.py:82-100): forward / backward of the train-mode network, cross-entropy, clip + Adam
+_PARAM_SCHEMA = ("Tensor[] conv_w, Tensor[] conv_b, Tensor[] bn_gamma, Tensor[] bn_beta, {m}[] bn_mean, {v}[] bn_var, "
+                 "Tensor fc_w, Tensor fc_b, Tensor? gf_w, Tensor? gf_w2, Tensor act_w, Tensor act_b")
+_LIB.define("train_fwd(int[] dims, bool message, Tensor states, Tensor? gso, "
+            + _PARAM_SCHEMA.format(m="Tensor(a!)", v="Tensor(b!)")
+            + ", Tensor(c!)[] bn_batches, Tensor(d!) workspace, int flags) -> Tensor")
+_LIB.define("train_bwd(int[] dims, bool message, Tensor states, Tensor? gso, "
+            + _PARAM_SCHEMA.format(m="Tensor", v="Tensor")
+            + ", Tensor(a!) workspace, Tensor dlogits, Tensor(b!)[] grads) -> ()")
+_LIB.define("ce_loss(Tensor logits, Tensor targets) -> (Tensor, Tensor)")
+_LIB.define("clip_adam(Tensor(a!) params, Tensor(b!) grads, Tensor(c!) exp_avg, Tensor(d!) exp_avg_sq, Tensor(e!) step, "
+            "Tensor lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, "
+            "Tensor(f!) grad_norm, Tensor(g!) scratch) -> ()")
+
+
 def net_params(dims, tensors=None) -> _lib.NetParams:
     p = _lib.NetParams()
     p.num_conv = int(dims[0])
@@ -219,7 +234,122 @@ def _env_step(pos, goal, actions, cells, time, done, fov, adj, board, d2_limit, 
         _lib.check(lib.mapf_env_step(a, _stream()), "env_step")
 
 
+def _train_tensors(conv_w, conv_b, bn_gamma, bn_beta, bn_mean, bn_var, fc_w, fc_b, gf_w, gf_w2, act_w, act_b):
+    return {"conv_w": list(conv_w), "conv_b": list(conv_b), "bn_gamma": list(bn_gamma), "bn_beta": list(bn_beta),
+            "bn_mean": list(bn_mean), "bn_var": list(bn_var), "fc_w": fc_w, "fc_b": fc_b, "gf_w": gf_w, "gf_w2": gf_w2,
+            "act_w": act_w, "act_b": act_b}
+
+
+def train_workspace_floats(dims, batch, agents) -> int:
+    """Floats of caller-owned scratch a train-mode forward / backward pair needs (mapf_train_workspace_size)."""
+    size = _lib.load().mapf_train_workspace_size(net_params(dims), int(batch), int(agents))
+    if size < 0:
+        raise RuntimeError("mapf_b200 train: unsupported network / batch dimensions")
+    return int(size)
+
+
+def _train_fwd(dims, message, states, gso, conv_w, conv_b, bn_gamma, bn_beta, bn_mean, bn_var, fc_w, fc_b, gf_w, gf_w2,
+               act_w, act_b, bn_batches, workspace, flags):
+    """Train-mode Network.forward (train.py:87): per-agent-slot BatchNorm statistics (framework_gnn.py:160-163);
+    bn_mean / bn_var / bn_batches receive the N sequential running-stat updates; workspace keeps what backward needs."""
+    lib = _lib.load()
+    B, N = int(states.shape[0]), int(states.shape[1])
+    p = net_params(dims, _train_tensors(conv_w, conv_b, bn_gamma, bn_beta, bn_mean, bn_var, fc_w, fc_b, gf_w, gf_w2,
+                                        act_w, act_b))
+    logits = torch.empty((B, N, p.num_actions), dtype=torch.float32, device=states.device)
+    a = _lib.TrainFwdArgs()
+    a.batch, a.agents, a.message, a.momentum = B, N, int(message), 0.1
+    a.states, a.workspace, a.logits = states.data_ptr(), workspace.data_ptr(), logits.data_ptr()
+    if p.taps > 0:
+        a.gso = gso.data_ptr()
+    for l, t in enumerate(bn_batches):
+        a.bn_batches[l] = t.data_ptr()
+    a.flags = int(flags)
+    with torch.cuda.device(states.device):
+        _lib.check(lib.mapf_train_forward(p, a, _stream()), "train_forward")
+    return logits
+
+
+def _train_bwd(dims, message, states, gso, conv_w, conv_b, bn_gamma, bn_beta, bn_mean, bn_var, fc_w, fc_b, gf_w, gf_w2,
+               act_w, act_b, workspace, dlogits, grads):
+    """Backward of train_fwd from d loss / d logits; `grads` in the order conv_w[], conv_b[], bn_gamma[], bn_beta[],
+    fc_w, fc_b, (gf_w), (gf_w2), act_w, act_b is overwritten."""
+    lib = _lib.load()
+    B, N = int(states.shape[0]), int(states.shape[1])
+    p = net_params(dims, _train_tensors(conv_w, conv_b, bn_gamma, bn_beta, bn_mean, bn_var, fc_w, fc_b, gf_w, gf_w2,
+                                        act_w, act_b))
+    a = _lib.TrainBwdArgs()
+    a.batch, a.agents, a.message = B, N, int(message)
+    a.states, a.workspace, a.dlogits = states.data_ptr(), workspace.data_ptr(), dlogits.data_ptr()
+    if p.taps > 0:
+        a.gso = gso.data_ptr()
+    L = p.num_conv
+    names = [("conv_w", i) for i in range(L)] + [("conv_b", i) for i in range(L)] + \
+            [("bn_gamma", i) for i in range(L)] + [("bn_beta", i) for i in range(L)] + [("fc_w", None), ("fc_b", None)]
+    if gf_w is not None:
+        names.append(("gf_w", None))
+    if gf_w2 is not None:
+        names.append(("gf_w2", None))
+    names += [("act_w", None), ("act_b", None)]
+    if len(names) != len(grads):
+        raise ValueError(f"train_bwd expects {len(names)} gradient buffers, got {len(grads)}")
+    for (name, i), t in zip(names, grads):
+        if i is None:
+            setattr(a.grads, name, t.data_ptr())
+        else:
+            getattr(a.grads, name)[i] = t.data_ptr()
+    with torch.cuda.device(states.device):
+        _lib.check(lib.mapf_train_backward(p, a, _stream()), "train_backward")
+
+
+def _ce_loss(logits, targets):
+    """nn.CrossEntropyLoss (mean over B*N rows, train.py:90-93) -> (loss[1], d loss / d logits)."""
+    lib = _lib.load()
+    logits = _f32c(logits)
+    A = int(logits.shape[-1])
+    rows = logits.numel() // A
+    targets = targets.to(dtype=torch.int32).reshape(rows).contiguous()
+    loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    a = _lib.CeLossArgs(rows, A, logits.data_ptr(), targets.data_ptr(), loss.data_ptr(), dlogits.data_ptr())
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.mapf_ce_loss(a, _stream()), "ce_loss")
+    return loss, dlogits
+
+
+def _clip_adam(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay, max_norm, grad_norm,
+               scratch):
+    """clip_grad_norm_(max_norm) + Adam with L2 weight decay (train.py:64,97,100) over flat fp32 buffers; `step`
+    (int32[1]) and `lr` (float32[1]) live on the device so that a captured graph can be replayed unchanged."""
+    lib = _lib.load()
+    a = _lib.ClipAdamArgs()
+    a.n = params.numel()
+    a.params, a.grads = params.data_ptr(), grads.data_ptr()
+    a.exp_avg, a.exp_avg_sq = exp_avg.data_ptr(), exp_avg_sq.data_ptr()
+    a.lr, a.beta1, a.beta2, a.eps = 0.0, float(beta1), float(beta2), float(eps)
+    a.weight_decay, a.max_norm, a.step = float(weight_decay), float(max_norm), 0
+    a.grad_norm, a.scratch = grad_norm.data_ptr(), scratch.data_ptr()
+    a.step_dev, a.lr_dev = step.data_ptr(), lr.data_ptr()
+    with torch.cuda.device(params.device):
+        _lib.check(lib.mapf_clip_adam(a, _stream()), "clip_adam")
+
+
+def _ce_loss_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.mark_non_differentiable(output[1])
+
+
+def _ce_loss_backward(ctx, g_loss, g_dlogits):
+    (dlogits,) = ctx.saved_tensors
+    return dlogits * g_loss.reshape(()), None
+
+
 _LIB.impl("pack_weights", _pack_weights, "CUDA")
+_LIB.impl("train_fwd", _train_fwd, "CUDA")
+_LIB.impl("train_bwd", _train_bwd, "CUDA")
+_LIB.impl("ce_loss", _ce_loss, "CUDA")
+_LIB.impl("clip_adam", _clip_adam, "CUDA")
+torch.library.register_autograd("mapf::ce_loss", _ce_loss_backward, setup_context=_ce_loss_setup, lib=_LIB)
 _LIB.impl("policy_fwd", _policy_fwd, "CUDA")
 _LIB.impl("encoder_fwd", _encoder_fwd, "CUDA")
 _LIB.impl("pack_graph_weights", _pack_graph_weights, "CUDA")

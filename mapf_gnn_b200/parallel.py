@@ -59,3 +59,69 @@ def gather_metrics(success: torch.Tensor, flow_time: torch.Tensor, group=None):
     dist.all_gather(s, success, group=group)
     dist.all_gather(f, flow_time, group=group)
     return torch.cat(s), torch.cat(f)
+
+
+class PeerGradients:
+    """Peer-mapped gradient buffers for the one-shot NVLink all-reduce (``mapf_peer_reduce_clip_adam``): per rank one CUDA
+    IPC allocation ``[2 parities x n floats | 16 int32 flags]``, handles exchanged once with ``all_gather_object``, every
+    peer's block mapped into this process.  ``grad[parity]`` are torch views of the local block (the backward kernels
+    write the gradient there directly); ``args(parity)`` fills the C struct.  Single node only (P2P over NVLink)."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self.lib = _lib.load()
+        self.n = int(n_floats)
+        assert self.n % 4 == 0
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("peer all-reduce supports up to 8 ranks (one NVSwitch box)")
+        self.device = torch.device(device)
+        self.bytes = 2 * self.n * 4 + 64
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mapf_peer_alloc(self.bytes, C.byref(ptr), handle), "peer_alloc")
+        self.local_ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local_ptr)
+                continue
+            p = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mapf_peer_open(h, C.byref(p)), "peer_open")
+            self.ptrs.append(p.value)
+        self.grad = [self._view(self.local_ptr + par * self.n * 4, self.n) for par in (0, 1)]
+        dist.barrier(group=group)        # every rank has mapped every block before anyone signals
+
+    def _view(self, ptr, n):
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+        t = torch.as_tensor(raw, device=self.device)
+        t._mapf_keepalive = self          # the allocation must outlive the view
+        return t
+
+    def args(self, parity: int):
+        from . import _lib
+        a = _lib.PeerReduceArgs()
+        a.world, a.rank = self.world, self.rank
+        for r in range(self.world):
+            a.peer_grads[r] = self.ptrs[r] + parity * self.n * 4
+            a.peer_flags[r] = self.ptrs[r] + 2 * self.n * 4
+        return a
+
+    def close(self):
+        if self.ptrs is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.lib.mapf_peer_close(p)
+        self.lib.mapf_peer_free(self.local_ptr)
+        self.ptrs = None

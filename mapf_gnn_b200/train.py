@@ -12,7 +12,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 from .ops import net_params
 
 _GRAD_ORDER = ("conv_w", "conv_b", "bn_gamma", "bn_beta", "fc_w", "fc_b", "gf_w", "gf_w2", "act_w", "act_b")
@@ -42,80 +42,90 @@ def _raw_params(net):
 
 
 class _Workspace:
-    """Caller-owned scratch for one (B, N) shape, reused across steps."""
+    """Caller-owned scratch for one (B, N) shape, reused across steps (the fused ``Trainer`` owns exactly one)."""
 
     def __init__(self):
         self.key, self.buf = None, None
 
-    def get(self, lib, p, B, N, device):
+    def get(self, dims, B, N, device):
         key = (B, N, device)
         if self.key != key:
-            size = lib.mapf_train_workspace_size(p, B, N)
-            if size < 0:
-                raise RuntimeError("mapf_b200 train: unsupported network / batch dimensions")
-            self.buf = torch.empty((size,), dtype=torch.float32, device=device)
+            self.buf = torch.empty((ops.train_workspace_floats(dims, B, N),), dtype=torch.float32, device=device)
             self.key = key
         return self.buf
 
 
-def _forward(net, states, gso, ws):
-    lib = _lib.load()
+class _WorkspacePool:
+    """Scratch buffers of the autograd path: every train-mode forward checks out its OWN workspace and its backward
+    hands it back, so several forwards may be alive at once (gradient accumulation over micro-batches, two losses from
+    two forwards) like with the reference's ordinary autograd graph.  A forward that never gets a backward simply drops
+    its buffer."""
+
+    def __init__(self, keep=4):
+        self.free, self.keep = {}, keep
+
+    def checkout(self, dims, B, N, device):
+        lst = self.free.get((B, N, device))
+        if lst:
+            return lst.pop()
+        return torch.empty((ops.train_workspace_floats(dims, B, N),), dtype=torch.float32, device=device)
+
+    def release(self, B, N, device, buf):
+        lst = self.free.setdefault((B, N, device), [])
+        if len(lst) < self.keep:
+            lst.append(buf)
+
+
+def _op_params(keep):
+    return (keep["conv_w"], keep["conv_b"], keep["bn_gamma"], keep["bn_beta"], keep["bn_mean"], keep["bn_var"],
+            keep["fc_w"], keep["fc_b"], keep["gf_w"], keep["gf_w2"], keep["act_w"], keep["act_b"])
+
+
+def _forward(net, states, gso, work):
+    """``mapf::train_fwd`` on the network's current parameters; returns logits and what backward needs."""
     states = states.contiguous()
-    B, N = int(states.shape[0]), int(states.shape[1])
     p, keep = _raw_params(net)
-    work = ws.get(lib, p, B, N, states.device)
-    logits = torch.empty((B, N, p.num_actions), dtype=torch.float32, device=states.device)
-    a = _lib.TrainFwdArgs()
-    a.batch, a.agents, a.message, a.momentum = B, N, int(net.message), 0.1
-    a.states, a.workspace, a.logits = states.data_ptr(), work.data_ptr(), logits.data_ptr()
     if p.taps > 0:
         gso = gso.to(torch.float32).contiguous()
-        a.gso = gso.data_ptr()
-    bns = [m for m in net.convLayers if isinstance(m, torch.nn.BatchNorm2d)]
-    for l, bn in enumerate(bns):
-        a.bn_batches[l] = bn.num_batches_tracked.data_ptr()
-    from . import ops
-    a.flags = ops.train_flags()
-    with torch.cuda.device(states.device):
-        _lib.check(lib.mapf_train_forward(p, a, _stream()), "train_forward")
+    else:
+        gso = None
+    bns = [m.num_batches_tracked for m in net.convLayers if isinstance(m, torch.nn.BatchNorm2d)]
+    logits = torch.ops.mapf.train_fwd(net.dims(), bool(net.message), states, gso, *_op_params(keep), bns, work,
+                                      ops.train_flags())
     net._weights_epoch = getattr(net, "_weights_epoch", 0) + 1   # running stats changed behind torch's back
     return logits, (states, gso, work, keep)
 
 
 def _backward(net, saved, dlogits, grads):
-    lib = _lib.load()
     states, gso, work, keep = saved
-    B, N = int(states.shape[0]), int(states.shape[1])
-    p = net_params(net.dims(), keep)
-    a = _lib.TrainBwdArgs()
-    a.batch, a.agents, a.message = B, N, int(net.message)
-    a.states, a.workspace, a.dlogits = states.data_ptr(), work.data_ptr(), dlogits.data_ptr()
-    if p.taps > 0:
-        a.gso = gso.data_ptr()
-    for (name, i), t in grads:
-        if i is None:
-            setattr(a.grads, name, t.data_ptr())
-        else:
-            getattr(a.grads, name)[i] = t.data_ptr()
-    with torch.cuda.device(states.device):
-        _lib.check(lib.mapf_train_backward(p, a, _stream()), "train_backward")
+    torch.ops.mapf.train_bwd(net.dims(), bool(net.message), states, gso, *_op_params(keep), work, dlogits,
+                             [t for _, t in grads])
 
 
 class _PolicyTrainFn(torch.autograd.Function):
+    """Autograd formula of the train-mode network: forward = ``mapf::train_fwd``, backward = ``mapf::train_bwd``."""
+
     @staticmethod
     def forward(ctx, net, states, gso, *params):
-        if not hasattr(net, "_train_ws"):
-            net._train_ws = _Workspace()
-        logits, saved = _forward(net, states.detach(), None if gso is None else gso.detach(), net._train_ws)
-        ctx.net, ctx.saved = net, saved
+        if not hasattr(net, "_train_pool"):
+            net._train_pool = _WorkspacePool()
+        B, N = int(states.shape[0]), int(states.shape[1])
+        work = net._train_pool.checkout(net.dims(), B, N, states.device)
+        logits, saved = _forward(net, states.detach(), None if gso is None else gso.detach(), work)
+        ctx.net, ctx.saved, ctx.key = net, saved, (B, N, states.device)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         net = ctx.net
+        if ctx.saved is None:
+            raise RuntimeError("mapf_b200: backward through the same train-mode forward twice (its workspace was "
+                               "returned after the first backward; retain_graph is not supported)")
         slots = _param_list(net.param_groups())
         grads = [(slot, torch.empty_like(t)) for slot, t in slots]
         _backward(net, ctx.saved, dlogits.contiguous(), grads)
+        net._train_pool.release(*ctx.key, ctx.saved[2])
+        ctx.saved = None
         return (None, None, None, *[g for _, g in grads])
 
 
@@ -148,18 +158,9 @@ def graph_filter_backward(x, gso, W, W2, self_loop, gy):
 
 
 def cross_entropy(logits, targets):
-    """nn.CrossEntropyLoss (mean over B*N rows, train.py:90-93) -> (loss[1], dlogits)."""
-    lib = _lib.load()
-    logits = logits.contiguous()
-    A = int(logits.shape[-1])
-    rows = logits.numel() // A
-    targets = targets.to(device=logits.device, dtype=torch.int32).reshape(rows).contiguous()
-    loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
-    dlogits = torch.empty_like(logits)
-    a = _lib.CeLossArgs(rows, A, logits.data_ptr(), targets.data_ptr(), loss.data_ptr(), dlogits.data_ptr())
-    with torch.cuda.device(logits.device):
-        _lib.check(lib.mapf_ce_loss(a, _stream()), "ce_loss")
-    return loss, dlogits
+    """nn.CrossEntropyLoss (mean over B*N rows, train.py:90-93) -> (loss[1], dlogits): ``mapf::ce_loss`` (differentiable
+    with respect to the logits through its registered autograd formula)."""
+    return torch.ops.mapf.ce_loss(logits, targets.to(device=logits.device))
 
 
 class Trainer:
@@ -173,7 +174,7 @@ class Trainer:
     """
 
     def __init__(self, net, lr=3e-4, weight_decay=1e-4, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, world_size=None, use_graph=False):
+                 process_group=None, world_size=None, use_graph=False, peer_allreduce=None):
         self.net, self.lib = net, _lib.load()
         self.lr, self.weight_decay, self.max_norm, self.betas, self.eps = lr, weight_decay, max_norm, betas, eps
         self.slots = _param_list(net.param_groups())
@@ -204,37 +205,77 @@ class Trainer:
         self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)     # device-resident Adam step count
         self.lr_dev = torch.full((1,), lr, dtype=torch.float32, device=dev)
         self.use_graph = use_graph
-        self._graph, self._graph_key = None, None
+        self._graphs, self._graph_key = None, None
         self.ws = _Workspace()
         self.group = process_group
         if world_size is None:
             import torch.distributed as dist
             world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.world = world_size
+        # world > 1: the gradient all-reduce runs over NVLink peer memory inside the gradient-norm kernel
+        # (mapf_peer_reduce_clip_adam: no NCCL call, capturable in the step's CUDA graph).  peer_allreduce=False keeps the
+        # NCCL all-reduce of the flat gradient (also the fallback when CUDA IPC is unavailable, e.g. ranks on several nodes).
+        self.peer = None
+        self._parity = 0
+        self.peer_grad_views = None
+        if self.world > 1 and peer_allreduce is not False:
+            import torch.distributed as dist
+            try:
+                if dist.get_backend(process_group) != "nccl":
+                    raise RuntimeError("peer all-reduce needs CUDA ranks")
+                from .parallel import PeerGradients
+                self.peer = PeerGradients(total, dev, process_group)
+                self.peer_grad_views = []
+                for par in (0, 1):
+                    views = [(slot, self.peer.grad[par][off:off + n].view_as(t))
+                             for (slot, t), off, n in zip(self.slots, offs, sizes)]
+                    self.peer_grad_views.append(views)
+            except Exception as exc:          # noqa: BLE001
+                if peer_allreduce is True:
+                    raise
+                import warnings
+                warnings.warn(f"mapf_b200: peer-memory all-reduce unavailable ({exc}); using the NCCL all-reduce")
+                self.peer = None
+
+    def close(self):
+        """Release the peer-mapped gradient buffers (world > 1); the trainer must not be stepped afterwards."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def set_lr(self, lr):
         """CosineAnnealingLR is stepped per epoch by the caller (train.py:65,151)."""
         self.lr = lr
         self.lr_dev.fill_(lr)
 
-    def _step_body(self, states, gso, targets):
+    def _step_body(self, states, gso, targets, parity=0):
         net = self.net
-        logits, saved = _forward(net, states, gso, self.ws)
+        B, N = int(states.shape[0]), int(states.shape[1])
+        logits, saved = _forward(net, states, gso, self.ws.get(net.dims(), B, N, states.device))
         loss, dlogits = cross_entropy(logits, targets)
+        if self.peer is not None:
+            # the backward kernels write this step's gradient straight into the peer-mapped buffer of this parity; the
+            # fused kernel sums all ranks' buffers over NVLink, leaves the mean in flat_grad and feeds clip + Adam
+            _backward(net, saved, dlogits, self.peer_grad_views[parity])
+            a = _lib.ClipAdamArgs()
+            a.n = self.flat.numel()
+            a.params, a.grads = self.flat.data_ptr(), self.flat_grad.data_ptr()
+            a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+            a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
+            a.weight_decay, a.max_norm, a.step = self.weight_decay, self.max_norm, 0
+            a.grad_norm, a.scratch = self.grad_norm.data_ptr(), self.scratch.data_ptr()
+            a.step_dev, a.lr_dev = self.step_dev.data_ptr(), self.lr_dev.data_ptr()
+            with torch.cuda.device(self.flat.device):
+                _lib.check(self.lib.mapf_peer_reduce_clip_adam(self.peer.args(parity), a, _stream()),
+                           "peer_reduce_clip_adam")
+            return loss
         _backward(net, saved, dlogits, self.grad_views)
         if self.world > 1:
             from .parallel import average_gradients
             average_gradients(self.flat_grad, self.group)
-        a = _lib.ClipAdamArgs()
-        a.n = self.flat.numel()
-        a.params, a.grads = self.flat.data_ptr(), self.flat_grad.data_ptr()
-        a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
-        a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        a.weight_decay, a.max_norm, a.step = self.weight_decay, self.max_norm, 0
-        a.grad_norm, a.scratch = self.grad_norm.data_ptr(), self.scratch.data_ptr()
-        a.step_dev, a.lr_dev = self.step_dev.data_ptr(), self.lr_dev.data_ptr()
-        with torch.cuda.device(self.flat.device):
-            _lib.check(self.lib.mapf_clip_adam(a, _stream()), "clip_adam")
+        torch.ops.mapf.clip_adam(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr_dev,
+                                 self.betas[0], self.betas[1], self.eps, self.weight_decay, self.max_norm,
+                                 self.grad_norm, self.scratch)
         return loss
 
     @torch.no_grad()
@@ -246,8 +287,11 @@ class Trainer:
         if not net.training:
             raise RuntimeError("Trainer.step needs the network in train() mode (train.py:80)")
         targets = targets.to(device=self.flat.device, dtype=torch.int32)
+        parity = self._parity
+        if self.peer is not None:
+            self._parity ^= 1
         if not self.use_graph:
-            loss = self._step_body(states, gso, targets)
+            loss = self._step_body(states, gso, targets, parity)
         else:
             key = (tuple(states.shape), None if gso is None else tuple(gso.shape))
             if self._graph_key != key:
@@ -256,8 +300,8 @@ class Trainer:
             if gso is not None:
                 self._g_gso.copy_(gso)
             self._g_targets.copy_(targets)
-            self._graph.replay()
-            loss = self._g_loss
+            self._graphs[parity].replay()
+            loss = self._g_loss[parity]
         self.step_count += 1
         net._weights_epoch = getattr(net, "_weights_epoch", 0) + 1   # parameters changed behind torch's back
         return loss
@@ -273,8 +317,8 @@ class Trainer:
         side = torch.cuda.Stream(device=self.flat.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(2):
-                self._step_body(self._g_states, self._g_gso, self._g_targets)
+            for par in (0, 1):          # executed for real on every rank: the peer epochs advance in lockstep
+                self._step_body(self._g_states, self._g_gso, self._g_targets, par)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
 
@@ -284,8 +328,13 @@ class Trainer:
             for b, old in zip(self.net.buffers(), snap[4]):
                 b.copy_(old)
         restore()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._g_loss = self._step_body(self._g_states, self._g_gso, self._g_targets)
+        self._graphs, self._g_loss = [], []
+        for par in ((0, 1) if self.peer is not None else (0,)):     # one graph per gradient-buffer parity
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                self._g_loss.append(self._step_body(self._g_states, self._g_gso, self._g_targets, par))
+            self._graphs.append(gph)
+        if self.peer is None:
+            self._graphs.append(self._graphs[0]), self._g_loss.append(self._g_loss[0])
         restore()       # capture does not execute, but keep the state exactly as before for safety
         self._graph_key = key

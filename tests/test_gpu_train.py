@@ -187,3 +187,50 @@ def test_cuda_graph_trainer_matches_eager(train_step):
             diff, scale = np.abs(an - bn_), max(np.abs(bn_).max(), 1e-12)
             assert (diff > 1e-4 * scale).mean() < 5e-3, k
             assert diff.max() <= 2 * 4 * 3e-4 + 1e-4 * scale, k
+
+
+def test_two_forwards_alive_before_backward():
+    """Gradient accumulation over micro-batches / two losses from two forwards: every train-mode forward owns its
+    workspace, so the first backward must not see the second forward's activations (shared workspace)."""
+    rng = np.random.default_rng(7)
+    N = 5
+    mk = lambda B: (torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float().cuda(),
+                    (torch.tensor((rng.random((B, N, N)) < 0.3).astype(np.float32)) + torch.eye(N)).cuda(),
+                    torch.tensor(rng.integers(0, 5, size=(B, N))).cuda())
+    (s1, g1, t1), (s2, g2, t2) = mk(24), mk(24)
+    ce = lambda out, t: torch.nn.functional.cross_entropy(out.reshape(-1, 5), t.reshape(-1))
+    # separately
+    ref = []
+    for s, g, t in ((s1, g1, t1), (s2, g2, t2)):
+        net = load_network("gnn_msg_k3").train()
+        ce(net(s, g), t).backward()
+        ref.append({k: p.grad.clone() for k, p in net.named_parameters()})
+    # both forwards first, then both backwards (same shapes -> the old code shared one buffer)
+    net = load_network("gnn_msg_k3").train()
+    o1 = net(s1, g1)
+    o2 = net(s2, g2)
+    ce(o1, t1).backward()
+    first = {k: p.grad.clone() for k, p in net.named_parameters()}
+    ce(o2, t2).backward()
+    total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref[0].values())))
+    for k, p in net.named_parameters():   # (the batch reductions use fp32 atomics: equal up to summation order)
+        assert rel_err(first[k].cpu().numpy(), ref[0][k].cpu().numpy(), 1e-3 * total) < 1e-5, k
+        assert rel_err(p.grad.cpu().numpy(), (ref[0][k] + ref[1][k]).cpu().numpy(), 1e-3 * total) < 1e-5, k
+
+
+def test_training_torch_ops_are_registered_and_differentiable():
+    """SURVEY 8b op surface: mapf::train_fwd / train_bwd / ce_loss / clip_adam exist with typed schemas; ce_loss carries
+    an autograd formula equal to torch's cross-entropy gradient; CPU tensors are refused by the dispatcher."""
+    for op in ("train_fwd", "train_bwd", "ce_loss", "clip_adam"):
+        assert hasattr(torch.ops.mapf, op)
+    rng = np.random.default_rng(3)
+    logits = torch.tensor(rng.normal(size=(17, 5, 5)), dtype=torch.float32, device="cuda", requires_grad=True)
+    targets = torch.tensor(rng.integers(0, 5, size=(17, 5)), device="cuda")
+    loss, _ = torch.ops.mapf.ce_loss(logits, targets)
+    (2.5 * loss.sum()).backward()
+    ref = logits.detach().clone().requires_grad_(True)
+    (2.5 * torch.nn.functional.cross_entropy(ref.reshape(-1, 5), targets.reshape(-1))).backward()
+    assert abs(loss.item() - torch.nn.functional.cross_entropy(ref.reshape(-1, 5), targets.reshape(-1)).item()) < 1e-6
+    assert torch.allclose(logits.grad, ref.grad, rtol=1e-5, atol=1e-8)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.mapf.ce_loss(logits.detach().cpu(), targets.cpu())
