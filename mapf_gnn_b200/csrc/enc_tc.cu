@@ -313,9 +313,10 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
             mma_f16_ts(tmem_u, ah, bl, idesc, true);
             mma_f16_ts(tmem_u, ah, bh, idesc, true);
           }
+          ETC_STAMP(7);
           tc::mma_commit(bar);
+          ETC_STAMP(8);
         }
-        ETC_STAMP(7);
       }
       __syncwarp();
       tc::mbar_wait(bar, phase);

@@ -150,8 +150,13 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
   const int nchunks = (g.K + KC - 1) / KC;
+  // warp-uniform copies for the MMA issuers: the whole issuing warp runs its (warp-uniform) branch and elect.sync picks the
+  // lane, so every MMA operand is a uniform-register value and ptxas emits plain UTCHMMAs instead of wrapping each one in
+  // an ELECT / R2UR.BROADCAST loop (~100 clocks per MMA behind a divergent `lane == 0` branch)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
-  if (warp < kTcProdWarps) {
+  if (warp_u < kTcProdWarps) {
     // ===== producers: warp w owns stage w =====
     const int s = warp;
     uint8_t* a_hi = s_tc + s * kStageBytes;
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     // ===== MMA issuers (warps 6 and 7: even / odd chunks) =====
     // A single thread issues every tcgen05.mma, so its instruction stream is the critical path: descriptors are
     // built once (stage 0) and advanced by adding the stage / K-slice byte offset to the 14-bit address field.
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_tf32(kTcM, NT);
       constexpr uint32_t sbo = KQ * 128, lbo = 128;
       const uint32_t base = tc::smem_u32(s_tc);
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       const uint64_t dbh0 = tc::smem_desc(base + 2 * kABytes, lbo, sbo);
       const uint64_t dbl0 = tc::smem_desc(base + 2 * kABytes + kBBytes, lbo, sbo);
       static_assert(NACC == 2 && (NSTAGE % 2) == 0, "issuer w owns accumulator w and the stages of its parity");
-      const int which = warp - kTcProdWarps;   // 0: even chunks, 1: odd chunks
+      const int which = warp_u - kTcProdWarps;   // 0: even chunks, 1: odd chunks
       int s = which;
       uint32_t ph = 0;
       const uint32_t accsel = which;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
         const uint64_t soff = uint64_t(uint32_t(s) * (kStageBytes >> 4));
-        const uint32_t acc = tmem + accsel * NT;
+        const uint32_t acc = tmem_u + accsel * NT;
         const bool first = c < 2;   // first touch of this accumulator overwrites
 #pragma unroll
         for (int ks = 0; ks < KC / 8; ++ks) {
@@ -396,12 +401,17 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
+  // warp-uniform copies for the MMA issuers: the whole issuing warp runs its (warp-uniform) branch and elect.sync picks the
+  // lane, so every MMA operand is a uniform-register value and ptxas emits plain UTCHMMAs instead of wrapping each one in
+  // an ELECT / R2UR.BROADCAST loop (~100 clocks per MMA behind a divergent `lane == 0` branch)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
   mapf_pdl_wait();      // the A operand (and its row scales) come from the conv kernel in front
   mapf_pdl_launch();
   const int nch = F16 ? (g.K + 15) >> 4 : (g.K + 7) >> 3;   // a chunk is 32 bytes of K per row: 8 TF32 or 16 fp16
   const int nsc = (nch + kPsChunks - 1) / kPsChunks;
 
-  if (warp == 0) {
+  if (warp_u == 0) {
     if (lane == 0) {
       const float* a_src = g.A + int64_t(blockIdx.x) * nch * (2 * kTcM * 8);   // (same bytes per chunk in both modes)
       for (int sc = 0; sc < nsc; ++sc) {
@@ -418,15 +428,15 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
       }
     }
     __syncwarp();
-  } else if (warp <= kPsChunks) {
+  } else if (warp_u <= kPsChunks) {
     // issuer warp w (1..kPsChunks) owns chunk w-1 of every stage and TMEM accumulator w-1: one thread issues only about
     // one MMA per 100 cycles, the issuers work in parallel; each accumulator is filled by one thread in a fixed order (reproducible)
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = F16 ? tc::idesc_f16(kTcM, NT) : tc::idesc_tf32(kTcM, NT);
       constexpr uint32_t sbo = 256, lbo = 128;
       const uint32_t base = tc::smem_u32(s_tc);
-      const int ci = warp - 1;
-      const uint32_t acc = tmem + uint32_t(ci) * NT;
+      const int ci = warp_u - 1;
+      const uint32_t acc = tmem_u + uint32_t(ci) * NT;
       for (int sc = 0; sc < nsc; ++sc) {
         const int s = sc % kPsStages;
         const uint32_t ph = uint32_t(sc / kPsStages) & 1u;

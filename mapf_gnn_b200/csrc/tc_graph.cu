@@ -121,11 +121,14 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
+  // warp-uniform copies for the MMA issuers (elect.sync inside a warp-uniform branch: plain UTCHMMAs, see tc_gemm.cu)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
   const int slices = F >> 3;                       // 8-feature slices (host guarantees slices % 4 == 0)
   const int per_warp = slices / kTgProd;
   const int chunks_per_slice = K + g.has_skip;
 
-  if (warp < kTgProd) {
+  if (warp_u < kTgProd) {
     // ===================== producers =====================
     const int p = warp;
     uint8_t* a_hi = stages + p * kTgStageBytes;
@@ -239,10 +242,10 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
         emit(K * slices + j, sv);
       }
     }
-  } else if (warp < kTgProd + 2) {
+  } else if (warp_u < kTgProd + 2) {
     // ===================== MMA issuers =====================
-    if (lane == 0) {
-      const int which = warp - kTgProd;
+    if (tc::elect_one()) {
+      const int which = warp_u - kTgProd;
       constexpr uint32_t idesc = tc::idesc_tf32(kTgM, kTgNT);
       constexpr uint32_t sbo = 256, lbo = 128;
       const uint32_t base = tc::smem_u32(stages);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
       const uint64_t dal0 = tc::smem_desc(base + kTgABytes, lbo, sbo);
       const uint64_t dbh0 = tc::smem_desc(base + 2 * kTgABytes, lbo, sbo);
       const uint64_t dbl0 = tc::smem_desc(base + 2 * kTgABytes + kTgBBytes, lbo, sbo);
-      const uint32_t acc = tmem + uint32_t(which) * kTgNT;
+      const uint32_t acc = tmem_u + uint32_t(which) * kTgNT;
       const int T = per_warp * chunks_per_slice;
       bool first = true;
       for (int t = 0; t < T; ++t) {

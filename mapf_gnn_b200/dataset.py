@@ -83,9 +83,17 @@ class GNNDataLoader:
     """``GNNDataLoader(config).train_loader`` (data_loader.py:9-21): iterating yields
     ``(states[B,N,2,5,5], actions[B,N], gso[B,N,N])`` float32 batches.  The whole dataset is kept in pinned host
     memory and every batch is one asynchronous upload to ``device`` (the reference uses DataLoader workers +
-    pin_memory; here a batch is a contiguous gather, so no worker processes are needed)."""
+    pin_memory; here a batch is a contiguous gather, so no worker processes are needed).
 
-    def __init__(self, config, mode="train", device="cuda", seed=None):
+    ``reference_len=True`` reproduces the reference's epoch: its ``Dataset.__len__`` returns the CASE count
+    (data_loader.py:112-113) although the arrays are flattened to ``count * min_time`` samples, so its shuffling
+    ``DataLoader`` only ever draws sample indices below ``count`` -- the first ``count`` flattened rows, i.e. the first
+    ``count / min_time`` cases -- and runs ``ceil(count / batch_size)`` iterations per epoch.  The default
+    (``reference_len=False``) serves every sample; this is a deliberate deviation (the reference trains on ~1/min_time
+    of its data), and the epoch length -- hence the per-epoch cosine LR schedule of train.py:65,151 -- differs
+    accordingly."""
+
+    def __init__(self, config, mode="train", device="cuda", seed=None, reference_len=False):
         cfg = config[mode]
         sub = {"train": "train", "valid": "val"}.get(mode, mode)
         self.states, self.targets, self.gso, self.count = load_cases(
@@ -96,12 +104,18 @@ class GNNDataLoader:
         if self.device.type == "cuda":
             self.states, self.targets, self.gso = (t.pin_memory() for t in (self.states, self.targets, self.gso))
         self.train_loader = self
+        self.reference_len = bool(reference_len)
+
+    @property
+    def num_samples(self):
+        """Samples an epoch draws from: every flattened row, or the first `count` rows in reference_len mode."""
+        return min(self.count, self.states.shape[0]) if self.reference_len else self.states.shape[0]
 
     def __len__(self):
-        return (self.states.shape[0] + self.batch_size - 1) // self.batch_size
+        return (self.num_samples + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
-        order = torch.from_numpy(self.rng.permutation(self.states.shape[0]))      # shuffle=True (data_loader.py:17)
+        order = torch.from_numpy(self.rng.permutation(self.num_samples))      # shuffle=True (data_loader.py:17)
         for lo in range(0, len(order), self.batch_size):
             idx = order[lo:lo + self.batch_size]
             yield tuple(t[idx].to(self.device, non_blocking=True) for t in (self.states, self.targets, self.gso))

@@ -55,6 +55,19 @@ def test_loader_matches_reference_semantics(tmp_path):
         assert bool((diag_ok | hole).all())
         seen += s.shape[0]
     assert seen == count * min_time and len(loader) == (seen + 15) // 16
+    # reference_len=True: the reference's Dataset.__len__ returns the case count (data_loader.py:112-113), so its
+    # DataLoader draws only flattened sample indices below `count` and runs ceil(count / batch) iterations per epoch
+    ref_loader_ = GNNDataLoader(cfg, "train", device="cpu", seed=1, reference_len=True)
+    assert len(ref_loader_) == (count + 15) // 16
+    rows = torch.cat([s for s, _, _ in ref_loader_])
+    assert rows.shape[0] == count
+    first = ref_loader_.states[:count]
+    assert sorted(map(lambda r: r.numpy().tobytes(), rows)) == sorted(map(lambda r: r.numpy().tobytes(), first))
+    if os.path.isdir("/root/reference"):
+        # the reference's own DataLoader over its Dataset object visits exactly `count` rows per epoch
+        from torch.utils.data import DataLoader
+        assert len(ds) == count
+        assert sum(b[0].shape[0] for b in DataLoader(ds, batch_size=16, shuffle=True)) == count
 
 
 @pytest.mark.gpu
