@@ -308,6 +308,8 @@ typedef struct {
 } mapf_train_fwd_args;
 #define MAPF_TRAIN_FFMA_FC 1     /* compressMLP forward on the FFMA GEMM */
 #define MAPF_TRAIN_FFMA_GRAPH 2  /* graph filter forward on the fused FFMA kernel */
+#define MAPF_TRAIN_FFMA_BWD 4    /* backward GEMMs on the FFMA2 kernels instead of mapf_tc_gemm_tn / mapf_tc_gemm */
+#define MAPF_TRAIN_TC_BWD_ALWAYS 8 /* tensor-core backward GEMMs also below 4096 rows (tests) */
 int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream);
 
 /* Backward of the above from d(loss)/d(logits); must follow mapf_train_forward on the same
@@ -320,6 +322,7 @@ typedef struct {
   float* workspace;
   const float* dlogits;      /* [B,N,A] */
   mapf_net_grads grads;
+  int32_t flags;             /* development switches MAPF_TRAIN_* ; 0 = tensor-core GEMMs */
 } mapf_train_bwd_args;
 int mapf_train_backward(const mapf_net_params* p, const mapf_train_bwd_args* a, mapf_stream_t stream);
 
@@ -410,6 +413,12 @@ int mapf_tc_pack_b(const float* b0, int32_t K0, const float* b1, int32_t K1, int
                    mapf_stream_t stream);
 int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
                  const float* bias, int32_t relu, mapf_stream_t stream);
+/* Weight-gradient GEMM of the training step (train.py:96): C (+)= A^T B with A [K, M] (lda) and B [K, N] (ldb) row-major
+ * fp32 activation matrices whose contraction index is the row index (K = B*N rows), 3xTF32 on the tensor cores with the
+ * transposition done on the way into shared memory and split-K partials meeting in C through red.global.add.
+ * transpose_c != 0 writes C^T [N, M] (ldc >= M).  accumulate == 0 zeroes C first. */
+int mapf_tc_gemm_tn(int32_t M, int32_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                    int64_t ldc, int32_t transpose_c, int32_t accumulate, mapf_stream_t stream);
 /* Encoder FC with the A operand pre-split by the conv kernel: mapf_encoder_conv_split_fwd writes the flattened conv
  * output (framework_gnn.py:160-163) as TF32 hi / lo halves in the tensor-core tile order (mapf_tc_presplit_a_size
  * floats), mapf_tc_fc_presplit computes relu(A W^T + b) (compressMLP, framework_gnn.py:93) from it with an all-TMA
@@ -418,9 +427,10 @@ int64_t mapf_tc_presplit_a_size(int64_t M, int32_t K);
 int mapf_encoder_conv_split_fwd(const mapf_net_params* p, const mapf_encoder_fwd_args* a, mapf_stream_t stream);
 int mapf_tc_fc_presplit(int32_t M, int32_t N, int32_t K, const float* Ap, const float* Bp, float* C, int64_t ldc,
                         const float* bias, int32_t relu, mapf_stream_t stream);
-/* Conv stack of the encoder on the tensor cores (framework_gnn.py:55-71,160-163 for 16-channel layers): each layer is
- * one 128 x 144 x Cin 3xTF32 GEMM per 4 agent images (all 9 taps at once, activations as the A operand in tensor
- * memory) followed by shifted adds in the epilogue.  a->x (mapf_tc_presplit_a_size floats) receives the FC operand
+/* Conv stack of the encoder on the tensor cores (framework_gnn.py:55-71,160-163; first layer 16 or 32 channels, 16
+ * behind it): each layer is one 128 x 48 x 48 GEMM per 4 agent images on fp16-split operands (3 kind::f16 MMAs per
+ * 16-wide K step; horizontal taps in K, filter rows in N, activations as the A operand in tensor memory) followed by
+ * the vertical shifted adds in the epilogue (csrc/enc_tc.cu).  a->x (mapf_tc_presplit_a_size floats) receives the FC operand
  * fp16-split (x * 2^-e = hi + lo, one scale per image) with its K index ordered pixel-major, followed by the rows' inverse
  * scales; mapf_tc_fc_presplit_f16 computes relu(A W^T + b) (compressMLP, framework_gnn.py:93) from it and the B operand
  * mapf_tc_pack_b_f16_pixel_major builds from compressMLP.0.weight (mapf_pack_weights does this).  mapf_policy_fwd

@@ -62,6 +62,9 @@ def is_fresh():
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Build (if stale) and return the path of the shared library.  Safe under concurrent ranks: an exclusive file
     lock serialises builders and the library is moved into place atomically."""
+    override = os.environ.get("MAPF_B200_LIB_OVERRIDE")     # development: an alternative build (tools/enc_tc_variants.py)
+    if override:
+        return override
     if not force and is_fresh():
         return LIB
     nvcc = nvcc_path()

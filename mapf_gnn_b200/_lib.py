@@ -15,7 +15,7 @@ MAX_CONV = 4
 # mapf_policy_fwd_args.flags / mapf_train_fwd_args.flags (include/mapf_b200.h)
 POLICY_FFMA_CONV, POLICY_FC_UNSPLIT, POLICY_UNFUSED_GRAPH, POLICY_FUSED_ENV_ON, POLICY_FUSED_ENV_OFF, POLICY_NO_PDL = \
     1, 2, 4, 8, 16, 32
-TRAIN_FFMA_FC, TRAIN_FFMA_GRAPH = 1, 2
+TRAIN_FFMA_FC, TRAIN_FFMA_GRAPH, TRAIN_FFMA_BWD, TRAIN_TC_BWD_ALWAYS = 1, 2, 4, 8
 c_f32p = C.c_void_p      # device pointers travel as integers
 c_i32p = C.c_void_p
 c_u8p = C.c_void_p
@@ -99,7 +99,7 @@ class TrainFwdArgs(C.Structure):
 class TrainBwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("message", C.c_int32),
                 ("states", c_f32p), ("gso", c_f32p), ("workspace", c_f32p), ("dlogits", c_f32p),
-                ("grads", NetGrads)]
+                ("grads", NetGrads), ("flags", C.c_int32)]
 
 
 class CeLossArgs(C.Structure):
@@ -167,6 +167,8 @@ _SIGNATURES = {
     "mapf_tc_pack_b": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mapf_tc_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mapf_tc_gemm_tn": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mapf_tc_presplit_a_size": (C.c_int64, [C.c_int64, C.c_int32]),
     "mapf_encoder_conv_split_fwd": (C.c_int, [C.POINTER(NetParams), C.POINTER(EncoderFwdArgs), C.c_void_p]),
     "mapf_tc_fc_presplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

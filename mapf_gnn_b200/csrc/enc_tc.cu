@@ -95,6 +95,30 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// wait for the group's MMAs (development variants, tools/enc_tc_variants.py): 0 = suspended try_wait (20 us hint),
+// 1 = polling test_wait, 2 = try_wait with a 1 us hint
+#ifndef MAPF_ETC_WAIT
+#define MAPF_ETC_WAIT 0
+#endif
+__device__ __forceinline__ void etc_mbar_wait(uint64_t* bar, uint32_t parity) {
+#if MAPF_ETC_WAIT == 0
+  tc::mbar_wait(bar, parity);
+#else
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t ok;
+#if MAPF_ETC_WAIT == 1
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+#else
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity), "r"(1000u) : "memory");
+#endif
+    if (ok) return;
+  }
+  asm volatile("trap;");
+#endif
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]^T (TS mode): A = 128 lanes x 8 columns (16 fp16, two per column) at a_tmem
 __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                            bool accumulate) {
@@ -309,8 +333,14 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
             const uint64_t bh = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4), 128, 256);
             const uint64_t bl = tc::smem_desc(wl + uint32_t(ks) * (2 * kEtBlk * 4) + kEtBlk * 4, 128, 256);
             const uint32_t ah = tmem_u + kEtColAHi + uint32_t(ks) * 8, al = tmem_u + kEtColALo + uint32_t(ks) * 8;
+#ifdef MAPF_ETC_L0_NOLO
+            // layer 0: the observations are small integers (exact in fp16), their lo part is identically zero
+            if (l > 0) mma_f16_ts(tmem_u, al, bh, idesc, ks > 0);
+            mma_f16_ts(tmem_u, ah, bl, idesc, l > 0 || ks > 0);
+#else
             mma_f16_ts(tmem_u, al, bh, idesc, ks > 0);     // small terms first
             mma_f16_ts(tmem_u, ah, bl, idesc, true);
+#endif
             mma_f16_ts(tmem_u, ah, bh, idesc, true);
           }
           ETC_STAMP(7);
@@ -319,7 +349,7 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
         }
       }
       __syncwarp();
-      tc::mbar_wait(bar, phase);
+      etc_mbar_wait(bar, phase);
       phase ^= 1u;
       tc::fence_after_sync();
       ETC_STAMP(2);
@@ -501,7 +531,11 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
     // start-up offset between the warpgroups: about a fifth of a layer for a long launch, less when every group sees
     // only a tile or two (measured optimum 400 / 700 / 1000 / 1400 clocks at 1 / 2 / 4 / 7 tiles per group)
     const int64_t rounds = (ntiles + int64_t(grid) * kGroups - 1) / (int64_t(grid) * kGroups);
+#ifdef MAPF_ETC_SKEW
+    g.skew = MAPF_ETC_SKEW;
+#else
     g.skew = int(rounds >= 6 ? 1400 : 300 + 200 * rounds);
+#endif
     mapf_launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), g);
     return MAPF_OK;
   };

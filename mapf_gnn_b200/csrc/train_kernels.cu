@@ -31,6 +31,8 @@ struct TrainLayout {
   int64_t dy, dz, dx, da0, da1;
   int64_t fcpk;                               // compressMLP weight, packed for the tensor-core GEMM (mapf_tc_pack_b)
   int64_t dwpart;                             // [grid <= 296][max cin*cout*9 + cmax] per-CTA weight-gradient partials
+  int64_t wtt, gfpk_bwd;                      // W_eff^T [KT][G] and its tensor-core packs, one per 128 rows of KT (dz = dy W_eff)
+  int64_t fcwt, fcpk_bwd;                     // fc_w^T [fc_in][F] and its packs, one per 128 rows of fc_in (da = dx W_fc)
   int64_t total;
   int cmax;
 };
@@ -77,6 +79,10 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
     T.dwpart = take(grid * (maxp * 9 + cmax));
   }
   T.fcpk = take(p.fc_out <= 128 ? mapf_tc_b_floats(p.fc_out, p.fc_in) : 0);
+  T.wtt = take(p.taps > 0 ? int64_t(KT) * p.node_dim : 0);
+  T.gfpk_bwd = take(p.taps > 0 ? int64_t((KT + 127) / 128) * mapf_tc_b_floats(128, p.node_dim) : 0);
+  T.fcwt = take(int64_t(p.fc_in) * p.fc_out);
+  T.fcpk_bwd = take(int64_t((p.fc_in + 127) / 128) * mapf_tc_b_floats(128, p.fc_out));
   T.total = off;
   return T;
 }
@@ -993,6 +999,34 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(mapf_clip_adam_args a, f
   }
 }
 
+// d act = (dlogits W) * [act > 0]: the ReLU-masked input gradient of the action head (actionMLP, framework_gnn.py:171-181
+// backward); rows x D outputs, A <= 8 actions.  Memory-bound: one float4 of D per thread.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w,
+                                                       const float* __restrict__ mask, int64_t rows, int D, int A,
+                                                       float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_hw[];   // [A][D]
+  mapf_pdl_wait();
+  mapf_pdl_launch();
+  for (int i = threadIdx.x; i < A * D; i += blockDim.x) s_hw[i] = mapf_ld_dep(w + i);
+  __syncthreads();
+  const int d4 = D >> 2;
+  const int64_t total = rows * d4;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / d4;
+    const int c = int(idx - r * d4) << 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < A; ++a) {
+      const float g = mapf_ld_dep(dl + r * A + a);
+      const float4 wv = *reinterpret_cast<const float4*>(s_hw + a * D + c);
+      acc.x = fmaf(g, wv.x, acc.x); acc.y = fmaf(g, wv.y, acc.y); acc.z = fmaf(g, wv.z, acc.z); acc.w = fmaf(g, wv.w, acc.w);
+    }
+    const float4 m = mapf_ld_dep(reinterpret_cast<const float4*>(mask + r * D + c));
+    acc.x = m.x > 0.0f ? acc.x : 0.0f; acc.y = m.y > 0.0f ? acc.y : 0.0f;
+    acc.z = m.z > 0.0f ? acc.z : 0.0f; acc.w = m.w > 0.0f ? acc.w : 0.0f;
+    *reinterpret_cast<float4*>(out + r * D + c) = acc;
+  }
+}
+
 int launch_conv_train(cudaStream_t s, const float* in, int cin, int cout, int B, int N, const float* wpk,
                       const float* bias, float* out, double* stats, int stat_c) {
   const size_t smem = sizeof(float) * (size_t(cin) * kFovCells * kCtPad + ((size_t(cout) * cin * 9 + 3) & ~size_t(3)));
@@ -1132,6 +1166,53 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   const float* head_act = K > 0 ? ws + T.y : ws + T.x;
   // actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0]
   mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, a->dlogits, rows, A, G.act_b);
+  // Tensor-core path (default): weight gradients = mapf_tc_gemm_tn (contraction over the rows, split K), activation
+  // gradients = mapf_tc_gemm against transposed-weight packs, head input gradient = head_bwd_kernel.
+  // MAPF_TRAIN_FFMA_BWD keeps the FFMA2 sgemm kernels (development switch).
+  // (small batches are launch-bound: below 4096 rows the extra pack launches cost more than the tensor cores save)
+  const bool tc_bwd = !(a->flags & MAPF_TRAIN_FFMA_BWD) && (head_in & 3) == 0 && (F & 3) == 0 && (fin & 3) == 0 &&
+                      (K == 0 || (Gd & 3) == 0) && F <= 128 && Gd <= 128 &&
+                      (rows >= 4096 || (a->flags & MAPF_TRAIN_TC_BWD_ALWAYS));
+  float* da = ws + T.da0;
+  float* da_next = ws + T.da1;
+  // C[rows, Ncols] = Asrc[rows, Kd] . Wt^T with Wt [Ncols, Kd] row-major (a transposed weight), 128 output columns per call
+  auto nn_gemm = [&](const float* Asrc, int Kd, const float* Wt, int Ncols, float* packs, float* Cout, int64_t ldc) -> int {
+    for (int j0 = 0, t = 0; j0 < Ncols; j0 += 128, ++t) {
+      const int nn = Ncols - j0 < 128 ? Ncols - j0 : 128;
+      float* pk = packs + int64_t(t) * mapf_tc_b_floats(128, Kd);
+      MAPF_TRY(mapf_tc_pack_b(Wt + int64_t(j0) * Kd, Kd, nullptr, 0, nn, pk, stream));
+      MAPF_TRY(mapf_tc_gemm(int32_t(rows), nn, Kd, Asrc, Kd, pk, Cout + j0, ldc, nullptr, 0, stream));
+    }
+    return MAPF_OK;
+  };
+  if (tc_bwd) {
+    MAPF_TRY(mapf_tc_gemm_tn(A, head_in, rows, a->dlogits, A, head_act, head_in, G.act_w, head_in, 0, 0, stream));
+    const size_t hsm = sizeof(float) * size_t(A) * head_in;
+    float* dhead = K > 0 ? ws + T.dy : ws + T.dx;
+    mapf_launch_pdl(head_bwd_kernel, dim3(unsigned(mapf_min64((rows * (head_in / 4) + 255) / 256, 148 * 8))), dim3(256), hsm, s,
+                    a->dlogits, p->act_w, head_act, rows, head_in, A, dhead);
+    if (K > 0) {
+      const int KF = K * F, KT = (K + (a->message ? 1 : 0)) * F;
+      // dW_eff[g][j] = sum_r dy[r][g] z[r][j]  -- row-major [G][K*F] IS the memory of GFL.0.W [F,K,G] (gnn.py:114-116)
+      MAPF_TRY(mapf_tc_gemm_tn(Gd, KF, rows, ws + T.dy, Gd, ws + T.z, KT, G.gf_w, KF, 0, 0, stream));
+      if (a->message)
+        MAPF_TRY(mapf_tc_gemm_tn(Gd, F, rows, ws + T.dy, Gd, ws + T.z + KF, KT, G.gf_w2, F, 0, 0, stream));
+      // dz[r][j] = sum_g dy[r][g] W_eff[g][j] (and the W2 columns behind them): W_eff^T rows are the packed B operand
+      MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, K, Gd, ws + T.wtt, stream));
+      MAPF_TRY(nn_gemm(ws + T.dy, Gd, ws + T.wtt, KT, ws + T.gfpk_bwd, ws + T.dz, KT));
+      const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
+      MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
+      if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(recurrence_bwd_kernel, size_t(smem), cache__); }())
+        return MAPF_ERR_CUDA;
+      mapf_launch_pdl(recurrence_bwd_kernel, dim3(B), dim3(128), smem, s, ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
+                                                 a->message ? 0 : 1, ws + T.dx, int64_t(N) * F, F, 1);
+    }
+    // compressMLP backward
+    mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, ws + T.dx, rows, F, G.fc_b);
+    MAPF_TRY(mapf_tc_gemm_tn(F, fin, rows, ws + T.dx, F, ws + T.a[L - 1], fin, G.fc_w, fin, 0, 0, stream));
+    MAPF_TRY(mapf_pack_graph_weights(p->fc_w, nullptr, fin, 1, F, ws + T.fcwt, stream));   // fc_w^T [fc_in][F]
+    MAPF_TRY(nn_gemm(ws + T.dx, F, ws + T.fcwt, fin, ws + T.fcpk_bwd, da, fin));
+  } else {
   MAPF_TRY(gemm(s, A, head_in, int(rows), a->dlogits, 1, A, head_act, head_in, 1, G.act_w, head_in, nullptr, 0, nullptr,
                 0, splits_for(rows, (head_in + 63) / 64)));
   if (K > 0) {
@@ -1160,9 +1241,8 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, ws + T.dx, rows, F, G.fc_b);
   MAPF_TRY(gemm(s, F, fin, int(rows), ws + T.dx, 1, F, ws + T.a[L - 1], fin, 1, G.fc_w, fin, nullptr, 0, nullptr, 0,
                 splits_for(rows, ((F + 127) / 128) * ((fin + 63) / 64))));
-  float* da = ws + T.da0;
-  float* da_next = ws + T.da1;
   MAPF_TRY(gemm(s, int(rows), fin, F, ws + T.dx, F, 1, p->fc_w, fin, 1, da, fin));
+  }
   (void)row_splits;
   const double count = double(B) * kFovCells;
   for (int l = L - 1; l >= 0; --l) {

@@ -103,18 +103,26 @@ class _PolicyBase(nn.Module):
         }
 
     def packed_weights(self):
-        """BatchNorm-folded, kernel-ordered weights; re-packed when any parameter/buffer changed."""
+        """BatchNorm-folded, kernel-ordered weights; re-packed when any parameter/buffer changed.  The buffer keeps its
+        ADDRESS across re-packs (new weights are copied in place), so launch sequences that captured its pointer in a
+        CUDA graph (HostSteppedRollout) read the current weights after the next call of this method instead of freed
+        memory."""
         g = self.param_groups()
         flat = [t for v in g.values() for t in (v if isinstance(v, list) else [v]) if t is not None]
         key = (getattr(self, "_weights_epoch", 0),) + tuple((t.data_ptr(), t._version) for t in flat)
         if self._packed is None or key != self._packed_key:
             d = lambda ts: [t.detach() for t in ts]
-            self._packed = torch.ops.mapf.pack_weights(
+            fresh = torch.ops.mapf.pack_weights(
                 self.dims(), d(g["conv_w"]), d(g["conv_b"]), d(g["bn_gamma"]), d(g["bn_beta"]), d(g["bn_mean"]),
                 d(g["bn_var"]), g["fc_w"].detach(), g["fc_b"].detach(),
                 None if g["gf_w"] is None else g["gf_w"].detach(),
                 None if g["gf_w2"] is None else g["gf_w2"].detach(), g["act_w"].detach(), g["act_b"].detach())
+            if self._packed is not None and self._packed.shape == fresh.shape and self._packed.device == fresh.device:
+                self._packed.copy_(fresh)
+            else:
+                self._packed = fresh
             self._packed_key = key
+            self._packed_serial = getattr(self, "_packed_serial", 0) + 1
         return self._packed
 
     def _forward(self, states, gso):

@@ -51,7 +51,9 @@ def policy_flags() -> int:
 def train_flags() -> int:
     env = os.environ
     return (_lib.TRAIN_FFMA_FC if env.get("MAPF_B200_TRAIN_FFMA_FC") else 0) | \
-           (_lib.TRAIN_FFMA_GRAPH if env.get("MAPF_B200_TRAIN_FFMA_GRAPH") else 0)
+           (_lib.TRAIN_FFMA_GRAPH if env.get("MAPF_B200_TRAIN_FFMA_GRAPH") else 0) | \
+           (_lib.TRAIN_FFMA_BWD if env.get("MAPF_B200_TRAIN_FFMA_BWD") else 0) | \
+           (_lib.TRAIN_TC_BWD_ALWAYS if env.get("MAPF_B200_TRAIN_TC_BWD_ALWAYS") else 0)
 
 
 def wants_encoder_workspace(p) -> bool:
@@ -298,6 +300,7 @@ def _train_bwd(dims, message, states, gso, conv_w, conv_b, bn_gamma, bn_beta, bn
             setattr(a.grads, name, t.data_ptr())
         else:
             getattr(a.grads, name)[i] = t.data_ptr()
+    a.flags = train_flags()
     with torch.cuda.device(states.device):
         _lib.check(lib.mapf_train_backward(p, a, _stream()), "train_backward")
 

@@ -49,7 +49,8 @@ class Rollout:
         p = a.policy
         p.batch, p.agents, p.message = env.episodes, env.nb_agents, int(self.net.message)
         p.states, p.gso = env.fov.data_ptr(), env.adj_matrix.data_ptr()
-        p.packed, p.workspace_x = self.net.packed_weights().data_ptr(), self.work.data_ptr()
+        self._packed = self.net.packed_weights()     # keep the buffer alive for as long as launches may read it
+        p.packed, p.workspace_x = self._packed.data_ptr(), self.work.data_ptr()
         p.workspace_z = None if self.workz is None else self.workz.data_ptr()
         p.workspace_act = None if self.worka is None else self.worka.data_ptr()
         p.logits, p.actions = self.logits.data_ptr(), self.actions.data_ptr()
@@ -124,6 +125,7 @@ class HostSteppedRollout:
         self._event = C.c_void_p(self.event.cuda_event)
         self._lib = _lib.load()
         self.in_flight = False
+        self._packed = rollout._packed               # the captured graphs read this buffer: same address for its lifetime
 
     @property
     def pos_in(self):
@@ -135,6 +137,13 @@ class HostSteppedRollout:
         env.pos.copy_(self.views[1 - k][1], non_blocking=True)           # H2D: this step's state
         ro.run(1)
         self.blocks[k].copy_(env.host_block, non_blocking=True)           # D2H: actions + new positions + done
+
+    def refresh_weights(self):
+        """Call after the network's parameters changed (optimizer step, load_state_dict): re-packs them into the buffer
+        the captured graphs read.  Raises if the packed buffer had to move (different device / size): re-create the
+        rollout then."""
+        if self.ro.net.packed_weights() is not self._packed:
+            raise RuntimeError("HostSteppedRollout: the packed weight buffer was re-allocated; build a new rollout")
 
     def launch(self):
         """Enqueue one step (upload, kernels, download) on this rollout's own stream and return immediately.  Work

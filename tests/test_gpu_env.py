@@ -275,3 +275,50 @@ def test_facade_rule_methods_and_writable_positions():
         assert env.distance_matrix is env.adj_matrix
         sr, _ = env.computeMetrics()
         assert abs(sr - float(np.mean(np.all(want2 == goals, axis=1)))) < 1e-7
+
+
+def test_device_scenarios_distribution_matches_reference_generator():
+    """Distributional parity of the on-device generator with the reference's numpy generator (create_obstacles :504-529,
+    create_goals :465-501, evaluate.py:207-208 order) over 10^5 episodes: the reference draws obstacles uniformly without
+    replacement, goals uniformly among the obstacle-free cells and (our explicit starts) likewise, so every cell marginal
+    is uniform.  Chi-square goodness of fit against the uniform law for the obstacle / goal / start cells, for single
+    slots (no slot is special), and two-sample chi-square of joint statistics (goal-start Manhattan distance of one agent,
+    goal-obstacle distance) against samples of the numpy generator itself.  Critical values at p = 1e-5."""
+    from scipy.stats import chi2
+    import mapf_gnn_b200 as m
+    E, N, H, M = 120_000, 5, 10, 8
+    cells = H * H
+    s, g, o = (t.cpu().numpy().astype(np.int64) for t in m.make_scenarios_device(E, N, H, M, seed=123))
+
+    def gof(points, what):
+        counts = np.bincount((points[..., 1] * H + points[..., 0]).ravel(), minlength=cells).astype(np.float64)
+        exp = counts.sum() / cells
+        stat = ((counts - exp) ** 2 / exp).sum()
+        assert stat < chi2.ppf(1 - 1e-5, cells - 1), (what, stat)
+
+    gof(o, "obstacles"), gof(g, "goals"), gof(s, "starts")
+    for slot in range(N):
+        gof(g[:, slot], f"goal slot {slot}"), gof(s[:, slot], f"start slot {slot}")
+    gof(o[:, 0], "obstacle slot 0"), gof(o[:, M - 1], f"obstacle slot {M - 1}")
+    # numpy generator of the reference's scheme (vectorised restatement in the oracle: make_scenarios)
+    rs, rg, ro = (a.astype(np.int64) for a in eo.make_scenarios(np.random.default_rng(9), E, N, H, M))
+
+    def two_sample(a, b, bins, what):
+        ca = np.bincount(a, minlength=bins).astype(np.float64)
+        cb = np.bincount(b, minlength=bins).astype(np.float64)
+        keep = (ca + cb) >= 20
+        ca, cb = ca[keep], cb[keep]
+        k1, k2 = np.sqrt(cb.sum() / ca.sum()), np.sqrt(ca.sum() / cb.sum())
+        stat = ((k1 * ca - k2 * cb) ** 2 / (ca + cb)).sum()
+        assert stat < chi2.ppf(1 - 1e-5, keep.sum() - 1), (what, stat)
+
+    man = lambda p, q: np.abs(p - q).sum(axis=-1)
+    two_sample(man(g[:, 0], s[:, 0]), man(rg[:, 0], rs[:, 0]), 2 * H, "goal-start distance of agent 0")
+    two_sample(man(g[:, 1], g[:, 3]), man(rg[:, 1], rg[:, 3]), 2 * H, "goal-goal distance")
+    two_sample(man(g[:, 2], o[:, 5]), man(rg[:, 2], ro[:, 5]), 2 * H, "goal-obstacle distance")
+    two_sample(man(s[:, 4], o[:, 0]), man(rs[:, 4], ro[:, 0]), 2 * H, "start-obstacle distance")
+    # exclusions hold in every episode (vectorised): obstacles unique, goals / starts unique and obstacle-free
+    key = lambda p: p[..., 1] * H + p[..., 0]
+    ko, kg, ks = np.sort(key(o), axis=1), np.sort(key(g), axis=1), np.sort(key(s), axis=1)
+    assert (np.diff(ko, axis=1) > 0).all() and (np.diff(kg, axis=1) > 0).all() and (np.diff(ks, axis=1) > 0).all()
+    assert not (key(g)[:, :, None] == key(o)[:, None, :]).any() and not (key(s)[:, :, None] == key(o)[:, None, :]).any()

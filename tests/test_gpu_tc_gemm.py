@@ -49,3 +49,54 @@ def test_structured_values_are_exact():
     B = (torch.arange(N * K, device="cuda", dtype=torch.float32).reshape(N, K) % 5) - 2
     out = tc_gemm(A, B)
     assert torch.equal(out, A @ B.t())
+
+
+def tc_gemm_tn(A, B, transpose_c=False, accumulate_into=None):
+    """C = A^T B through mapf_tc_gemm_tn (A [K, M], B [K, N] row-major, possibly strided views)."""
+    from mapf_gnn_b200 import _lib
+    lib = _lib.load()
+    K, M = A.shape
+    N = B.shape[1]
+    if accumulate_into is not None:
+        out = accumulate_into
+    else:
+        out = torch.full((N, M) if transpose_c else (M, N), float("nan"), dtype=torch.float32, device=A.device)
+    rc = lib.mapf_tc_gemm_tn(M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(), out.stride(0),
+                             int(transpose_c), int(accumulate_into is not None), _lib.current_stream())
+    _lib.check(rc, "tc_gemm_tn")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,tr", [(128, 192, 40960, False), (128, 64, 40960, False), (400, 64, 5000, True),
+                                      (128, 5, 3000, False), (64, 400, 2048, False), (5, 128, 777, True), (16, 16, 7, False),
+                                      (130, 257, 33, False), (128, 128, 16, False)])
+def test_tn_weight_gradient_gemm_matches_float64(M, N, K, tr):
+    """dW = A^T B with the contraction over the row index (split K, transposing producers): fp32-level accuracy against
+    float64, every tile / split / tail shape, row-major and transposed output, unaligned leading dimensions."""
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
+    A = torch.randn(K, M, device="cuda", generator=g)
+    B = torch.randn(K, N, device="cuda", generator=g) * 0.1
+    ref = A.double().t() @ B.double()
+    out = tc_gemm_tn(A, B, transpose_c=tr)
+    if tr:
+        out = out.t()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    err32 = ((A.t() @ B).double() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"M={M} N={N} K={K}: 3xTF32 TN rel err {err:.2e}, cuBLAS fp32 {err32:.2e}")
+    assert err < 4e-6, err
+    # strided operands (columns of wider matrices) and accumulation into an existing C
+    wide_a = torch.randn(K, M + 12, device="cuda", generator=g)
+    wide_b = torch.randn(K, N + 8, device="cuda", generator=g)
+    Av, Bv = wide_a[:, 4:4 + M], wide_b[:, 8:8 + N]
+    base = torch.randn(M, N, device="cuda", generator=g)
+    out2 = tc_gemm_tn(Av, Bv, accumulate_into=base.clone())
+    ref2 = base.double() + Av.double().t() @ Bv.double()
+    assert (out2.double() - ref2).abs().max().item() / ref2.abs().max().item() < 4e-6
+
+
+def test_tn_structured_values_are_exact():
+    K, M, N = 64, 128, 128
+    A = (torch.arange(K * M, device="cuda", dtype=torch.float32).reshape(K, M) % 7) - 3
+    B = (torch.arange(K * N, device="cuda", dtype=torch.float32).reshape(K, N) % 5) - 2
+    assert torch.equal(tc_gemm_tn(A, B), A.t() @ B)

@@ -234,3 +234,39 @@ def test_training_torch_ops_are_registered_and_differentiable():
     assert torch.allclose(logits.grad, ref.grad, rtol=1e-5, atol=1e-8)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.mapf.ce_loss(logits.detach().cpu(), targets.cpu())
+
+
+@pytest.mark.parametrize("mode", ["MAPF_B200_TRAIN_TC_BWD_ALWAYS", "MAPF_B200_TRAIN_FFMA_BWD"])
+@pytest.mark.parametrize("name", ["gnn_msg_k3", "gnn_k3", "baseline"])
+def test_backward_gemm_paths_match_reference(train_step, name, mode, monkeypatch):
+    """Both backward GEMM paths -- tensor cores (mapf_tc_gemm_tn weight gradients + mapf_tc_gemm activation gradients,
+    the default from 4096 rows on) and the FFMA2 kernels -- against the reference's recorded gradients."""
+    monkeypatch.setenv(mode, "1")
+    t = train_step
+    net = load_network(name).train()
+    states, gso, targets = _batch(t)
+    out = net(states) if name == "baseline" else net(states, gso)
+    torch.nn.functional.cross_entropy(out.reshape(-1, 5), targets.reshape(-1)).backward()
+    floor = GRAD_FLOOR * t[f"{name}/total_norm"][0]
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), t[f"{name}/grad/{k}"], floor) < REL, k
+
+
+def test_large_batch_gradients_match_oracle():
+    """4096+ rows: the tensor-core backward path is the default; gradients vs the torch-CPU oracle."""
+    name, B, N = "gnn_msg_k3", 1024, 5
+    rng = np.random.default_rng(12)
+    states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+    adj = torch.tensor((rng.random((B, N, N)) < 0.3).astype(np.float32))
+    adj[:, torch.arange(N), torch.arange(N)] = 0
+    gso = adj + torch.eye(N)
+    targets = torch.tensor(rng.integers(0, 5, size=(B, N)))
+    params = oracle_params(name)
+    loss_ref, grads_ref, _ = mo.loss_and_grads(params, states, gso, targets)
+    total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads_ref.values())))
+    net = load_network(name, num_agents=N).train()
+    loss = torch.nn.functional.cross_entropy(net(states.cuda(), gso.cuda()).reshape(-1, 5), targets.cuda().reshape(-1))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy(), GRAD_FLOOR * total) < REL, k
