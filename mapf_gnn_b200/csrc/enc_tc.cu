@@ -466,7 +466,338 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
   if (warp == 0) tc::tmem_dealloc(s_tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// ONE 3x3 convolution layer (16 output channels, 2 or 16 input channels) of the TRAINING step on the same tensor-core
+// formulation: forward convolutions (pre-BatchNorm output u = conv + bias; the per-slot statistics are a separate pass)
+// and data gradients (the same convolution with mirrored, transposed filters) of train.py:87,96.  Activations live in
+// global memory as [rows][C*25] (C,H,W order): lane = pixel, so a warp reads / writes 25 contiguous floats per channel.
+// Per tile of 4 images: operand into TMEM (fp16 hi / lo split, one power-of-two scale per image) -> 3 (or 9) MMAs ->
+// vertical shifted adds -> store.  Five warpgroups per CTA with private TMEM sets, as in encoder_tc_kernel.
+// ---------------------------------------------------------------------------------------------------------
+struct ConvTcArgs {
+  int64_t rows;
+  const float* in;     // [rows][CIN*25]
+  const float* wtc;    // [kEtHdr floats: inverse filter scale][K steps x (hi block | lo block)] (pack_tc_conv_raw_kernel)
+  const float* bias;   // [16] or NULL
+  float* out;          // [rows][16*25]
+  int skew;
+  // per-slot BatchNorm statistics of the output (forward layers; NULL for data gradients): fp64 sums [N][stat_c][2]
+  double* stats;
+  int slots, stat_c;   // N agent slots (row = b * N + n), channel pitch of `stats`
+};
+
+// raw filters [Cout][Cin][3][3] (mode 0) or their data-gradient form W'[o][i][ky][kx] = W[i][o][2-ky][2-kx] (mode 1,
+// o = forward input channel) -> B operand blocks for 16 output channels; one block, scale from the largest |w|
+__global__ void pack_tc_conv_raw_kernel(const float* __restrict__ w, int cin_fwd, int cout_fwd, int mode,
+                                        float* __restrict__ out) {
+  __shared__ float s_red[256];
+  mapf_pdl_wait();
+  mapf_pdl_launch();
+  const int nw = cout_fwd * cin_fwd * 9;
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) m = fmaxf(m, fabsf(mapf_ld_dep(w + i)));
+  s_red[threadIdx.x] = m;
+  __syncthreads();
+  for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+    if (threadIdx.x < st) s_red[threadIdx.x] = fmaxf(s_red[threadIdx.x], s_red[threadIdx.x + st]);
+    __syncthreads();
+  }
+  float scale, inv;
+  pow2_scale(s_red[0], scale, inv);
+  if (blockIdx.x == 0 && threadIdx.x < kEtHdr) out[threadIdx.x] = threadIdx.x == 0 ? inv : 0.0f;
+  const int cin = mode == 0 ? cin_fwd : cout_fwd;      // input channels of THIS convolution (its output has 16)
+  const int ks = (3 * cin + 15) >> 4;
+  __half* o = reinterpret_cast<__half*>(out + kEtHdr);
+  const int n = ks * 2 * kEtBlk * 2;
+  // (every block recomputes the scale -- a few loads per thread -- and converts its share of the operand)
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    int r = idx;
+    const int step = r / (4 * kEtBlk);
+    r -= step * 4 * kEtBlk;
+    const int is_lo = r >= 2 * kEtBlk;
+    if (is_lo) r -= 2 * kEtBlk;
+    const int k8i = r & 7, n8 = (r >> 3) & 7, kq = (r >> 6) & 1, ng = r >> 7;
+    const int nn = ng * 8 + n8, k = step * 16 + kq * 8 + k8i;
+    const int ky = nn / kEtCout, co = nn % kEtCout;
+    float v = 0.0f;
+    if (k < 3 * cin) {
+      const int kx = k / cin, ci = k - kx * cin;
+      v = (mode == 0 ? mapf_ld_dep(w + ((co * cin_fwd + ci) * 3 + ky) * 3 + kx)
+                     : mapf_ld_dep(w + ((ci * cin_fwd + co) * 3 + (2 - ky)) * 3 + (2 - kx))) * scale;
+    }
+    const __half hi = __float2half_rn(v);
+    o[idx] = is_lo ? __float2half_rn(v - __half2float(hi)) : hi;
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(ConvTcArgs g) {
+  constexpr int kGroups = EtCfg<16>::kGroups, kThreads = EtCfg<16>::kThreads;
+  constexpr uint32_t kColALo = EtCfg<16>::kColALo, kSetCols = EtCfg<16>::kSetCols;
+  constexpr int kSteps = (3 * CIN + 15) / 16;
+  constexpr int kWFloats = kEtHdr + kSteps * 2 * kEtBlk;
+  __shared__ __align__(128) float s_w[kWFloats];
+  __shared__ __align__(16) float s_b[kEtCout];
+  __shared__ __align__(8) uint64_t s_bar[kGroups];
+  __shared__ uint32_t s_tmem;
+  extern __shared__ __align__(16) double s_stat[];     // [warp][slot][32]: a warp's private per-slot sums (g.stats only)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, quad = warp & 3;
+  const bool do_stats = g.stats != nullptr;
+  double* const my_stat = s_stat + warp * g.slots * 32 + lane;
+
+  if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kGroups; ++i) tc::mbar_init(&s_bar[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (do_stats)
+    for (int i = tid; i < (kThreads / 32) * g.slots * 32; i += kThreads) s_stat[i] = 0.0;
+  mapf_pdl_wait();      // filters (packed by the kernel in front), input activations and bias all come from earlier kernels
+  mapf_pdl_launch();
+  for (int i = tid; i < kWFloats / 4; i += kThreads)
+    reinterpret_cast<float4*>(s_w)[i] = mapf_ld_dep(reinterpret_cast<const float4*>(g.wtc) + i);
+  if (tid < kEtCout) s_b[tid] = g.bias != nullptr ? mapf_ld_dep(g.bias + tid) : 0.0f;
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem + uint32_t(wg) * kSetCols;
+  const uint32_t tlane = tmem + (uint32_t(quad * 32) << 16);
+  uint64_t* const bar = &s_bar[wg];
+  uint32_t phase = 0;
+  const bool issuer_warp = __shfl_sync(0xffffffffu, quad, 0) == 0;
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t w_base_u = __shfl_sync(0xffffffffu, tc::smem_u32(s_w), 0);
+
+  const int py = (lane + 5) / 6 - 1, px = lane - 1 - 6 * py;
+  const bool pix_ok = lane >= 1 && lane <= 29 && px >= 0 && px < kFov;
+  const int pidx = pix_ok ? py * kFov + px : 0;
+  const float m_up = (pix_ok && py > 0) ? 1.0f : 0.0f, m_dn = (pix_ok && py < kFov - 1) ? 1.0f : 0.0f;
+  constexpr int kRow = kFov + 1;
+  constexpr uint32_t idesc = tc::idesc_f16(128, kEtN);
+  const int64_t ntiles = (g.rows + 3) >> 2;
+  const int64_t stride = int64_t(gridDim.x) * kGroups;
+
+  auto load_in = [&](int64_t tile, float (&x)[CIN]) {
+    const int64_t img = tile * 4 + quad;
+    const bool live = tile < ntiles && img < g.rows && pix_ok;
+    const float* src = g.in + img * (CIN * kFovCells) + pidx;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) x[c] = live ? mapf_ld_dep(src + c * kFovCells) : 0.0f;
+  };
+  auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); };
+  auto left_of = [&](uint32_t w) { return __shfl_up_sync(0xffffffffu, w, 1); };
+  auto right_of = [&](uint32_t w) { return __shfl_down_sync(0xffffffffu, w, 1); };
+  auto warp_max = [&](float m) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))); };
+
+  int64_t tile = int64_t(blockIdx.x) * kGroups + wg;
+  float x[CIN];
+  load_in(tile, x);
+  if (wg > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < g.skew * wg) {}
+  }
+  for (; tile < ntiles; tile += stride) {
+    float inv_a;
+    {
+      float amax = 0.0f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) amax = fmaxf(amax, fabsf(x[c]));
+      float sc;
+      pow2_scale(warp_max(amax), sc, inv_a);
+      sc = pix_ok ? sc : 0.0f;
+      if (CIN == 2) {
+        uint32_t hi[8], lo[8];
+        split_h2(x[0] * sc, x[CIN - 1] * sc, hi[1], lo[1]);
+        hi[0] = left_of(hi[1]);  lo[0] = left_of(lo[1]);
+        hi[2] = right_of(hi[1]); lo[2] = right_of(lo[1]);
+#pragma unroll
+        for (int i = 3; i < 8; ++i) hi[i] = lo[i] = 0u;
+        tmem_st8(tlane + kEtColAHi, hi);
+        tmem_st8(tlane + kColALo, lo);
+      } else {
+        constexpr int kW = 8;
+        uint32_t h[kW], o[kW], t[kW];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) split_h2(x[c % CIN] * sc, x[(c + 1) % CIN] * sc, h[c >> 1], o[c >> 1]);
+        tmem_st8(tlane + kEtColAHi + kW, h);
+        tmem_st8(tlane + kColALo + kW, o);
+#pragma unroll
+        for (int j = 0; j < kW; ++j) t[j] = left_of(h[j]);
+        tmem_st8(tlane + kEtColAHi, t);
+#pragma unroll
+        for (int j = 0; j < kW; ++j) t[j] = left_of(o[j]);
+        tmem_st8(tlane + kColALo, t);
+#pragma unroll
+        for (int j = 0; j < kW; ++j) t[j] = right_of(h[j]);
+        tmem_st8(tlane + kEtColAHi + 2 * kW, t);
+#pragma unroll
+        for (int j = 0; j < kW; ++j) t[j] = right_of(o[j]);
+        tmem_st8(tlane + kColALo + 2 * kW, t);
+      }
+    }
+    const int64_t img = tile * 4 + quad;
+    load_in(tile + stride, x);          // next tile's activations arrive while this one is computed
+    tmem_st_wait();
+    tc::fence_before_sync();
+    wg_sync();
+    if (issuer_warp) {
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kSteps; ++ks) {
+          const uint32_t wl = w_base_u + uint32_t(kEtHdr * 4) + uint32_t(ks) * (2 * kEtBlk * 4);
+          const uint64_t bh = tc::smem_desc(wl, 128, 256);
+          const uint64_t bl = tc::smem_desc(wl + kEtBlk * 4, 128, 256);
+          const uint32_t ah = tmem_u + kEtColAHi + uint32_t(ks) * 8, al = tmem_u + kColALo + uint32_t(ks) * 8;
+          mma_f16_ts(tmem_u, al, bh, idesc, ks > 0);     // small terms first; fixed order: reproducible
+          mma_f16_ts(tmem_u, ah, bl, idesc, true);
+          mma_f16_ts(tmem_u, ah, bh, idesc, true);
+        }
+        tc::mma_commit(bar);
+      }
+    }
+    __syncwarp();
+    etc_mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+
+    uint32_t r[3][kEtCout];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) tmem_ld16(tlane + uint32_t(u * kEtCout), r[u]);
+    tc::tmem_ld_wait();
+    const float f = inv_a * s_w[0];
+    const float f_up = m_up * f, f_dn = m_dn * f;
+    float* dst = g.out + img * (kEtCout * kFovCells) + pidx;
+    const bool live = img < g.rows && pix_ok;
+    float sv[2 * kEtCout];        // this pixel's outputs and their squares (statistics)
+#pragma unroll
+    for (int c = 0; c < kEtCout; ++c) {
+      const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow);
+      const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kRow);
+      float a = fmaf(__uint_as_float(r[1][c]), f, s_b[c]);
+      a = fmaf(up, f_up, a);
+      a = fmaf(dn, f_dn, a);
+      if (live) dst[c * kFovCells] = a;
+      sv[c] = live ? a : 0.0f;
+      sv[kEtCout + c] = live ? a * a : 0.0f;
+    }
+    if (do_stats) {
+      // Per-slot BatchNorm sums (framework_gnn.py:160-163: statistics per agent slot): a warp = one image = one slot.
+      // Recursive halving over the 32 lanes: after 16 + 8 + 4 + 2 + 1 shuffles lane L holds the image's total of value L
+      // (L < 16: sum of channel L, else sum of squares of channel L - 16); it goes into the warp's private fp64 table.
+#pragma unroll
+      for (int h = kEtCout; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float send = upper ? sv[i] : sv[h + i];
+          const float keep = upper ? sv[h + i] : sv[i];
+          sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+      }
+      if (img < g.rows) my_stat[int(img % g.slots) * 32] += double(sv[0]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(s_tmem, 512);
+  if (do_stats) {
+    for (int i = tid; i < g.slots * 32; i += kThreads) {
+      double t = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) t += s_stat[w * g.slots * 32 + i];
+      const int n = i >> 5, L = i & 31;
+      atomicAdd(g.stats + (int64_t(n) * g.stat_c + (L & 15)) * 2 + (L >> 4), t);
+    }
+  }
+}
+
+// per-slot BatchNorm batch statistics of a conv output u [rows][C*25], rows = b * N + n (framework_gnn.py:160-163: the
+// reference runs the conv stack once per agent slot, so the statistics are per slot over B*25 values): fp64 sums
+// [N][stat_c][2] accumulated with one atomic pair per (CTA, channel).  grid (ceil(B/64), N), one warp per channel.
+__global__ void __launch_bounds__(512) bn_stats_kernel(const float* __restrict__ u, int B, int N, int C, int stat_c,
+                                                       double* __restrict__ stats) {
+  mapf_pdl_wait();
+  mapf_pdl_launch();
+  const int n = blockIdx.y, b0 = blockIdx.x * 64, lane = threadIdx.x & 31;
+  const int nb = B - b0 < 64 ? B - b0 : 64;
+  for (int c = threadIdx.x >> 5; c < C; c += blockDim.x >> 5) {
+    float s1 = 0.0f;
+    double s2 = 0.0;
+    if (lane < kFovCells) {
+      const float* p = u + (int64_t(b0) * N + n) * (C * kFovCells) + c * kFovCells + lane;
+      float q1 = 0.0f, q2 = 0.0f;
+      for (int b = 0; b < nb; ++b) {
+        const float v = mapf_ld_dep(p + int64_t(b) * N * (C * kFovCells));
+        q1 += v;
+        q2 = fmaf(v, v, q2);
+        if ((b & 15) == 15) { s2 += double(q2); q2 = 0.0f; }
+      }
+      s1 = q1;
+      s2 += double(q2);
+    }
+    double t1 = double(s1), t2 = s2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (lane == 0) {
+      atomicAdd(stats + (int64_t(n) * stat_c + c) * 2, t1);
+      atomicAdd(stats + (int64_t(n) * stat_c + c) * 2 + 1, t2);
+    }
+  }
+}
+
 }  // namespace
+
+// One training-step convolution layer on the tensor cores (declared in train_kernels.cu): in [rows][cin*25] -> out
+// [rows][16*25] = conv3x3(in, w) + bias, w raw [cout_fwd][cin_fwd][3][3]; mode 1 = data gradient (mirrored, transposed
+// filters: the input then has cout_fwd channels and the output cin_fwd = 16).  wtc_scratch: kEtHdr + 3*2*384 floats.
+// stats != NULL: per-slot BatchNorm sums of the output are accumulated (B, N = batch and agent slots, rows = B*N).
+int mapf_conv_tc_layer_floats() { return kEtHdr + 3 * 2 * kEtBlk; }
+bool mapf_conv_tc_layer_ok(int cin_fwd, int cout_fwd, int mode) {
+  const int cin = mode == 0 ? cin_fwd : cout_fwd, cout = mode == 0 ? cout_fwd : cin_fwd;
+  return cout == kEtCout && (cin == 2 || cin == 16);
+}
+int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int cin_fwd, int cout_fwd, int mode, int B,
+                       int N, float* wtc_scratch, float* out, double* stats, int stat_c, mapf_stream_t stream) {
+  MAPF_REQUIRE(in && w && wtc_scratch && out, MAPF_ERR_NULL);
+  MAPF_REQUIRE(mapf_conv_tc_layer_ok(cin_fwd, cout_fwd, mode), MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(wtc_scratch, 16), MAPF_ERR_ALIGN);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cin = mode == 0 ? cin_fwd : cout_fwd;
+  mapf_launch_pdl(pack_tc_conv_raw_kernel, dim3(cin == 2 ? 3 : 9), dim3(256), 0, s, w, cin_fwd, cout_fwd, mode, wtc_scratch);
+  ConvTcArgs g{};
+  g.rows = int64_t(B) * N;
+  g.in = in; g.wtc = wtc_scratch; g.bias = bias; g.out = out;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = (g.rows + 3) >> 2;
+  const int64_t want = (ntiles + 4) / 5;
+  const int grid = int(want < sms ? want : sms);
+  const int64_t rounds = (ntiles + int64_t(grid) * 5 - 1) / (int64_t(grid) * 5);
+  g.skew = int(rounds >= 6 ? 700 : 200 + 100 * rounds);
+  // statistics in the conv epilogue while the warps' private tables fit shared memory (N <= 16); else a second pass
+  const bool fused_stats = stats != nullptr && N <= 16;
+  size_t smem = 0;
+  if (fused_stats) {
+    g.stats = stats; g.slots = N; g.stat_c = stat_c;
+    smem = sizeof(double) * size_t(EtCfg<16>::kThreads / 32) * N * 32;
+  }
+  auto launch = [&](auto kernel, int* cache) -> int {
+    if (smem > 40 * 1024 && !mapf_ensure_smem(kernel, smem, cache)) return MAPF_ERR_CUDA;
+    mapf_launch_pdl(kernel, dim3(grid), dim3(EtCfg<16>::kThreads), smem, s, g);
+    return MAPF_OK;
+  };
+  static int c2[16] = {0}, c16[16] = {0};
+  const int rc = cin == 2 ? launch(conv_tc_layer_kernel<2>, c2) : launch(conv_tc_layer_kernel<16>, c16);
+  if (rc != MAPF_OK) return rc;
+  if (stats != nullptr && !fused_stats)
+    mapf_launch_pdl(bn_stats_kernel, dim3((B + 63) / 64, N), dim3(512), 0, s, out, B, N, kEtCout, stat_c, stats);
+  return mapf_launch_status();
+}
 
 #ifdef MAPF_ENC_DEBUG
 extern "C" int mapf_enc_tc_set_debug(long long* p) {

@@ -61,6 +61,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a tensor-core pipeline bug must never hang the GPU.  On timeout the kernel traps (the launch
 // then reports an error instead of spinning forever).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1   // (ptxas otherwise unrolls the poll loop several times at every call site: kilobytes of cold code)
   for (uint32_t spin = 0; spin < (1u << 20); ++spin)   // each try sleeps at most 20 us: a dead pipeline traps within ~20 s
     if (mbar_try_wait(bar, parity)) return;
   asm volatile("trap;");

@@ -18,6 +18,14 @@ constexpr float kBnEpsT = 1e-5f;
 // ---------------------------------------------------------------------------------------------
 // workspace layout (offsets in floats)
 // ---------------------------------------------------------------------------------------------
+}  // namespace
+// enc_tc.cu: one conv layer of the training step on the tensor cores
+int mapf_conv_tc_layer_floats();
+bool mapf_conv_tc_layer_ok(int cin_fwd, int cout_fwd, int mode);
+int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int cin_fwd, int cout_fwd, int mode, int B,
+                       int N, float* wtc_scratch, float* out, double* stats, int stat_c, mapf_stream_t stream);
+namespace {
+
 struct TrainLayout {
   int64_t stat_fwd, stat_bwd;                 // fp64 [L][N][Cmax][2] each (offset in floats, 8-byte aligned)
   int64_t meaninv[MAPF_MAX_CONV];             // [N][C][2]  (mean, invstd)
@@ -31,6 +39,7 @@ struct TrainLayout {
   int64_t dy, dz, dx, da0, da1;
   int64_t fcpk;                               // compressMLP weight, packed for the tensor-core GEMM (mapf_tc_pack_b)
   int64_t dwpart;                             // [grid <= 296][max cin*cout*9 + cmax] per-CTA weight-gradient partials
+  int64_t convtc[MAPF_MAX_CONV], convtc_bwd[MAPF_MAX_CONV];   // tensor-core filter operands (enc_tc.cu mapf_conv_tc_layer)
   int64_t wtt, gfpk_bwd;                      // W_eff^T [KT][G] and its tensor-core packs, one per 128 rows of KT (dz = dy W_eff)
   int64_t fcwt, fcpk_bwd;                     // fc_w^T [fc_in][F] and its packs, one per 128 rows of fc_in (da = dx W_fc)
   int64_t total;
@@ -79,6 +88,10 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
     T.dwpart = take(grid * (maxp * 9 + cmax));
   }
   T.fcpk = take(p.fc_out <= 128 ? mapf_tc_b_floats(p.fc_out, p.fc_in) : 0);
+  for (int l = 0; l < p.num_conv; ++l) {
+    T.convtc[l] = take(mapf_conv_tc_layer_floats());
+    T.convtc_bwd[l] = take(mapf_conv_tc_layer_floats());
+  }
   T.wtt = take(p.taps > 0 ? int64_t(KT) * p.node_dim : 0);
   T.gfpk_bwd = take(p.taps > 0 ? int64_t((KT + 127) / 128) * mapf_tc_b_floats(128, p.node_dim) : 0);
   T.fcwt = take(int64_t(p.fc_in) * p.fc_out);
@@ -1080,10 +1093,17 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   for (int l = 0; l < L; ++l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
     MAPF_REQUIRE(p->conv_w[l] && p->conv_b[l] && p->bn_gamma[l] && p->bn_beta[l], MAPF_ERR_NULL);
-    mapf_launch_pdl(pack_conv_kernel, dim3((cout * cin * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
     double* st = stat + int64_t(l) * N * T.cmax * 2;
-    MAPF_TRY(launch_conv_train(s, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, B, N, ws + T.convpk[l],
-                               p->conv_b[l], ws + T.u[l], st, T.cmax));
+    // tensor-core convolution (fp16-split operands, enc_tc.cu) from 4096 rows on; FFMA2 kernel otherwise
+    if (!(a->flags & MAPF_TRAIN_FFMA_CONV) && (rows >= 4096 || (a->flags & MAPF_TRAIN_TC_BWD_ALWAYS)) &&
+        mapf_conv_tc_layer_ok(cin, cout, 0)) {
+      MAPF_TRY(mapf_conv_tc_layer(l == 0 ? a->states : ws + T.a[l - 1], p->conv_w[l], p->conv_b[l], cin, cout, 0, B, N,
+                                  ws + T.convtc[l], ws + T.u[l], st, T.cmax, stream));
+    } else {
+      mapf_launch_pdl(pack_conv_kernel, dim3((cout * cin * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
+      MAPF_TRY(launch_conv_train(s, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, B, N, ws + T.convpk[l],
+                                 p->conv_b[l], ws + T.u[l], st, T.cmax));
+    }
     mapf_launch_pdl(bn_finalize_kernel, dim3((cout + 63) / 64), dim3(64), 0, s, st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
                                                       const_cast<float*>(p->bn_mean[l]),
                                                       const_cast<float*>(p->bn_var[l]), a->bn_batches[l], p->bn_gamma[l],
@@ -1289,10 +1309,16 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     }
     if (l > 0) {
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
-      const int cin_pad = int(r4(cin));
-      mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
-      MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
-      MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
+      if (!(a->flags & MAPF_TRAIN_FFMA_CONV) && (rows >= 4096 || (a->flags & MAPF_TRAIN_TC_BWD_ALWAYS)) &&
+          mapf_conv_tc_layer_ok(cin, cout, 1)) {
+        MAPF_TRY(mapf_conv_tc_layer(da, p->conv_w[l], nullptr, cin, cout, 1, B, N, ws + T.convtc_bwd[l], da_next, nullptr, 0,
+                                    stream));
+      } else {
+        const int cin_pad = int(r4(cin));
+        mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
+        MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
+        MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
+      }
       float* t = da; da = da_next; da_next = t;
     }
   }

@@ -53,7 +53,8 @@ def train_flags() -> int:
     return (_lib.TRAIN_FFMA_FC if env.get("MAPF_B200_TRAIN_FFMA_FC") else 0) | \
            (_lib.TRAIN_FFMA_GRAPH if env.get("MAPF_B200_TRAIN_FFMA_GRAPH") else 0) | \
            (_lib.TRAIN_FFMA_BWD if env.get("MAPF_B200_TRAIN_FFMA_BWD") else 0) | \
-           (_lib.TRAIN_TC_BWD_ALWAYS if env.get("MAPF_B200_TRAIN_TC_BWD_ALWAYS") else 0)
+           (_lib.TRAIN_TC_BWD_ALWAYS if env.get("MAPF_B200_TRAIN_TC_BWD_ALWAYS") else 0) | \
+           (_lib.TRAIN_FFMA_CONV if env.get("MAPF_B200_TRAIN_FFMA_CONV") else 0)
 
 
 def wants_encoder_workspace(p) -> bool:
@@ -73,6 +74,7 @@ _LIB.define("pack_graph_weights(Tensor w, Tensor? w2) -> Tensor")
 _LIB.define("graph_filter_fwd(Tensor x, Tensor gso, Tensor wt, int taps, bool add_self_loop, bool has_skip, "
             "bool relu) -> Tensor")
 _LIB.define("head_fwd(Tensor x, Tensor act_w, Tensor act_b) -> (Tensor, Tensor)")
+_LIB.define("linear(Tensor x, Tensor w, Tensor? b, bool relu) -> Tensor")
 _LIB.define("env_step(Tensor(a!) pos, Tensor goal, Tensor? actions, Tensor(b!) cells, Tensor(c!) time, "
             "Tensor(d!) done, Tensor(e!) fov, Tensor(f!) adj, int board, int d2_limit, bool do_move) -> ()")
 
@@ -223,6 +225,25 @@ def _head_fwd(x, act_w, act_b):
     return logits, actions
 
 
+def _linear(x, w, b, relu):
+    """act(x W^T + b) on the tensor cores (3xTF32, fp32-level accuracy): nn.Linear (+ ReLU) of the encoder / action MLPs
+    (framework_gnn.py:90-96) for x [rows, K], W [N <= 128, K], K a multiple of 4."""
+    lib = _lib.load()
+    x, w = _f32c(x), _f32c(w)
+    rows, K = int(x.shape[0]), int(x.shape[1])
+    Nout = int(w.shape[0])
+    if int(w.shape[1]) != K or Nout > 128 or (K & 3):
+        raise ValueError(f"mapf::linear supports W [N <= 128, K % 4 == 0] matching x; got x {tuple(x.shape)}, W {tuple(w.shape)}")
+    out = torch.empty((rows, Nout), dtype=torch.float32, device=x.device)
+    pk = torch.empty((lib.mapf_tc_packed_b_size(Nout, K),), dtype=torch.float32, device=x.device)
+    bias = None if b is None else _f32c(b)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mapf_tc_pack_b(w.data_ptr(), K, None, 0, Nout, pk.data_ptr(), _stream()), "tc_pack_b")
+        _lib.check(lib.mapf_tc_gemm(rows, Nout, K, x.data_ptr(), K, pk.data_ptr(), out.data_ptr(), Nout,
+                                    None if bias is None else bias.data_ptr(), int(relu), _stream()), "tc_gemm")
+    return out
+
+
 def _env_step(pos, goal, actions, cells, time, done, fov, adj, board, d2_limit, do_move):
     lib = _lib.load()
     E, N = int(pos.shape[0]), int(pos.shape[1])
@@ -358,4 +379,5 @@ _LIB.impl("encoder_fwd", _encoder_fwd, "CUDA")
 _LIB.impl("pack_graph_weights", _pack_graph_weights, "CUDA")
 _LIB.impl("graph_filter_fwd", _graph_filter_fwd, "CUDA")
 _LIB.impl("head_fwd", _head_fwd, "CUDA")
+_LIB.impl("linear", _linear, "CUDA")
 _LIB.impl("env_step", _env_step, "CUDA")

@@ -575,3 +575,40 @@ def test_pipelined_host_rollout_matches_device_rollout():
     assert torch.equal(pl.envs[1].pos.cpu(), torch.as_tensor(starts[30:60]).int())
     with pytest.raises(RuntimeError):
         pl.groups[0].wait()
+
+
+@pytest.mark.parametrize("msg_type", ["gcn", "message"])
+def test_general_configs_staged_inference_matches_oracle(msg_type):
+    """framework_gnn.py:90-123 allows deeper encoder MLPs (`encoder_layers`) and several graph filtering layers
+    (`graph_filters` / `node_dims` lists): no shipped config uses them, they run stage by stage on the same kernels
+    (inference only).  Logits vs the torch-CPU oracle on the module's own state_dict; action_layers > 1 cannot be built
+    by the reference either (IndexError) and raises the same here."""
+    import mapf_gnn_b200 as m
+    torch.manual_seed(5)
+    N, B = 7, 33
+    cfg = dict(map_shape=[5, 5], num_actions=5, last_convs=[400], channels=[16, 16, 16], node_dims=[128, 64],
+               graph_filters=[3, 2], encoder_dims=[64, 32], encoder_layers=2, action_layers=1, num_agents=N,
+               net_type="gnn", msg_type=msg_type)
+    net = m.build_network(cfg).cuda().eval()
+    assert not net.fused
+    for mod in net.modules():                       # non-trivial running statistics
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0.0, 0.3)
+            mod.running_var.uniform_(0.5, 1.5)
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    assert {"compressMLP.2.weight", "GFL.2.W"} <= set(params)
+    rng = np.random.default_rng(8)
+    states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+    adj = torch.tensor((rng.random((B, N, N)) < 0.35).astype(np.float32))
+    adj[:, torch.arange(N), torch.arange(N)] = 0
+    with torch.no_grad():
+        ref = mo.forward(params, states, adj).numpy()
+        out = net(states.cuda(), adj.cuda())
+        logits, actions = net.act(states.cuda(), adj.cuda())
+    assert rel_err(out.cpu().numpy(), ref) < REL
+    assert torch.equal(out, logits)
+    assert _check_actions(actions.cpu().numpy(), ref) == 0
+    with pytest.raises(NotImplementedError):
+        net.train()(states.cuda(), adj.cuda())
+    with pytest.raises(IndexError):
+        m.build_network(dict(cfg, action_layers=2))

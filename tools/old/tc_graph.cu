@@ -121,14 +121,11 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
-  // warp-uniform copies for the MMA issuers (elect.sync inside a warp-uniform branch: plain UTCHMMAs, see tc_gemm.cu)
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
   const int slices = F >> 3;                       // 8-feature slices (host guarantees slices % 4 == 0)
   const int per_warp = slices / kTgProd;
   const int chunks_per_slice = K + g.has_skip;
 
-  if (warp_u < kTgProd) {
+  if (warp < kTgProd) {
     // ===================== producers =====================
     const int p = warp;
     uint8_t* a_hi = stages + p * kTgStageBytes;
@@ -242,10 +239,10 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
         emit(K * slices + j, sv);
       }
     }
-  } else if (warp_u < kTgProd + 2) {
+  } else if (warp < kTgProd + 2) {
     // ===================== MMA issuers =====================
-    if (tc::elect_one()) {
-      const int which = warp_u - kTgProd;
+    if (lane == 0) {
+      const int which = warp - kTgProd;
       constexpr uint32_t idesc = tc::idesc_tf32(kTgM, kTgNT);
       constexpr uint32_t sbo = 256, lbo = 128;
       const uint32_t base = tc::smem_u32(stages);
@@ -253,7 +250,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
       const uint64_t dal0 = tc::smem_desc(base + kTgABytes, lbo, sbo);
       const uint64_t dbh0 = tc::smem_desc(base + 2 * kTgABytes, lbo, sbo);
       const uint64_t dbl0 = tc::smem_desc(base + 2 * kTgABytes + kTgBBytes, lbo, sbo);
-      const uint32_t acc = tmem_u + uint32_t(which) * kTgNT;
+      const uint32_t acc = tmem + uint32_t(which) * kTgNT;
       const int T = per_warp * chunks_per_slice;
       bool first = true;
       for (int t = 0; t < T; ++t) {
@@ -392,7 +389,7 @@ int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t
   if (env != nullptr) {
     MAPF_REQUIRE(actions != nullptr && env->episodes == batch && env->agents == agents, MAPF_ERR_SHAPE);
     MAPF_REQUIRE(mapf_tc_graph_env_fusable(agents, env->cell_stride) && gso_is_old, MAPF_ERR_UNSUPPORTED);
-    envl = 8;   // mapf_tc_graph_env_fusable: agents <= 8
+    envl = agents <= 8 ? 8 : agents <= 16 ? 16 : 32;
     g.env = *env;
     smem += sizeof(int32_t) * kTgM + ((sizeof(EnvShared<8, kTgThreads>) + 15) & ~size_t(15)) + size_t(epc) * env->cell_stride;
   }
@@ -403,8 +400,9 @@ int mapf_tc_graph_head_ex(int32_t batch, int32_t agents, int32_t in_dim, int32_t
     mapf_launch_pdl(kernel, dim3(ntiles), dim3(kTgThreads), smem, s, g, epc);
     return MAPF_OK;
   };
-  static int c0[16] = {0}, c8[16] = {0};
-  const int rc = envl == 0 ? launch(tc_graph_kernel<0>, c0) : launch(tc_graph_kernel<8>, c8);
+  static int c0[16] = {0}, c8[16] = {0}, c16[16] = {0}, c32[16] = {0};
+  const int rc = envl == 0 ? launch(tc_graph_kernel<0>, c0) : envl == 8 ? launch(tc_graph_kernel<8>, c8)
+               : envl == 16 ? launch(tc_graph_kernel<16>, c16) : launch(tc_graph_kernel<32>, c32);
   if (rc != MAPF_OK) return rc;
   return mapf_launch_status();
 }

@@ -29,6 +29,17 @@ constexpr int kTgNT = 128;
 constexpr int kTgABytes = kTgM * 8 * 4, kTgBBytes = kTgNT * 8 * 4;
 constexpr int kTgStageBytes = 2 * kTgABytes + 2 * kTgBBytes;   // 16 KB
 
+// x / n for 0 <= x < 2^20 and small n, with rcp = 1.0f / n: no integer-division sequence (dozens of instructions each; this
+// kernel runs its code once per CTA from a cold instruction cache, so code size is latency).  Exact: x + 0.5 is at least
+// 0.5 away from every multiple of n, far more than the rounding error of the product.
+__device__ __forceinline__ int div_small(int x, float rcp) { return int((float(x) + 0.5f) * rcp); }
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
 struct TcGraphArgs {
   int batch, agents, F, K, G;
   int has_skip, add_self_loop, num_actions;
@@ -47,8 +58,11 @@ struct TcGraphArgs {
 // that chose the actions of its episodes also moves them and writes their next observation (env_step.cuh), so a rollout
 // step is three kernels; the boards / positions are staged in the prologue, ahead of the grid wait (they were last written
 // two kernels back).
+#ifndef TG_MINB
+#define TG_MINB 2
+#endif
 template <int ENVL>
-__global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int epc) {
+__global__ void __launch_bounds__(kTgThreads, TG_MINB) tc_graph_kernel(TcGraphArgs g, int epc) {
   extern __shared__ __align__(128) uint8_t s_tg[];
   __shared__ __align__(8) uint64_t s_full[kTgProd], s_empty[kTgProd], s_done;
   __shared__ uint32_t s_tmem;
@@ -96,24 +110,25 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
   if (ENVL > 0) env_ag = env_step_stage<kEL, kTgThreads>(g.env, e0, nep, tid, s_boards, s_env);
   if (!g.gso_is_old) { mapf_pdl_wait(); mapf_pdl_launch(); }
   // ---- graph shift operator of the tile's episodes ----
+  const float rcp_n = 1.0f / float(N), rcp_nn = 1.0f / float(N * N);
   for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
-    const int el = idx / (N * N), rem = idx - el * N * N;
-    const int i = rem / N, j = rem - i * N;
+    const int el = div_small(idx, rcp_nn), rem = idx - el * N * N;
+    const int i = div_small(rem, rcp_n), j = rem - i * N;
     float v = mapf_ld_dep(g.gso + int64_t(e0 + el) * N * N + rem);
     if (g.add_self_loop && i == j) v += 1.0f;
     sm[idx] = v;
   }
   __syncthreads();
   if (tid < rows_used) {
-    const int el = tid / N, i = tid - el * N;
+    const int el = div_small(tid, rcp_n), i = tid - el * N;
     float deg = 0.0f;
     for (int j = 0; j < N; ++j) deg += sm[(el * N + i) * N + j];
     dinv[tid] = deg > 0.0f ? __fdiv_rn(1.0f, __fsqrt_rn(deg)) : 0.0f;
   }
   __syncthreads();
   for (int idx = tid; idx < nep * N * N; idx += kTgThreads) {
-    const int el = idx / (N * N), rem = idx - el * N * N;
-    const int i = rem / N, j = rem - i * N;
+    const int el = div_small(idx, rcp_nn), rem = idx - el * N * N;
+    const int i = div_small(rem, rcp_n), j = rem - i * N;
     sm[idx] = (dinv[el * N + i] * sm[idx]) * dinv[el * N + j];
   }
   if (g.gso_is_old) { mapf_pdl_wait(); mapf_pdl_launch(); }
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     for (int i = 0; i < 4; ++i) {
       rr[i] = lane + 32 * i;
       rlive[i] = rr[i] < rows_used;
-      rep[i] = rlive[i] ? rr[i] / N : 0;
+      rep[i] = rlive[i] ? div_small(rr[i], rcp_n) : 0;
       rjl[i] = rr[i] - rep[i] * N;
     }
     auto emit = [&](int c, const float (*v)[8]) {
@@ -182,6 +197,9 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     };
     float4 nlo[4], nhi[4];
     load_slice(p, nlo, nhi);
+    // The chunk loops are deliberately NOT unrolled: a CTA runs this code once, from a cold instruction cache, and the
+    // fully unrolled kernel (111 KB of SASS) spent most of its time in instruction fetch (ncu: top stall no_instruction).
+#pragma unroll 1
     for (int si = 0; si < per_warp; ++si) {
       const int j = p + kTgProd * si;
       float xv[4][8];
@@ -191,8 +209,11 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
         xv[i][4] = nhi[i].x; xv[i][5] = nhi[i].y; xv[i][6] = nhi[i].z; xv[i][7] = nhi[i].w;
       }
       load_slice(si + 1 < per_warp ? j + kTgProd : slices, nlo, nhi);
-      for (int k = 0; k < K; ++k) {
-        if (k > 0) {
+#ifndef TG_CHUNK_UNROLL
+#pragma unroll 1
+#endif
+      for (int c = 0; c < chunks_per_slice; ++c) {
+        if (c > 0 && c < K) {
           // x_k[row j] = sum_i S[i][j] x_{k-1}[row i] over the rows of the same episode (held by other lanes)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -208,6 +229,9 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
             if (rlive[i]) {
               const float* scol = sm + rep[i] * N * N + rjl[i];
               const float* prev = xs + rep[i] * N * 8;
+#ifndef TG_HOP_UNROLL
+#pragma unroll 1
+#endif
               for (int n = 0; n < N; ++n) {
                 const float s = scol[n * N];
                 const float4 p0 = *reinterpret_cast<const float4*>(prev + n * 8);
@@ -222,24 +246,23 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
             for (int f = 0; f < 8; ++f) xv[i][f] = acc[f];
           }
           __syncwarp();   // everyone has read the exchange buffer before it is overwritten
-        }
-        emit(k * slices + j, xv);
-      }
-      if (g.has_skip) {
-        // Xr[n'][f'] = X_flat[n'F + f'] with X_flat index of X[b,f,n] = f*N + n   (gnn.py:201-204)
-        float sv[4][8];
+        } else if (c == K) {
+          // message-passing skip chunk: Xr[n'][f'] = X_flat[n'F + f'] with X_flat index of X[b,f,n] = f*N + n
+          // (gnn.py:201-204); q = n'F + f' walks 8 consecutive flat indices: (q % N, q / N) advance incrementally
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) {
+            const int q0 = rjl[i] * F + 8 * j;
+            int qd = div_small(q0, rcp_n);
+            int qn = q0 - qd * N;
+            const float* xe = g.x + (row0 + rep[i] * N) * F;
 #pragma unroll
-          for (int f = 0; f < 8; ++f) {
-            float v = 0.0f;
-            if (rlive[i]) {
-              const int q = rjl[i] * F + 8 * j + f;
-              v = mapf_ld_dep(g.x + (row0 + rep[i] * N + (q % N)) * F + (q / N));
+            for (int f = 0; f < 8; ++f) {
+              xv[i][f] = rlive[i] ? mapf_ld_dep(xe + qn * F + qd) : 0.0f;
+              if (++qn == N) { qn = 0; ++qd; }
             }
-            sv[i][f] = v;
           }
-        emit(K * slices + j, sv);
+        }
+        emit(c * slices + j, xv);
       }
     }
   } else if (warp_u < kTgProd + 2) {
@@ -284,7 +307,39 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
     float part[kMaxActions];
 #pragma unroll
     for (int q = 0; q < kMaxActions; ++q) part[q] = 0.0f;
+#ifndef TG_EPI_COLS
+#define TG_EPI_COLS 32
+#endif
+#if TG_EPI_COLS == 8
+    // eight columns per (rolled) iteration: small code, same accumulation order as ever (column ascending per action)
+#pragma unroll 1
+    for (int cbl = 0; cbl < kTgNT / 2; cbl += 8) {
+      const int cb = half * (kTgNT / 2) + cbl;
+      uint32_t r0[8], r1[8];
+      tmem_ld8_nowait(tmem + (uint32_t(quad * 32) << 16) + cb, r0);
+      tmem_ld8_nowait(tmem + (uint32_t(quad * 32) << 16) + kTgNT + cb, r1);
+      tc::tmem_ld_wait();
+      float v[8];
 #pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r0[j]) + __uint_as_float(r1[j]), 0.0f);
+#pragma unroll
+      for (int q = 0; q < kMaxActions; ++q) {
+        if (q < g.num_actions) {
+          const float4* wq = reinterpret_cast<const float4*>(s_head + q * kTgNT + cb);
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const float4 w4 = wq[j >> 2];
+            part[q] = fmaf(v[j], w4.x, part[q]);
+            part[q] = fmaf(v[j + 1], w4.y, part[q]);
+            part[q] = fmaf(v[j + 2], w4.z, part[q]);
+            part[q] = fmaf(v[j + 3], w4.w, part[q]);
+          }
+        }
+      }
+    }
+#else
+    // 32 columns per iteration (rolled: the two iterations share their code; column ascending per action as ever)
+#pragma unroll 1
     for (int cbl = 0; cbl < kTgNT / 2; cbl += 32) {
       const int cb = half * (kTgNT / 2) + cbl;
       uint32_t r0[32], r1[32];
@@ -309,6 +364,7 @@ __global__ void __launch_bounds__(kTgThreads) tc_graph_kernel(TcGraphArgs g, int
         }
       }
     }
+#endif
     float* ex = reinterpret_cast<float*>(stages);   // [128 rows][kMaxActions], the stages are idle now
     if (half == 1) {
 #pragma unroll
