@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
     const float f_up = m_up * f, f_dn = m_dn * f;
     float* dst = g.out + img * (kEtCout * kFovCells) + pidx;
     const bool live = img < g.rows && pix_ok;
-    float sv[2 * kEtCout];        // this pixel's outputs and their squares (statistics)
+    float sv[kEtCout];            // this pixel's outputs (statistics)
 #pragma unroll
     for (int c = 0; c < kEtCout; ++c) {
       const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow);
@@ -681,23 +681,32 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
       a = fmaf(dn, f_dn, a);
       if (live) dst[c * kFovCells] = a;
       sv[c] = live ? a : 0.0f;
-      sv[kEtCout + c] = live ? a * a : 0.0f;
     }
     if (do_stats) {
       // Per-slot BatchNorm sums (framework_gnn.py:160-163: statistics per agent slot): a warp = one image = one slot.
-      // Recursive halving over the 32 lanes: after 16 + 8 + 4 + 2 + 1 shuffles lane L holds the image's total of value L
-      // (L < 16: sum of channel L, else sum of squares of channel L - 16); it goes into the warp's private fp64 table.
+      // Recursive halving over the lanes (8 + 4 + 2 + 1 shuffles, then one across the two half warps): lanes L and L + 16
+      // hold the image's total of channel L.  The squares are summed in fp64 -- the variance is a difference of large
+      // numbers (E[x^2] - mean^2) and must not inherit fp32 rounding -- the plain sums in fp32 (25 terms, as ever).
+      double sq[kEtCout];
 #pragma unroll
-      for (int h = kEtCout; h >= 1; h >>= 1) {
+      for (int c = 0; c < kEtCout; ++c) sq[c] = double(sv[c]) * double(sv[c]);
+#pragma unroll
+      for (int h = kEtCout / 2; h >= 1; h >>= 1) {
         const bool upper = (lane & h) != 0;
 #pragma unroll
         for (int i = 0; i < h; ++i) {
           const float send = upper ? sv[i] : sv[h + i];
           const float keep = upper ? sv[h + i] : sv[i];
           sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+          const double dsend = upper ? sq[i] : sq[h + i];
+          const double dkeep = upper ? sq[h + i] : sq[i];
+          sq[i] = dkeep + __shfl_xor_sync(0xffffffffu, dsend, h);
         }
       }
-      if (img < g.rows) my_stat[int(img % g.slots) * 32] += double(sv[0]);
+      const float s1 = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 16);
+      const double s2 = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 16);
+      // lane L < 16 adds the plain sum of channel L, lane L >= 16 the sum of squares of channel L - 16
+      if (img < g.rows) my_stat[int(img % g.slots) * 32] += lane < 16 ? double(s1) : s2;
     }
   }
   tc::fence_before_sync();
