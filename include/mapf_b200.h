@@ -414,6 +414,9 @@ int mapf_tc_pack_b(const float* b0, int32_t K0, const float* b1, int32_t K1, int
                    mapf_stream_t stream);
 int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
                  const float* bias, int32_t relu, mapf_stream_t stream);
+/* same contract, work decomposition for the training step (4 stages, one accumulator, three CTAs per SM) */
+int mapf_tc_gemm_w3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
+                    const float* bias, int32_t relu, mapf_stream_t stream);
 /* Weight-gradient GEMM of the training step (train.py:96): C (+)= A^T B with A [K, M] (lda) and B [K, N] (ldb) row-major
  * fp32 activation matrices whose contraction index is the row index (K = B*N rows), 3xTF32 on the tensor cores with the
  * transposition done on the way into shared memory and split-K partials meeting in C through red.global.add.

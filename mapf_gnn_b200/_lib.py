@@ -167,6 +167,8 @@ _SIGNATURES = {
     "mapf_tc_pack_b": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mapf_tc_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mapf_tc_gemm_w3": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_tc_gemm_tn": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mapf_tc_presplit_a_size": (C.c_int64, [C.c_int64, C.c_int32]),

@@ -111,9 +111,11 @@ __global__ void tc_pack_b_f16_kernel(const float* __restrict__ b, int C, int N, 
   }
 }
 
-template <int NT, int KC, int NACC, int EPI>
+// NP = producer warps = shared-memory stages (6: two CTAs per SM; 4 with NACC = 1: three CTAs per SM -- the variant the
+// training step uses, whose 320 row tiles at B = 8192 then fit one wave instead of 296 + 24); NACC = MMA issuers.
+template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps>
 __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
-  constexpr int NSTAGE = kTcProdWarps;
+  constexpr int NSTAGE = NP;
   constexpr uint32_t kColsNeeded = NT * NACC;
   constexpr uint32_t kCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                              : kColsNeeded <= 256 ? 256 : 512;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       tc::mbar_init(&s_full[s], 32);
       tc::mbar_init(&s_empty[s], 1);
     }
-    tc::mbar_init(&s_done, 2);
+    tc::mbar_init(&s_done, NACC);
     tc::fence_mbar_init();
   }
   if (EPI == EPI_HEAD) {
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
-  if (warp_u < kTcProdWarps) {
+  if (warp_u < NP) {
     // ===== producers: warp w owns stage w =====
     const int s = warp;
     uint8_t* a_hi = s_tc + s * kStageBytes;
@@ -186,8 +188,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     float4 v[kPerLane], vn[kPerLane];
     load_chunk(warp, v);
     uint32_t ph = 0;
-    for (int c = warp; c < nchunks; c += kTcProdWarps, ph ^= 1) {
-      load_chunk(c + kTcProdWarps, vn);   // next chunk's loads overlap this chunk's wait / convert / store
+    for (int c = warp; c < nchunks; c += NP, ph ^= 1) {
+      load_chunk(c + NP, vn);   // next chunk's loads overlap this chunk's wait / convert / store
       tc::mbar_wait(&s_empty[s], ph ^ 1);
       if (lane == 0) {
         tc::mbar_expect_tx(&s_full[s], 2 * kBBytes);
@@ -208,8 +210,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
 #pragma unroll
       for (int it = 0; it < kPerLane; ++it) v[it] = vn[it];
     }
-  } else {
-    // ===== MMA issuers (warps 6 and 7: even / odd chunks) =====
+  } else if (warp_u < NP + NACC) {
+    // ===== MMA issuers (NACC warps behind the producers: chunks c = w, w + NACC, ... into accumulator w) =====
     // A single thread issues every tcgen05.mma, so its instruction stream is the critical path: descriptors are
     // built once (stage 0) and advanced by adding the stage / K-slice byte offset to the 14-bit address field.
     if (tc::elect_one()) {
@@ -220,17 +222,17 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       const uint64_t dal0 = tc::smem_desc(base + kABytes, lbo, sbo);
       const uint64_t dbh0 = tc::smem_desc(base + 2 * kABytes, lbo, sbo);
       const uint64_t dbl0 = tc::smem_desc(base + 2 * kABytes + kBBytes, lbo, sbo);
-      static_assert(NACC == 2 && (NSTAGE % 2) == 0, "issuer w owns accumulator w and the stages of its parity");
-      const int which = warp_u - kTcProdWarps;   // 0: even chunks, 1: odd chunks
+      static_assert(NACC == 1 || (NACC == 2 && (NSTAGE % 2) == 0), "issuer w owns accumulator w and the stages of its parity");
+      const int which = warp_u - NP;
       int s = which;
       uint32_t ph = 0;
       const uint32_t accsel = which;
-      for (int c = which; c < nchunks; c += 2) {
+      for (int c = which; c < nchunks; c += NACC) {
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
         const uint64_t soff = uint64_t(uint32_t(s) * (kStageBytes >> 4));
         const uint32_t acc = tmem_u + accsel * NT;
-        const bool first = c < 2;   // first touch of this accumulator overwrites
+        const bool first = c < NACC;   // first touch of this accumulator overwrites
 #pragma unroll
         for (int ks = 0; ks < KC / 8; ++ks) {
           const uint64_t o = soff + uint64_t(ks * 16);   // one 8-wide K slice = 2 core matrices = 256 bytes
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
           tc::mma_tf32(acc, dah0 + o, dbh0 + o, idesc, true);
         }
         tc::mma_commit(&s_empty[s]);
-        s += 2;
+        s += NACC;
         if (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
       }
       tc::mma_commit(&s_done);
@@ -355,10 +357,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   if (warp == 0) tc::tmem_dealloc(tmem, kCols);
 }
 
-template <int NT, int KC, int NACC, int EPI>
+template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps>
 int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
-  constexpr size_t smem = size_t(kTcProdWarps) * (2 * kTcM * KC * 4 + 2 * NT * KC * 4);
-  auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI>;
+  constexpr size_t smem = size_t(NP) * (2 * kTcM * KC * 4 + 2 * NT * KC * 4);
+  static_assert(smem >= 8 * 32 * 33 * 4 + 128 * kMaxActions * 4, "the epilogue transposes through the operand stages");
+  auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI, NP>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   dim3 grid((g.M + kTcM - 1) / kTcM, 1);
@@ -602,6 +605,23 @@ extern "C" int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (N <= 64) return launch_tc<64, kTcKC, 2, EPI_STORE>(g, s);
   return launch_tc<128, kTcKC, 2, EPI_STORE>(g, s);
+}
+
+// Same GEMM with 4 stages and one accumulator (three CTAs per SM): the training step's activation-gradient and
+// forward GEMMs (K <= 400), where the number of row tiles is close to the number of CTA slots.
+extern "C" int mapf_tc_gemm_w3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C,
+                               int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream) {
+  MAPF_REQUIRE(A && Bp && C, MAPF_ERR_NULL);
+  MAPF_REQUIRE(M > 0 && N > 0 && K > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(N <= 128, MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE((lda & 3) == 0 && mapf_aligned(A, 16) && mapf_aligned(Bp, 16), MAPF_ERR_ALIGN);
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.Bp = Bp;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (N <= 64) return launch_tc<64, kTcKC, 1, EPI_STORE, 4>(g, s);
+  return launch_tc<128, kTcKC, 1, EPI_STORE, 4>(g, s);
 }
 
 // logits / greedy actions = head(relu(Z Wp^T)): Z [M, K] row-major filter taps, Wp = packed [W | W2] (mapf_tc_pack_b).

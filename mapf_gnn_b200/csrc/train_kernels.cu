@@ -1201,7 +1201,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       const int nn = Ncols - j0 < 128 ? Ncols - j0 : 128;
       float* pk = packs + int64_t(t) * mapf_tc_b_floats(128, Kd);
       MAPF_TRY(mapf_tc_pack_b(Wt + int64_t(j0) * Kd, Kd, nullptr, 0, nn, pk, stream));
-      MAPF_TRY(mapf_tc_gemm(int32_t(rows), nn, Kd, Asrc, Kd, pk, Cout + j0, ldc, nullptr, 0, stream));
+      MAPF_TRY(mapf_tc_gemm_w3(int32_t(rows), nn, Kd, Asrc, Kd, pk, Cout + j0, ldc, nullptr, 0, stream));
     }
     return MAPF_OK;
   };
