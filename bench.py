@@ -641,6 +641,17 @@ def run_train(args, w, env, dev, rank, world, barrier):
                  "allreduce": None if world == 1 else ("peer-memory one-shot, fused with the gradient norm"
                                                        if trainer.peer is not None else "nccl"),
                  "samples_per_s": B * world * steps / (ms * 1e-3), "loss": float(loss.item())}
+        # ~3x forward FLOPs per agent -> 5.46 MFLOP (msg_k3) / 5.22 MFLOP (gcn_k3) per N = 5 sample;
+        # other shapes: 3 x the workload's forward figure per agent
+        per_sample = {"gnn_msg_k3": 5.46e6, "gnn_k3": 5.22e6}.get(model, 3.0 * w["flops"] * N) if N == 5 else 3.0 * w["flops"] * N
+        pk = peaks()
+        tfl = B * per_sample / (ms / steps * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        entry["roofline"] = {"bound": "mixed: tensor-core contractions (3 MMAs per product, fp32 accuracy), FFMA2 conv weight "
+                                      "gradients, HBM-bound BatchNorm kernels", "achieved": tfl, "unit": "TFLOP/s",
+                             "algorithmic_flops_per_step": B * per_sample,
+                             "frac_of_fp32_ffma_peak": tfl / fp32_peak, "fp32_ffma_peak": fp32_peak,
+                             "frac_of_tensor_peak": tfl / pk["tensor_tflops"], "tensor_peak": pk["tensor_tflops"]}
         if rank == 0 and world == 1 and not args.no_cpu_baseline and B <= 1024:
             entry["cpu_samples_per_s"], entry["cpu_kind"] = cpu_train_steps(model, states.cpu(), gso.cpu(),
                                                                             targets.cpu().long(), 3)
