@@ -408,7 +408,9 @@ def measure_workload(m, name, w, args, dev, rank, world, barrier, flush, K, W):
                                                                          ac.data_ptr(), None, st), "tc_mix_head"), flush)
             t_bytes = rows * (4 * F + 4 * N + 4 * KT)        # SURVEY 8d recurrence kernel: read X, A; write Z
             gbs = t_bytes / (taps_ms * 1e-3) / 1e9
-            roof_graph = {"bound": "hbm", "kernel": "graph_taps_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
+            hops_tc = N == 64 and F == 64 and not skip
+            roof_graph = {"bound": "hbm", "kernel": "graph_hops_tc_kernel (hops on tcgen05, M = 64 per episode)" if hops_tc
+                          else "graph_taps_kernel", "achieved": gbs, "peak": pk["hbm_gbs"],
                           "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "ms_per_launch": taps_ms,
                           "share_of_step": taps_ms / ms_step, "algorithmic_bytes_per_launch": t_bytes,
                           "traffic": _traffic(name, "graph_taps_kernel", full),

@@ -254,6 +254,7 @@ typedef struct {
 #define MAPF_POLICY_FUSED_ENV_ON 8   /* mapf_rollout: always run the env step in the tail of the graph kernel */
 #define MAPF_POLICY_FUSED_ENV_OFF 16 /* mapf_rollout: never */
 #define MAPF_POLICY_NO_PDL 32        /* launch the call's kernels without programmatic stream serialization */
+#define MAPF_POLICY_FFMA_HOPS 64     /* 64-agent teams: filter taps on the FFMA kernel instead of the tensor-core hops */
 int mapf_policy_fwd(const mapf_net_params* p, const mapf_policy_fwd_args* a, mapf_stream_t stream);
 
 /* `steps` iterations of the rollout protocol of evaluate.py:223-241 for E resident episodes,
@@ -459,6 +460,9 @@ int mapf_tc_graph_head(int32_t batch, int32_t agents, int32_t in_dim, int32_t ou
 /* Filter taps Z [B*N, (K+has_skip)*F] (x_k = x_{k-1} S, gnn.py:104-109, + skip columns gnn.py:201-204) from
  * agent-major x; uses the x / gso / z / size / flag fields of the argument struct. */
 int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);
+/* same result from the FFMA kernel for every team size (mapf_graph_taps runs the hops of 64-agent teams on the tensor
+ * cores: 3xTF32, equal to ~1e-6 relative) */
+int mapf_graph_taps_ffma(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -422,7 +422,18 @@ int launch_taps(const mapf_graph_filter_fwd_args& a, int epc, int ntiles, size_t
 
 // Z [B*N, (K+has_skip)*F] from agent-major x [B*N, F] and gso [B,N,N]; only x, gso, z and the size / flag fields of
 // the argument struct are used.
+int mapf_hops_tc_supported(const mapf_graph_filter_fwd_args* a);                       // tc_hops.cu
+int mapf_graph_hops_tc(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);     // tc_hops.cu
+
 extern "C" int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream) {
+  MAPF_REQUIRE(a && a->x && a->gso && a->z, MAPF_ERR_NULL);
+  // 64-agent teams: hops on the tensor cores (tc_hops.cu); everything else: the FFMA kernel below
+  if (a->x_sf == 1 && a->x_sn == a->in_dim && a->x_sb == int64_t(a->agents) * a->in_dim && mapf_hops_tc_supported(a))
+    return mapf_graph_hops_tc(a, stream);
+  return mapf_graph_taps_ffma(a, stream);
+}
+
+extern "C" int mapf_graph_taps_ffma(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream) {
   MAPF_REQUIRE(a && a->x && a->gso && a->z, MAPF_ERR_NULL);
   MAPF_REQUIRE(a->batch > 0 && a->agents > 0 && a->in_dim > 0 && a->taps > 0, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(a->agents <= 64 && (a->in_dim & 3) == 0, MAPF_ERR_UNSUPPORTED);

@@ -280,7 +280,7 @@ static int policy_fwd_impl(const mapf_net_params* p, const mapf_policy_fwd_args*
   }
   // two-kernel tensor-core path: filter taps -> Z (tiny kernel), then 3xTF32 tcgen05 mix + ReLU + head + argmax
   g.z = a->workspace_z;
-  rc = mapf_graph_taps(&g, stream);
+  rc = (a->flags & MAPF_POLICY_FFMA_HOPS) ? mapf_graph_taps_ffma(&g, stream) : mapf_graph_taps(&g, stream);
   if (rc != MAPF_OK) return rc;
   const int KT = (p->taps + (a->message ? 1 : 0)) * p->fc_out;
   return mapf_tc_mix_head(int32_t(rows), p->node_dim, KT, a->workspace_z, KT, a->packed + L.tc_gf, a->packed + L.act_w,

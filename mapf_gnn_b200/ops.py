@@ -42,6 +42,8 @@ def policy_flags() -> int:
         f |= _lib.POLICY_UNFUSED_GRAPH
     if env.get("MAPF_B200_NO_PDL"):
         f |= _lib.POLICY_NO_PDL
+    if env.get("MAPF_B200_FFMA_HOPS"):
+        f |= _lib.POLICY_FFMA_HOPS
     fe = env.get("MAPF_B200_FUSED_ENV")
     if fe:
         f |= _lib.POLICY_FUSED_ENV_ON if fe[0] == "1" else _lib.POLICY_FUSED_ENV_OFF

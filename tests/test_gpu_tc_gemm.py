@@ -100,3 +100,45 @@ def test_tn_structured_values_are_exact():
     A = (torch.arange(K * M, device="cuda", dtype=torch.float32).reshape(K, M) % 7) - 3
     B = (torch.arange(K * N, device="cuda", dtype=torch.float32).reshape(K, N) % 5) - 2
     assert torch.equal(tc_gemm_tn(A, B), A.t() @ B)
+
+
+@pytest.mark.parametrize("B,K,self_loop", [(7, 4, True), (2, 2, False), (33, 3, True), (1, 4, True)])
+def test_tensor_core_hops_match_ffma_taps_and_float64(B, K, self_loop):
+    """Filter taps of 64-agent teams (gnn.py:87-109): the tensor-core hops kernel (tc_hops.cu, block-diagonal S per pair of
+    episodes, 3xTF32) against the FFMA taps kernel and a float64 restatement; odd episode counts cover the half tile."""
+    from mapf_gnn_b200 import _lib
+    lib = _lib.load()
+    N, F = 64, 64
+    g = torch.Generator(device="cuda").manual_seed(B * 10 + K)
+    x = torch.randn(B * N, F, device="cuda", generator=g)
+    adj = (torch.rand(B, N, N, device="cuda", generator=g) < 0.08).float()
+    adj[:, torch.arange(N), torch.arange(N)] = 0
+    if not self_loop:
+        adj[0, 5, :] = 0          # zero-degree row: inf -> 0 (gnn.py:185-199)
+
+    def run(fn):
+        z = torch.full((B * N, K * F), float("nan"), device="cuda")
+        a = _lib.GraphFilterFwdArgs()
+        a.batch, a.agents, a.in_dim, a.out_dim, a.taps = B, N, F, 128, K
+        a.add_self_loop, a.has_skip = int(self_loop), 0
+        a.x, a.x_sb, a.x_sn, a.x_sf = x.data_ptr(), N * F, F, 1
+        a.gso, a.z = adj.data_ptr(), z.data_ptr()
+        _lib.check(fn(a, _lib.current_stream()), "graph_taps")
+        torch.cuda.synchronize()
+        return z
+
+    z_tc, z_ff = run(lib.mapf_graph_taps), run(lib.mapf_graph_taps_ffma)
+    A = adj.double() + (torch.eye(N, device="cuda", dtype=torch.float64) if self_loop else 0)
+    dinv = A.sum(dim=2).pow(-0.5)
+    dinv[torch.isinf(dinv)] = 0
+    S = dinv[:, :, None] * A * dinv[:, None, :]
+    xk = x.double().view(B, N, F)
+    taps = [xk]
+    for _ in range(1, K):
+        taps.append(torch.einsum("bij,bif->bjf", S, taps[-1]))
+    ref = torch.cat(taps, dim=2).reshape(B * N, K * F)
+    scale = ref.abs().max().item()
+    assert not torch.isnan(z_tc).any()
+    assert (z_tc.double() - ref).abs().max().item() / scale < 5e-6
+    assert (z_ff.double() - ref).abs().max().item() / scale < 5e-6
+    assert torch.equal(z_tc[:, :F], x) and torch.equal(z_ff[:, :F], x)

@@ -49,13 +49,19 @@ for name in ("c2a", "c1", "c3"):
 print(" | ".join(out))
 '''
 
+CHILD_TAPS = r'''
+import os, sys, runpy
+sys.argv = ["taps_time.py"]
+runpy.run_path(os.path.join(%r, "tools", "taps_time.py"), run_name="__main__")
+'''
+
 def main():
     from mapf_gnn_b200 import _build
     _build.build_library()
     src, child = sys.argv[1], sys.argv[2]
     stem = os.path.basename(src)[:-3]
     objs = [os.path.join(_build.LIBDIR, f) for f in os.listdir(_build.LIBDIR) if f.endswith(".o") and f != stem + ".o"]
-    code = {"graph": CHILD_GRAPH}[child] % (ROOT,)
+    code = {"graph": CHILD_GRAPH, "taps": CHILD_TAPS}[child] % (ROOT,)
     for i, flags in enumerate(sys.argv[3:] or [""]):
         obj, so = f"/tmp/{stem}_v{i}.o", f"/tmp/libmapf_{stem}_v{i}.so"
         path = src if os.path.isabs(src) or os.path.exists(src) else os.path.join(_build.CSRC, src)
@@ -65,6 +71,6 @@ def main():
                        check=True)
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MAPF_B200_LIB_OVERRIDE=so),
                              capture_output=True, text=True)
-        print(f"[{flags or 'default'}] {out.stdout.strip()} {out.stderr.strip()[-300:]}", flush=True)
+        print(f"[{flags or 'default'}] {' | '.join(out.stdout.strip().splitlines())} {out.stderr.strip()[-300:]}", flush=True)
 
 main()
