@@ -312,6 +312,7 @@ typedef struct {
 #define MAPF_TRAIN_FFMA_BWD 4    /* backward GEMMs on the FFMA2 kernels instead of mapf_tc_gemm_tn / mapf_tc_gemm */
 #define MAPF_TRAIN_FFMA_CONV 16   /* forward / data-gradient convolutions on the FFMA2 kernel (tensor cores from 4096 rows) */
 #define MAPF_TRAIN_TC_BWD_ALWAYS 8 /* tensor-core convolutions and backward GEMMs also below 4096 rows (tests) */
+#define MAPF_TRAIN_SINGLE_LANE 32 /* every launch on the caller's stream: no auxiliary lanes for weight packs / weight gradients */
 int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream);
 
 /* Backward of the above from d(loss)/d(logits); must follow mapf_train_forward on the same

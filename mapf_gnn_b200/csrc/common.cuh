@@ -161,6 +161,11 @@ __device__ __forceinline__ int mapf_ld_dep(const int* p) {
   asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ double mapf_ld_dep(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 
 // Per-thread, per-call launch option: the entry points that take a `flags` field (mapf_policy_fwd, mapf_rollout) switch
 // programmatic launches off for the duration of the call when MAPF_POLICY_NO_PDL is set.  Thread-local and restored on

@@ -770,14 +770,29 @@ bool mapf_conv_tc_layer_ok(int cin_fwd, int cout_fwd, int mode) {
   const int cin = mode == 0 ? cin_fwd : cout_fwd, cout = mode == 0 ? cout_fwd : cin_fwd;
   return cout == kEtCout && (cin == 2 || cin == 16);
 }
+// filter bank -> the layer kernel's fp16 hi/lo operand blocks (depends on the parameters only: callers may run it on
+// another stream than the layer itself)
+int mapf_conv_tc_layer_pack(const float* w, int cin_fwd, int cout_fwd, int mode, float* wtc_scratch, mapf_stream_t stream) {
+  MAPF_REQUIRE(w && wtc_scratch, MAPF_ERR_NULL);
+  MAPF_REQUIRE(mapf_conv_tc_layer_ok(cin_fwd, cout_fwd, mode), MAPF_ERR_UNSUPPORTED);
+  MAPF_REQUIRE(mapf_aligned(wtc_scratch, 16), MAPF_ERR_ALIGN);
+  const int cin = mode == 0 ? cin_fwd : cout_fwd;
+  mapf_launch_pdl(pack_tc_conv_raw_kernel, dim3(cin == 2 ? 3 : 9), dim3(256), 0, static_cast<cudaStream_t>(stream), w, cin_fwd,
+                  cout_fwd, mode, wtc_scratch);
+  return mapf_launch_status();
+}
+// `packed` != 0: wtc_scratch already holds mapf_conv_tc_layer_pack's output for these filters
 int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int cin_fwd, int cout_fwd, int mode, int B,
-                       int N, float* wtc_scratch, float* out, double* stats, int stat_c, mapf_stream_t stream) {
+                       int N, float* wtc_scratch, int packed, float* out, double* stats, int stat_c, mapf_stream_t stream) {
   MAPF_REQUIRE(in && w && wtc_scratch && out, MAPF_ERR_NULL);
   MAPF_REQUIRE(mapf_conv_tc_layer_ok(cin_fwd, cout_fwd, mode), MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(mapf_aligned(wtc_scratch, 16), MAPF_ERR_ALIGN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cin = mode == 0 ? cin_fwd : cout_fwd;
-  mapf_launch_pdl(pack_tc_conv_raw_kernel, dim3(cin == 2 ? 3 : 9), dim3(256), 0, s, w, cin_fwd, cout_fwd, mode, wtc_scratch);
+  if (!packed) {
+    const int prc = mapf_conv_tc_layer_pack(w, cin_fwd, cout_fwd, mode, wtc_scratch, stream);
+    if (prc != MAPF_OK) return prc;
+  }
   ConvTcArgs g{};
   g.rows = int64_t(B) * N;
   g.in = in; g.wtc = wtc_scratch; g.bias = bias; g.out = out;

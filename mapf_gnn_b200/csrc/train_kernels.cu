@@ -22,8 +22,9 @@ constexpr float kBnEpsT = 1e-5f;
 // enc_tc.cu: one conv layer of the training step on the tensor cores
 int mapf_conv_tc_layer_floats();
 bool mapf_conv_tc_layer_ok(int cin_fwd, int cout_fwd, int mode);
+int mapf_conv_tc_layer_pack(const float* w, int cin_fwd, int cout_fwd, int mode, float* wtc_scratch, mapf_stream_t stream);
 int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int cin_fwd, int cout_fwd, int mode, int B,
-                       int N, float* wtc_scratch, float* out, double* stats, int stat_c, mapf_stream_t stream);
+                       int N, float* wtc_scratch, int packed, float* out, double* stats, int stat_c, mapf_stream_t stream);
 namespace {
 
 struct TrainLayout {
@@ -315,6 +316,64 @@ __global__ void bn_apply4_kernel(const float4* __restrict__ u, const float* __re
   }
 }
 
+// bn_finalize + bn_apply4 in one launch for small tables (N*C <= kBnFusedMax): every CTA derives the (slot, channel)
+// scale / shift pairs from the fp64 sums into shared memory (the same arithmetic as bn_finalize_kernel); CTA 0 also
+// stores the tables the backward pass reads and advances the running statistics.  One launch less on the chain of a
+// latency-bound small-batch step.
+constexpr int kBnFusedMax = 256;
+__global__ void __launch_bounds__(256) bn_finalize_apply4_kernel(
+    const float4* __restrict__ u, const double* __restrict__ stats, int N, int C, int stat_c, double count, float momentum,
+    float* __restrict__ meaninv, float* running_mean, float* running_var, int64_t* batches, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ scale_shift, int64_t rows, float4* __restrict__ a) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
+  __shared__ float2 s_tab[kBnFusedMax];
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    const int n = i / C, c = i - n * C;
+    const double s1 = mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2), s2 = mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2 + 1);
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double invstd = 1.0 / sqrt(var + double(kBnEpsT));
+    const float w = gamma[c] * float(invstd);
+    s_tab[i] = make_float2(w, beta[c] - float(mean) * w);
+    if (blockIdx.x == 0) {
+      meaninv[i * 2] = float(mean);
+      meaninv[i * 2 + 1] = float(invstd);
+      scale_shift[i * 2] = w;
+      scale_shift[i * 2 + 1] = beta[c] - float(mean) * w;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float rm = running_mean ? running_mean[c] : 0.0f, rv = running_var ? running_var[c] : 0.0f;
+    for (int n = 0; n < N; ++n) {
+      const double s1 = mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2), s2 = mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2 + 1);
+      const double mean = s1 / count;
+      double var = s2 / count - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      const float unbiased = float(count > 1.0 ? var * count / (count - 1.0) : var);
+      rm = (1.0f - momentum) * rm + momentum * float(mean);
+      rv = (1.0f - momentum) * rv + momentum * unbiased;
+    }
+    if (running_mean) running_mean[c] = rm;
+    if (running_var) running_var[c] = rv;
+    if (c == 0 && batches != nullptr) *batches += N;
+  }
+  __syncthreads();
+  const uint32_t row4 = uint32_t(C * kFovCells) >> 2;
+  const int64_t total = rows * row4;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / row4;
+    const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
+    const float2* tab = s_tab + n * C;
+    const float4 v = mapf_ld_dep(u + idx);
+    const float2 w0 = tab[o / kFovCells], w1 = tab[(o + 1) / kFovCells], w2 = tab[(o + 2) / kFovCells], w3 = tab[(o + 3) / kFovCells];
+    a[idx] = make_float4(fmaxf(fmaf(v.x, w0.x, w0.y), 0.0f), fmaxf(fmaf(v.y, w1.x, w1.y), 0.0f),
+                         fmaxf(fmaf(v.z, w2.x, w2.y), 0.0f), fmaxf(fmaf(v.w, w3.x, w3.y), 0.0f));
+  }
+}
+
 // sums over (batch, pixels) per (slot, channel) of dy and dy*xhat, dy = da * [a > 0]
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ a,
                                                             const float* __restrict__ u,
@@ -395,6 +454,43 @@ __global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __re
       const uint32_t c = (o + j) / kFovCells;
       const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
       const float4 k = mapf_ld_dep(reinterpret_cast<const float4*>(coef) + (n * C + c));
+      const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
+      const float xhat = (uu[j] - mi.x) * mi.y;
+      r[j] = k.x * (dy - k.y - xhat * k.z);
+    }
+    da[idx] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// bn_bwd_coef + bn_bwd_apply4 in one launch for small tables (N*C <= kBnFusedMax): the coefficients go to shared memory
+__global__ void __launch_bounds__(256) bn_bwd_coef_apply4_kernel(
+    float4* __restrict__ da, const float4* __restrict__ a, const float4* __restrict__ u, const float* __restrict__ meaninv,
+    const double* __restrict__ stats, const float* __restrict__ gamma, int N, int C, int stat_c, double count, int64_t rows) {
+  mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
+  mapf_pdl_launch();
+  __shared__ float4 s_k[kBnFusedMax];
+  __shared__ float2 s_mi[kBnFusedMax];
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    const int n = i / C, c = i - n * C;
+    const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + i);
+    s_mi[i] = mi;
+    s_k[i] = make_float4(gamma[c] * mi.y, float(mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2) / count),
+                         float(mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2 + 1) / count), 0.0f);
+  }
+  __syncthreads();
+  const uint32_t row4 = uint32_t(C * kFovCells) >> 2;
+  const int64_t total = rows * row4;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / row4;
+    const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
+    const float4 av = a[idx], dv = mapf_ld_dep(da + idx), uv = u[idx];
+    const float aa[4] = {av.x, av.y, av.z, av.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t c = (o + j) / kFovCells;
+      const float2 mi = s_mi[n * C + c];
+      const float4 k = s_k[n * C + c];
       const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
       const float xhat = (uu[j] - mi.x) * mi.y;
       r[j] = k.x * (dy - k.y - xhat * k.z);
@@ -1068,6 +1164,61 @@ int check_train(const mapf_net_params* p, int B, int N) {
   return MAPF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Auxiliary lanes.  A training step is a chain of ~55 short launches; at batch 128 each is latency-bound and
+// the chain length IS the step time.  Two classes of launches hang off the chain without feeding it: the weight
+// packs (depend on the parameters only) and the weight / bias gradients (nothing downstream reads them).  They
+// run on two auxiliary streams per host thread and device, ordered against the caller's stream by events --
+// under stream capture the same calls become parallel branches of the graph.  The lanes are created on the
+// first un-captured call; a first call made under capture stays on the caller's stream.
+// ---------------------------------------------------------------------------------------------
+struct Lanes {
+  cudaStream_t lane[2] = {nullptr, nullptr};
+  cudaEvent_t ev[40] = {};
+  bool ready = false;
+};
+
+Lanes* lanes_for(cudaStream_t main, int flags) {
+  if (flags & MAPF_TRAIN_SINGLE_LANE) return nullptr;
+  thread_local Lanes tl[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  Lanes& L = tl[dev];
+  if (!L.ready) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    for (auto& ln : L.lane)
+      if (cudaStreamCreateWithFlags(&ln, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : L.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    L.ready = true;
+  }
+  return &L;
+}
+
+// Event bookkeeping of one forward / backward call: mark(stream) = "everything issued on `stream` so far",
+// wait(stream, mark) orders later work on `stream` behind it.  With lanes == nullptr everything is one stream
+// and both are no-ops.
+struct LaneOrder {
+  Lanes* lanes;
+  int used = 0;
+  bool ok = true;
+  explicit LaneOrder(Lanes* l) : lanes(l) {}
+  int mark(cudaStream_t from) {
+    if (!lanes) return -1;
+    if (used >= int(sizeof(lanes->ev) / sizeof(lanes->ev[0]))) { ok = false; return -1; }
+    ok = ok && cudaEventRecord(lanes->ev[used], from) == cudaSuccess;
+    return used++;
+  }
+  void wait(cudaStream_t to, int m) {
+    if (!lanes || m < 0) return;
+    ok = ok && cudaStreamWaitEvent(to, lanes->ev[m], 0) == cudaSuccess;
+  }
+};
+
 }  // namespace
 
 extern "C" int64_t mapf_train_workspace_size(const mapf_net_params* p, int32_t batch, int32_t agents) {
@@ -1088,28 +1239,66 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   const TrainLayout T = train_layout(*p, B, N, 1);
   float* ws = a->workspace;
   double* stat = reinterpret_cast<double*>(ws + T.stat_fwd);
-  if (cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, s) != cudaSuccess) return MAPF_ERR_CUDA;
   const double count = double(B) * kFovCells;
+  const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
+  const int KT = (p->taps + (a->message ? 1 : 0)) * F;
+  // tensor-core convolutions (fp16-split operands, enc_tc.cu) wherever the layer shape allows; FFMA2 kernel otherwise
+  const bool conv_tc = !(a->flags & MAPF_TRAIN_FFMA_CONV);
+  const bool fc_tc = F <= 128 && (fin & 3) == 0 && !(a->flags & MAPF_TRAIN_FFMA_FC);
+  const bool graph_tc = p->taps > 0 && N <= 64 && p->node_dim <= 128 && (p->node_dim & 15) == 0 && (F & 3) == 0 &&
+                        mapf_aligned(p->act_w, 16) && !(a->flags & MAPF_TRAIN_FFMA_GRAPH);
+  // weight packs (they depend on the parameters only) and the zeroing of the BatchNorm sums on the pack lane, in the
+  // order the chain consumes them
+  LaneOrder ord(lanes_for(s, a->flags));
+  cudaStream_t sp = ord.lanes ? ord.lanes->lane[1] : s;
+  ord.wait(sp, ord.mark(s));
+  if (cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) != cudaSuccess) return MAPF_ERR_CUDA;
+  int m_conv[MAPF_MAX_CONV];
   for (int l = 0; l < L; ++l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
     MAPF_REQUIRE(p->conv_w[l] && p->conv_b[l] && p->bn_gamma[l] && p->bn_beta[l], MAPF_ERR_NULL);
+    if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 0))
+      MAPF_TRY(mapf_conv_tc_layer_pack(p->conv_w[l], cin, cout, 0, ws + T.convtc[l], sp));
+    else
+      mapf_launch_pdl(pack_conv_kernel, dim3((cout * cin * 9 + 255) / 256), dim3(256), 0, sp, p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
+    m_conv[l] = ord.mark(sp);
+  }
+  // 3xTF32 tcgen05 operand of the current compressMLP weights (re-packed every step: 100 KB)
+  if (fc_tc) MAPF_TRY(mapf_tc_pack_b(p->fc_w, fin, nullptr, 0, F, ws + T.fcpk, sp));
+  const int m_fc = ord.mark(sp);
+  if (graph_tc)
+    MAPF_TRY(mapf_tc_pack_b(p->gf_w, p->taps * F, a->message ? p->gf_w2 : nullptr, a->message ? F : 0, p->node_dim,
+                            ws + T.wt, sp));
+  else if (p->taps > 0)
+    MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, p->taps, p->node_dim, ws + T.wt, sp));
+  const int m_gf = ord.mark(sp);
+
+  for (int l = 0; l < L; ++l) {
+    const int cin = p->channels[l], cout = p->channels[l + 1];
     double* st = stat + int64_t(l) * N * T.cmax * 2;
-    // tensor-core convolution (fp16-split operands, enc_tc.cu) from 4096 rows on; FFMA2 kernel otherwise
-    if (!(a->flags & MAPF_TRAIN_FFMA_CONV) && (rows >= 4096 || (a->flags & MAPF_TRAIN_TC_BWD_ALWAYS)) &&
-        mapf_conv_tc_layer_ok(cin, cout, 0)) {
+    ord.wait(s, m_conv[l]);
+    if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 0)) {
       MAPF_TRY(mapf_conv_tc_layer(l == 0 ? a->states : ws + T.a[l - 1], p->conv_w[l], p->conv_b[l], cin, cout, 0, B, N,
-                                  ws + T.convtc[l], ws + T.u[l], st, T.cmax, stream));
+                                  ws + T.convtc[l], 1, ws + T.u[l], st, T.cmax, stream));
     } else {
-      mapf_launch_pdl(pack_conv_kernel, dim3((cout * cin * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 0, ws + T.convpk[l]);
       MAPF_TRY(launch_conv_train(s, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, B, N, ws + T.convpk[l],
                                  p->conv_b[l], ws + T.u[l], st, T.cmax));
+    }
+    const int64_t planes = rows * cout;
+    const bool vec4 = (cout * kFovCells) % 4 == 0;
+    if (vec4 && N * cout <= kBnFusedMax) {
+      // batch statistics -> scale / shift -> BatchNorm + ReLU in one launch
+      mapf_launch_pdl(bn_finalize_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s,
+          reinterpret_cast<const float4*>(ws + T.u[l]), st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
+          const_cast<float*>(p->bn_mean[l]), const_cast<float*>(p->bn_var[l]), a->bn_batches[l], p->bn_gamma[l], p->bn_beta[l],
+          ws + T.scsh[l], rows, reinterpret_cast<float4*>(ws + T.a[l]));
+      continue;
     }
     mapf_launch_pdl(bn_finalize_kernel, dim3((cout + 63) / 64), dim3(64), 0, s, st, N, cout, T.cmax, count, a->momentum, ws + T.meaninv[l],
                                                       const_cast<float*>(p->bn_mean[l]),
                                                       const_cast<float*>(p->bn_var[l]), a->bn_batches[l], p->bn_gamma[l],
                                                       p->bn_beta[l], ws + T.scsh[l]);
-    const int64_t planes = rows * cout;
-    if ((cout * kFovCells) % 4 == 0)
+    if (vec4)
       mapf_launch_pdl(bn_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s, 
           reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.scsh[l], N, cout, rows, reinterpret_cast<float4*>(ws + T.a[l]));
     else
@@ -1117,15 +1306,15 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
                                                                                         cout, planes, ws + T.a[l]);
   }
   MAPF_TRY(mapf_launch_status());
-  const int F = p->fc_out, fin = p->fc_in, A = p->num_actions;
   // compressMLP: x = relu(a_L Wfc^T + b)
-  if (F <= 128 && (fin & 3) == 0 && !(a->flags & MAPF_TRAIN_FFMA_FC)) {
-    // 3xTF32 tcgen05 GEMM on the current weights (re-packed every step: 100 KB)
-    MAPF_TRY(mapf_tc_pack_b(p->fc_w, fin, nullptr, 0, F, ws + T.fcpk, stream));
+  ord.wait(s, m_fc);
+  if (fc_tc) {
     MAPF_TRY(mapf_tc_gemm(int32_t(rows), F, fin, ws + T.a[L - 1], fin, ws + T.fcpk, ws + T.x, F, p->fc_b, 1, stream));
   } else {
     MAPF_TRY(gemm(s, int(rows), F, fin, ws + T.a[L - 1], fin, 1, p->fc_w, 1, fin, ws + T.x, F, p->fc_b, 1));
   }
+  ord.wait(s, m_gf);         // also the join of the pack lane
+  MAPF_REQUIRE(ord.ok, MAPF_ERR_CUDA);
   if (p->taps == 0) return gemm(s, int(rows), A, F, ws + T.x, F, 1, p->act_w, 1, F, a->logits, A, p->act_b, 0);
   mapf_graph_filter_fwd_args g{};
   g.batch = B; g.agents = N; g.in_dim = F; g.out_dim = p->node_dim; g.taps = p->taps;
@@ -1140,18 +1329,12 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   g.z = ws + T.z;
   g.act_w = p->act_w; g.act_b = p->act_b;
   g.logits = a->logits; g.actions = nullptr;
-  const int KT = (p->taps + (a->message ? 1 : 0)) * F;
-  const bool tensor_path = N <= 64 && p->node_dim <= 128 && (p->node_dim & 15) == 0 && (F & 3) == 0 &&
-                           mapf_aligned(p->act_w, 16) && !(a->flags & MAPF_TRAIN_FFMA_GRAPH);
-  if (tensor_path) {
+  if (graph_tc) {
     // filter taps Z (saved for the weight gradient) + 3xTF32 tcgen05 mix with relu(Y) stored for the backward pass
-    MAPF_TRY(mapf_tc_pack_b(p->gf_w, p->taps * F, a->message ? p->gf_w2 : nullptr, a->message ? F : 0, p->node_dim,
-                            ws + T.wt, stream));
     MAPF_TRY(mapf_graph_taps(&g, stream));
     return mapf_tc_mix_head(int32_t(rows), p->node_dim, KT, ws + T.z, KT, ws + T.wt, p->act_w, p->act_b, A, a->logits,
                             nullptr, ws + T.y, stream);
   }
-  MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, p->taps, p->node_dim, ws + T.wt, stream));
   return mapf_graph_filter_fwd(&g, stream);
 }
 
@@ -1170,7 +1353,17 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   const TrainLayout T = train_layout(*p, B, N, 1);
   float* ws = a->workspace;
   const int head_in = K > 0 ? Gd : F;
-  auto zero = [&](float* ptr, int64_t n) { return cudaMemsetAsync(ptr, 0, sizeof(float) * size_t(n), s) == cudaSuccess; };
+  // Lanes: `s` carries the activation-gradient chain; `sw` the weight / bias gradients (read the chain's tensors, feed
+  // nothing downstream); `sp` the transposed-weight packs (depend on the parameters only).
+  LaneOrder ord(lanes_for(s, a->flags));
+  cudaStream_t sw = ord.lanes ? ord.lanes->lane[0] : s;
+  cudaStream_t sp = ord.lanes ? ord.lanes->lane[1] : s;
+  {
+    const int m0 = ord.mark(s);
+    ord.wait(sw, m0);
+    ord.wait(sp, m0);
+  }
+  auto zero = [&](float* ptr, int64_t n) { return cudaMemsetAsync(ptr, 0, sizeof(float) * size_t(n), sw) == cudaSuccess; };
   bool ok = zero(G.act_w, int64_t(A) * head_in) && zero(G.act_b, A) && zero(G.fc_w, int64_t(F) * fin) && zero(G.fc_b, F);
   if (K > 0) ok = ok && zero(G.gf_w, int64_t(F) * K * Gd);
   if (a->message) ok = ok && zero(G.gf_w2, int64_t(F) * Gd);
@@ -1179,74 +1372,97 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     ok = ok && zero(G.conv_w[l], int64_t(p->channels[l]) * p->channels[l + 1] * 9) && zero(G.conv_b[l], p->channels[l + 1]);
   }
   double* stat = reinterpret_cast<double*>(ws + T.stat_bwd);
-  ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, s) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) == cudaSuccess;
   if (!ok) return MAPF_ERR_CUDA;
+  const int m_stat = ord.mark(sp);
 
-  const int row_splits = splits_for(rows, 4);
   const float* head_act = K > 0 ? ws + T.y : ws + T.x;
-  // actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0]
-  mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, a->dlogits, rows, A, G.act_b);
+  const int KF = K * F, KT = (K + (a->message ? 1 : 0)) * F;
   // Tensor-core path (default): weight gradients = mapf_tc_gemm_tn (contraction over the rows, split K), activation
   // gradients = mapf_tc_gemm against transposed-weight packs, head input gradient = head_bwd_kernel.
   // MAPF_TRAIN_FFMA_BWD keeps the FFMA2 sgemm kernels (development switch).
-  // (small batches are launch-bound: below 4096 rows the extra pack launches cost more than the tensor cores save)
   const bool tc_bwd = !(a->flags & MAPF_TRAIN_FFMA_BWD) && (head_in & 3) == 0 && (F & 3) == 0 && (fin & 3) == 0 &&
-                      (K == 0 || (Gd & 3) == 0) && F <= 128 && Gd <= 128 &&
-                      (rows >= 4096 || (a->flags & MAPF_TRAIN_TC_BWD_ALWAYS));
+                      (K == 0 || (Gd & 3) == 0) && F <= 128 && Gd <= 128;
+  const bool conv_tc = !(a->flags & MAPF_TRAIN_FFMA_CONV);
   float* da = ws + T.da0;
   float* da_next = ws + T.da1;
-  // C[rows, Ncols] = Asrc[rows, Kd] . Wt^T with Wt [Ncols, Kd] row-major (a transposed weight), 128 output columns per call
-  auto nn_gemm = [&](const float* Asrc, int Kd, const float* Wt, int Ncols, float* packs, float* Cout, int64_t ldc) -> int {
+  // C[rows, Ncols] = Asrc[rows, Kd] . Wt^T with Wt [Ncols, Kd] row-major (a transposed weight), 128 output columns per
+  // call: the packs on the pack lane, the GEMMs on the chain
+  auto nn_pack = [&](int Kd, const float* Wt, int Ncols, float* packs) -> int {
     for (int j0 = 0, t = 0; j0 < Ncols; j0 += 128, ++t) {
       const int nn = Ncols - j0 < 128 ? Ncols - j0 : 128;
-      float* pk = packs + int64_t(t) * mapf_tc_b_floats(128, Kd);
-      MAPF_TRY(mapf_tc_pack_b(Wt + int64_t(j0) * Kd, Kd, nullptr, 0, nn, pk, stream));
-      MAPF_TRY(mapf_tc_gemm_w3(int32_t(rows), nn, Kd, Asrc, Kd, pk, Cout + j0, ldc, nullptr, 0, stream));
+      MAPF_TRY(mapf_tc_pack_b(Wt + int64_t(j0) * Kd, Kd, nullptr, 0, nn, packs + int64_t(t) * mapf_tc_b_floats(128, Kd), sp));
     }
     return MAPF_OK;
   };
+  auto nn_gemm = [&](const float* Asrc, int Kd, int Ncols, const float* packs, float* Cout, int64_t ldc) -> int {
+    for (int j0 = 0, t = 0; j0 < Ncols; j0 += 128, ++t) {
+      const int nn = Ncols - j0 < 128 ? Ncols - j0 : 128;
+      MAPF_TRY(mapf_tc_gemm_w3(int32_t(rows), nn, Kd, Asrc, Kd, packs + int64_t(t) * mapf_tc_b_floats(128, Kd), Cout + j0,
+                               ldc, nullptr, 0, stream));
+    }
+    return MAPF_OK;
+  };
+  // ---- pack lane ----
+  int m_gfpk = -1, m_fcpk = -1, m_convpk[MAPF_MAX_CONV];
   if (tc_bwd) {
-    MAPF_TRY(mapf_tc_gemm_tn(A, head_in, rows, a->dlogits, A, head_act, head_in, G.act_w, head_in, 0, 0, stream));
+    if (K > 0) {
+      // dz = dy W_eff (and the W2 columns behind): W_eff^T rows are the packed B operand
+      MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, K, Gd, ws + T.wtt, sp));
+      MAPF_TRY(nn_pack(Gd, ws + T.wtt, KT, ws + T.gfpk_bwd));
+      m_gfpk = ord.mark(sp);
+    }
+    MAPF_TRY(mapf_pack_graph_weights(p->fc_w, nullptr, fin, 1, F, ws + T.fcwt, sp));   // fc_w^T [fc_in][F]
+    MAPF_TRY(nn_pack(F, ws + T.fcwt, fin, ws + T.fcpk_bwd));
+    m_fcpk = ord.mark(sp);
+  }
+  for (int l = L - 1; l >= 1; --l) {
+    const int cin = p->channels[l], cout = p->channels[l + 1];
+    if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 1)) {
+      MAPF_TRY(mapf_conv_tc_layer_pack(p->conv_w[l], cin, cout, 1, ws + T.convtc_bwd[l], sp));
+    } else {
+      const int cin_pad = int(r4(cin));
+      MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
+      mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, sp, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
+    }
+    m_convpk[l] = ord.mark(sp);
+  }
+  const int m_sp_end = ord.mark(sp);
+
+  // ---- actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0] ----
+  mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, sw, a->dlogits, rows, A, G.act_b);
+  if (tc_bwd) {
+    MAPF_TRY(mapf_tc_gemm_tn(A, head_in, rows, a->dlogits, A, head_act, head_in, G.act_w, head_in, 0, 1, sw));
     const size_t hsm = sizeof(float) * size_t(A) * head_in;
     float* dhead = K > 0 ? ws + T.dy : ws + T.dx;
     mapf_launch_pdl(head_bwd_kernel, dim3(unsigned(mapf_min64((rows * (head_in / 4) + 255) / 256, 148 * 8))), dim3(256), hsm, s,
                     a->dlogits, p->act_w, head_act, rows, head_in, A, dhead);
-    if (K > 0) {
-      const int KF = K * F, KT = (K + (a->message ? 1 : 0)) * F;
-      // dW_eff[g][j] = sum_r dy[r][g] z[r][j]  -- row-major [G][K*F] IS the memory of GFL.0.W [F,K,G] (gnn.py:114-116)
-      MAPF_TRY(mapf_tc_gemm_tn(Gd, KF, rows, ws + T.dy, Gd, ws + T.z, KT, G.gf_w, KF, 0, 0, stream));
-      if (a->message)
-        MAPF_TRY(mapf_tc_gemm_tn(Gd, F, rows, ws + T.dy, Gd, ws + T.z + KF, KT, G.gf_w2, F, 0, 0, stream));
-      // dz[r][j] = sum_g dy[r][g] W_eff[g][j] (and the W2 columns behind them): W_eff^T rows are the packed B operand
-      MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, K, Gd, ws + T.wtt, stream));
-      MAPF_TRY(nn_gemm(ws + T.dy, Gd, ws + T.wtt, KT, ws + T.gfpk_bwd, ws + T.dz, KT));
-      const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
-      MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
-      if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(recurrence_bwd_kernel, size_t(smem), cache__); }())
-        return MAPF_ERR_CUDA;
-      mapf_launch_pdl(recurrence_bwd_kernel, dim3(B), dim3(128), smem, s, ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
-                                                 a->message ? 0 : 1, ws + T.dx, int64_t(N) * F, F, 1);
-    }
-    // compressMLP backward
-    mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, ws + T.dx, rows, F, G.fc_b);
-    MAPF_TRY(mapf_tc_gemm_tn(F, fin, rows, ws + T.dx, F, ws + T.a[L - 1], fin, G.fc_w, fin, 0, 0, stream));
-    MAPF_TRY(mapf_pack_graph_weights(p->fc_w, nullptr, fin, 1, F, ws + T.fcwt, stream));   // fc_w^T [fc_in][F]
-    MAPF_TRY(nn_gemm(ws + T.dx, F, ws + T.fcwt, fin, ws + T.fcpk_bwd, da, fin));
   } else {
-  MAPF_TRY(gemm(s, A, head_in, int(rows), a->dlogits, 1, A, head_act, head_in, 1, G.act_w, head_in, nullptr, 0, nullptr,
-                0, splits_for(rows, (head_in + 63) / 64)));
+    MAPF_TRY(gemm(sw, A, head_in, int(rows), a->dlogits, 1, A, head_act, head_in, 1, G.act_w, head_in, nullptr, 0, nullptr,
+                  0, splits_for(rows, (head_in + 63) / 64)));
+    if (K > 0)
+      MAPF_TRY(gemm(s, int(rows), Gd, A, a->dlogits, A, 1, p->act_w, Gd, 1, ws + T.dy, Gd, nullptr, 0, ws + T.y, Gd));
+    else
+      MAPF_TRY(gemm(s, int(rows), F, A, a->dlogits, A, 1, p->act_w, F, 1, ws + T.dx, F, nullptr, 0, ws + T.x, F));
+  }
+  // ---- graph filter ----
   if (K > 0) {
-    const int KF = K * F, KT = (K + (a->message ? 1 : 0)) * F;
-    MAPF_TRY(gemm(s, int(rows), Gd, A, a->dlogits, A, 1, p->act_w, Gd, 1, ws + T.dy, Gd, nullptr, 0, ws + T.y, Gd));
+    ord.wait(sw, ord.mark(s));        // dy
     // dW_eff[g][j] = sum_r dy[r][g] z[r][j]  -- row-major [G][K*F] IS the memory of GFL.0.W [F,K,G] (gnn.py:114-116)
-    MAPF_TRY(gemm(s, Gd, KF, int(rows), ws + T.dy, 1, Gd, ws + T.z, KT, 1, G.gf_w, KF, nullptr, 0, nullptr, 0,
-                  splits_for(rows, ((Gd + 127) / 128) * ((KF + 63) / 64))));
-    // dz[r][j] = sum_g dy[r][g] W_eff[g][j]
-    MAPF_TRY(gemm(s, int(rows), KF, Gd, ws + T.dy, Gd, 1, p->gf_w, KF, 1, ws + T.dz, KT));
-    if (a->message) {
-      MAPF_TRY(gemm(s, Gd, F, int(rows), ws + T.dy, 1, Gd, ws + T.z + KF, KT, 1, G.gf_w2, F, nullptr, 0, nullptr, 0,
-                    splits_for(rows, ((Gd + 127) / 128) * ((F + 63) / 64))));
-      MAPF_TRY(gemm(s, int(rows), F, Gd, ws + T.dy, Gd, 1, p->gf_w2, F, 1, ws + T.dz + KF, KT));
+    if (tc_bwd) {
+      MAPF_TRY(mapf_tc_gemm_tn(Gd, KF, rows, ws + T.dy, Gd, ws + T.z, KT, G.gf_w, KF, 0, 1, sw));
+      if (a->message) MAPF_TRY(mapf_tc_gemm_tn(Gd, F, rows, ws + T.dy, Gd, ws + T.z + KF, KT, G.gf_w2, F, 0, 1, sw));
+      ord.wait(s, m_gfpk);
+      MAPF_TRY(nn_gemm(ws + T.dy, Gd, KT, ws + T.gfpk_bwd, ws + T.dz, KT));
+    } else {
+      MAPF_TRY(gemm(sw, Gd, KF, int(rows), ws + T.dy, 1, Gd, ws + T.z, KT, 1, G.gf_w, KF, nullptr, 0, nullptr, 0,
+                    splits_for(rows, ((Gd + 127) / 128) * ((KF + 63) / 64))));
+      if (a->message)
+        MAPF_TRY(gemm(sw, Gd, F, int(rows), ws + T.dy, 1, Gd, ws + T.z + KF, KT, 1, G.gf_w2, F, nullptr, 0, nullptr, 0,
+                      splits_for(rows, ((Gd + 127) / 128) * ((F + 63) / 64))));
+      // dz[r][j] = sum_g dy[r][g] W_eff[g][j]
+      MAPF_TRY(gemm(s, int(rows), KF, Gd, ws + T.dy, Gd, 1, p->gf_w, KF, 1, ws + T.dz, KT));
+      if (a->message) MAPF_TRY(gemm(s, int(rows), F, Gd, ws + T.dy, Gd, 1, p->gf_w2, F, 1, ws + T.dz + KF, KT));
     }
     const size_t smem = sizeof(float) * (size_t(N) * N + ((N + 3) & ~3) + size_t(N) * KT);
     MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
@@ -1254,17 +1470,24 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       return MAPF_ERR_CUDA;
     mapf_launch_pdl(recurrence_bwd_kernel, dim3(B), dim3(128), smem, s, ws + T.dz, a->gso, ws + T.x, N, F, K, a->message ? 1 : 0,
                                                a->message ? 0 : 1, ws + T.dx, int64_t(N) * F, F, 1);
+  }
+  // ---- compressMLP ----
+  ord.wait(sw, ord.mark(s));          // dx
+  mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, sw, ws + T.dx, rows, F, G.fc_b);
+  if (tc_bwd) {
+    MAPF_TRY(mapf_tc_gemm_tn(F, fin, rows, ws + T.dx, F, ws + T.a[L - 1], fin, G.fc_w, fin, 0, 1, sw));
+    ord.wait(s, m_fcpk);
+    MAPF_TRY(nn_gemm(ws + T.dx, F, fin, ws + T.fcpk_bwd, da, fin));
   } else {
-    MAPF_TRY(gemm(s, int(rows), F, A, a->dlogits, A, 1, p->act_w, F, 1, ws + T.dx, F, nullptr, 0, ws + T.x, F));
+    MAPF_TRY(gemm(sw, F, fin, int(rows), ws + T.dx, 1, F, ws + T.a[L - 1], fin, 1, G.fc_w, fin, nullptr, 0, nullptr, 0,
+                  splits_for(rows, ((F + 127) / 128) * ((fin + 63) / 64))));
+    MAPF_TRY(gemm(s, int(rows), fin, F, ws + T.dx, F, 1, p->fc_w, fin, 1, da, fin));
   }
-  // compressMLP backward
-  mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, s, ws + T.dx, rows, F, G.fc_b);
-  MAPF_TRY(gemm(s, F, fin, int(rows), ws + T.dx, 1, F, ws + T.a[L - 1], fin, 1, G.fc_w, fin, nullptr, 0, nullptr, 0,
-                splits_for(rows, ((F + 127) / 128) * ((fin + 63) / 64))));
-  MAPF_TRY(gemm(s, int(rows), fin, F, ws + T.dx, F, 1, p->fc_w, fin, 1, da, fin));
-  }
-  (void)row_splits;
+  // ---- conv stack ----
   const double count = double(B) * kFovCells;
+  ord.wait(s, m_stat);
+  int m_dw_prev = -1;                 // weight-gradient kernel of the layer above: it reads the buffer this layer's
+                                      // data gradient is about to overwrite
   for (int l = L - 1; l >= 0; --l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
     double* st = stat + int64_t(l) * N * T.cmax * 2;
@@ -1276,17 +1499,24 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
                                                  T.cmax, st);
     else
       mapf_launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
-    mapf_launch_pdl(bn_bwd_coef_kernel, dim3((N * cout + 127) / 128), dim3(128), 0, s, st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
-                                                             ws + T.coef[l]);
     const int64_t planes = rows * cout;
-    if ((cout * kFovCells) % 4 == 0)
-      mapf_launch_pdl(bn_bwd_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s, 
+    if ((cout * kFovCells) % 4 == 0 && N * cout <= kBnFusedMax) {
+      mapf_launch_pdl(bn_bwd_coef_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s,
           reinterpret_cast<float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]), reinterpret_cast<const float4*>(ws + T.u[l]),
-          ws + T.meaninv[l], ws + T.coef[l], N, cout, rows);
-    else
-      mapf_launch_pdl(bn_bwd_apply_kernel, dim3(unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16))), dim3(256), 0, s, 
-          da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
-    mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, s, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
+          ws + T.meaninv[l], st, p->bn_gamma[l], N, cout, T.cmax, count, rows);
+    } else {
+      mapf_launch_pdl(bn_bwd_coef_kernel, dim3((N * cout + 127) / 128), dim3(128), 0, s, st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
+                                                               ws + T.coef[l]);
+      if ((cout * kFovCells) % 4 == 0)
+        mapf_launch_pdl(bn_bwd_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s, 
+            reinterpret_cast<float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]), reinterpret_cast<const float4*>(ws + T.u[l]),
+            ws + T.meaninv[l], ws + T.coef[l], N, cout, rows);
+      else
+        mapf_launch_pdl(bn_bwd_apply_kernel, dim3(unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16))), dim3(256), 0, s, 
+            da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
+    }
+    ord.wait(sw, ord.mark(s));        // du_l (in `da`) and the BatchNorm sums
+    mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, sw, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
       const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
       MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
@@ -1298,30 +1528,33 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       if (cin * cout <= kCwThreads) {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<1>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        mapf_launch_pdl(conv_bwd_weight_kernel<1>, dim3(gridw), dim3(kCwThreads), smem, s, da, lin, cin, cout, rows, part);
+        mapf_launch_pdl(conv_bwd_weight_kernel<1>, dim3(gridw), dim3(kCwThreads), smem, sw, da, lin, cin, cout, rows, part);
       } else {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<4>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        mapf_launch_pdl(conv_bwd_weight_kernel<4>, dim3(gridw), dim3(kCwThreads), smem, s, da, lin, cin, cout, rows, part);
+        mapf_launch_pdl(conv_bwd_weight_kernel<4>, dim3(gridw), dim3(kCwThreads), smem, sw, da, lin, cin, cout, rows, part);
       }
       const int nw = cin * cout * 9;
-      mapf_launch_pdl(conv_bwd_weight_reduce_kernel, dim3((nw + cout + 31) / 32), dim3(256), 0, s, part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
+      mapf_launch_pdl(conv_bwd_weight_reduce_kernel, dim3((nw + cout + 31) / 32), dim3(256), 0, sw, part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
     }
+    const int m_dw = ord.mark(sw);
     if (l > 0) {
+      ord.wait(s, m_dw_prev);
+      ord.wait(s, m_convpk[l]);
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
-      if (!(a->flags & MAPF_TRAIN_FFMA_CONV) && (rows >= 4096 || (a->flags & MAPF_TRAIN_TC_BWD_ALWAYS)) &&
-          mapf_conv_tc_layer_ok(cin, cout, 1)) {
-        MAPF_TRY(mapf_conv_tc_layer(da, p->conv_w[l], nullptr, cin, cout, 1, B, N, ws + T.convtc_bwd[l], da_next, nullptr, 0,
+      if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 1)) {
+        MAPF_TRY(mapf_conv_tc_layer(da, p->conv_w[l], nullptr, cin, cout, 1, B, N, ws + T.convtc_bwd[l], 1, da_next, nullptr, 0,
                                     stream));
       } else {
-        const int cin_pad = int(r4(cin));
-        mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, s, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
-        MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
         MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
       }
       float* t = da; da = da_next; da_next = t;
     }
+    m_dw_prev = m_dw;
   }
+  ord.wait(s, m_dw_prev);             // join both lanes
+  ord.wait(s, m_sp_end);
+  MAPF_REQUIRE(ord.ok, MAPF_ERR_CUDA);
   return mapf_launch_status();
 }
 
