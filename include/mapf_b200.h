@@ -310,8 +310,8 @@ typedef struct {
 #define MAPF_TRAIN_FFMA_FC 1     /* compressMLP forward on the FFMA GEMM */
 #define MAPF_TRAIN_FFMA_GRAPH 2  /* graph filter forward on the fused FFMA kernel */
 #define MAPF_TRAIN_FFMA_BWD 4    /* backward GEMMs on the FFMA2 kernels instead of mapf_tc_gemm_tn / mapf_tc_gemm */
-#define MAPF_TRAIN_FFMA_CONV 16   /* forward / data-gradient convolutions on the FFMA2 kernel (tensor cores from 4096 rows) */
-#define MAPF_TRAIN_TC_BWD_ALWAYS 8 /* tensor-core convolutions and backward GEMMs also below 4096 rows (tests) */
+#define MAPF_TRAIN_FFMA_CONV 16   /* forward / data-gradient convolutions on the FFMA2 kernel instead of the tensor cores */
+#define MAPF_TRAIN_TC_BWD_ALWAYS 8 /* accepted, no effect: the tensor-core paths are the default at every batch size */
 #define MAPF_TRAIN_SINGLE_LANE 32 /* every launch on the caller's stream: no auxiliary lanes for weight packs / weight gradients */
 int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream);
 
@@ -419,6 +419,11 @@ int mapf_tc_gemm(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, c
 /* same contract, work decomposition for the training step (4 stages, one accumulator, three CTAs per SM) */
 int mapf_tc_gemm_w3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
                     const float* bias, int32_t relu, mapf_stream_t stream);
+/* wide outputs (any N): B packed as ceil(N / 128) tiles of 128 rows, mapf_tc_packed_b_size(128, K) floats apart, and all
+ * tiles computed by one launch (the training step's activation gradients dz = dy W_eff, da = dx W_fc) */
+int mapf_tc_pack_b_tiles(const float* b, int32_t K, int32_t N, float* out, mapf_stream_t stream);
+int mapf_tc_gemm_tiles(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C, int64_t ldc,
+                       const float* bias, int32_t relu, mapf_stream_t stream);
 /* Weight-gradient GEMM of the training step (train.py:96): C (+)= A^T B with A [K, M] (lda) and B [K, N] (ldb) row-major
  * fp32 activation matrices whose contraction index is the row index (K = B*N rows), 3xTF32 on the tensor cores with the
  * transposition done on the way into shared memory and split-K partials meeting in C through red.global.add.

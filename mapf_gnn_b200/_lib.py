@@ -169,6 +169,9 @@ _SIGNATURES = {
                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_tc_gemm_w3": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mapf_tc_pack_b_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mapf_tc_gemm_tiles": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_tc_gemm_tn": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mapf_tc_presplit_a_size": (C.c_int64, [C.c_int64, C.c_int32]),

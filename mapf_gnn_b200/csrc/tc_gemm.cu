@@ -38,6 +38,7 @@ struct TcGemmArgs {
   int M, N, K;
   const float* A; int64_t lda;
   const float* Bp;     // pre-tiled B: [chunk][hi | lo][NT/8][KC/4][8][4]
+  int64_t bp_tile;     // EPI_STORE with N > NT: floats between the packs of consecutive NT-column tiles (grid.y), else 0
   // EPI_STORE
   float* C; int64_t ldc;
   const float* bias;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     }
     if (tid < g.num_actions) s_head[kMaxActions * NT + tid] = __ldg(g.act_b + tid);
   } else {
-    for (int i = tid; i < NT; i += kTcThreads) s_head[i] = (g.bias != nullptr && i < g.N) ? __ldg(g.bias + i) : 0.0f;
+    for (int i = tid; i < NT; i += kTcThreads) s_head[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       tc::mbar_wait(&s_empty[s], ph ^ 1);
       if (lane == 0) {
         tc::mbar_expect_tx(&s_full[s], 2 * kBBytes);
-        tc::bulk_g2s(b_hi, g.Bp + int64_t(c) * (2 * NT * KC), 2 * kBBytes, &s_full[s]);
+        tc::bulk_g2s(b_hi, g.Bp + int64_t(blockIdx.y) * g.bp_tile + int64_t(c) * (2 * NT * KC), 2 * kBBytes, &s_full[s]);
       }
 #pragma unroll
       for (int it = 0; it < kPerLane; ++it) {
@@ -364,7 +365,7 @@ int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
   auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI, NP>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
-  dim3 grid((g.M + kTcM - 1) / kTcM, 1);
+  dim3 grid((g.M + kTcM - 1) / kTcM, g.bp_tile ? (g.N + NT - 1) / NT : 1);
   kernel<<<grid, kTcThreads, smem, s>>>(g);
   return mapf_launch_status();
 }
@@ -622,6 +623,33 @@ extern "C" int mapf_tc_gemm_w3(int32_t M, int32_t N, int32_t K, const float* A, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (N <= 64) return launch_tc<64, kTcKC, 1, EPI_STORE, 4>(g, s);
   return launch_tc<128, kTcKC, 1, EPI_STORE, 4>(g, s);
+}
+
+// Wide outputs: B [N, K] with any N, packed as ceil(N / 128) tiles of 128 rows (mapf_tc_b_floats(128, K) floats apart),
+// and the GEMM over all tiles in ONE launch (grid.y = tile): the training step's dz = dy W_eff and da = dx W_fc.
+extern "C" int mapf_tc_pack_b_tiles(const float* b, int32_t K, int32_t N, float* out, mapf_stream_t stream) {
+  MAPF_REQUIRE(b && out, MAPF_ERR_NULL);
+  MAPF_REQUIRE(N > 0 && K > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE(mapf_aligned(out, 16), MAPF_ERR_ALIGN);
+  const int64_t tile = mapf_tc_packed_b_size(128, K);
+  for (int n0 = 0, t = 0; n0 < N; n0 += 128, ++t) {
+    const int nn = N - n0 < 128 ? N - n0 : 128;
+    tc_pack_b_kernel<<<int((tile + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        b + int64_t(n0) * K, K, nullptr, 0, nn, 128, kTcKC, out + int64_t(t) * tile);
+  }
+  return mapf_launch_status();
+}
+
+extern "C" int mapf_tc_gemm_tiles(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* Bp, float* C,
+                                  int64_t ldc, const float* bias, int32_t relu, mapf_stream_t stream) {
+  MAPF_REQUIRE(A && Bp && C, MAPF_ERR_NULL);
+  MAPF_REQUIRE(M > 0 && N > 0 && K > 0, MAPF_ERR_SHAPE);
+  MAPF_REQUIRE((lda & 3) == 0 && mapf_aligned(A, 16) && mapf_aligned(Bp, 16), MAPF_ERR_ALIGN);
+  TcGemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.Bp = Bp; g.bp_tile = mapf_tc_packed_b_size(128, K);
+  g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
+  return launch_tc<128, kTcKC, 1, EPI_STORE, 4>(g, static_cast<cudaStream_t>(stream));
 }
 
 // logits / greedy actions = head(relu(Z Wp^T)): Z [M, K] row-major filter taps, Wp = packed [W | W2] (mapf_tc_pack_b).

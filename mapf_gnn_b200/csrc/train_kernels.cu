@@ -1386,22 +1386,13 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   const bool conv_tc = !(a->flags & MAPF_TRAIN_FFMA_CONV);
   float* da = ws + T.da0;
   float* da_next = ws + T.da1;
-  // C[rows, Ncols] = Asrc[rows, Kd] . Wt^T with Wt [Ncols, Kd] row-major (a transposed weight), 128 output columns per
-  // call: the packs on the pack lane, the GEMMs on the chain
+  // C[rows, Ncols] = Asrc[rows, Kd] . Wt^T with Wt [Ncols, Kd] row-major (a transposed weight): tiles of 128 output
+  // columns packed on the pack lane, one GEMM launch over all tiles on the chain
   auto nn_pack = [&](int Kd, const float* Wt, int Ncols, float* packs) -> int {
-    for (int j0 = 0, t = 0; j0 < Ncols; j0 += 128, ++t) {
-      const int nn = Ncols - j0 < 128 ? Ncols - j0 : 128;
-      MAPF_TRY(mapf_tc_pack_b(Wt + int64_t(j0) * Kd, Kd, nullptr, 0, nn, packs + int64_t(t) * mapf_tc_b_floats(128, Kd), sp));
-    }
-    return MAPF_OK;
+    return mapf_tc_pack_b_tiles(Wt, Kd, Ncols, packs, sp);
   };
   auto nn_gemm = [&](const float* Asrc, int Kd, int Ncols, const float* packs, float* Cout, int64_t ldc) -> int {
-    for (int j0 = 0, t = 0; j0 < Ncols; j0 += 128, ++t) {
-      const int nn = Ncols - j0 < 128 ? Ncols - j0 : 128;
-      MAPF_TRY(mapf_tc_gemm_w3(int32_t(rows), nn, Kd, Asrc, Kd, packs + int64_t(t) * mapf_tc_b_floats(128, Kd), Cout + j0,
-                               ldc, nullptr, 0, stream));
-    }
-    return MAPF_OK;
+    return mapf_tc_gemm_tiles(int32_t(rows), Ncols, Kd, Asrc, Kd, packs, Cout, ldc, nullptr, 0, stream);
   };
   // ---- pack lane ----
   int m_gfpk = -1, m_fcpk = -1, m_convpk[MAPF_MAX_CONV];

@@ -51,6 +51,28 @@ def test_structured_values_are_exact():
     assert torch.equal(out, A @ B.t())
 
 
+@pytest.mark.parametrize("M,N,K", [(640, 400, 128), (300, 256, 128), (5000, 144, 64), (130, 128, 32), (257, 513, 40)])
+def test_column_tiled_gemm_matches_float64(M, N, K):
+    """mapf_tc_pack_b_tiles + mapf_tc_gemm_tiles: any number of output columns in one launch (grid.y = 128-column tile)."""
+    from mapf_gnn_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g)
+    tiles = (N + 127) // 128
+    Bp = torch.empty((tiles * lib.mapf_tc_packed_b_size(128, K),), dtype=torch.float32, device="cuda")
+    _lib.check(lib.mapf_tc_pack_b_tiles(B.data_ptr(), K, N, Bp.data_ptr(), _lib.current_stream()), "pack_b_tiles")
+    out = torch.full((M, N + 3), float("nan"), dtype=torch.float32, device="cuda")      # ldc > N: the pad stays untouched
+    _lib.check(lib.mapf_tc_gemm_tiles(M, N, K, A.data_ptr(), K, Bp.data_ptr(), out.data_ptr(), N + 3, bias.data_ptr(), 0,
+                                      _lib.current_stream()), "gemm_tiles")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t() + bias.double()
+    err = (out[:, :N].double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 4e-6, err
+    assert torch.isnan(out[:, N:]).all()
+
+
 def tc_gemm_tn(A, B, transpose_c=False, accumulate_into=None):
     """C = A^T B through mapf_tc_gemm_tn (A [K, M], B [K, N] row-major, possibly strided views)."""
     from mapf_gnn_b200 import _lib

@@ -236,11 +236,12 @@ def test_training_torch_ops_are_registered_and_differentiable():
         torch.ops.mapf.ce_loss(logits.detach().cpu(), targets.cpu())
 
 
-@pytest.mark.parametrize("mode", ["MAPF_B200_TRAIN_TC_BWD_ALWAYS", "MAPF_B200_TRAIN_FFMA_BWD"])
+@pytest.mark.parametrize("mode", ["MAPF_B200_TRAIN_FFMA_BWD", "MAPF_B200_TRAIN_FFMA_CONV", "MAPF_B200_TRAIN_SINGLE_LANE"])
 @pytest.mark.parametrize("name", ["gnn_msg_k3", "gnn_k3", "baseline"])
 def test_backward_gemm_paths_match_reference(train_step, name, mode, monkeypatch):
-    """Both backward GEMM paths -- tensor cores (mapf_tc_gemm_tn weight gradients + mapf_tc_gemm activation gradients,
-    the default from 4096 rows on) and the FFMA2 kernels -- against the reference's recorded gradients."""
+    """The development switches against the reference's recorded gradients: FFMA2 GEMMs instead of the tensor-core
+    backward (mapf_tc_gemm_tn weight gradients + mapf_tc_gemm activation gradients), FFMA2 convolutions instead of
+    the tensor-core layer kernel, and every launch on the caller's stream instead of the three lanes."""
     monkeypatch.setenv(mode, "1")
     t = train_step
     net = load_network(name).train()
@@ -270,3 +271,31 @@ def test_large_batch_gradients_match_oracle():
     assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
     for k, p in net.named_parameters():
         assert rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy(), GRAD_FLOOR * total) < REL, k
+
+
+def test_lanes_are_ordered_under_load():
+    """The weight-gradient and pack lanes run beside the activation-gradient chain (train_kernels.cu Lanes): repeated
+    steps at a size where the lanes really overlap must keep reproducing the single-lane gradients (a missing event
+    edge shows up as a sporadic mismatch)."""
+    import os
+    name, B, N = "gnn_msg_k3", 2048, 5
+    g = torch.Generator(device="cuda").manual_seed(5)
+    states = torch.randint(0, 4, (B, N, 2, 5, 5), device="cuda", generator=g).float()
+    gso = (torch.rand(B, N, N, device="cuda", generator=g) < 0.4).float() + torch.eye(N, device="cuda")
+    targets = torch.randint(0, 5, (B, N), device="cuda", generator=g)
+
+    def grads():
+        net = load_network(name, num_agents=N).train()
+        loss = torch.nn.functional.cross_entropy(net(states, gso).reshape(-1, 5), targets.reshape(-1))
+        loss.backward()
+        return torch.cat([p.grad.reshape(-1) for p in net.parameters()]).double()
+
+    os.environ["MAPF_B200_TRAIN_SINGLE_LANE"] = "1"
+    try:
+        ref = grads()
+    finally:
+        del os.environ["MAPF_B200_TRAIN_SINGLE_LANE"]
+    scale = float(ref.abs().max())
+    for it in range(12):
+        got = grads()
+        assert float((got - ref).abs().max()) < 2e-4 * scale, it
