@@ -213,9 +213,11 @@ def test_two_forwards_alive_before_backward():
     first = {k: p.grad.clone() for k, p in net.named_parameters()}
     ce(o2, t2).backward()
     total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref[0].values())))
-    for k, p in net.named_parameters():   # (the batch reductions use fp32 atomics: equal up to summation order)
-        assert rel_err(first[k].cpu().numpy(), ref[0][k].cpu().numpy(), 1e-3 * total) < 1e-5, k
-        assert rel_err(p.grad.cpu().numpy(), (ref[0][k] + ref[1][k]).cpu().numpy(), 1e-3 * total) < 1e-5, k
+    # the batch reductions use fp32 atomics: equal up to summation order.  (The conv biases sit in front of a BatchNorm:
+    # their gradient is analytically zero and what is compared there is ~1e-7 of cancellation noise.)
+    for k, p in net.named_parameters():
+        assert rel_err(first[k].cpu().numpy(), ref[0][k].cpu().numpy(), 1e-3 * total) < 3e-5, k
+        assert rel_err(p.grad.cpu().numpy(), (ref[0][k] + ref[1][k]).cpu().numpy(), 1e-3 * total) < 3e-5, k
 
 
 def test_training_torch_ops_are_registered_and_differentiable():
