@@ -548,6 +548,7 @@ def run_mine(args, w):
             "clocks": clocks,
             "train": train,
             "workloads": others,
+            "expert": run_expert(args) if world == 1 and not args.no_cpu_baseline else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -662,6 +663,49 @@ def run_train(args, w, env, dev, rank, world, barrier):
     return {"metric": "train samples/sec (forward + CE + backward + clip + Adam" + (" + gradient all-reduce)" if world > 1
                                                                                     else ")"),
             "model": model, "agents": N, "results": results}
+
+
+def run_expert(args):
+    """SURVEY 8f row 4, compact: CBS plans per second of the native expert (one host thread, and the batch call on all
+    host threads) on main_data.py's instance shape (28x28, 5 agents, 8 obstacles; np.random.seed(0) through gen_input),
+    beside the unmodified reference's `CBS(Environment(...)).search()` on a bounded sample of the same instances.  Host
+    code on both sides: the search is branchy and sequential; no GPU kernel is involved."""
+    import mapf_gnn_b200.cbs as cbs
+    np.random.seed(0)
+    inputs = [cbs.gen_input((28, 28), 8, 5) for _ in range(256)]
+    insts = [(i["map"]["dimensions"], [a["start"] for a in i["agents"]], [a["goal"] for a in i["agents"]],
+              i["map"]["obstacles"]) for i in inputs]
+    cbs.solve_batch(insts[:8], threads=1)
+    t0 = time.perf_counter()
+    one = cbs.solve_batch(insts, threads=1)
+    t1 = time.perf_counter()
+    many = cbs.solve_batch(insts, threads=0)
+    t2 = time.perf_counter()
+    assert all((a is None) == (b is None) and (a is None or a[1] == b[1]) for a, b in zip(one, many))
+    out = {"metric": "CBS instances/s (28x28, 5 agents, 8 obstacles)", "instances": len(insts),
+           "solved": sum(p is not None for p in many), "native_1_thread": len(insts) / (t1 - t0),
+           "native_all_threads": len(insts) / (t2 - t1), "host_threads": os.cpu_count()}
+    try:
+        from oracle import ref_loader
+        root = ref_loader.root()
+        if root is not None and os.path.exists(os.path.join(root, "cbs", "cbs.py")):
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            import importlib
+            ref = importlib.import_module("cbs.cbs")
+            sample = 16
+            t0 = time.perf_counter()
+            same = True
+            for inp, mine in zip(inputs[:sample], many[:sample]):
+                plan = ref.CBS(ref.Environment(inp["map"]["dimensions"], inp["agents"], inp["map"]["obstacles"]), verbose=False).search()
+                got = None if not plan else [[(s["x"], s["y"]) for s in plan[a["name"]]] for a in inp["agents"]]
+                same = same and (got is None) == (mine is None) and (got is None or got == [[tuple(c) for c in p] for p in mine[0]])
+            out["reference_1_thread"] = sample / (time.perf_counter() - t0)
+            out["reference_sample"] = f"first {sample} of the same instances, unmodified cbs/cbs.py staged under oracle/_ref"
+            out["plans_identical_on_sample"] = bool(same)
+    except Exception as exc:            # the expert line is an extra: never fail the bench on it
+        out["reference_error"] = repr(exc)[:200]
+    return out
 
 
 def main():

@@ -470,6 +470,39 @@ int mapf_graph_taps(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);
  * cores: 3xTF32, equal to ~1e-6 relative) */
 int mapf_graph_taps_ffma(const mapf_graph_filter_fwd_args* a, mapf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Conflict-Based Search expert (host code; reference cbs/cbs.py `CBS(env).search()` :326-410 over
+ * `Environment(dimension, agents, obstacles)` :148-157 and cbs/a_star.py `AStar.search` :29-102): the offline label
+ * generator of the imitation data set.  The plans are identical to the reference's (same neighbour order, same
+ * (f, push counter) / (cost, push counter) orderings, same first-conflict rule, same iteration caps).
+ * Coordinates are (x, y) pairs as in the reference's YAML; a path is one cell per time step starting at t = 0.
+ * mapf_cbs_solve fills path_len[agent] with the TRUE lengths and paths[agent][t < min(len, max_path)]; `truncated` = 1
+ * when some path did not fit (call again with a larger max_path).  solved = 0: no plan within the caps (the reference
+ * returns {}), path_len = 0.  mapf_cbs_solve_batch solves independent instances on `threads` host threads (0 = all). */
+typedef struct {
+  int32_t width, height;              /* dimension[0], dimension[1]: 0 <= x < width, 0 <= y < height */
+  int32_t num_agents;
+  const int32_t* starts;              /* [num_agents][2] */
+  const int32_t* goals;               /* [num_agents][2] */
+  int32_t num_obstacles;
+  const int32_t* obstacles;           /* [num_obstacles][2] */
+  int32_t max_high_level_iterations;  /* <= 0: 5000 (cbs.py:353) */
+  int32_t max_low_level_iterations;   /* <= 0: 10000 (a_star.py:59) */
+  int32_t max_path;                   /* capacity of `paths` per agent, in cells */
+  int32_t* path_len;                  /* out [num_agents] */
+  int32_t* paths;                     /* out [num_agents][max_path][2] */
+  int32_t solved, truncated;          /* out */
+  int32_t expanded, generated;        /* out: high-level nodes closed / pushed */
+  int64_t cost;                       /* out: sum of path lengths (compute_solution_cost, cbs.py:302-303) */
+} mapf_cbs_args;
+int mapf_cbs_solve(mapf_cbs_args* a);
+int mapf_cbs_solve_batch(mapf_cbs_args* items, int32_t count, int32_t threads);
+/* one low-level search for `agent` under explicit constraints (Environment.a_star.search with env.constraints set):
+ * vertex constraints [nv][3] = (t, x, y), edge constraints [ne][5] = (t, x1, y1, x2, y2); fills path_len[agent] and
+ * paths[agent]; *found = 0 when there is no path within the cap (the reference returns False) */
+int mapf_cbs_a_star(mapf_cbs_args* a, int32_t agent, const int32_t* vertex_constraints, int32_t nv,
+                    const int32_t* edge_constraints, int32_t ne, int32_t* found);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,8 @@ from .network import BaselineNetwork, GNNNetwork, MessageNetwork, weights_init  
 from .rollout import HostSteppedRollout, PipelinedHostRollout, Rollout, build_network  # noqa: E402,F401
 from .scenarios import make_scenarios, make_scenarios_device  # noqa: E402,F401
 from .evaluate import evaluate  # noqa: E402,F401
+from . import cbs  # noqa: E402,F401
 
 __all__ = ["BatchedGraphEnv", "GraphEnv", "create_goals", "create_obstacles", "d2_limit_from_range", "GCNLayer",
            "MessagePassingLayer", "GNNNetwork", "MessageNetwork", "BaselineNetwork", "weights_init", "Rollout", "HostSteppedRollout", "PipelinedHostRollout",
-           "build_network", "make_scenarios", "make_scenarios_device", "evaluate"]
+           "build_network", "make_scenarios", "make_scenarios_device", "evaluate", "cbs"]

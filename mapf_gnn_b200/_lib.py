@@ -118,6 +118,16 @@ class PeerReduceArgs(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("peer_grads", C.c_void_p * 8), ("peer_flags", C.c_void_p * 8)]
 
 
+class CbsArgs(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32),
+                ("starts", C.POINTER(C.c_int32)), ("goals", C.POINTER(C.c_int32)),
+                ("num_obstacles", C.c_int32), ("obstacles", C.POINTER(C.c_int32)),
+                ("max_high_level_iterations", C.c_int32), ("max_low_level_iterations", C.c_int32),
+                ("max_path", C.c_int32), ("path_len", C.POINTER(C.c_int32)), ("paths", C.POINTER(C.c_int32)),
+                ("solved", C.c_int32), ("truncated", C.c_int32), ("expanded", C.c_int32), ("generated", C.c_int32),
+                ("cost", C.c_int64)]
+
+
 class GraphFilterBwdArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("agents", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
                 ("taps", C.c_int32), ("add_self_loop", C.c_int32),
@@ -169,6 +179,10 @@ _SIGNATURES = {
                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "mapf_tc_gemm_w3": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mapf_cbs_solve": (C.c_int, [C.POINTER(CbsArgs)]),
+    "mapf_cbs_solve_batch": (C.c_int, [C.POINTER(CbsArgs), C.c_int32, C.c_int32]),
+    "mapf_cbs_a_star": (C.c_int, [C.POINTER(CbsArgs), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
+                                  C.c_int32, C.POINTER(C.c_int32)]),
     "mapf_tc_pack_b_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mapf_tc_gemm_tiles": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

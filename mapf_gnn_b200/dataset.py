@@ -40,6 +40,50 @@ def record_cases(config, goals, starts, obstacles, trajectories, sensing_range=6
     return states_np, gso_np, traj
 
 
+def generate_dataset(path, num_cases, config, threads=0, device="cuda"):
+    """The reference's whole data-generation driver (data_generation/main_data.py:24-27): random instances -> CBS plans
+    (``create_solutions``, dataset_gen.py:151-206: native batch search on the host cores, ``cbs.generate_cases``) ->
+    action matrices (``parse_dataset_trajectories``, trajectory_parser.py:68-106) -> recorded observations
+    (``record_env``, record.py:39-97: here ALL cases of one length replay together on the GPU).  Writes, per solved
+    instance, ``case_<i>/{input.yaml, solution.yaml, trajectory.npy, startings.npy, states.npy, gso.npy,
+    trajectory_record.npy}`` in the reference's formats and returns the number of cases.  ``config`` carries main_data.py's
+    keys (map_shape, nb_agents, nb_obstacles, sensor_range, board_size, num_agents, max_time, min_time); instances are
+    drawn from ``np.random`` (seed it).  Deviation, on purpose: record.py's loop bound ``len(cases) - 1`` leaves the
+    last case without recordings; every case is recorded here."""
+    import yaml
+    from . import cbs
+    cases = cbs.generate_cases(num_cases, config["map_shape"], config["nb_agents"], config["nb_obstacles"], threads=threads)
+    os.makedirs(path, exist_ok=True)
+    by_len = {}
+    for i, c in enumerate(cases):
+        case_dir = os.path.join(path, f"case_{i}")
+        os.makedirs(case_dir, exist_ok=True)
+        inp = {"agents": c["input"]["agents"],
+               "map": {"dimensions": c["input"]["map"]["dimensions"], "obstacles": [list(o) for o in c["input"]["map"]["obstacles"]]}}
+        with open(os.path.join(case_dir, "input.yaml"), "w") as fh:
+            yaml.safe_dump(inp, fh)
+        with open(os.path.join(case_dir, "solution.yaml"), "w") as fh:
+            yaml.safe_dump({"schedule": c["schedule"], "cost": c["cost"]}, fh)
+        np.save(os.path.join(case_dir, "trajectory.npy"), c["trajectory"])
+        np.save(os.path.join(case_dir, "startings.npy"), c["startings"])
+        by_len.setdefault(c["trajectory"].shape[1], []).append(i)
+    for T, idx in by_len.items():
+        if T < 2:            # a plan of one state has no action to replay (record.py would write empty arrays)
+            for i in idx:
+                n = cases[i]["trajectory"].shape[0]
+                save_case(os.path.join(path, f"case_{i}"), np.zeros((0, n, 2, 5, 5)), np.zeros((0, n, n, n)),
+                          cases[i]["trajectory"][:, 1:])
+            continue
+        goals = np.array([[a["goal"] for a in cases[i]["input"]["agents"]] for i in idx], dtype=np.int32)
+        starts = np.array([[a["start"] for a in cases[i]["input"]["agents"]] for i in idx], dtype=np.int32)
+        obst = np.array([cases[i]["input"]["map"]["obstacles"] for i in idx], dtype=np.int32).reshape(len(idx), -1, 2)
+        traj = np.stack([cases[i]["trajectory"] for i in idx])
+        states, gso, rec = record_cases(config, goals, starts, obst, traj, sensing_range=config["sensor_range"], device=device)
+        for k, i in enumerate(idx):
+            save_case(os.path.join(path, f"case_{i}"), states[k], gso[k], rec[k])
+    return len(cases)
+
+
 def save_case(case_dir, states, gso, trajectory_record):
     """Write one case in the reference's file layout (record.py:90-94)."""
     os.makedirs(case_dir, exist_ok=True)

@@ -29,6 +29,10 @@ FILES = [
     "models/networks/__init__.py", "models/networks/gnn.py", "models/networks/utils_weights.py",
     "data_loader.py",
     "tests/test_env.py",
+    # the expert: the search, the instance generator / schedule parser and the reference's own tests
+    "cbs/__init__.py", "cbs/cbs.py", "cbs/a_star.py",
+    "data_generation/__init__.py", "data_generation/dataset_gen.py", "data_generation/trajectory_parser.py",
+    "tests/test_cbs.py",
 ]
 
 

@@ -96,3 +96,48 @@ def test_record_cases_matches_oracle_replay():
         for a in range(N):
             assert np.array_equal(gso[e, :, a], exp_a), e
         assert np.array_equal(rec[e], traj[e, :, 1:])
+
+
+@pytest.mark.gpu
+def test_generate_dataset_end_to_end(tmp_path):
+    """main_data.py:24-27 in one call: CBS plans (native, batch) -> action matrices -> GPU recording -> the reference's
+    files; the recordings equal the numpy oracle env replaying each case's expert actions, the expert actions lead every
+    agent to its goal, and the loader serves the cases."""
+    import yaml
+    from mapf_gnn_b200.dataset import GNNDataLoader, generate_dataset
+    N, H, M = 4, 12, 6
+    cfg = {"num_agents": N, "nb_agents": N, "map_shape": [H, H], "board_size": [H, H], "nb_obstacles": M, "sensor_range": 4,
+           "max_time": 32, "min_time": 3}
+    np.random.seed(3)
+    root = tmp_path / "train"
+    count = generate_dataset(str(root), 16, cfg, threads=2)
+    assert 10 <= count <= 16
+    for i in range(count):
+        d = root / f"case_{i}"
+        inp = yaml.safe_load(open(d / "input.yaml"))
+        sol = yaml.safe_load(open(d / "solution.yaml"))
+        traj, rec = np.load(d / "trajectory.npy"), np.load(d / "trajectory_record.npy")
+        states, gso = np.load(d / "states.npy"), np.load(d / "gso.npy")
+        T = traj.shape[1] - 1
+        assert sol["cost"] == sum(len(p) for p in sol["schedule"].values())
+        assert np.array_equal(rec, traj[:, 1:]) and states.shape == (T, N, 2, 5, 5) and gso.shape == (T, N, N, N)
+        goals = np.array([a["goal"] for a in inp["agents"]])
+        starts = np.array([a["start"] for a in inp["agents"]])
+        assert np.array_equal(starts, np.load(d / "startings.npy"))
+        env = eo.EnvOracle(N, H, goals, starts, np.array(inp["map"]["obstacles"]).reshape(-1, 2), sensing_range=4)
+        full = eo.EnvOracle(N, H, goals, starts, np.array(inp["map"]["obstacles"]).reshape(-1, 2), sensing_range=4)
+        for k in range(traj.shape[1]):
+            full.step(traj[:, k])
+        assert np.array_equal(np.stack([full.px, full.py], axis=1), goals)      # the expert arrives
+        obs = env.observe()
+        for k in range(T):
+            if k < T - 1:
+                assert np.array_equal(states[k], obs["fov"]) and np.array_equal(gso[k, 0], obs["adj_matrix"])
+            obs, _ = env.step(traj[:, 1 + k])
+        if T > 0:
+            assert np.array_equal(states[T - 1], obs["fov"])
+    loader = GNNDataLoader({**cfg, "batch_size": 8, "train": {"root_dir": str(tmp_path), "mode": "train", "min_time": 3,
+                                                              "max_time_dl": 25, "nb_agents": N}}, device="cuda")
+    assert loader.num_samples > 0
+    states, actions, gso = next(iter(loader))
+    assert states.shape[1:] == (N, 2, 5, 5) and actions.shape[1:] == (N,) and gso.shape[1:] == (N, N) and states.is_cuda
