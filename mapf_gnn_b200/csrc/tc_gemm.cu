@@ -114,21 +114,27 @@ __global__ void tc_pack_b_f16_kernel(const float* __restrict__ b, int C, int N, 
 
 // NP = producer warps = shared-memory stages (6: two CTAs per SM; 4 with NACC = 1: three CTAs per SM -- the variant the
 // training step uses, whose 320 row tiles at B = 8192 then fit one wave instead of 296 + 24); NACC = MMA issuers.
-template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps>
+// NTL = column tiles of NT per CTA (EPI_STORE, NACC = 1): the A chunk is loaded and split ONCE and multiplied with NTL
+// B tiles into NTL accumulators -- wide outputs (the training step's da = dx W_fc, 400 columns) re-read A per pair of
+// tiles instead of per tile.
+template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps, int NTL = 1>
 __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
+  static_assert(NTL == 1 || (NACC == 1 && EPI == EPI_STORE), "several column tiles per CTA: store epilogue, one accumulator each");
   constexpr int NSTAGE = NP;
-  constexpr uint32_t kColsNeeded = NT * NACC;
+  constexpr uint32_t kColsNeeded = NT * NACC * NTL;
   constexpr uint32_t kCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                              : kColsNeeded <= 256 ? 256 : 512;
   constexpr int kABytes = kTcM * KC * 4, kBBytes = NT * KC * 4;
-  constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr int kStageBytes = 2 * kABytes + NTL * 2 * kBBytes;
   constexpr int KQ = KC / 4;
   extern __shared__ __align__(128) uint8_t s_tc[];
   __shared__ __align__(8) uint64_t s_full[NSTAGE], s_empty[NSTAGE], s_done;
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? kMaxActions * NT + kMaxActions : NT];
+  __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? kMaxActions * NT + kMaxActions : NT * NTL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * NT;
+  const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * NT * NTL;
+  // column tiles this CTA really has (the last CTA of a row of tiles may own fewer than NTL)
+  const int my_tiles = NTL == 1 ? 1 : min(NTL, (g.N - n0 + NT - 1) / NT);
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, kCols);
   if (tid == 0) {
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     }
     if (tid < g.num_actions) s_head[kMaxActions * NT + tid] = __ldg(g.act_b + tid);
   } else {
-    for (int i = tid; i < NT; i += kTcThreads) s_head[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
+    for (int i = tid; i < NT * NTL; i += kTcThreads) s_head[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.0f;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -193,8 +199,10 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       load_chunk(c + NP, vn);   // next chunk's loads overlap this chunk's wait / convert / store
       tc::mbar_wait(&s_empty[s], ph ^ 1);
       if (lane == 0) {
-        tc::mbar_expect_tx(&s_full[s], 2 * kBBytes);
-        tc::bulk_g2s(b_hi, g.Bp + int64_t(blockIdx.y) * g.bp_tile + int64_t(c) * (2 * NT * KC), 2 * kBBytes, &s_full[s]);
+        tc::mbar_expect_tx(&s_full[s], uint32_t(my_tiles) * 2 * kBBytes);
+        for (int t = 0; t < my_tiles; ++t)
+          tc::bulk_g2s(b_hi + t * 2 * kBBytes, g.Bp + (int64_t(blockIdx.y) * NTL + t) * g.bp_tile + int64_t(c) * (2 * NT * KC),
+                       2 * kBBytes, &s_full[s]);
       }
 #pragma unroll
       for (int it = 0; it < kPerLane; ++it) {
@@ -232,14 +240,20 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
         const uint64_t soff = uint64_t(uint32_t(s) * (kStageBytes >> 4));
-        const uint32_t acc = tmem_u + accsel * NT;
         const bool first = c < NACC;   // first touch of this accumulator overwrites
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {
-          const uint64_t o = soff + uint64_t(ks * 16);   // one 8-wide K slice = 2 core matrices = 256 bytes
-          tc::mma_tf32(acc, dal0 + o, dbh0 + o, idesc, !(first && ks == 0));   // small terms first
-          tc::mma_tf32(acc, dah0 + o, dbl0 + o, idesc, true);
-          tc::mma_tf32(acc, dah0 + o, dbh0 + o, idesc, true);
+        for (int t = 0; t < NTL; ++t) {
+          if (t < my_tiles) {
+            const uint32_t acc = tmem_u + (accsel * NTL + t) * NT;
+            const uint64_t bo = uint64_t(t * ((2 * kBBytes) >> 4));
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+              const uint64_t o = soff + uint64_t(ks * 16);   // one 8-wide K slice = 2 core matrices = 256 bytes
+              tc::mma_tf32(acc, dal0 + o, dbh0 + o + bo, idesc, !(first && ks == 0));   // small terms first
+              tc::mma_tf32(acc, dah0 + o, dbl0 + o + bo, idesc, true);
+              tc::mma_tf32(acc, dah0 + o, dbh0 + o + bo, idesc, true);
+            }
+          }
         }
         tc::mma_commit(&s_empty[s]);
         s += NACC;
@@ -264,12 +278,15 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
 #pragma unroll
     for (int q = 0; q < kMaxActions; ++q) part[q] = 0.0f;
 #pragma unroll
+    for (int tl = 0; tl < NTL; ++tl) {
+    if (tl >= my_tiles) break;
+#pragma unroll
     for (int cbl = 0; cbl < kHalfCols; cbl += 32) {
-      const int cb = half * kHalfCols + cbl;
+      const int cb = tl * NT + half * kHalfCols + cbl;      // column inside this CTA's NT * NTL (TMEM column with NACC = 1)
       uint32_t raw[NACC][32];
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
-        if (a < nacc_used) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + a * NT + cb, raw[a]);   // warp-uniform
+        if (a < nacc_used) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + a * NT * NTL + cb, raw[a]);   // warp-uniform
       tc::tmem_ld_wait();
       float v[32];
 #pragma unroll
@@ -330,6 +347,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
         }
       }
     }
+    }
     if (EPI == EPI_HEAD) {
       // the two column halves of a row meet in shared memory (after the y transposes are done with it)
       float* ex = s_scr + 8 * (32 * 33);   // [128 rows][kMaxActions]
@@ -358,14 +376,14 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   if (warp == 0) tc::tmem_dealloc(tmem, kCols);
 }
 
-template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps>
+template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps, int NTL = 1>
 int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
-  constexpr size_t smem = size_t(NP) * (2 * kTcM * KC * 4 + 2 * NT * KC * 4);
+  constexpr size_t smem = size_t(NP) * (2 * kTcM * KC * 4 + NTL * 2 * NT * KC * 4);
   static_assert(smem >= 8 * 32 * 33 * 4 + 128 * kMaxActions * 4, "the epilogue transposes through the operand stages");
-  auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI, NP>;
+  auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI, NP, NTL>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
-  dim3 grid((g.M + kTcM - 1) / kTcM, g.bp_tile ? (g.N + NT - 1) / NT : 1);
+  dim3 grid((g.M + kTcM - 1) / kTcM, g.bp_tile ? (g.N + NT * NTL - 1) / (NT * NTL) : 1);
   kernel<<<grid, kTcThreads, smem, s>>>(g);
   return mapf_launch_status();
 }
@@ -649,7 +667,8 @@ extern "C" int mapf_tc_gemm_tiles(int32_t M, int32_t N, int32_t K, const float* 
   g.M = M; g.N = N; g.K = K;
   g.A = A; g.lda = lda; g.Bp = Bp; g.bp_tile = mapf_tc_packed_b_size(128, K);
   g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu;
-  return launch_tc<128, kTcKC, 1, EPI_STORE, 4>(g, static_cast<cudaStream_t>(stream));
+  if (N <= 128) return launch_tc<128, kTcKC, 1, EPI_STORE, 4>(g, static_cast<cudaStream_t>(stream));
+  return launch_tc<128, kTcKC, 1, EPI_STORE, 4, 2>(g, static_cast<cudaStream_t>(stream));   // pairs of tiles share the A operand
 }
 
 // logits / greedy actions = head(relu(Z Wp^T)): Z [M, K] row-major filter taps, Wp = packed [W | W2] (mapf_tc_pack_b).

@@ -374,8 +374,10 @@ __global__ void __launch_bounds__(256) bn_finalize_apply4_kernel(
   }
 }
 
-// sums over (batch, pixels) per (slot, channel) of dy and dy*xhat, dy = da * [a > 0]
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ a,
+// sums over (batch, pixels) per (slot, channel) of dy and dy*xhat, dy = da * [a > 0].  The ReLU mask is recomputed from
+// the pre-BatchNorm value with the forward pass's own scale / shift and fmaf (a > 0 <=> fmaf(u, scale, shift) > 0, bit for
+// bit what bn_apply stored), so the backward kernels do not read the activations at all.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ scale_shift,
                                                             const float* __restrict__ u,
                                                             const float* __restrict__ meaninv, int B, int N, int C,
                                                             int stat_c, double* __restrict__ stats) {
@@ -386,13 +388,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
   const int nb = min(32, B - b0);
   for (int c = warp; c < C; c += 8) {
     const float mean = meaninv[(n * C + c) * 2], invstd = meaninv[(n * C + c) * 2 + 1];
+    const float sc = scale_shift[(n * C + c) * 2], sh = scale_shift[(n * C + c) * 2 + 1];
     float s1 = 0.0f, s2 = 0.0f;
     if (lane < kFovCells) {
       for (int r = 0; r < nb; ++r) {
         const int64_t idx = ((int64_t(b0 + r) * N + n) * C + c) * kFovCells + lane;
-        const float dy = a[idx] > 0.0f ? da[idx] : 0.0f;
+        const float uv = u[idx];
+        const float dy = fmaf(uv, sc, sh) > 0.0f ? da[idx] : 0.0f;
         s1 += dy;
-        s2 = fmaf(dy, (u[idx] - mean) * invstd, s2);
+        s2 = fmaf(dy, (uv - mean) * invstd, s2);
       }
     }
     const double t1 = warp_sum(double(s1)), t2 = warp_sum(double(s2));
@@ -419,7 +423,7 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ stats, const float
 }
 
 // du = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)), in place over da (coalesced, element per thread)
-__global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ a, const float* __restrict__ u,
+__global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ scale_shift, const float* __restrict__ u,
                                     const float* __restrict__ meaninv, const float* __restrict__ coef, int N, int C,
                                     int64_t planes) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
@@ -430,13 +434,15 @@ __global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restr
     const uint32_t c = pl % uint32_t(C), n = (pl / uint32_t(C)) % uint32_t(N);
     const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
     const float4 k = mapf_ld_dep(reinterpret_cast<const float4*>(coef) + (n * C + c));
-    const float dy = a[idx] > 0.0f ? da[idx] : 0.0f;
-    const float xhat = (u[idx] - mi.x) * mi.y;
+    const float2 ss = mapf_ld_dep(reinterpret_cast<const float2*>(scale_shift) + (n * C + c));
+    const float uv = u[idx];
+    const float dy = fmaf(uv, ss.x, ss.y) > 0.0f ? da[idx] : 0.0f;
+    const float xhat = (uv - mi.x) * mi.y;
     da[idx] = k.x * (dy - k.y - xhat * k.z);
   }
 }
 
-__global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __restrict__ a, const float4* __restrict__ u,
+__global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float* __restrict__ scale_shift, const float4* __restrict__ u,
                                      const float* __restrict__ meaninv, const float* __restrict__ coef, int N, int C,
                                      int64_t rows) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
@@ -446,15 +452,16 @@ __global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __re
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const int64_t row = idx / row4;
     const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
-    const float4 av = a[idx], dv = da[idx], uv = u[idx];
-    const float aa[4] = {av.x, av.y, av.z, av.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+    const float4 dv = da[idx], uv = u[idx];
+    const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
     float r[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t c = (o + j) / kFovCells;
       const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + (n * C + c));
       const float4 k = mapf_ld_dep(reinterpret_cast<const float4*>(coef) + (n * C + c));
-      const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
+      const float2 ss = mapf_ld_dep(reinterpret_cast<const float2*>(scale_shift) + (n * C + c));
+      const float dy = fmaf(uu[j], ss.x, ss.y) > 0.0f ? dd[j] : 0.0f;
       const float xhat = (uu[j] - mi.x) * mi.y;
       r[j] = k.x * (dy - k.y - xhat * k.z);
     }
@@ -464,16 +471,17 @@ __global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float4* __re
 
 // bn_bwd_coef + bn_bwd_apply4 in one launch for small tables (N*C <= kBnFusedMax): the coefficients go to shared memory
 __global__ void __launch_bounds__(256) bn_bwd_coef_apply4_kernel(
-    float4* __restrict__ da, const float4* __restrict__ a, const float4* __restrict__ u, const float* __restrict__ meaninv,
+    float4* __restrict__ da, const float* __restrict__ scale_shift, const float4* __restrict__ u, const float* __restrict__ meaninv,
     const double* __restrict__ stats, const float* __restrict__ gamma, int N, int C, int stat_c, double count, int64_t rows) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
   mapf_pdl_launch();
   __shared__ float4 s_k[kBnFusedMax];
-  __shared__ float2 s_mi[kBnFusedMax];
+  __shared__ float2 s_mi[kBnFusedMax], s_ss[kBnFusedMax];
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
     const int n = i / C, c = i - n * C;
     const float2 mi = mapf_ld_dep(reinterpret_cast<const float2*>(meaninv) + i);
     s_mi[i] = mi;
+    s_ss[i] = mapf_ld_dep(reinterpret_cast<const float2*>(scale_shift) + i);
     s_k[i] = make_float4(gamma[c] * mi.y, float(mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2) / count),
                          float(mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2 + 1) / count), 0.0f);
   }
@@ -483,15 +491,15 @@ __global__ void __launch_bounds__(256) bn_bwd_coef_apply4_kernel(
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
     const int64_t row = idx / row4;
     const uint32_t o = uint32_t(idx - row * row4) * 4u, n = uint32_t(row % N);
-    const float4 av = a[idx], dv = mapf_ld_dep(da + idx), uv = u[idx];
-    const float aa[4] = {av.x, av.y, av.z, av.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+    const float4 dv = mapf_ld_dep(da + idx), uv = u[idx];
+    const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
     float r[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t c = (o + j) / kFovCells;
-      const float2 mi = s_mi[n * C + c];
+      const float2 mi = s_mi[n * C + c], ss = s_ss[n * C + c];
       const float4 k = s_k[n * C + c];
-      const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
+      const float dy = fmaf(uu[j], ss.x, ss.y) > 0.0f ? dd[j] : 0.0f;
       const float xhat = (uu[j] - mi.x) * mi.y;
       r[j] = k.x * (dy - k.y - xhat * k.z);
     }
@@ -502,7 +510,7 @@ __global__ void __launch_bounds__(256) bn_bwd_coef_apply4_kernel(
 // bn_bwd_reduce for C*25 % 4 == 0: one CTA per (32 batch rows, slot); thread t < 2*row4 owns the float4 column
 // t % row4 of the rows of its parity, so every warp reads whole 512-byte pieces of a row; a float4 touches at most two
 // channels, whose partial sums meet in shared memory before one fp64 atomic per (CTA, channel).
-__global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __restrict__ da, const float4* __restrict__ a,
+__global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __restrict__ da, const float* __restrict__ scale_shift,
                                                              const float4* __restrict__ u,
                                                              const float* __restrict__ meaninv, int B, int N, int C,
                                                              int stat_c, double* __restrict__ stats) {
@@ -519,22 +527,24 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __res
   if (grp < groups) {
     const int o = f4 * 4;
     int ch[4];
-    float mean[4], inv[4];
+    float mean[4], inv[4], sc[4], sh[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       ch[j] = (o + j) / kFovCells;
       mean[j] = meaninv[(n * C + ch[j]) * 2];
       inv[j] = meaninv[(n * C + ch[j]) * 2 + 1];
+      sc[j] = scale_shift[(n * C + ch[j]) * 2];
+      sh[j] = scale_shift[(n * C + ch[j]) * 2 + 1];
     }
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int r = grp; r < nb; r += groups) {
       const int64_t idx = (int64_t(b0 + r) * N + n) * row4 + f4;
-      const float4 av = a[idx], dv = da[idx], uv = u[idx];
-      const float aa[4] = {av.x, av.y, av.z, av.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+      const float4 dv = da[idx], uv = u[idx];
+      const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float dy = aa[j] > 0.0f ? dd[j] : 0.0f;
+        const float dy = fmaf(uu[j], sc[j], sh[j]) > 0.0f ? dd[j] : 0.0f;
         s1[j] += dy;
         s2[j] = fmaf(dy, (uu[j] - mean[j]) * inv[j], s2[j]);
       }
@@ -1485,26 +1495,26 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     dim3 grid((B + 31) / 32, N);
     const bool vec4 = (cout * kFovCells) % 4 == 0 && cout * kFovCells / 4 <= 256 && cout <= 64;
     if (vec4)
-      mapf_launch_pdl(bn_bwd_reduce4_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]),
+      mapf_launch_pdl(bn_bwd_reduce4_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(da), ws + T.scsh[l],
                                                  reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.meaninv[l], B, N, cout,
                                                  T.cmax, st);
     else
-      mapf_launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
+      mapf_launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, da, ws + T.scsh[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
     const int64_t planes = rows * cout;
     if ((cout * kFovCells) % 4 == 0 && N * cout <= kBnFusedMax) {
       mapf_launch_pdl(bn_bwd_coef_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s,
-          reinterpret_cast<float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]), reinterpret_cast<const float4*>(ws + T.u[l]),
+          reinterpret_cast<float4*>(da), ws + T.scsh[l], reinterpret_cast<const float4*>(ws + T.u[l]),
           ws + T.meaninv[l], st, p->bn_gamma[l], N, cout, T.cmax, count, rows);
     } else {
       mapf_launch_pdl(bn_bwd_coef_kernel, dim3((N * cout + 127) / 128), dim3(128), 0, s, st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
                                                                ws + T.coef[l]);
       if ((cout * kFovCells) % 4 == 0)
         mapf_launch_pdl(bn_bwd_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s, 
-            reinterpret_cast<float4*>(da), reinterpret_cast<const float4*>(ws + T.a[l]), reinterpret_cast<const float4*>(ws + T.u[l]),
+            reinterpret_cast<float4*>(da), ws + T.scsh[l], reinterpret_cast<const float4*>(ws + T.u[l]),
             ws + T.meaninv[l], ws + T.coef[l], N, cout, rows);
       else
         mapf_launch_pdl(bn_bwd_apply_kernel, dim3(unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16))), dim3(256), 0, s, 
-            da, ws + T.a[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
+            da, ws + T.scsh[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
     }
     ord.wait(sw, ord.mark(s));        // du_l (in `da`) and the BatchNorm sums
     mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, sw, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
