@@ -513,12 +513,12 @@ __global__ void __launch_bounds__(256) bn_bwd_coef_apply4_kernel(
 __global__ void __launch_bounds__(256) bn_bwd_reduce4_kernel(const float4* __restrict__ da, const float* __restrict__ scale_shift,
                                                              const float4* __restrict__ u,
                                                              const float* __restrict__ meaninv, int B, int N, int C,
-                                                             int stat_c, double* __restrict__ stats) {
+                                                             int stat_c, double* __restrict__ stats, int rows_per_cta) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
   mapf_pdl_launch();
   __shared__ float s_sum[64 * 2];
-  const int n = blockIdx.y, b0 = blockIdx.x * 32;
-  const int nb = min(32, B - b0);
+  const int n = blockIdx.y, b0 = blockIdx.x * rows_per_cta;
+  const int nb = min(rows_per_cta, B - b0);
   const int row4 = (C * kFovCells) >> 2;
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) s_sum[i] = 0.0f;
   __syncthreads();
@@ -1494,10 +1494,12 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     double* st = stat + int64_t(l) * N * T.cmax * 2;
     dim3 grid((B + 31) / 32, N);
     const bool vec4 = (cout * kFovCells) % 4 == 0 && cout * kFovCells / 4 <= 256 && cout <= 64;
+    // small batches are latency-bound: fewer rows per CTA (a CTA walks its rows serially) until the grid fills the SMs
+    const int rpc = int64_t(B) * N >= 32 * 2 * 148 ? 32 : (int64_t(B) * N >= 8 * 2 * 148 ? 8 : 4);
     if (vec4)
-      mapf_launch_pdl(bn_bwd_reduce4_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(da), ws + T.scsh[l],
+      mapf_launch_pdl(bn_bwd_reduce4_kernel, dim3((B + rpc - 1) / rpc, N), dim3(256), 0, s, reinterpret_cast<const float4*>(da), ws + T.scsh[l],
                                                  reinterpret_cast<const float4*>(ws + T.u[l]), ws + T.meaninv[l], B, N, cout,
-                                                 T.cmax, st);
+                                                 T.cmax, st, rpc);
     else
       mapf_launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, da, ws + T.scsh[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
     const int64_t planes = rows * cout;
