@@ -63,7 +63,10 @@ struct Constraints {                       // cbs.py:128-145
 
 struct Grid {
   int32_t w, h;
-  std::unordered_set<Cell, CellHash> obstacles;
+  std::vector<uint8_t> blocked;            // [h][w]: 1 = obstacle (obstacles outside the grid can never be stepped on anyway)
+  void block(int32_t x, int32_t y) {
+    if (x >= 0 && x < w && y >= 0 && y < h) blocked[int64_t(y) * w + x] = 1;
+  }
 };
 
 using Path = std::vector<Cell>;            // index = time step
@@ -72,22 +75,38 @@ using Path = std::vector<Cell>;            // index = time step
 bool a_star(const Grid& g, const Constraints& c, Cell start, Cell goal, int max_pops, Path* out) {
   struct Node { St s; int32_t gscore; int32_t parent; bool open, closed; };
   std::vector<Node> nodes;
-  std::unordered_map<St, int32_t, StHash> index;
+  // state -> node: one dense W x H layer of node indices per time step, allocated when the search first reaches that
+  // step (states outside the grid -- only a start cell can be -- go through the hash map)
+  const int64_t cells = int64_t(g.w) * g.h;
+  std::vector<std::vector<int32_t>> layers;
+  std::unordered_map<St, int32_t, StHash> outside;
+  auto inside = [&](const St& s) { return s.x >= 0 && s.x < g.w && s.y >= 0 && s.y < g.h; };
   auto node_of = [&](const St& s) -> int32_t {          // -1: never seen (no g_score entry)
-    auto it = index.find(s);
-    return it == index.end() ? -1 : it->second;
+    if (!inside(s)) {
+      auto it = outside.find(s);
+      return it == outside.end() ? -1 : it->second;
+    }
+    if (s.t >= int32_t(layers.size()) || layers[s.t].empty()) return -1;
+    return layers[s.t][int64_t(s.y) * g.w + s.x];
+  };
+  auto remember = [&](const St& s, int32_t idx) {
+    if (!inside(s)) { outside.emplace(s, idx); return; }
+    if (s.t >= int32_t(layers.size())) layers.resize(s.t + 1);
+    if (layers[s.t].empty()) layers[s.t].assign(size_t(cells), -1);
+    layers[s.t][int64_t(s.y) * g.w + s.x] = idx;
   };
   struct Entry { int32_t f; int64_t count; int32_t node; };
   struct Later { bool operator()(const Entry& a, const Entry& b) const { return a.f != b.f ? a.f > b.f : a.count > b.count; } };
   std::priority_queue<Entry, std::vector<Entry>, Later> heap;
   auto heuristic = [&](int32_t x, int32_t y) { return (x > goal.x ? x - goal.x : goal.x - x) + (y > goal.y ? y - goal.y : goal.y - y); };
+  const bool any_vertex = !c.vertex.empty(), any_edge = !c.edge.empty();
   auto state_valid = [&](const St& s) {
-    return s.x >= 0 && s.x < g.w && s.y >= 0 && s.y < g.h && c.vertex.find(s) == c.vertex.end() &&
-           g.obstacles.find(Cell{s.x, s.y}) == g.obstacles.end();
+    return s.x >= 0 && s.x < g.w && s.y >= 0 && s.y < g.h && !(any_vertex && c.vertex.find(s) != c.vertex.end()) &&
+           !g.blocked[int64_t(s.y) * g.w + s.x];
   };
   int64_t counter = 0;
   nodes.push_back(Node{St{0, start.x, start.y}, 0, -1, true, false});
-  index.emplace(nodes[0].s, 0);
+  remember(nodes[0].s, 0);
   heap.push(Entry{heuristic(start.x, start.y), counter++, 0});
   static const int dx[5] = {0, 0, 0, -1, 1}, dy[5] = {0, 1, -1, 0, 0};
   int pops = 0;
@@ -108,7 +127,7 @@ bool a_star(const Grid& g, const Constraints& c, Cell start, Cell goal, int max_
     for (int k = 0; k < 5; ++k) {
       const St n{s.t + 1, s.x + dx[k], s.y + dy[k]};
       if (!state_valid(n)) continue;
-      if (k > 0 && c.edge.find(Edge{s.t, s.x, s.y, n.x, n.y}) != c.edge.end()) continue;
+      if (k > 0 && any_edge && c.edge.find(Edge{s.t, s.x, s.y, n.x, n.y}) != c.edge.end()) continue;
       int32_t ni = node_of(n);
       if (ni >= 0 && nodes[ni].closed) continue;
       const int32_t tentative = nodes[cur].gscore + 1;
@@ -116,7 +135,7 @@ bool a_star(const Grid& g, const Constraints& c, Cell start, Cell goal, int max_
         if (ni < 0) {
           ni = int32_t(nodes.size());
           nodes.push_back(Node{n, tentative, cur, true, false});
-          index.emplace(n, ni);
+          remember(n, ni);
         } else {
           nodes[ni].gscore = tentative;
           nodes[ni].parent = cur;
@@ -246,8 +265,8 @@ int check_args(const mapf_cbs_args* a) {
 }
 
 void solve_one(mapf_cbs_args* a) {
-  Grid g{a->width, a->height, {}};
-  for (int i = 0; i < a->num_obstacles; ++i) g.obstacles.insert(Cell{a->obstacles[2 * i], a->obstacles[2 * i + 1]});
+  Grid g{a->width, a->height, std::vector<uint8_t>(size_t(a->width) * a->height, 0)};
+  for (int i = 0; i < a->num_obstacles; ++i) g.block(a->obstacles[2 * i], a->obstacles[2 * i + 1]);
   std::vector<Cell> starts(a->num_agents), goals(a->num_agents);
   for (int i = 0; i < a->num_agents; ++i) {
     starts[i] = Cell{a->starts[2 * i], a->starts[2 * i + 1]};
@@ -313,8 +332,8 @@ extern "C" int mapf_cbs_a_star(mapf_cbs_args* a, int32_t agent, const int32_t* v
   if (rc != MAPF_OK) return rc;
   if (found == nullptr || (nv > 0 && !vertex_constraints) || (ne > 0 && !edge_constraints)) return MAPF_ERR_NULL;
   if (agent < 0 || agent >= a->num_agents || nv < 0 || ne < 0) return MAPF_ERR_SHAPE;
-  Grid g{a->width, a->height, {}};
-  for (int i = 0; i < a->num_obstacles; ++i) g.obstacles.insert(Cell{a->obstacles[2 * i], a->obstacles[2 * i + 1]});
+  Grid g{a->width, a->height, std::vector<uint8_t>(size_t(a->width) * a->height, 0)};
+  for (int i = 0; i < a->num_obstacles; ++i) g.block(a->obstacles[2 * i], a->obstacles[2 * i + 1]);
   Constraints c;
   for (int i = 0; i < nv; ++i) c.vertex.insert(St{vertex_constraints[3 * i], vertex_constraints[3 * i + 1], vertex_constraints[3 * i + 2]});
   for (int i = 0; i < ne; ++i)
