@@ -172,36 +172,22 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     uint8_t* a_lo = a_hi + kABytes;
     uint8_t* b_hi = a_lo + kABytes;
     constexpr int kPerLane = kTcM * KQ / 32;
-    // kPerLane independent 128-bit loads of one chunk in flight per lane.  Element `it` of a lane is row
-    // r0 + it * (256 / KC) of the tile, K offset k0 inside the chunk -- fixed per lane, so the row pointer and the row
-    // validity are computed ONCE (the per-chunk address is one 64-bit add per load; recomputing rows, bounds and the
-    // 64-bit products per load was half of this kernel's instruction stream).
-    constexpr int kRowStep = 32 / KQ;                       // rows between consecutive elements of a lane
-    const int r0 = (lane / (8 * KQ)) * 8 + (lane & 7), k0 = ((lane >> 3) % KQ) * 4;
-    const float* const lane_base = g.A + int64_t(m0 + r0) * g.lda + k0;
-    const int64_t row_step = int64_t(kRowStep) * g.lda;
-    uint32_t row_ok = 0;
-#pragma unroll
-    for (int it = 0; it < kPerLane; ++it) row_ok |= (m0 + r0 + it * kRowStep < g.M ? 1u : 0u) << it;
+    // kPerLane independent 128-bit loads of one chunk in flight per lane
     auto load_chunk = [&](int c, float4* v) {
-      const float* p = lane_base + int64_t(c) * KC;
-      if (c < nchunks && (c + 1) * KC <= g.K) {             // whole chunk inside K (warp-uniform): no per-element K tests
 #pragma unroll
-        for (int it = 0; it < kPerLane; ++it, p += row_step)
-          v[it] = (row_ok >> it) & 1u ? mapf_ld_dep(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-      }
-#pragma unroll
-      for (int it = 0; it < kPerLane; ++it, p += row_step) {
-        const int gk = c * KC + k0;
+      for (int it = 0; it < kPerLane; ++it) {
+        const int idx = lane + it * 32;
+        const int r8 = idx & 7, k4 = (idx >> 3) % KQ, rg = idx / (8 * KQ);
+        const int grow = m0 + rg * 8 + r8, gk = c * KC + k4 * 4;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < nchunks && ((row_ok >> it) & 1u)) {
+        if (c < nchunks && grow < g.M) {
+          const float* p = g.A + int64_t(grow) * g.lda;
           if (gk + 3 < g.K) {
-            v[it] = mapf_ld_dep(reinterpret_cast<const float4*>(p));
+            v[it] = mapf_ld_dep(reinterpret_cast<const float4*>(p + gk));
           } else {
-            if (gk + 0 < g.K) v[it].x = mapf_ld_dep(p + 0);
-            if (gk + 1 < g.K) v[it].y = mapf_ld_dep(p + 1);
-            if (gk + 2 < g.K) v[it].z = mapf_ld_dep(p + 2);
+            if (gk + 0 < g.K) v[it].x = mapf_ld_dep(p + gk + 0);
+            if (gk + 1 < g.K) v[it].y = mapf_ld_dep(p + gk + 1);
+            if (gk + 2 < g.K) v[it].z = mapf_ld_dep(p + gk + 2);
           }
         }
       }
@@ -212,7 +198,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     for (int c = warp; c < nchunks; c += NP, ph ^= 1) {
       load_chunk(c + NP, vn);   // next chunk's loads overlap this chunk's wait / convert / store
       tc::mbar_wait(&s_empty[s], ph ^ 1);
-      if (tc::elect_one()) {      // (warp-uniform branch: plain UBLKCP, no ELECT / R2UR.BROADCAST loop around it)
+      if (lane == 0) {
         tc::mbar_expect_tx(&s_full[s], uint32_t(my_tiles) * 2 * kBBytes);
         for (int t = 0; t < my_tiles; ++t)
           tc::bulk_g2s(b_hi + t * 2 * kBBytes, g.Bp + (int64_t(blockIdx.y) * NTL + t) * g.bp_tile + int64_t(c) * (2 * NT * KC),

@@ -55,13 +55,21 @@ sys.argv = ["taps_time.py"]
 runpy.run_path(os.path.join(%r, "tools", "taps_time.py"), run_name="__main__")
 '''
 
+CHILD_MIX = r'''
+import os, sys, runpy
+sys.argv = ["mix_time.py"]
+runpy.run_path(os.path.join(%r, "tools", "mix_time.py"), run_name="__main__")
+'''
+
 def main():
     from mapf_gnn_b200 import _build
     _build.build_library()
     src, child = sys.argv[1], sys.argv[2]
     stem = os.path.basename(src)[:-3]
+    if len(sys.argv) > 3 and sys.argv[3].startswith("--replaces="):      # an alternative source standing in for csrc/<name>.cu
+        stem = sys.argv.pop(3).split("=", 1)[1][:-3]
     objs = [os.path.join(_build.LIBDIR, f) for f in os.listdir(_build.LIBDIR) if f.endswith(".o") and f != stem + ".o"]
-    code = {"graph": CHILD_GRAPH, "taps": CHILD_TAPS}[child] % (ROOT,)
+    code = {"graph": CHILD_GRAPH, "taps": CHILD_TAPS, "mix": CHILD_MIX}[child] % (ROOT,)
     for i, flags in enumerate(sys.argv[3:] or [""]):
         obj, so = f"/tmp/{stem}_v{i}.o", f"/tmp/libmapf_{stem}_v{i}.so"
         path = src if os.path.isabs(src) or os.path.exists(src) else os.path.join(_build.CSRC, src)
