@@ -31,7 +31,8 @@
 // horizontal exchange needs no border masks).  A CTA holds five independent warpgroups; each walks its own M tiles
 // through all layers with its own 96 TMEM columns (D 48 | A hi 24 | A lo 24), its own mbarrier and named barrier; one
 // thread per group issues its MMAs in a fixed order (reproducible results), and the groups start a fraction of a layer
-// apart so that one group's MMA round trip falls under the others' epilogues.  The last layer's epilogue emits the
+// apart (a chain of mbarriers: group g starts when group g - 1 has issued its first MMAs) so that one group's MMA round
+// trip falls under the others' epilogues.  The last layer's epilogue emits the
 // flattened activations as the fp16-split, pre-tiled A operand of the encoder FC (mapf_tc_fc_presplit_f16: one scale per
 // image, its inverse stored behind the operand) with the K index ordered pixel-major (k = pixel * 16 + channel); the
 // four images of a tile meet in shared memory so that the global stores are whole 64-byte runs.  The FC's B operand is
@@ -77,7 +78,6 @@ struct EncTcArgs {
   float* ap;                      // pre-split FC operand out
   float* row_inv;                 // inverse scale of every FC operand row out
   int nch;                        // 16-wide K chunks of the FC (fc_in / 16)
-  int skew;                       // start-up offset between the warpgroups, clocks
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
   extern __shared__ __align__(128) float s_w[];          // weight image (header + B blocks), then the output staging buffers
   __shared__ __align__(16) float s_bias[MAPF_MAX_CONV][kEtMaxC];
   __shared__ __align__(8) uint64_t s_bar[kEtGroups];     // MMAs of the group's current layer complete (tcgen05.commit)
+  __shared__ __align__(8) uint64_t s_go[kEtGroups];      // start-up chain: group g's first MMAs are issued / complete
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_lw[MAPF_MAX_CONV], s_lnm[MAPF_MAX_CONV];   // per layer: byte offset of its B blocks, 16-wide K steps
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
   if (tid == 0) {
-    for (int i = 0; i < kEtGroups; ++i) tc::mbar_init(&s_bar[i], 1);
+    for (int i = 0; i < kEtGroups; ++i) { tc::mbar_init(&s_bar[i], 1); tc::mbar_init(&s_go[i], 1); }
     tc::fence_mbar_init();
   }
   for (int i = tid; i < (g.w_floats >> 2); i += kEtThreads)
@@ -282,10 +283,13 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
   mapf_pdl_wait();      // everything above touched only the packed weights; the observations come from the env kernel
   mapf_pdl_launch();
   load_obs(tile, o0, o1);
-  if (wg > 0) {   // start the groups a fraction of a layer apart: one group's MMA wait falls under the others' epilogues
-    const long long t0 = clock64();
-    while (clock64() - t0 < g.skew * wg) {}
-  }
+  // Start the groups a fraction of a layer apart (one group's MMA wait then falls under the others' epilogues) as a
+  // chain of events instead of timed waits: group g starts once group g - 1 has issued its first MMAs -- one operand
+  // build + issue (~1 100 clocks) per link, the spacing the tuned clock64() offsets of round 1 had converged to
+  // (35.4 us against 35.6 us at 20 480 images; 12.6 against 12.3 us at 5 920).
+  if (wg > 0 && tile < ntiles) tc::mbar_wait(&s_go[wg - 1], 0);
+  if (tile >= ntiles && (tid & 127) == 0) tc::mbar_arrive(&s_go[wg]);     // a group without work releases its successor
+  bool first_issue = true;
   for (; tile < ntiles; tile += stride) {
     float inv_a;     // inverse of the scale of the A operand now in TMEM (one per image)
     // ---- layer-0 A operand: k = kx*2 + c, K padded to 16 ----
@@ -345,8 +349,10 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
           }
           ETC_STAMP(7);
           tc::mma_commit(bar);
+          if (first_issue) tc::mbar_arrive(&s_go[wg]);     // the next group may start
           ETC_STAMP(8);
         }
+        first_issue = false;
       }
       __syncwarp();
       etc_mbar_wait(bar, phase);
@@ -480,7 +486,6 @@ struct ConvTcArgs {
   const float* wtc;    // [kEtHdr floats: inverse filter scale][K steps x (hi block | lo block)] (pack_tc_conv_raw_kernel)
   const float* bias;   // [16] or NULL
   float* out;          // [rows][16*25]
-  int skew;
   // per-slot BatchNorm statistics of the output (forward layers; NULL for data gradients): fp64 sums [N][stat_c][2]
   double* stats;
   int slots, stat_c;   // N agent slots (row = b * N + n), channel pitch of `stats`
@@ -539,6 +544,7 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
   __shared__ __align__(128) float s_w[kWFloats];
   __shared__ __align__(16) float s_b[kEtCout];
   __shared__ __align__(8) uint64_t s_bar[kGroups];
+  __shared__ __align__(8) uint64_t s_go[kGroups];      // start-up chain (see encoder_tc_kernel)
   __shared__ uint32_t s_tmem;
   extern __shared__ __align__(16) double s_stat[];     // [warp][slot][32]: a warp's private per-slot sums (g.stats only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
 
   if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
   if (tid == 0) {
-    for (int i = 0; i < kGroups; ++i) tc::mbar_init(&s_bar[i], 1);
+    for (int i = 0; i < kGroups; ++i) { tc::mbar_init(&s_bar[i], 1); tc::mbar_init(&s_go[i], 1); }
     tc::fence_mbar_init();
   }
   if (do_stats)
@@ -594,10 +600,9 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
   int64_t tile = int64_t(blockIdx.x) * kGroups + wg;
   float x[CIN];
   load_in(tile, x);
-  if (wg > 0) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < g.skew * wg) {}
-  }
+  if (wg > 0 && tile < ntiles) tc::mbar_wait(&s_go[wg - 1], 0);        // start-up chain of the groups (see encoder_tc_kernel)
+  if (tile >= ntiles && (tid & 127) == 0) tc::mbar_arrive(&s_go[wg]);
+  bool first_issue = true;
   for (; tile < ntiles; tile += stride) {
     float inv_a;
     {
@@ -656,7 +661,9 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
           mma_f16_ts(tmem_u, ah, bh, idesc, true);
         }
         tc::mma_commit(bar);
+        if (first_issue) tc::mbar_arrive(&s_go[wg]);
       }
+      first_issue = false;
     }
     __syncwarp();
     etc_mbar_wait(bar, phase);
@@ -802,7 +809,7 @@ int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int c
   const int64_t want = (ntiles + 4) / 5;
   const int grid = int(want < sms ? want : sms);
   const int64_t rounds = (ntiles + int64_t(grid) * 5 - 1) / (int64_t(grid) * 5);
-  g.skew = int(rounds >= 6 ? 700 : 200 + 100 * rounds);
+
   // statistics in the conv epilogue while the warps' private tables fit shared memory (N <= 16); else a second pass
   const bool fused_stats = stats != nullptr && N <= 16;
   size_t smem = 0;
@@ -883,14 +890,6 @@ extern "C" int mapf_encoder_tc_conv_fwd(const mapf_net_params* p, const mapf_enc
     if (!mapf_ensure_smem(kernel, smem, cache)) return MAPF_ERR_CUDA;
     const int64_t want = (ntiles + kGroups - 1) / kGroups;
     const int grid = int(want < sms ? want : sms);
-    // start-up offset between the warpgroups: about a fifth of a layer for a long launch, less when every group sees
-    // only a tile or two (measured optimum 400 / 700 / 1000 / 1400 clocks at 1 / 2 / 4 / 7 tiles per group)
-    const int64_t rounds = (ntiles + int64_t(grid) * kGroups - 1) / (int64_t(grid) * kGroups);
-#ifdef MAPF_ETC_SKEW
-    g.skew = MAPF_ETC_SKEW;
-#else
-    g.skew = int(rounds >= 6 ? 1400 : 300 + 200 * rounds);
-#endif
     mapf_launch_pdl(kernel, dim3(grid), dim3(kThreads), smem, static_cast<cudaStream_t>(stream), g);
     return MAPF_OK;
   };

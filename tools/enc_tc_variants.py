@@ -18,7 +18,7 @@ for model in ("gnn_k2", "baseline"):
     net = load_network(model, num_agents=1).eval()
     dims, packed = net.dims(), net.packed_weights()
     p = net_params(dims); s = _lib.current_stream()
-    for rows in ((20480, 81920) if model == "gnn_k2" else (20480,)):
+    for rows in ((2560, 5920, 20480, 81920) if model == "gnn_k2" else (20480,)):
         torch.manual_seed(0)
         st = torch.randint(0, 4, (rows, 2, 5, 5), device="cuda").float()
         Ap = torch.zeros((lib.mapf_tc_presplit_a_size(rows, 400),), device="cuda")
