@@ -454,6 +454,73 @@ def parse_trajectories(schedule):
     return actions, starts
 
 
+def data_gen(input_dict, output_path):
+    """dataset_gen.py:111-148: plan one instance and write ``solution.yaml`` ({schedule, cost}) and ``input.yaml`` into
+    ``output_path``; False (and no solution file) when there is no plan."""
+    import os
+    import yaml
+    os.makedirs(output_path, exist_ok=True)
+    env = Environment(input_dict["map"]["dimensions"], input_dict["agents"], input_dict["map"]["obstacles"])
+    solution = CBS(env, verbose=False).search()
+    if not solution:
+        print(f"No solution found for case {os.path.basename(str(output_path))}")
+        return False
+    with open(os.path.join(output_path, "solution.yaml"), "w") as fh:
+        yaml.safe_dump({"schedule": solution, "cost": env.compute_solution_cost(solution)}, fh)
+    with open(os.path.join(output_path, "input.yaml"), "w") as fh:
+        yaml.safe_dump(input_dict, fh)
+    return True
+
+
+def create_solutions(path, num_cases, config):
+    """dataset_gen.py:151-206: cases ``case_<i>`` for i from the number of existing case directories up to ``num_cases``;
+    instances from ``gen_input`` (np.random, in the reference's order -- drawing does not depend on the plans, so all
+    instances are drawn first and planned in ONE batch call), failed cases leave no directory."""
+    import os
+    import shutil
+    import yaml
+    os.makedirs(path, exist_ok=True)
+    ready = len([d for d in os.listdir(path) if d.startswith("case_") and os.path.isdir(os.path.join(path, d))])
+    todo = []
+    for i in range(ready, num_cases):
+        inp = gen_input(tuple(config["map_shape"]), config["nb_obstacles"], config["nb_agents"])
+        if inp is not None:
+            todo.append((i, inp))
+    plans = solve_batch([(inp["map"]["dimensions"], [a["start"] for a in inp["agents"]], [a["goal"] for a in inp["agents"]],
+                          _obstacle_cells(inp["map"]["obstacles"])) for _, inp in todo])
+    done = 0
+    for (i, inp), plan in zip(todo, plans):
+        case = os.path.join(path, f"case_{i}")
+        if plan is None:
+            shutil.rmtree(case, ignore_errors=True)
+            continue
+        os.makedirs(case, exist_ok=True)
+        paths, cost = plan
+        with open(os.path.join(case, "solution.yaml"), "w") as fh:
+            yaml.safe_dump({"schedule": schedule_of(paths, [a["name"] for a in inp["agents"]]), "cost": cost}, fh)
+        with open(os.path.join(case, "input.yaml"), "w") as fh:
+            yaml.safe_dump(inp, fh)
+        done += 1
+    print(f"Generation complete: {done} successful, {num_cases - ready - done} failed")
+    return done
+
+
+def parse_dataset_trajectories(path):
+    """trajectory_parser.py:68-106: ``trajectory.npy`` / ``startings.npy`` next to every ``case_*/solution.yaml``."""
+    import os
+    import yaml
+    for name in sorted(d for d in os.listdir(path) if d.startswith("case_") and os.path.isdir(os.path.join(path, d))):
+        sol = os.path.join(path, name, "solution.yaml")
+        if not os.path.exists(sol):
+            print(f"Warning: Solution file not found for {name}")
+            continue
+        with open(sol) as fh:
+            schedule = yaml.load(fh, Loader=yaml.FullLoader)["schedule"]
+        trajectory, startings = parse_trajectories(dict(schedule))
+        np.save(os.path.join(path, name, "trajectory.npy"), trajectory)
+        np.save(os.path.join(path, name, "startings.npy"), startings)
+
+
 def schedule_of(paths, names=None):
     """``solve_batch`` paths -> the reference's schedule dict."""
     names = names or [f"agent{k}" for k in range(len(paths))]
