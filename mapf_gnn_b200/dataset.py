@@ -84,6 +84,49 @@ def generate_dataset(path, num_cases, config, threads=0, device="cuda"):
     return len(cases)
 
 
+def record_env(path, config, device="cuda", skip_last_case=False):
+    """``record_env`` of data_generation/record.py:39-97 over a directory of ``case_<i>/{input.yaml, trajectory.npy}``
+    (written by ``cbs.create_solutions`` + ``cbs.parse_dataset_trajectories`` or by the reference's scripts): all cases
+    of one trajectory length and obstacle count replay together on the GPU, then ``states.npy`` / ``gso.npy`` /
+    ``trajectory_record.npy`` are written per case and ``stats.txt`` like the reference's.  ``skip_last_case=True``
+    reproduces the reference's loop bound (``range(len(cases) - 1)``, record.py:44,59: the case with the highest
+    number gets no recordings)."""
+    import yaml
+    cases = sorted((d for d in os.listdir(path) if d.startswith("case_") and os.path.isdir(os.path.join(path, d))),
+                   key=lambda d: int(d.split("_")[1]))
+    if skip_last_case:
+        cases = cases[:-1]
+    groups, lengths = {}, []
+    for name in cases:
+        tpath = os.path.join(path, name, "trajectory.npy")
+        if not os.path.exists(tpath):
+            continue
+        with open(os.path.join(path, name, "input.yaml")) as fh:
+            params = yaml.load(fh, Loader=yaml.FullLoader)
+        traj = np.load(tpath, allow_pickle=True)
+        goals = np.array([[int(a["goal"][0]), int(a["goal"][1])] for a in params["agents"]], dtype=np.int32)
+        starts = np.array([[int(a["start"][0]), int(a["start"][1])] for a in params["agents"]], dtype=np.int32)
+        obst = np.array([[int(o[0]), int(o[1])] for o in params["map"]["obstacles"]], dtype=np.int32).reshape(-1, 2)
+        lengths.append(traj.shape[1])
+        key = (traj.shape[0], traj.shape[1], obst.shape[0], int(params["map"]["dimensions"][0]))
+        groups.setdefault(key, []).append((name, goals, starts, obst, traj))
+    if lengths:
+        with open(os.path.join(path, "stats.txt"), "w") as fh:
+            fh.write(f"max steps {float(np.max(lengths))}\nmin steps {float(np.min(lengths))}\nmean steps {np.mean(lengths)}\n")
+    for (n, t, m, board), items in groups.items():
+        cfg = dict(config, num_agents=n, board_size=[board, board])
+        if t < 2:
+            for name, *_ in items:
+                save_case(os.path.join(path, name), np.zeros((0, n, 2, 5, 5)), np.zeros((0, n, n, n)), np.zeros((n, 0), np.int32))
+            continue
+        states, gso, rec = record_cases(cfg, np.stack([i[1] for i in items]), np.stack([i[2] for i in items]),
+                                        np.stack([i[3] for i in items]), np.stack([i[4] for i in items]),
+                                        sensing_range=config["sensor_range"], device=device)
+        for k, (name, *_) in enumerate(items):
+            save_case(os.path.join(path, name), states[k], gso[k], rec[k])
+    return sum(len(v) for v in groups.values())
+
+
 def save_case(case_dir, states, gso, trajectory_record):
     """Write one case in the reference's file layout (record.py:90-94)."""
     os.makedirs(case_dir, exist_ok=True)

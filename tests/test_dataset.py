@@ -141,3 +141,30 @@ def test_generate_dataset_end_to_end(tmp_path):
     assert loader.num_samples > 0
     states, actions, gso = next(iter(loader))
     assert states.shape[1:] == (N, 2, 5, 5) and actions.shape[1:] == (N,) and gso.shape[1:] == (N, N) and states.is_cuda
+
+
+@pytest.mark.gpu
+def test_record_env_over_a_case_directory(tmp_path):
+    """The three scripts of main_data.py:24-27 one after the other on a directory: create_solutions ->
+    parse_dataset_trajectories -> record_env; the recordings equal generate_dataset's (same seed) file for file."""
+    from mapf_gnn_b200 import cbs
+    from mapf_gnn_b200.dataset import generate_dataset, record_env
+    N, H, M = 3, 9, 4
+    cfg = {"num_agents": N, "nb_agents": N, "map_shape": [H, H], "board_size": [H, H], "nb_obstacles": M, "sensor_range": 4,
+           "max_time": 32, "min_time": 3}
+    a, b = tmp_path / "a", tmp_path / "b"
+    np.random.seed(11)
+    cbs.create_solutions(str(a), 10, cfg)
+    cbs.parse_dataset_trajectories(str(a))
+    count = record_env(str(a), cfg)
+    np.random.seed(11)
+    assert generate_dataset(str(b), 10, cfg) == count > 5
+    names_a = sorted(d for d in os.listdir(a) if d.startswith("case_"))
+    names_b = sorted(d for d in os.listdir(b) if d.startswith("case_"))
+    assert len(names_a) == len(names_b) == count
+    # create_solutions numbers the cases by their draw (failed ones leave holes), generate_dataset consecutively
+    for da, db in zip(sorted(names_a, key=lambda d: int(d.split("_")[1])), sorted(names_b, key=lambda d: int(d.split("_")[1]))):
+        for f in ("trajectory.npy", "startings.npy", "states.npy", "gso.npy", "trajectory_record.npy"):
+            assert np.array_equal(np.load(a / da / f), np.load(b / db / f)), (da, db, f)
+    assert (a / "stats.txt").exists()
+    assert record_env(str(a), cfg, skip_last_case=True) == count - 1
