@@ -338,3 +338,66 @@ class Trainer:
             self._graphs.append(self._graphs[0]), self._g_loss.append(self._g_loss[0])
         restore()       # capture does not execute, but keep the state exactly as before for safety
         self._graph_key = key
+
+
+def fit(config, net=None, data_loader=None, results_dir=None, tests_episodes=25, device="cuda", seed=None, use_graph=True,
+        log=print):
+    """The epoch loop of train.py:56-165 on the kernels of this package: per epoch one pass over the loader
+    (``Trainer.step`` = forward + CrossEntropyLoss + backward + clip_grad_norm_(1.0) + Adam(3e-4, weight_decay 1e-4),
+    train.py:82-100), then ``tests_episodes`` validation rollouts advancing TOGETHER (``evaluate(validation=True)`` =
+    the per-episode loop of train.py:105-141: ``max_steps`` steps, goals drawn independently of the obstacles), the best
+    model by success rate saved as ``best_model.pt``, CosineAnnealingLR(T_max = epochs) stepped per epoch (train.py:65,151)
+    and ``loss.npy / success_rate.npy / flow_time.npy / model.pt`` written at the end (train.py:153-165).
+
+    config: the reference's YAML dict (``epochs``, network keys, ``train`` loader block, ``board_size``, ``max_steps`` ...).
+    Returns ``{"loss", "success_rate", "flow_time", "best_success_rate", "net"}``."""
+    import math
+    import os
+
+    import numpy as np
+
+    from .dataset import GNNDataLoader
+    from .evaluate import evaluate
+    from .rollout import build_network
+    if seed is not None:
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+    loader = data_loader if data_loader is not None else GNNDataLoader(config, device=device, seed=seed)
+    net = (net if net is not None else build_network(config)).to(device)
+    trainer = Trainer(net, lr=3e-4, weight_decay=1e-4, use_graph=use_graph)
+    epochs = int(config["epochs"])
+    if results_dir is not None:
+        os.makedirs(results_dir, exist_ok=True)
+    losses, rates, flows, best = [], [], [], 0.0
+    try:
+        for epoch in range(epochs):
+            trainer.set_lr(3e-4 * (1.0 + math.cos(math.pi * epoch / epochs)) / 2.0)      # CosineAnnealingLR, eta_min = 0
+            net.train()
+            total = torch.zeros((), dtype=torch.float32, device=device)
+            batches = 0
+            full = None
+            for states, trajectories, gso in loader.train_loader:
+                full = states.shape[0] if full is None else full
+                trainer.use_graph = use_graph and states.shape[0] == full      # the ragged last batch runs eagerly
+                total += trainer.step(states, gso, trajectories).reshape(())
+                batches += 1
+            losses.append(float(total.item()) / max(1, batches))
+            net.eval()
+            summary, _ = evaluate(net, config, episodes=tests_episodes, seed=(seed or 0) * 100003 + epoch, device=device,
+                                  validation=True)
+            rates.append(summary["avg_success_rate"])
+            flows.append(summary["avg_flow_time"])
+            log(f"Epoch {epoch}  Loss: {losses[-1]:.4f}  Success rate: {rates[-1]:.3f}  Flow time: {flows[-1]:.2f}  "
+                f"Learning rate: {trainer.lr:.6f}")
+            if rates[-1] > best:
+                best = rates[-1]
+                if results_dir is not None:
+                    torch.save(net.state_dict(), os.path.join(results_dir, "best_model.pt"))
+    finally:
+        trainer.close()
+    if results_dir is not None:
+        np.save(os.path.join(results_dir, "success_rate.npy"), np.array(rates))
+        np.save(os.path.join(results_dir, "flow_time.npy"), np.array(flows))
+        np.save(os.path.join(results_dir, "loss.npy"), np.array(losses))
+        torch.save(net.state_dict(), os.path.join(results_dir, "model.pt"))
+    return {"loss": losses, "success_rate": rates, "flow_time": flows, "best_success_rate": best, "net": net}

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_network, oracle_params, rel_err
+from helpers import load_network, model_config, oracle_params, rel_err
 from oracle import model_oracle as mo
 
 pytestmark = pytest.mark.gpu
@@ -301,3 +301,26 @@ def test_lanes_are_ordered_under_load():
     for it in range(12):
         got = grads()
         assert float((got - ref).abs().max()) < 2e-4 * scale, it
+
+
+def test_fit_runs_the_epoch_loop_of_train_py(tmp_path):
+    """train.py:56-165 end to end on a small generated data set: expert plans (native CBS) -> recordings (GPU) -> loader ->
+    epochs of Trainer.step + batched validation -> the reference's result files; the imitation loss falls."""
+    from mapf_gnn_b200.dataset import generate_dataset
+    from mapf_gnn_b200.train import fit
+    N, H = 4, 10
+    cfg = model_config("gnn_msg_k3", N, board_size=[H, H])
+    cfg.update({"nb_agents": N, "map_shape": [5, 5], "nb_obstacles": 4, "obstacles": 4, "sensor_range": 4, "sensing_range": 4,
+                "max_time": 32, "min_time": 4, "max_steps": 24, "epochs": 3, "batch_size": 64, "tests_episodes": 16,
+                "train": {"root_dir": str(tmp_path / "data"), "mode": "train", "min_time": 4, "max_time_dl": 25, "nb_agents": N}})
+    np.random.seed(2)
+    gen_cfg = dict(cfg, map_shape=[H, H])
+    assert generate_dataset(str(tmp_path / "data" / "train"), 96, gen_cfg) > 60
+    out = fit(cfg, results_dir=str(tmp_path / "results"), tests_episodes=16, seed=1, log=lambda *_: None)
+    assert len(out["loss"]) == 3 and all(np.isfinite(out["loss"]))
+    assert out["loss"][-1] < out["loss"][0]
+    assert 0.0 <= min(out["success_rate"]) and max(out["success_rate"]) <= 1.0
+    for f in ("loss.npy", "success_rate.npy", "flow_time.npy", "model.pt"):
+        assert (tmp_path / "results" / f).exists()
+    state = torch.load(tmp_path / "results" / "model.pt")
+    assert set(state) == set(out["net"].state_dict())
