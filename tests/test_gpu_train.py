@@ -256,7 +256,7 @@ def test_backward_gemm_paths_match_reference(train_step, name, mode, monkeypatch
 
 
 def test_large_batch_gradients_match_oracle():
-    """4096+ rows: the tensor-core backward path is the default; gradients vs the torch-CPU oracle."""
+    """A batch that fills the machine (5120 rows, several CTAs per kernel): gradients vs the torch-CPU oracle."""
     name, B, N = "gnn_msg_k3", 1024, 5
     rng = np.random.default_rng(12)
     states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
