@@ -32,7 +32,7 @@ FILES = [
     # the expert: the search, the instance generator / schedule parser and the reference's own tests
     "cbs/__init__.py", "cbs/cbs.py", "cbs/a_star.py",
     "data_generation/__init__.py", "data_generation/dataset_gen.py", "data_generation/trajectory_parser.py",
-    "tests/test_cbs.py", "tests/test_data_pipeline.py",
+    "tests/test_cbs.py", "tests/test_cbs_performance.py", "tests/test_data_pipeline.py",
 ]
 
 

@@ -1,4 +1,5 @@
-"""The reference's OWN CBS test file (tests/test_cbs.py, unmodified) executed against ``mapf_gnn_b200.cbs``: the module
+"""The reference's OWN CBS test files (tests/test_cbs.py and tests/test_cbs_performance.py, unmodified) executed against
+``mapf_gnn_b200.cbs``: the module
 names it imports (``cbs.cbs``, ``cbs.a_star``) are bound to shims exporting this package's classes.  The file comes from
 ``oracle/_ref/tests/`` (staged, digest checked) or from ``/root/reference``.  Host code: no GPU needed."""
 import ast
@@ -12,16 +13,19 @@ import pytest
 from oracle import ref_loader
 
 
-def _path():
+FILES = ("test_cbs.py", "test_cbs_performance.py")
+
+
+def _path(name="test_cbs.py"):
     root = ref_loader.root()
     if root is None:
         return None
-    p = os.path.join(root, "tests", "test_cbs.py")
+    p = os.path.join(root, "tests", name)
     return p if os.path.exists(p) else None
 
 
-def _load():
-    path = _path()
+def _load(name="test_cbs.py"):
+    path = _path(name)
     if path is None:
         pytest.skip("reference tests neither staged under oracle/_ref nor present at /root/reference")
     import mapf_gnn_b200.cbs as mine
@@ -34,7 +38,7 @@ def _load():
     saved = {k: sys.modules.get(k) for k in ("cbs", "cbs.cbs", "cbs.a_star")}
     sys.modules.update({"cbs": pkg, "cbs.cbs": m_cbs, "cbs.a_star": m_astar})
     try:
-        spec = importlib.util.spec_from_file_location("reference_test_cbs", path)
+        spec = importlib.util.spec_from_file_location("reference_" + name[:-3], path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:
@@ -48,31 +52,34 @@ def _load():
 
 
 def _cases():
-    path = _path()
-    if path is None:
-        return [("-", "-")]
     out = []
-    for node in ast.parse(open(path).read()).body:
-        if isinstance(node, ast.ClassDef) and node.name.startswith("Test"):
-            out += [(node.name, f.name) for f in node.body if isinstance(f, ast.FunctionDef) and f.name.startswith("test_")]
-        elif isinstance(node, ast.FunctionDef) and node.name.startswith("test_"):
-            out.append((None, node.name))
-    return out
+    for fname in FILES:
+        path = _path(fname)
+        if path is None:
+            continue
+        for node in ast.parse(open(path).read()).body:
+            if isinstance(node, ast.ClassDef) and node.name.startswith("Test"):
+                out += [(fname, node.name, f.name) for f in node.body
+                        if isinstance(f, ast.FunctionDef) and f.name.startswith("test_")]
+            elif isinstance(node, ast.FunctionDef) and node.name.startswith("test_"):
+                out.append((fname, None, node.name))
+    return out or [("-", "-", "-")]
 
 
 @pytest.fixture(scope="module")
 def reference_tests():
-    return _load()
+    return {f: _load(f) for f in FILES if _path(f) is not None}
 
 
-@pytest.mark.parametrize("cls,name", _cases())
-def test_reference_cbs_test(reference_tests, cls, name):
+@pytest.mark.parametrize("fname,cls,name", _cases())
+def test_reference_cbs_test(reference_tests, fname, cls, name):
     if name == "-":
         pytest.skip("reference test file not available")
+    mod = reference_tests[fname]
     if cls is None:
-        getattr(reference_tests, name)()
+        getattr(mod, name)()
         return
-    inst = getattr(reference_tests, cls)()
+    inst = getattr(mod, cls)()
     if hasattr(inst, "setup_method"):
         inst.setup_method()
     getattr(inst, name)()
