@@ -477,10 +477,15 @@ def run_mine(args, w):
     barrier()
     t0 = time.perf_counter()
     pl.start()
+    hs, sls = pl.groups, pl.slices
     for i in range(ke):
+        row, again = done_log[i + 1], i + 1 < ke
         for g in range(G):
-            _, pos_out, done_out = pl.advance(g, relaunch=i + 1 < ke)   # wait for group g's step, launch its next one
-            done_log[i + 1, pl.slices[g]] = done_out.numpy()           # (returned positions are, in place, the next input)
+            h = hs[g]
+            _, pos_out, done_out = h.wait(True)      # group g's step is in pinned host memory (numpy views of it)
+            if again:
+                h.launch()                           # its next step: the returned positions are, in place, the next input
+            row[sls[g]] = done_out
     e2e_s = time.perf_counter() - t0
     e2e_units = float((E - done_log[:ke].astype(np.int64).sum(axis=1)).sum()) * N   # episodes alive before each step
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

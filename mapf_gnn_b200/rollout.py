@@ -90,6 +90,7 @@ class HostSteppedRollout:
         view = lambda b: (b[nb_pos:nb_pos + nb_act].view(torch.int32).view(E, N),
                           b[:nb_pos].view(torch.int32).view(E, N, 2), b[nb_pos + nb_act:nb_pos + nb_act + E])
         self.views = [view(b) for b in self.blocks]
+        self.views_np = [tuple(t.numpy() for t in v) for v in self.views]     # the same pinned memory as numpy arrays
         self.h2d_bytes = nb_pos
         self.d2h_bytes = self.blocks[0].numel()
         self.cur = 0                                   # block that the next step() fills; its input is the other one
@@ -155,8 +156,9 @@ class HostSteppedRollout:
             _lib.check(rc, "graph_launch")
         self.in_flight = True
 
-    def wait(self):
-        """Block until the step enqueued by ``launch()`` is visible in pinned host memory; returns its views."""
+    def wait(self, numpy=False):
+        """Block until the step enqueued by ``launch()`` is visible in pinned host memory; returns its views
+        (``numpy=True``: the same memory as numpy arrays, without creating tensor wrappers per step)."""
         if not self.in_flight:
             raise RuntimeError("HostSteppedRollout.wait(): nothing in flight")
         rc = self._lib.mapf_event_wait(self._event)
@@ -165,7 +167,7 @@ class HostSteppedRollout:
         self.in_flight = False
         k = self.cur
         self.cur = 1 - k
-        return self.views[k]
+        return self.views_np[k] if numpy else self.views[k]
 
     def step(self):
         """One host-driven step; returns after the results are visible in pinned host memory."""
@@ -242,9 +244,9 @@ class PipelinedHostRollout:
         for h in self.groups:
             h.launch()
 
-    def advance(self, g, relaunch=True):
+    def advance(self, g, relaunch=True, numpy=False):
         h = self.groups[g]
-        out = h.wait()
+        out = h.wait(numpy)
         if relaunch:
             h.launch()
         return out
