@@ -467,7 +467,8 @@ def run_mine(args, w):
     # full upload / step / download / wait protocol every step.
     ke = max(8, min(K, 64))
     G = max(1, min(args.e2e_groups, E))
-    pl = m.PipelinedHostRollout(net, cfg, goals, starts, obst, groups=G, sensing_range=w["r"], device=dev)
+    pl = m.PipelinedHostRollout(net, cfg, goals, starts, obst, groups=G, sensing_range=w["r"], device=dev,
+                                zero_copy=not args.e2e_copies)
     done_log = np.zeros((ke + 1, E), dtype=np.uint8)
     pl.start()
     for i in range(4):
@@ -544,11 +545,17 @@ def run_mine(args, w):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": ke, "groups": G,
-                    "api": "PipelinedHostRollout: per group and step pinned upload of the state (agent POSITIONS only: "
-                           "boards, goals and weights are resident, observations are produced on the device), CUDA-graph "
-                           "replay, pinned download of actions + new positions + done flags, event wait; the groups' "
-                           "host round trips overlap each other's kernels.  This is not the reference caller protocol "
-                           "of shipping fov / gso tensors per step (evaluate.py:225-226)"},
+                    "api": ("PipelinedHostRollout: the state a host caller holds (agent POSITIONS and done flags only: boards, "
+                            "goals and weights are resident, observations are produced on the device) lives in pinned host "
+                            "memory; per group and step " +
+                            ("the positions are uploaded (cudaMemcpyAsync), the step's CUDA graph replays, actions + new "
+                             "positions + done flags are downloaded" if args.e2e_copies else
+                             "the step's CUDA graph replays and its kernels READ the positions / done flags from and WRITE "
+                             "actions + new positions + done flags to the pinned blocks themselves (mapped host memory, "
+                             "no copy nodes; h2d / d2h bytes = what those loads / stores move over the bus)") +
+                            ", then the host waits for the step's event and reads the results; the groups' host round "
+                            "trips overlap each other's kernels.  This is not the reference caller protocol of shipping "
+                            "fov / gso tensors per step (evaluate.py:225-226)")},
             "gpu_launches": K * res["launches_per_step"],
             "clocks": clocks,
             "train": train,
@@ -725,8 +732,11 @@ def main():
     ap.add_argument("--cpu-episodes", type=int, default=1024)
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=4,
+    ap.add_argument("--e2e-groups", type=int, default=2,
                     help="independent episode groups whose host round trips overlap in the end-to-end measurement")
+    ap.add_argument("--e2e-copies", action="store_true",
+                    help="end-to-end loop: cudaMemcpyAsync nodes around the kernels instead of the kernels reading / "
+                         "writing the pinned host blocks themselves")
     ap.add_argument("--no-other-workloads", action="store_true",
                     help="skip the compact lines of the other BASELINE configs (key `workloads`)")
     ap.add_argument("--other-workloads", nargs="*", default=["c1", "c2b", "c3", "c5"], choices=sorted(WORKLOADS))

@@ -109,6 +109,9 @@ typedef struct {
   float* adj;             /* [E,N,N] out (may be NULL) */
   int32_t episodes_per_cta; /* work decomposition: 0 = chosen by the library; else 1 .. 128 / next_pow2(N).  Results are
                              * identical for every value (tests sweep it). */
+  int32_t* pos_out;       /* NULL: positions are updated in place.  Else [E,N,2]: the new positions of EVERY agent go here and
+                           * `pos` is only read -- for callers that keep the state in two alternating (host-mapped) blocks */
+  uint8_t* done_out;      /* NULL: in place.  Else [E]: the done flags after this step (frozen episodes keep theirs) */
 } mapf_env_step_args;
 int mapf_env_step(const mapf_env_step_args* a, mapf_stream_t stream);
 

@@ -33,7 +33,7 @@ class EnvStepArgs(C.Structure):
                 ("d2_limit", C.c_int32), ("do_move", C.c_int32),
                 ("pos", c_i32p), ("goal", c_i32p), ("actions", c_i32p), ("cells", c_u8p),
                 ("time", c_i32p), ("done", c_u8p), ("fov", c_f32p), ("adj", c_f32p),
-                ("episodes_per_cta", C.c_int32)]
+                ("episodes_per_cta", C.c_int32), ("pos_out", c_i32p), ("done_out", c_u8p)]
 
 
 class EnvRulesArgs(C.Structure):

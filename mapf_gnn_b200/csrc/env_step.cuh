@@ -88,9 +88,10 @@ __device__ __forceinline__ void env_step_finish(const mapf_env_step_args& a, int
   int act = 0;
   if (moving) act = s_actions != nullptr ? 0 : mapf_ld_dep(a.actions + int64_t(e) * N + lane);   // not __ldg (common.cuh)
   int ep_time = 0;
-  bool ep_live = false;
+  bool ep_live = false, ep_done_in = false;
   if ((a.do_move & 3) && tid < nep) {
-    ep_live = !a.done[e0 + tid] || (a.do_move & 2);
+    ep_done_in = a.done[e0 + tid] != 0;
+    ep_live = !ep_done_in || (a.do_move & 2);
     if (ep_live) ep_time = a.time[e0 + tid];
   }
   __syncthreads();
@@ -134,7 +135,9 @@ __device__ __forceinline__ void env_step_finish(const mapf_env_step_args& a, int
     uint8_t* gcells = a.cells + int64_t(e) * stride;
     gcells[oy * H + ox] = cells[oy * H + ox];
     gcells[ny * H + nx] = cells[ny * H + nx];
-    reinterpret_cast<int2*>(a.pos)[int64_t(e) * N + lane] = make_int2(nx, ny);
+    reinterpret_cast<int2*>(a.pos_out != nullptr ? a.pos_out : a.pos)[int64_t(e) * N + lane] = make_int2(nx, ny);
+  } else if (agent && a.pos_out != nullptr) {
+    reinterpret_cast<int2*>(a.pos_out)[int64_t(e) * N + lane] = make_int2(nx, ny);   // out-of-place: every agent is written
   }
 
   // A2: per-row closest-4 rule on integer squared distances (:117-136,174-181).  u = d2 - 1 as an unsigned number
@@ -260,7 +263,9 @@ __device__ __forceinline__ void env_step_finish(const mapf_env_step_args& a, int
 
   if (ep_live) {  // time += 1; done = checkAllInGoal() (:195-197)
     a.time[e0 + tid] = ep_time + 1;
-    a.done[e0 + tid] = sh.notgoal[tid] ? 0 : 1;
+    (a.done_out != nullptr ? a.done_out : a.done)[e0 + tid] = sh.notgoal[tid] ? 0 : 1;
+  } else if (a.done_out != nullptr && (a.do_move & 3) && tid < nep) {
+    a.done_out[e0 + tid] = ep_done_in ? 1 : 0;      // out-of-place: frozen episodes keep their flag
   }
   if (bulk) {   // the staging area must outlive the copies' reads
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -42,6 +42,10 @@ class Rollout:
                       if dims[8] > 0 and ops.USE_TENSOR_CORES else None)
         self.params = net_params(dims)
         self.is_graph = dims[8] > 0
+        # host-resident state (HostSteppedRollout(zero_copy=True)): addresses in mapped pinned host memory
+        # (positions in, done flags in, positions out, actions out, done flags out) that the kernels read and write
+        # directly instead of env.pos / actions / done
+        self.host_state = None
 
     def _args(self, steps):
         env, a = self.env, _lib.RolloutArgs()
@@ -54,6 +58,10 @@ class Rollout:
         p.workspace_z = None if self.workz is None else self.workz.data_ptr()
         p.workspace_act = None if self.worka is None else self.worka.data_ptr()
         p.logits, p.actions = self.logits.data_ptr(), self.actions.data_ptr()
+        if self.host_state is not None:
+            pos_in, done_in, pos_out, act_out, done_out = self.host_state
+            a.env.pos, a.env.done, a.env.pos_out, a.env.done_out = pos_in, done_in, pos_out, done_out
+            a.env.actions = p.actions = act_out
         from . import ops
         p.flags = ops.policy_flags()
         a.steps = int(steps)
@@ -82,17 +90,22 @@ class HostSteppedRollout:
     ``pos_in`` int32[E,N,2] is the input of the next ``step()``; ``step()`` returns views ``(actions int32[E,N],
     pos_out int32[E,N,2], done uint8[E])`` of the block it just filled."""
 
-    def __init__(self, rollout: Rollout):
+    def __init__(self, rollout: Rollout, zero_copy=False):
         self.ro, env = rollout, rollout.env
         E, N = env.episodes, env.nb_agents
         nb_pos, nb_act = E * N * 8, E * N * 4
+        # zero_copy: the kernels themselves read the input block (positions, done flags) and write the output block
+        # (actions, new positions, done flags) over the bus -- no copy nodes in the step's graph; the two pinned blocks
+        # ARE the state (mapf_env_step_args.pos_out / done_out), alternating like with the copies.
+        self.zero_copy = bool(zero_copy)
         self.blocks = [torch.empty((env.host_block.numel(),), dtype=torch.uint8).pin_memory() for _ in range(2)]
         view = lambda b: (b[nb_pos:nb_pos + nb_act].view(torch.int32).view(E, N),
                           b[:nb_pos].view(torch.int32).view(E, N, 2), b[nb_pos + nb_act:nb_pos + nb_act + E])
         self.views = [view(b) for b in self.blocks]
         self.views_np = [tuple(t.numpy() for t in v) for v in self.views]     # the same pinned memory as numpy arrays
-        self.h2d_bytes = nb_pos
+        self.h2d_bytes = nb_pos + (2 * E if self.zero_copy else 0)      # zero copy: + the done flags, read twice
         self.d2h_bytes = self.blocks[0].numel()
+        self._nb = (nb_pos, nb_act)
         self.cur = 0                                   # block that the next step() fills; its input is the other one
         snap = (env.pos.clone(), env.cells.clone(), env.time.clone(), env.done.clone(), env.fov.clone(),
                 env.adj_matrix.clone())
@@ -135,6 +148,12 @@ class HostSteppedRollout:
 
     def _body(self, k):
         env, ro = self.ro.env, self.ro
+        if self.zero_copy:
+            nb_pos, nb_act = self._nb      # (unified addressing: the pinned host addresses are valid on the device)
+            src, dst = self.blocks[1 - k].data_ptr(), self.blocks[k].data_ptr()
+            ro.host_state = (src, src + nb_pos + nb_act, dst, dst + nb_pos, dst + nb_pos + nb_act)
+            ro.run(1)                                                     # the kernels read / write the pinned blocks
+            return
         env.pos.copy_(self.views[1 - k][1], non_blocking=True)           # H2D: this step's state
         ro.run(1)
         self.blocks[k].copy_(env.host_block, non_blocking=True)           # D2H: actions + new positions + done
@@ -200,7 +219,7 @@ class PipelinedHostRollout:
         return [size] * (groups - 1) + [E - size * (groups - 1)]
 
     def __init__(self, net, config, goals, starts, obstacles=None, groups=2, sensing_range=6, device="cuda",
-                 group_sizes=None):
+                 group_sizes=None, zero_copy=False):
         import numpy as np
         goals, starts = np.asarray(goals), np.asarray(starts)
         E = goals.shape[0]
@@ -227,7 +246,7 @@ class PipelinedHostRollout:
             ob = None if obstacles is None or np.asarray(obstacles).shape[1] == 0 else np.asarray(obstacles)[sl]
             env = BatchedGraphEnv(config, goals[sl], starts[sl], ob, sensing_range=sensing_range, device=device)
             ro = Rollout(net, env)
-            self.envs.append(env), self.rollouts.append(ro), self.groups.append(HostSteppedRollout(ro))
+            self.envs.append(env), self.rollouts.append(ro), self.groups.append(HostSteppedRollout(ro, zero_copy=zero_copy))
         self.h2d_bytes = sum(h.h2d_bytes for h in self.groups)
         self.d2h_bytes = sum(h.d2h_bytes for h in self.groups)
 
@@ -238,6 +257,9 @@ class PipelinedHostRollout:
                 h.wait()
             env.reset()
             h.pos_in.copy_(env.pos.cpu())
+            if h.zero_copy:                                  # the blocks are the state: done flags too
+                for b in h.blocks:
+                    b.copy_(env.host_block.cpu())
         torch.cuda.synchronize()
 
     def start(self):

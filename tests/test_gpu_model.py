@@ -454,10 +454,14 @@ def test_evaluator_with_device_scenarios():
     assert abs(s1["avg_success_rate"] - s3["avg_success_rate"]) < 0.12      # same distribution family
 
 
-def test_host_stepped_rollout_matches_device_rollout():
-    """HostSteppedRollout (pinned host buffers + CUDA-graph replay) must walk the same trajectory as Rollout.run."""
+@pytest.mark.parametrize("zero_copy", [False, True])
+@pytest.mark.parametrize("E", [64, 2000])
+def test_host_stepped_rollout_matches_device_rollout(zero_copy, E):
+    """HostSteppedRollout (pinned host buffers + CUDA-graph replay) must walk the same trajectory as Rollout.run --
+    with copy nodes around the kernels, and with the kernels reading / writing the pinned block themselves (zero_copy);
+    64 episodes take the env step fused into the graph kernel, 2000 the separate env kernel."""
     import mapf_gnn_b200 as m
-    E, N, H, M = 64, 5, 18, 5
+    N, H, M = 5, 18, 5
     rng = np.random.default_rng(9)
     starts, goals, obst = m.make_scenarios(rng, E, N, H, M)
     cfg = model_config("gnn_k3", N, board_size=[H, H])
@@ -465,8 +469,12 @@ def test_host_stepped_rollout_matches_device_rollout():
     env_a = m.BatchedGraphEnv(cfg, goals, starts, obst)
     env_b = m.BatchedGraphEnv(cfg, goals, starts, obst)
     ra, rb = m.Rollout(net, env_a), m.Rollout(net, env_b)
-    hs = m.HostSteppedRollout(rb)
+    hs = m.HostSteppedRollout(rb, zero_copy=zero_copy)
     for t in range(6):
+        if t == 3:      # the host edits the state it holds: swap two episodes' positions (on both sides)
+            p = hs.pos_in
+            p[[0, 1]] = p[[1, 0]].clone()
+            env_a.pos[[0, 1]] = env_a.pos[[1, 0]].clone()
         ra.run(1)
         actions, pos_out, done = hs.step()
         assert torch.equal(actions, ra.actions.cpu()) and torch.equal(pos_out, env_a.pos.cpu())
@@ -548,7 +556,8 @@ def test_env_edge_sizes(E, N, H):
             alive[e] = not d
 
 
-def test_pipelined_host_rollout_matches_device_rollout():
+@pytest.mark.parametrize("zero_copy", [False, True])
+def test_pipelined_host_rollout_matches_device_rollout(zero_copy):
     """PipelinedHostRollout: groups stepped with overlapping host round trips walk the same trajectories as one
     on-device Rollout over all episodes (episodes are independent)."""
     import mapf_gnn_b200 as m
@@ -561,7 +570,7 @@ def test_pipelined_host_rollout_matches_device_rollout():
     ro = m.Rollout(net, env)
     assert m.PipelinedHostRollout.round_aligned_sizes(4096, 5, 2, 148) == [1894, 2202]
     assert m.PipelinedHostRollout.round_aligned_sizes(90, 5, 3, 148) == [30, 30, 30]
-    pl = m.PipelinedHostRollout(net, cfg, goals, starts, obst, groups=3)
+    pl = m.PipelinedHostRollout(net, cfg, goals, starts, obst, groups=3, zero_copy=zero_copy)
     assert [s.stop - s.start for s in pl.slices] == [30, 30, 30]
     pl.start()
     for t in range(5):
