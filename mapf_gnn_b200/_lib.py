@@ -240,7 +240,18 @@ def load():
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().mapf_last_error_string(rc).decode()
-        raise RuntimeError(f"mapf_b200 {what}: {msg} (status {rc})")
+        hint = ""
+        if rc == -5:      # MAPF_ERR_CUDA: the most common cause outside a B200 box is the wrong architecture
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    cap = torch.cuda.get_device_capability()
+                    if cap != (10, 0):
+                        hint = (f"; the library is built for sm_100a only (tcgen05 / TMEM kernels) and this device is "
+                                f"sm_{cap[0]}{cap[1]}: there is no other code path")
+            except Exception:      # noqa: BLE001
+                pass
+        raise RuntimeError(f"mapf_b200 {what}: {msg} (status {rc}){hint}")
 
 
 def ptr(t):
