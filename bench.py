@@ -694,9 +694,16 @@ def run_expert(args):
     many = cbs.solve_batch(insts, threads=0)
     t2 = time.perf_counter()
     assert all((a is None) == (b is None) and (a is None or a[1] == b[1]) for a, b in zip(one, many))
+    per = []
+    for it in insts[:64]:                      # per-instance times: the totals above are dominated by the few capped searches
+        ta = time.perf_counter()
+        cbs.solve_batch([it], threads=1)
+        per.append(time.perf_counter() - ta)
     out = {"metric": "CBS instances/s (28x28, 5 agents, 8 obstacles)", "instances": len(insts),
            "solved": sum(p is not None for p in many), "native_1_thread": len(insts) / (t1 - t0),
-           "native_all_threads": len(insts) / (t2 - t1), "host_threads": os.cpu_count()}
+           "native_all_threads": len(insts) / (t2 - t1), "host_threads": os.cpu_count(),
+           "native_median_ms_per_instance": float(np.median(per)) * 1e3,
+           "note": "instances that hit the 5000-node cap (one here) take ~1000x the median and bound the batch call"}
     try:
         from oracle import ref_loader
         root = ref_loader.root()
@@ -708,11 +715,15 @@ def run_expert(args):
             sample = 16
             t0 = time.perf_counter()
             same = True
+            ref_per = []
             for inp, mine in zip(inputs[:sample], many[:sample]):
+                ta = time.perf_counter()
                 plan = ref.CBS(ref.Environment(inp["map"]["dimensions"], inp["agents"], inp["map"]["obstacles"]), verbose=False).search()
+                ref_per.append(time.perf_counter() - ta)
                 got = None if not plan else [[(s["x"], s["y"]) for s in plan[a["name"]]] for a in inp["agents"]]
                 same = same and (got is None) == (mine is None) and (got is None or got == [[tuple(c) for c in p] for p in mine[0]])
             out["reference_1_thread"] = sample / (time.perf_counter() - t0)
+            out["reference_median_ms_per_instance"] = float(np.median(ref_per)) * 1e3
             out["reference_sample"] = f"first {sample} of the same instances, unmodified cbs/cbs.py staged under oracle/_ref"
             out["plans_identical_on_sample"] = bool(same)
     except Exception as exc:            # the expert line is an extra: never fail the bench on it
