@@ -18,6 +18,7 @@
 //               `max_high_level_iterations` pops (cbs.py:352-357).
 // The reference re-plans EVERY agent of a child node (cbs.py:399 -> compute_solution); A* is deterministic and an agent's
 // path depends on its own constraints only, so re-planning just the newly constrained agent gives the same node.
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -75,25 +76,35 @@ using Path = std::vector<Cell>;            // index = time step
 bool a_star(const Grid& g, const Constraints& c, Cell start, Cell goal, int max_pops, Path* out) {
   struct Node { St s; int32_t gscore; int32_t parent; bool open, closed; };
   std::vector<Node> nodes;
-  // state -> node: one dense W x H layer of node indices per time step, allocated when the search first reaches that
-  // step (states outside the grid -- only a start cell can be -- go through the hash map)
+  // state -> node: a dense [time step][W x H] table of node indices in a per-thread scratch buffer that is never
+  // cleared -- an entry counts only if its stamp is this call's generation (states outside the grid -- only a start cell
+  // can be -- go through the hash map)
   const int64_t cells = int64_t(g.w) * g.h;
-  std::vector<std::vector<int32_t>> layers;
+  thread_local std::vector<int32_t> tab_idx;
+  thread_local std::vector<uint32_t> tab_gen;
+  thread_local uint32_t generation = 0;
+  if (++generation == 0) { std::fill(tab_gen.begin(), tab_gen.end(), 0u); generation = 1; }
   std::unordered_map<St, int32_t, StHash> outside;
   auto inside = [&](const St& s) { return s.x >= 0 && s.x < g.w && s.y >= 0 && s.y < g.h; };
+  auto slot_of = [&](const St& s) { return int64_t(s.t) * cells + int64_t(s.y) * g.w + s.x; };
   auto node_of = [&](const St& s) -> int32_t {          // -1: never seen (no g_score entry)
     if (!inside(s)) {
       auto it = outside.find(s);
       return it == outside.end() ? -1 : it->second;
     }
-    if (s.t >= int32_t(layers.size()) || layers[s.t].empty()) return -1;
-    return layers[s.t][int64_t(s.y) * g.w + s.x];
+    const int64_t k = slot_of(s);
+    return k < int64_t(tab_gen.size()) && tab_gen[k] == generation ? tab_idx[k] : -1;
   };
   auto remember = [&](const St& s, int32_t idx) {
     if (!inside(s)) { outside.emplace(s, idx); return; }
-    if (s.t >= int32_t(layers.size())) layers.resize(s.t + 1);
-    if (layers[s.t].empty()) layers[s.t].assign(size_t(cells), -1);
-    layers[s.t][int64_t(s.y) * g.w + s.x] = idx;
+    const int64_t k = slot_of(s);
+    if (k >= int64_t(tab_gen.size())) {
+      const size_t want = size_t(k + 1 + 16 * cells);
+      tab_gen.resize(want, 0u);
+      tab_idx.resize(want, -1);
+    }
+    tab_gen[k] = generation;
+    tab_idx[k] = idx;
   };
   struct Entry { int32_t f; int64_t count; int32_t node; };
   struct Later { bool operator()(const Entry& a, const Entry& b) const { return a.f != b.f ? a.f > b.f : a.count > b.count; } };
