@@ -141,6 +141,26 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// The same split of (a * sc, b * sc) with the two multiplies and the two subtractions as ONE packed instruction each
+// (mul.rn.f32x2 / fma.rn.f32x2 with -1: the same IEEE operations, half the issue slots)
+__device__ __forceinline__ void split_h2_scaled(float a, float b, float sc, uint32_t& hi, uint32_t& lo) {
+  unsigned long long P, S, B, M1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(P) : "f"(a), "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(S) : "f"(sc));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(P) : "l"(P), "l"(S));
+  float pa, pb;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(pa), "=f"(pb) : "l"(P));
+  const __half2 h = __floats2half2_rn(pa, pb);
+  const float2 back = __half22float2(h);
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(back.x), "f"(back.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(M1) : "f"(-1.0f));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(B), "l"(M1), "l"(P));      // (a, b) * sc - hi
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(pa), "=f"(pb) : "l"(P));
+  const __half2 l = __floats2half2_rn(pa, pb);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // power-of-two scale that brings a maximum magnitude `amax` into [2^9, 2^10), and its inverse
 __device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
   int eb = int(__float_as_uint(amax) >> 23) & 0xFF;
@@ -378,15 +398,20 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
         }
       }
       float amax = 0.0f;
+      // two channels per packed FMA (fma.rn.f32x2: the same two IEEE FMAs, one issue slot)
 #pragma unroll
-      for (int c = 0; c < kEtCout; ++c) {
-        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow);
-        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kRow);
-        float a = fmaf(__uint_as_float(r[1][c]), f, v[c]);
-        a = fmaf(up, f_up, a);
-        a = fmaf(dn, f_dn, a);
-        v[c] = fmaxf(a, 0.0f);                                          // ReLU
-        amax = fmaxf(amax, v[c]);
+      for (int c = 0; c < kEtCout; c += 2) {
+        const float2 up = make_float2(__shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow),
+                                      __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c + 1]), kRow));
+        const float2 dn = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kRow),
+                                      __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c + 1]), kRow));
+        float2 a = make_float2(v[c], v[c + 1]);
+        mapf_ffma2(a, f, make_float2(__uint_as_float(r[1][c]), __uint_as_float(r[1][c + 1])));
+        mapf_ffma2(a, f_up, up);
+        mapf_ffma2(a, f_dn, dn);
+        v[c] = fmaxf(a.x, 0.0f);                                        // ReLU
+        v[c + 1] = fmaxf(a.y, 0.0f);
+        amax = fmaxf(amax, fmaxf(v[c], v[c + 1]));
       }
       amax = pix_ok ? amax : 0.0f;   // lanes that are not pixels hold finite garbage: they are zeroed by their scale below
       ETC_STAMP(4);
@@ -411,7 +436,7 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
 #pragma unroll
           for (int c = 0; c < kEtCout; c += 2) {
             const float a0 = (wide && part == 0) ? v0[c] : v[c], a1 = (wide && part == 0) ? v0[c + 1] : v[c + 1];
-            split_h2(a0 * sc, a1 * sc, h[c >> 1], o[c >> 1]);
+            split_h2_scaled(a0, a1, sc, h[c >> 1], o[c >> 1]);
           }
           tmem_st8(tlane + kEtColAHi + nw + cb, h);
           tmem_st8(tlane + kEtColALo + nw + cb, o);
@@ -439,7 +464,7 @@ __global__ void __launch_bounds__(EtCfg<C1>::kThreads, 1) encoder_tc_kernel(EncT
         if (pix_ok) {
           uint32_t h[8], o[8];
 #pragma unroll
-          for (int c = 0; c < kEtCout; c += 2) split_h2(v[c] * sc, v[c + 1] * sc, h[c >> 1], o[c >> 1]);
+          for (int c = 0; c < kEtCout; c += 2) split_h2_scaled(v[c], v[c + 1], sc, h[c >> 1], o[c >> 1]);
           uint32_t* dst = reinterpret_cast<uint32_t*>(s_out) + pidx * kEtOutPitch + quad * 4;
           *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(dst + 16) = make_uint4(h[4], h[5], h[6], h[7]);
@@ -625,7 +650,7 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
         constexpr int kW = 8;
         uint32_t h[kW], o[kW], t[kW];
 #pragma unroll
-        for (int c = 0; c < 16; c += 2) split_h2(x[c % CIN] * sc, x[(c + 1) % CIN] * sc, h[c >> 1], o[c >> 1]);
+        for (int c = 0; c < 16; c += 2) split_h2_scaled(x[c % CIN], x[(c + 1) % CIN], sc, h[c >> 1], o[c >> 1]);
         tmem_st8(tlane + kEtColAHi + kW, h);
         tmem_st8(tlane + kColALo + kW, o);
 #pragma unroll
@@ -680,14 +705,18 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
     const bool live = img < g.rows && pix_ok;
     float sv[kEtCout];            // this pixel's outputs (statistics)
 #pragma unroll
-    for (int c = 0; c < kEtCout; ++c) {
-      const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow);
-      const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kRow);
-      float a = fmaf(__uint_as_float(r[1][c]), f, s_b[c]);
-      a = fmaf(up, f_up, a);
-      a = fmaf(dn, f_dn, a);
-      if (live) dst[c * kFovCells] = a;
-      sv[c] = live ? a : 0.0f;
+    for (int c = 0; c < kEtCout; c += 2) {      // two channels per packed FMA (fma.rn.f32x2)
+      const float2 up = make_float2(__shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c]), kRow),
+                                    __shfl_up_sync(0xffffffffu, __uint_as_float(r[0][c + 1]), kRow));
+      const float2 dn = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), kRow),
+                                    __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c + 1]), kRow));
+      float2 a = make_float2(s_b[c], s_b[c + 1]);
+      mapf_ffma2(a, f, make_float2(__uint_as_float(r[1][c]), __uint_as_float(r[1][c + 1])));
+      mapf_ffma2(a, f_up, up);
+      mapf_ffma2(a, f_dn, dn);
+      if (live) { dst[c * kFovCells] = a.x; dst[(c + 1) * kFovCells] = a.y; }
+      sv[c] = live ? a.x : 0.0f;
+      sv[c + 1] = live ? a.y : 0.0f;
     }
     if (do_stats) {
       // Per-slot BatchNorm sums (framework_gnn.py:160-163: statistics per agent slot): a warp = one image = one slot.
