@@ -142,21 +142,13 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
 }
 
 // The same split of (a * sc, b * sc) with the two multiplies and the two subtractions as ONE packed instruction each
-// (mul.rn.f32x2 / fma.rn.f32x2 with -1: the same IEEE operations, half the issue slots)
+// (fma.rn.f32x2 with the scalar-broadcast multiplicand: the same IEEE operations, half the issue slots)
 __device__ __forceinline__ void split_h2_scaled(float a, float b, float sc, uint32_t& hi, uint32_t& lo) {
-  unsigned long long P, S, B, M1;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(P) : "f"(a), "f"(b));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(S) : "f"(sc));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(P) : "l"(P), "l"(S));
-  float pa, pb;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(pa), "=f"(pb) : "l"(P));
-  const __half2 h = __floats2half2_rn(pa, pb);
-  const float2 back = __half22float2(h);
-  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(back.x), "f"(back.y));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(M1) : "f"(-1.0f));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(B), "l"(M1), "l"(P));      // (a, b) * sc - hi
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(pa), "=f"(pb) : "l"(P));
-  const __half2 l = __floats2half2_rn(pa, pb);
+  float2 p = make_float2(0.0f, 0.0f);
+  mapf_ffma2(p, sc, make_float2(a, b));              // (a, b) * sc  (+ 0: exact)
+  const __half2 h = __floats2half2_rn(p.x, p.y);
+  mapf_ffma2(p, -1.0f, __half22float2(h));           // (a, b) * sc - hi  (exact: the difference fits fp32)
+  const __half2 l = __floats2half2_rn(p.x, p.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
