@@ -158,6 +158,19 @@ class HostSteppedRollout:
         ro.run(1)
         self.blocks[k].copy_(env.host_block, non_blocking=True)           # D2H: actions + new positions + done
 
+    def reset(self):
+        """Back to the initial scenario: the device environment AND the pinned state this rollout steps from (with
+        ``zero_copy`` the pinned blocks are the state; an ``env.reset()`` alone would leave them where they were)."""
+        if self.in_flight:
+            self.wait()
+        self.ro.env.reset()
+        torch.cuda.synchronize()
+        if self.zero_copy:
+            for b in self.blocks:
+                b.copy_(self.ro.env.host_block.cpu())
+        else:
+            self.pos_in.copy_(self.ro.env.pos.cpu())
+
     def refresh_weights(self):
         """Call after the network's parameters changed (optimizer step, load_state_dict): re-packs them into the buffer
         the captured graphs read.  Raises if the packed buffer had to move (different device / size): re-create the
@@ -252,14 +265,8 @@ class PipelinedHostRollout:
 
     def reset(self):
         """Back to the initial scenario in every group (device state and pinned input positions)."""
-        for env, h in zip(self.envs, self.groups):
-            if h.in_flight:
-                h.wait()
-            env.reset()
-            h.pos_in.copy_(env.pos.cpu())
-            if h.zero_copy:                                  # the blocks are the state: done flags too
-                for b in h.blocks:
-                    b.copy_(env.host_block.cpu())
+        for h in self.groups:
+            h.reset()
         torch.cuda.synchronize()
 
     def start(self):

@@ -481,6 +481,11 @@ def test_host_stepped_rollout_matches_device_rollout(zero_copy, E):
         assert torch.equal(done, env_a.done.cpu())
         assert hs.pos_in.data_ptr() == pos_out.data_ptr()      # the result is, in place, the next step's input
     assert torch.equal(env_a.fov, env_b.fov) and torch.equal(env_a.time, env_b.time)
+    hs.reset()                                                 # device state and pinned state back to the scenario
+    env_a.reset()
+    ra.run(1)
+    actions, pos_out, done = hs.step()
+    assert torch.equal(actions, ra.actions.cpu()) and torch.equal(pos_out, env_a.pos.cpu())
 
 
 @pytest.mark.parametrize("path", ["fused_tc", "unfused_tc", "ffma", "tc_fc", "ffma_encoder"])
