@@ -208,3 +208,36 @@ def test_generate_cases_feeds_the_recorder_format():
         for k in range(t):
             pos += delta[c["trajectory"][:, k]]
         assert np.array_equal(pos, np.array([a["goal"] for a in c["input"]["agents"]]))
+
+
+def test_low_level_search_matches_oracle_under_random_constraints():
+    """mapf_cbs_a_star (Environment.a_star.search with env.constraints set) against the Python restatement on random small
+    grids with random obstacles, vertex and edge constraints -- including searches that fail."""
+    rng = np.random.default_rng(5)
+    found = failed = 0
+    for trial in range(300):
+        w, h = int(rng.integers(2, 7)), int(rng.integers(2, 7))
+        cells = [(x, y) for x in range(w) for y in range(h)]
+        rng.shuffle(cells)
+        start, goal = cells[0], cells[1]
+        obstacles = set(cells[2:2 + int(rng.integers(0, max(1, len(cells) // 3)))])
+        vertex = {(int(rng.integers(0, 8)), int(rng.integers(0, w)), int(rng.integers(0, h))) for _ in range(int(rng.integers(0, 12)))}
+        edge = set()
+        for _ in range(int(rng.integers(0, 10))):
+            x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+            dx, dy = [(0, 1), (0, -1), (1, 0), (-1, 0)][int(rng.integers(0, 4))]
+            edge.add((int(rng.integers(0, 8)), x, y, x + dx, y + dy))
+        want = cbs_oracle.low_level((w, h), obstacles, start, goal, vertex, edge, max_pops=2000)
+        env = cbs.Environment([w, h], [{"name": "a", "start": list(start), "goal": list(goal)}], sorted(obstacles))
+        env.constraints.vertex_constraints |= {cbs.VertexConstraint(t, cbs.Location(x, y)) for t, x, y in vertex}
+        env.constraints.edge_constraints |= {cbs.EdgeConstraint(t, cbs.Location(a, b), cbs.Location(c, d)) for t, a, b, c, d in edge}
+        inst = env._instance(max_low=2000)
+        env._instance = lambda *a, **k: inst            # same pop budget as the oracle call
+        got = env.a_star.search("a")
+        if want is None:
+            assert got is False, trial
+            failed += 1
+        else:
+            assert [(s.location.x, s.location.y) for s in got] == want, trial
+            found += 1
+    assert found > 100 and failed >= 3
