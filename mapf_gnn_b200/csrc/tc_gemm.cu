@@ -22,6 +22,7 @@
 // The tensor core's fp32 accumulation loses a little precision per accumulate, so consecutive chunks rotate over
 // NACC independent TMEM accumulators that are summed in registers in the epilogue.
 #include <cuda_fp16.h>
+#include <cstdio>
 
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -112,6 +113,37 @@ __global__ void tc_pack_b_f16_kernel(const float* __restrict__ b, int C, int N, 
   }
 }
 
+// Epilogue store of a warp-private 32 x 32 block (lane = output row, v[j] = column j) to row-major global memory through the
+// warp's transpose scratch t (kTcTP floats).  vec (rows 16-byte aligned, N % 4 == 0): 8 STS.128 + 8 LDS.128 + 8 STG.128, every
+// store instruction writing four 128-byte row segments; otherwise 32 STS + 32 (LDS + STG.32), one row segment each.
+// (The 32-bit form cost 1.7 us per block -- 2 to 6.6 us of a 640-row GEMM's 11 to 15 us.)
+constexpr int kTcTP = 32 * 36;
+__device__ __forceinline__ void tc_store_block32(float* t, const float (&v)[32], float* __restrict__ C, int64_t ldc, int row0,
+                                                 int col0, int M, int N, bool vec, int lane) {
+  if (vec) {
+    float4* t4 = reinterpret_cast<float4*>(t + lane * 36);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+    float* dst = C + int64_t(row0 + rr) * ldc + col0 + c4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float4 o = *reinterpret_cast<const float4*>(t + (it * 4 + rr) * 36 + c4);
+      if (row0 + it * 4 + rr < M && col0 + c4 < N) *reinterpret_cast<float4*>(dst + int64_t(it * 4) * ldc) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int n = col0 + lane;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r)
+      if (row0 + r < M && n < N) C[int64_t(row0 + r) * ldc + n] = t[r * 33 + lane];
+  }
+  __syncwarp();
+}
+
 // NP = producer warps = shared-memory stages (6: two CTAs per SM; 4 with NACC = 1: three CTAs per SM -- the variant the
 // training step uses, whose 320 row tiles at B = 8192 then fit one wave instead of 296 + 24); NACC = MMA issuers.
 // NTL = column tiles of NT per CTA (EPI_STORE, NACC = 1): the A chunk is loaded and split ONCE and multiplied with NTL
@@ -132,6 +164,15 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? kMaxActions * NT + kMaxActions : NT * NTL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef MAPF_TCG_STAMP
+  __shared__ unsigned long long s_ts[16], s_tw[8][4];
+#define TCG_WSTAMP(i) do { if (lane == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); s_tw[warp][i] = t__; } } while (0)
+#define TCG_STAMP(i) do { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); s_ts[i] = t__; } while (0)
+  if (tid == 0) TCG_STAMP(0);
+#else
+#define TCG_STAMP(i) do {} while (0)
+#define TCG_WSTAMP(i) do {} while (0)
+#endif
   const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * NT * NTL;
   // column tiles this CTA really has (the last CTA of a row of tiles may own fewer than NTL)
   const int my_tiles = NTL == 1 ? 1 : min(NTL, (g.N - n0 + NT - 1) / NT);
@@ -145,6 +186,10 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     tc::mbar_init(&s_done, NACC);
     tc::fence_mbar_init();
   }
+  // programmatic dependent launch: the CTA is resident, its TMEM columns and barriers set up, before the kernel in front
+  // has drained; every global read (A, the packed B, bias / head weights) stays behind this wait
+  mapf_pdl_wait();
+  mapf_pdl_launch();
   if (EPI == EPI_HEAD) {
     for (int i = tid; i < g.num_actions * NT; i += kTcThreads) {
       const int q = i / NT, n = i - q * NT;
@@ -158,6 +203,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
+  if (tid == 0) TCG_STAMP(1);
   const int nchunks = (g.K + KC - 1) / KC;
   // warp-uniform copies for the MMA issuers: the whole issuing warp runs its (warp-uniform) branch and elect.sync picks the
   // lane, so every MMA operand is a uniform-register value and ptxas emits plain UTCHMMAs instead of wrapping each one in
@@ -216,6 +262,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&s_full[s]);
+      if (tid == 0 && c == 0) TCG_STAMP(2);
 #pragma unroll
       for (int it = 0; it < kPerLane; ++it) v[it] = vn[it];
     }
@@ -239,6 +286,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       for (int c = which; c < nchunks; c += NACC) {
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
+        if (c == 0) TCG_STAMP(3);
         const uint64_t soff = uint64_t(uint32_t(s) * (kStageBytes >> 4));
         const bool first = c < NACC;   // first touch of this accumulator overwrites
 #pragma unroll
@@ -260,6 +308,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
         if (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
       }
       tc::mma_commit(&s_done);
+      if (which == 0) TCG_STAMP(4);
     }
     __syncwarp();   // lanes 1-31 park here instead of spinning on s_done next to the issuing lane
   }
@@ -269,11 +318,16 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     // half w/4.  The operand stages are free once s_done fires and are reused as transpose / exchange scratch. =====
     tc::mbar_wait(&s_done, 0);
     tc::fence_after_sync();
+    if (tid == 0) TCG_STAMP(5);
+    TCG_WSTAMP(0);
     const int quad = warp & 3, half = warp >> 2;
     const int row = m0 + quad * 32 + lane;
     const int nacc_used = nchunks < NACC ? nchunks : NACC;
     constexpr int kHalfCols = NT / 2;
     float* s_scr = reinterpret_cast<float*>(s_tc);
+    // 128-bit epilogue stores when every output row is 16-byte aligned
+    const bool vec_c = EPI == EPI_STORE ? ((g.ldc & 3) == 0 && (g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0)
+                                        : ((g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.y) & 15) == 0);
     float part[kMaxActions];
 #pragma unroll
     for (int q = 0; q < kMaxActions; ++q) part[q] = 0.0f;
@@ -288,6 +342,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       for (int a = 0; a < NACC; ++a)
         if (a < nacc_used) tc::tmem_ld32_nowait(tmem + (uint32_t(quad * 32) << 16) + a * NT * NTL + cb, raw[a]);   // warp-uniform
       tc::tmem_ld_wait();
+      if (tl == 0 && cbl == 0) TCG_WSTAMP(1);
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[0][j]);
@@ -300,37 +355,18 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       if (EPI == EPI_STORE) {
         // bias / ReLU, then a warp-private 32x32 transpose through shared memory so that every global store
         // instruction writes 128 contiguous bytes of one output row
-        float* t = s_scr + warp * (32 * 33);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float o = v[j] + s_head[cb + j];
-          if (g.relu) o = fmaxf(o, 0.0f);
-          t[lane * 33 + j] = o;
+          v[j] += s_head[cb + j];
+          if (g.relu) v[j] = fmaxf(v[j], 0.0f);
         }
-        __syncwarp();
-        const int n = n0 + cb + lane;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int grow = m0 + quad * 32 + r;
-          if (grow < g.M && n < g.N) g.C[int64_t(grow) * g.ldc + n] = t[r * 33 + lane];
-        }
-        __syncwarp();
+        if (tl == 0 && cbl == 0) TCG_WSTAMP(2);
+        tc_store_block32(s_scr + warp * kTcTP, v, g.C, g.ldc, m0 + quad * 32, n0 + cb, g.M, g.N, vec_c, lane);
+        if (tl == 0 && cbl == 0) TCG_WSTAMP(3);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        if (g.y != nullptr) {
-          float* t = s_scr + warp * (32 * 33);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) t[lane * 33 + j] = v[j];
-          __syncwarp();
-          const int n = cb + lane;
-#pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int grow = m0 + quad * 32 + r;
-            if (grow < g.M && n < g.N) g.y[int64_t(grow) * g.N + n] = t[r * 33 + lane];
-          }
-          __syncwarp();
-        }
+        if (g.y != nullptr) tc_store_block32(s_scr + warp * kTcTP, v, g.y, g.N, m0 + quad * 32, cb, g.M, g.N, vec_c, lane);
 #pragma unroll
         for (int q = 0; q < kMaxActions; ++q) {
           if (q < g.num_actions) {
@@ -350,7 +386,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     }
     if (EPI == EPI_HEAD) {
       // the two column halves of a row meet in shared memory (after the y transposes are done with it)
-      float* ex = s_scr + 8 * (32 * 33);   // [128 rows][kMaxActions]
+      float* ex = s_scr + 8 * kTcTP;   // [128 rows][kMaxActions]
       if (half == 1) {
 #pragma unroll
         for (int q = 0; q < kMaxActions; ++q) ex[(quad * 32 + lane) * kMaxActions + q] = part[q];
@@ -374,17 +410,27 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, kCols);
+#ifdef MAPF_TCG_STAMP
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    TCG_STAMP(6);
+    printf("tcg<%d,%d,%d> K=%d: setup %llu first-full %llu first-mma-wake %llu last-commit %llu done-wake %llu end %llu ns\n", NT, NP, NTL, g.K,
+           s_ts[1] - s_ts[0], s_ts[2] - s_ts[0], s_ts[3] - s_ts[0], s_ts[4] - s_ts[0], s_ts[5] - s_ts[0], s_ts[6] - s_ts[0]);
+    if (EPI == EPI_STORE)
+      for (int w = 0; w < 8; ++w)
+        printf("   K=%d warp %d: wake %llu ld %llu sts %llu stores %llu\n", g.K, w, s_tw[w][0] - s_ts[0], s_tw[w][1] - s_ts[0], s_tw[w][2] - s_ts[0], s_tw[w][3] - s_ts[0]);
+  }
+#endif
 }
 
 template <int NT, int KC, int NACC, int EPI, int NP = kTcProdWarps, int NTL = 1>
 int launch_tc(const TcGemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = size_t(NP) * (2 * kTcM * KC * 4 + NTL * 2 * NT * KC * 4);
-  static_assert(smem >= 8 * 32 * 33 * 4 + 128 * kMaxActions * 4, "the epilogue transposes through the operand stages");
+  static_assert(smem >= 8 * kTcTP * 4 + 128 * kMaxActions * 4, "the epilogue transposes through the operand stages");
   auto kernel = tc_gemm_kernel<NT, KC, NACC, EPI, NP, NTL>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
   dim3 grid((g.M + kTcM - 1) / kTcM, g.bp_tile ? (g.N + NT * NTL - 1) / (NT * NTL) : 1);
-  kernel<<<grid, kTcThreads, smem, s>>>(g);
+  mapf_launch_pdl(kernel, grid, dim3(kTcThreads), smem, s, g);
   return mapf_launch_status();
 }
 
@@ -495,6 +541,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
     constexpr int kHalfCols = NT / 2;
     float* s_scr = reinterpret_cast<float*>(s_tc);
     const int nacc = nch < kPsChunks ? nch : kPsChunks;   // accumulators that were written
+    const bool vec_c = (g.ldc & 3) == 0 && (g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
 #pragma unroll
     for (int cbl = 0; cbl < kHalfCols; cbl += 32) {
       const int cb = half * kHalfCols + cbl;
@@ -512,7 +559,6 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r0[j]) + (nacc > 3 ? __uint_as_float(r1[j]) : 0.0f);
       }
-      float* t = s_scr + warp * (32 * 33);
       float rs = 1.0f;   // fp16-split operands: undo the row's and the matrix' power-of-two scales
       if (F16) {
         const int row = m0 + quad * 32 + lane;
@@ -520,18 +566,10 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float o = fmaf(v[j], rs, s_bias[cb + j]);
-        if (g.relu) o = fmaxf(o, 0.0f);
-        t[lane * 33 + j] = o;
+        v[j] = fmaf(v[j], rs, s_bias[cb + j]);
+        if (g.relu) v[j] = fmaxf(v[j], 0.0f);
       }
-      __syncwarp();
-      const int n = cb + lane;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int grow = m0 + quad * 32 + r;
-        if (grow < g.M && n < g.N) g.C[int64_t(grow) * g.ldc + n] = t[r * 33 + lane];
-      }
-      __syncwarp();
+      tc_store_block32(s_scr + warp * kTcTP, v, g.C, g.ldc, m0 + quad * 32, cb, g.M, g.N, vec_c, lane);
     }
   }
   tc::fence_before_sync();
@@ -542,7 +580,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_presplit_kernel(TcGemmArgs g) {
 template <int NT, bool F16>
 int launch_presplit(const TcGemmArgs& g, cudaStream_t s) {
   constexpr size_t smem = size_t(kPsStages) * kPsChunks * (2 * kTcM * 8 * 4 + 2 * NT * 8 * 4);
-  static_assert(smem >= 8 * 32 * 33 * 4, "the epilogue transposes through the operand stages");
+  static_assert(smem >= 8 * kTcTP * 4, "the epilogue transposes through the operand stages");
   auto kernel = tc_presplit_kernel<NT, F16>;
   if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(kernel, size_t(smem), cache__); }())
     return MAPF_ERR_CUDA;
