@@ -20,6 +20,25 @@ static inline int mapf_launch_status() {
   return MAPF_OK;
 }
 
+// BatchNorm + ReLU of a training conv layer's INPUT applied on load (enc_tc.cu mapf_conv_tc_layer; train.py:82-100 forward):
+// the layer reads the pre-BatchNorm output u of the layer in front, every CTA derives the (slot, channel) scale / shift pairs
+// from that layer's fp64 batch sums, CTA 0 also writes the tables the backward pass reads and advances the running
+// statistics, and act_out receives relu(bn(u)) -- the activation tensor the weight-gradient kernels read.
+struct MapfConvBnIn {
+  const double* stats;        // [N][stat_c][2] fp64 (sum, sum of squares) of the layer in front
+  const float* gamma;         // [16]
+  const float* beta;          // [16]
+  double count;               // values per (slot, channel): B * 25
+  float momentum;
+  int stat_c;
+  float* meaninv;             // out [N][16][2] (mean, invstd)
+  float* scale_shift;         // out [N][16][2]
+  float* running_mean;        // in / out [16] or NULL
+  float* running_var;
+  int64_t* batches;           // num_batches_tracked or NULL
+  float* act_out;             // out [rows][16*25]
+};
+
 static inline bool mapf_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 constexpr int kFov = 5;          // FOV side, env_graph_gridv1.py:252 with pad = 3

@@ -506,7 +506,11 @@ struct ConvTcArgs {
   // per-slot BatchNorm statistics of the output (forward layers; NULL for data gradients): fp64 sums [N][stat_c][2]
   double* stats;
   int slots, stat_c;   // N agent slots (row = b * N + n), channel pitch of `stats`
+  // BatchNorm + ReLU of the input on load (bn.stats != NULL; CIN = 16, slots * 16 <= kEtBnTab): see MapfConvBnIn
+  MapfConvBnIn bn;
 };
+constexpr int kEtBnTab = 256;
+constexpr float kEtBnEps = 1e-5f;   // nn.BatchNorm2d default (framework_gnn.py:64)
 
 // raw filters [Cout][Cin][3][3] (mode 0) or their data-gradient form W'[o][i][ky][kx] = W[i][o][2-ky][2-kx] (mode 1,
 // o = forward input channel) -> B operand blocks for 16 output channels; one block, scale from the largest |w|
@@ -563,6 +567,7 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
   __shared__ __align__(8) uint64_t s_bar[kGroups];
   __shared__ __align__(8) uint64_t s_go[kGroups];      // start-up chain (see encoder_tc_kernel)
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float2 s_tab[CIN == 16 ? kEtBnTab : 1];   // (slot, channel) scale / shift of the input's BatchNorm (g.bn.stats only)
   extern __shared__ __align__(16) double s_stat[];     // [warp][slot][32]: a warp's private per-slot sums (g.stats only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, quad = warp & 3;
@@ -581,6 +586,46 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
   for (int i = tid; i < kWFloats / 4; i += kThreads)
     reinterpret_cast<float4*>(s_w)[i] = mapf_ld_dep(reinterpret_cast<const float4*>(g.wtc) + i);
   if (tid < kEtCout) s_b[tid] = g.bias != nullptr ? mapf_ld_dep(g.bias + tid) : 0.0f;
+  const bool bn_in = CIN == 16 && g.bn.stats != nullptr;
+  if (CIN == 16 && bn_in) {
+    // the arithmetic of bn_finalize_apply4_kernel (train_kernels.cu), so that both forms of the step agree bit for bit
+    const int N = g.slots, C = CIN;
+    for (int i = tid; i < N * C; i += kThreads) {
+      const int n = i / C, c = i - n * C;
+      const double s1 = mapf_ld_dep(g.bn.stats + (int64_t(n) * g.bn.stat_c + c) * 2);
+      const double s2 = mapf_ld_dep(g.bn.stats + (int64_t(n) * g.bn.stat_c + c) * 2 + 1);
+      const double mean = s1 / g.bn.count;
+      double var = s2 / g.bn.count - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      const double invstd = 1.0 / sqrt(var + double(kEtBnEps));
+      const float w = mapf_ld_dep(g.bn.gamma + c) * float(invstd);
+      const float sh = mapf_ld_dep(g.bn.beta + c) - float(mean) * w;
+      s_tab[i] = make_float2(w, sh);
+      if (blockIdx.x == 0) {
+        g.bn.meaninv[i * 2] = float(mean);
+        g.bn.meaninv[i * 2 + 1] = float(invstd);
+        g.bn.scale_shift[i * 2] = w;
+        g.bn.scale_shift[i * 2 + 1] = sh;
+      }
+    }
+    if (blockIdx.x == 0 && tid < C) {
+      const int c = tid;
+      float rm = g.bn.running_mean ? g.bn.running_mean[c] : 0.0f, rv = g.bn.running_var ? g.bn.running_var[c] : 0.0f;
+      for (int n = 0; n < N; ++n) {
+        const double s1 = mapf_ld_dep(g.bn.stats + (int64_t(n) * g.bn.stat_c + c) * 2);
+        const double s2 = mapf_ld_dep(g.bn.stats + (int64_t(n) * g.bn.stat_c + c) * 2 + 1);
+        const double mean = s1 / g.bn.count;
+        double var = s2 / g.bn.count - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const float unbiased = float(g.bn.count > 1.0 ? var * g.bn.count / (g.bn.count - 1.0) : var);
+        rm = (1.0f - g.bn.momentum) * rm + g.bn.momentum * float(mean);
+        rv = (1.0f - g.bn.momentum) * rv + g.bn.momentum * unbiased;
+      }
+      if (g.bn.running_mean) g.bn.running_mean[c] = rm;
+      if (g.bn.running_var) g.bn.running_var[c] = rv;
+      if (c == 0 && g.bn.batches != nullptr) *g.bn.batches += N;
+    }
+  }
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -622,6 +667,22 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
   bool first_issue = true;
   for (; tile < ntiles; tile += stride) {
     float inv_a;
+    if (CIN == 16 && bn_in) {
+      // x holds the pre-BatchNorm values of this pixel: normalise, ReLU, and leave the activations for the backward pass
+      const int64_t im = tile * 4 + quad;
+      if (im < g.rows && pix_ok) {
+        const float4* tab = reinterpret_cast<const float4*>(s_tab + int(im % g.slots) * CIN);
+        float* ao = g.bn.act_out + im * (CIN * kFovCells) + pidx;
+#pragma unroll
+        for (int c = 0; c < CIN; c += 2) {
+          const float4 t = tab[c >> 1];
+          x[c] = fmaxf(fmaf(x[c], t.x, t.y), 0.0f);
+          x[c + 1] = fmaxf(fmaf(x[c + 1], t.z, t.w), 0.0f);
+          ao[c * kFovCells] = x[c];
+          ao[(c + 1) * kFovCells] = x[c + 1];
+        }
+      }
+    }
     {
       float amax = 0.0f;
 #pragma unroll
@@ -810,9 +871,18 @@ int mapf_conv_tc_layer_pack(const float* w, int cin_fwd, int cout_fwd, int mode,
   return mapf_launch_status();
 }
 // `packed` != 0: wtc_scratch already holds mapf_conv_tc_layer_pack's output for these filters
+bool mapf_conv_tc_layer_bn_ok(int cin_fwd, int cout_fwd, int N) {
+  return mapf_conv_tc_layer_ok(cin_fwd, cout_fwd, 0) && cin_fwd == 16 && N * 16 <= kEtBnTab;
+}
+// bn != NULL (mode 0, mapf_conv_tc_layer_bn_ok): `in` is the pre-BatchNorm output of the layer in front, see MapfConvBnIn
 int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int cin_fwd, int cout_fwd, int mode, int B,
-                       int N, float* wtc_scratch, int packed, float* out, double* stats, int stat_c, mapf_stream_t stream) {
+                       int N, float* wtc_scratch, int packed, float* out, double* stats, int stat_c, const MapfConvBnIn* bn,
+                       mapf_stream_t stream) {
   MAPF_REQUIRE(in && w && wtc_scratch && out, MAPF_ERR_NULL);
+  if (bn != nullptr) {
+    MAPF_REQUIRE(mode == 0 && mapf_conv_tc_layer_bn_ok(cin_fwd, cout_fwd, N), MAPF_ERR_UNSUPPORTED);
+    MAPF_REQUIRE(bn->stats && bn->gamma && bn->beta && bn->meaninv && bn->scale_shift && bn->act_out, MAPF_ERR_NULL);
+  }
   MAPF_REQUIRE(mapf_conv_tc_layer_ok(cin_fwd, cout_fwd, mode), MAPF_ERR_UNSUPPORTED);
   MAPF_REQUIRE(mapf_aligned(wtc_scratch, 16), MAPF_ERR_ALIGN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -824,6 +894,8 @@ int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int c
   ConvTcArgs g{};
   g.rows = int64_t(B) * N;
   g.in = in; g.wtc = wtc_scratch; g.bias = bias; g.out = out;
+  g.slots = N;
+  if (bn != nullptr) g.bn = *bn;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (g.rows + 3) >> 2;

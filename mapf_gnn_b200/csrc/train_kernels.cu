@@ -23,8 +23,10 @@ constexpr float kBnEpsT = 1e-5f;
 int mapf_conv_tc_layer_floats();
 bool mapf_conv_tc_layer_ok(int cin_fwd, int cout_fwd, int mode);
 int mapf_conv_tc_layer_pack(const float* w, int cin_fwd, int cout_fwd, int mode, float* wtc_scratch, mapf_stream_t stream);
+bool mapf_conv_tc_layer_bn_ok(int cin_fwd, int cout_fwd, int N);
 int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int cin_fwd, int cout_fwd, int mode, int B,
-                       int N, float* wtc_scratch, int packed, float* out, double* stats, int stat_c, mapf_stream_t stream);
+                       int N, float* wtc_scratch, int packed, float* out, double* stats, int stat_c, const MapfConvBnIn* bn,
+                       mapf_stream_t stream);
 namespace {
 
 struct TrainLayout {
@@ -1283,19 +1285,37 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
     MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, p->taps, p->node_dim, ws + T.wt, sp));
   const int m_gf = ord.mark(sp);
 
+  // BatchNorm + ReLU of layer l - 1 applied by layer l's tensor-core kernel on load (one launch less per layer on the
+  // step's dependent chain, one pass over the activations less): the last layer keeps its own pass (the FC reads a_L)
+  bool bn_pending = false;
   for (int l = 0; l < L; ++l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
     double* st = stat + int64_t(l) * N * T.cmax * 2;
     ord.wait(s, m_conv[l]);
     if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 0)) {
-      MAPF_TRY(mapf_conv_tc_layer(l == 0 ? a->states : ws + T.a[l - 1], p->conv_w[l], p->conv_b[l], cin, cout, 0, B, N,
-                                  ws + T.convtc[l], 1, ws + T.u[l], st, T.cmax, stream));
+      MapfConvBnIn bn{};
+      if (bn_pending) {
+        bn.stats = stat + int64_t(l - 1) * N * T.cmax * 2;
+        bn.gamma = p->bn_gamma[l - 1]; bn.beta = p->bn_beta[l - 1];
+        bn.count = count; bn.momentum = a->momentum; bn.stat_c = T.cmax;
+        bn.meaninv = ws + T.meaninv[l - 1]; bn.scale_shift = ws + T.scsh[l - 1];
+        bn.running_mean = const_cast<float*>(p->bn_mean[l - 1]); bn.running_var = const_cast<float*>(p->bn_var[l - 1]);
+        bn.batches = a->bn_batches[l - 1];
+        bn.act_out = ws + T.a[l - 1];
+      }
+      MAPF_TRY(mapf_conv_tc_layer(l == 0 ? a->states : (bn_pending ? ws + T.u[l - 1] : ws + T.a[l - 1]), p->conv_w[l], p->conv_b[l],
+                                  cin, cout, 0, B, N, ws + T.convtc[l], 1, ws + T.u[l], st, T.cmax, bn_pending ? &bn : nullptr, stream));
+      bn_pending = false;
     } else {
       MAPF_TRY(launch_conv_train(s, l == 0 ? a->states : ws + T.a[l - 1], cin, cout, B, N, ws + T.convpk[l],
                                  p->conv_b[l], ws + T.u[l], st, T.cmax));
     }
     const int64_t planes = rows * cout;
     const bool vec4 = (cout * kFovCells) % 4 == 0;
+    if (l + 1 < L && conv_tc && !(a->flags & MAPF_TRAIN_BN_PASS) && mapf_conv_tc_layer_bn_ok(cout, p->channels[l + 2], N)) {
+      bn_pending = true;      // the next layer's kernel normalises on load
+      continue;
+    }
     if (vec4 && N * cout <= kBnFusedMax) {
       // batch statistics -> scale / shift -> BatchNorm + ReLU in one launch
       mapf_launch_pdl(bn_finalize_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s,
@@ -1546,7 +1566,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       ord.wait(s, m_convpk[l]);
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
       if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 1)) {
-        MAPF_TRY(mapf_conv_tc_layer(da, p->conv_w[l], nullptr, cin, cout, 1, B, N, ws + T.convtc_bwd[l], 1, da_next, nullptr, 0,
+        MAPF_TRY(mapf_conv_tc_layer(da, p->conv_w[l], nullptr, cin, cout, 1, B, N, ws + T.convtc_bwd[l], 1, da_next, nullptr, 0, nullptr,
                                     stream));
       } else {
         MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
