@@ -1393,13 +1393,34 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     ord.wait(sw, m0);
     ord.wait(sp, m0);
   }
-  auto zero = [&](float* ptr, int64_t n) { return cudaMemsetAsync(ptr, 0, sizeof(float) * size_t(n), sw) == cudaSuccess; };
-  bool ok = zero(G.act_w, int64_t(A) * head_in) && zero(G.act_b, A) && zero(G.fc_w, int64_t(F) * fin) && zero(G.fc_b, F);
-  if (K > 0) ok = ok && zero(G.gf_w, int64_t(F) * K * Gd);
-  if (a->message) ok = ok && zero(G.gf_w2, int64_t(F) * Gd);
+  // Zero the accumulated gradients: adjacent buffers (a trainer keeps every gradient as a view of ONE flat tensor) are
+  // merged into one memset -- twelve separate memset nodes were a 40 us chain at the head of the weight-gradient lane,
+  // the lane that finishes last at small batches.  The BatchNorm gradients are overwritten later on the same lane
+  // (bn_param_grads_kernel): they are only swept along where they bridge two ranges.
+  struct Range { float* p; int64_t n; bool needed; };
+  Range rg[6 + 4 * MAPF_MAX_CONV];
+  int nrg = 0;
+  auto want = [&](float* ptr, int64_t n, bool needed) { if (ptr != nullptr && n > 0) rg[nrg++] = Range{ptr, n, needed}; };
+  want(G.act_w, int64_t(A) * head_in, true); want(G.act_b, A, true); want(G.fc_w, int64_t(F) * fin, true); want(G.fc_b, F, true);
+  if (K > 0) want(G.gf_w, int64_t(F) * K * Gd, true);
+  if (a->message) want(G.gf_w2, int64_t(F) * Gd, true);
   for (int l = 0; l < L; ++l) {
     MAPF_REQUIRE(G.conv_w[l] && G.conv_b[l] && G.bn_gamma[l] && G.bn_beta[l], MAPF_ERR_NULL);
-    ok = ok && zero(G.conv_w[l], int64_t(p->channels[l]) * p->channels[l + 1] * 9) && zero(G.conv_b[l], p->channels[l + 1]);
+    want(G.conv_w[l], int64_t(p->channels[l]) * p->channels[l + 1] * 9, true);
+    want(G.conv_b[l], p->channels[l + 1], true);
+    want(G.bn_gamma[l], p->channels[l + 1], false);
+    want(G.bn_beta[l], p->channels[l + 1], false);
+  }
+  for (int i = 1; i < nrg; ++i)          // insertion sort by address (at most 18 entries)
+    for (int j = i; j > 0 && rg[j].p < rg[j - 1].p; --j) { const Range t = rg[j]; rg[j] = rg[j - 1]; rg[j - 1] = t; }
+  bool ok = true;
+  for (int i = 0; i < nrg;) {
+    int j = i;
+    float* end = rg[i].p + rg[i].n;
+    bool needed = rg[i].needed;
+    while (j + 1 < nrg && rg[j + 1].p == end) { ++j; end += rg[j].n; needed = needed || rg[j].needed; }
+    if (needed) ok = ok && cudaMemsetAsync(rg[i].p, 0, sizeof(float) * size_t(end - rg[i].p), sw) == cudaSuccess;
+    i = j + 1;
   }
   double* stat = reinterpret_cast<double*>(ws + T.stat_bwd);
   ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) == cudaSuccess;

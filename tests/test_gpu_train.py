@@ -158,6 +158,31 @@ def test_eval_after_training_uses_updated_weights(train_step):
     assert rel_err(after.cpu().numpy(), ref.numpy()) < REL
 
 
+def test_static_input_buffers_skip_the_staging_copies(train_step):
+    """Trainer.input_buffers: batches written straight into the captured step's input tensors give the same losses as
+    batches passed to step() (which stages them), and step() leaves tensors that are those inputs alone."""
+    import mapf_gnn_b200.train as tr
+    states, gso, targets = _batch(train_step)
+    nets = [load_network("gnn_msg_k3").train() for _ in range(2)]
+    staged, static = tr.Trainer(nets[0], use_graph=True), tr.Trainer(nets[1], use_graph=True)
+    bs, bg, bt = static.input_buffers(states, gso, targets)
+    assert bt.dtype == torch.int32 and bs.shape == states.shape
+    with pytest.raises(RuntimeError, match="use_graph"):
+        tr.Trainer(load_network("gnn_msg_k3").train()).input_buffers(states, gso, targets)
+    for it in range(3):
+        perm = torch.randperm(states.shape[0], device="cuda")
+        s, g, t = states[perm], gso[perm], targets[perm]
+        l0 = staged.step(s, g, t)
+        bs.copy_(s), bg.copy_(g), bt.copy_(t)
+        ptrs = (bs.data_ptr(), bg.data_ptr(), bt.data_ptr())
+        l1 = static.step(bs, bg, bt)
+        assert ptrs == (static._g_states.data_ptr(), static._g_gso.data_ptr(), static._g_targets.data_ptr())
+        assert abs(l0.item() - l1.item()) < 1e-5 * abs(l0.item()), it
+    # the same call with ordinary tensors afterwards still stages them
+    l0, l1 = staged.step(states, gso, targets), static.step(states, gso, targets)
+    assert abs(l0.item() - l1.item()) < 1e-5 * abs(l0.item())
+
+
 def test_cuda_graph_trainer_matches_eager(train_step):
     """Trainer(use_graph=True) replays the captured launch sequence; parameters must track the eager trainer."""
     import mapf_gnn_b200.train as tr
