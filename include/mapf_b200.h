@@ -316,6 +316,10 @@ typedef struct {
 #define MAPF_TRAIN_FFMA_CONV 16   /* forward / data-gradient convolutions on the FFMA2 kernel instead of the tensor cores */
 #define MAPF_TRAIN_TC_BWD_ALWAYS 8 /* accepted, no effect: the tensor-core paths are the default at every batch size */
 #define MAPF_TRAIN_SINGLE_LANE 32 /* every launch on the caller's stream: no auxiliary lanes for weight packs / weight gradients */
+#define MAPF_TRAIN_PREPARED 128   /* mapf_train_forward: also prepare what mapf_train_backward needs from the parameters alone
+                                     (transposed-weight packs, mirrored filter operands, zeroed BatchNorm sums) on the pack lane;
+                                     mapf_train_backward: the forward call on this workspace did so (same parameters, same other
+                                     flags).  Without it each call is self-contained. */
 #define MAPF_TRAIN_BN_PASS 64     /* BatchNorm + ReLU of every conv layer as its own pass (default: applied on load by the next
                                      layer's tensor-core kernel, which also writes the activations the backward pass reads) */
 int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd_args* a, mapf_stream_t stream);

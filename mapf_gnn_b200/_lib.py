@@ -15,8 +15,8 @@ MAX_CONV = 4
 # mapf_policy_fwd_args.flags / mapf_train_fwd_args.flags (include/mapf_b200.h)
 POLICY_FFMA_CONV, POLICY_FC_UNSPLIT, POLICY_UNFUSED_GRAPH, POLICY_FUSED_ENV_ON, POLICY_FUSED_ENV_OFF, POLICY_NO_PDL, \
     POLICY_FFMA_HOPS = 1, 2, 4, 8, 16, 32, 64
-TRAIN_FFMA_FC, TRAIN_FFMA_GRAPH, TRAIN_FFMA_BWD, TRAIN_TC_BWD_ALWAYS, TRAIN_FFMA_CONV, TRAIN_SINGLE_LANE, TRAIN_BN_PASS = \
-    1, 2, 4, 8, 16, 32, 64
+TRAIN_FFMA_FC, TRAIN_FFMA_GRAPH, TRAIN_FFMA_BWD, TRAIN_TC_BWD_ALWAYS, TRAIN_FFMA_CONV, TRAIN_SINGLE_LANE, TRAIN_BN_PASS, \
+    TRAIN_PREPARED = 1, 2, 4, 8, 16, 32, 64, 128
 c_f32p = C.c_void_p      # device pointers travel as integers
 c_i32p = C.c_void_p
 c_u8p = C.c_void_p

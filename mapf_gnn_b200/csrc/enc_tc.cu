@@ -659,7 +659,9 @@ __global__ void __launch_bounds__(EtCfg<16>::kThreads, 1) conv_tc_layer_kernel(C
   auto right_of = [&](uint32_t w) { return __shfl_down_sync(0xffffffffu, w, 1); };
   auto warp_max = [&](float m) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))); };
 
-  int64_t tile = int64_t(blockIdx.x) * kGroups + wg;
+  // tiles are dealt to the CTAs first, then to the groups of a CTA: a small batch (fewer tiles than 5 x SMs) spreads over
+  // all SMs with one or two busy groups each instead of filling a fifth of the SMs with five
+  int64_t tile = int64_t(wg) * gridDim.x + blockIdx.x;
   float x[CIN];
   load_in(tile, x);
   if (wg > 0 && tile < ntiles) tc::mbar_wait(&s_go[wg - 1], 0);        // start-up chain of the groups (see encoder_tc_kernel)
@@ -899,9 +901,7 @@ int mapf_conv_tc_layer(const float* in, const float* w, const float* bias, int c
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (g.rows + 3) >> 2;
-  const int64_t want = (ntiles + 4) / 5;
-  const int grid = int(want < sms ? want : sms);
-  const int64_t rounds = (ntiles + int64_t(grid) * 5 - 1) / (int64_t(grid) * 5);
+  const int grid = int(ntiles < sms ? ntiles : sms);
 
   // statistics in the conv epilogue while the warps' private tables fit shared memory (N <= 16); else a second pass
   const bool fused_stats = stats != nullptr && N <= 16;

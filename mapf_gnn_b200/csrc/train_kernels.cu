@@ -39,7 +39,7 @@ struct TrainLayout {
   int64_t wt;                                 // [(K(+1))F][G]
   int64_t u[MAPF_MAX_CONV], a[MAPF_MAX_CONV]; // pre-BN conv outputs, post BN+ReLU activations [rows][C*25]
   int64_t x, z, y;                            // [rows][F], [rows][KT], [rows][G]
-  int64_t dy, dz, dx, da0, da1;
+  int64_t dy, dz, dx, da0, da1, da2;
   int64_t fcpk;                               // compressMLP weight, packed for the tensor-core GEMM (mapf_tc_pack_b)
   int64_t dwpart;                             // [grid <= 296][max cin*cout*9 + cmax] per-CTA weight-gradient partials
   int64_t convtc[MAPF_MAX_CONV], convtc_bwd[MAPF_MAX_CONV];   // tensor-core filter operands (enc_tc.cu mapf_conv_tc_layer)
@@ -84,6 +84,7 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
   T.dx = take(rows * p.fc_out);
   T.da0 = take(rows * cmax * 25);
   T.da1 = take(rows * cmax * 25);
+  T.da2 = take(rows * cmax * 25);
   {
     int64_t maxp = 0;
     for (int l = 0; l < p.num_conv; ++l) maxp = max(maxp, int64_t(p.channels[l]) * p.channels[l + 1]);
@@ -1286,6 +1287,44 @@ struct LaneOrder {
   }
 };
 
+// The backward pass' parameter-only operands -- transposed weights and their tensor-core packs for the activation-gradient
+// GEMMs, mirrored / transposed filter operands for the data-gradient convolutions -- on stream `sp`.  Called from the
+// FORWARD call's pack lane under MAPF_TRAIN_PREPARED (the packs are then long complete when the backward chain needs them:
+// at batch 128 the first activation-gradient GEMM otherwise waits ~15 us for them), else from the backward call itself.
+struct BwdPackMarks { int gf = -1, fc = -1, conv[MAPF_MAX_CONV]; };
+int pack_backward_operands(const mapf_net_params* p, int message, int flags, const TrainLayout& T, float* ws, cudaStream_t sp,
+                           LaneOrder* ord, BwdPackMarks* m) {
+  const int L = p->num_conv, F = p->fc_out, fin = p->fc_in, Gd = p->node_dim, K = p->taps;
+  const int head_in = K > 0 ? Gd : F;
+  const int KT = (K + (message ? 1 : 0)) * F;
+  const bool tc_bwd = !(flags & MAPF_TRAIN_FFMA_BWD) && (head_in & 3) == 0 && (F & 3) == 0 && (fin & 3) == 0 &&
+                      (K == 0 || (Gd & 3) == 0) && F <= 128 && Gd <= 128;
+  const bool conv_tc = !(flags & MAPF_TRAIN_FFMA_CONV);
+  if (tc_bwd) {
+    if (K > 0) {
+      // dz = dy W_eff (and the W2 columns behind): W_eff^T rows are the packed B operand
+      MAPF_TRY(mapf_pack_graph_weights(p->gf_w, message ? p->gf_w2 : nullptr, F, K, Gd, ws + T.wtt, sp));
+      MAPF_TRY(mapf_tc_pack_b_tiles(ws + T.wtt, Gd, KT, ws + T.gfpk_bwd, sp));
+      if (ord) m->gf = ord->mark(sp);
+    }
+    MAPF_TRY(mapf_pack_graph_weights(p->fc_w, nullptr, fin, 1, F, ws + T.fcwt, sp));   // fc_w^T [fc_in][F]
+    MAPF_TRY(mapf_tc_pack_b_tiles(ws + T.fcwt, F, fin, ws + T.fcpk_bwd, sp));
+    if (ord) m->fc = ord->mark(sp);
+  }
+  for (int l = L - 1; l >= 1; --l) {
+    const int cin = p->channels[l], cout = p->channels[l + 1];
+    if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 1)) {
+      MAPF_TRY(mapf_conv_tc_layer_pack(p->conv_w[l], cin, cout, 1, ws + T.convtc_bwd[l], sp));
+    } else {
+      const int cin_pad = int(r4(cin));
+      MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
+      mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, sp, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
+    }
+    if (ord) m->conv[l] = ord->mark(sp);
+  }
+  return MAPF_OK;
+}
+
 }  // namespace
 
 extern "C" int64_t mapf_train_workspace_size(const mapf_net_params* p, int32_t batch, int32_t agents) {
@@ -1319,7 +1358,11 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   LaneOrder ord(lanes_for(s, a->flags));
   cudaStream_t sp = ord.lanes ? ord.lanes->lane[1] : s;
   ord.wait(sp, ord.mark(s));
-  if (cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) != cudaSuccess) return MAPF_ERR_CUDA;
+  const bool prepare = (a->flags & MAPF_TRAIN_PREPARED) != 0;
+  // (the backward call's sums sit right behind the forward's: one memset zeroes both)
+  static_assert(sizeof(double) == 2 * sizeof(float), "stat blocks are sized in floats");
+  MAPF_REQUIRE(!prepare || T.stat_bwd == T.stat_fwd + int64_t(2) * L * N * T.cmax * 2, MAPF_ERR_UNSUPPORTED);
+  if (cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax * (prepare ? 2 : 1), sp) != cudaSuccess) return MAPF_ERR_CUDA;
   int m_conv[MAPF_MAX_CONV];
   for (int l = 0; l < L; ++l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
@@ -1333,6 +1376,9 @@ extern "C" int mapf_train_forward(const mapf_net_params* p, const mapf_train_fwd
   // 3xTF32 tcgen05 operand of the current compressMLP weights (re-packed every step: 100 KB)
   if (fc_tc) MAPF_TRY(mapf_tc_pack_b(p->fc_w, fin, nullptr, 0, F, ws + T.fcpk, sp));
   const int m_fc = ord.mark(sp);
+  // the backward call's operands: behind the packs the forward chain needs first, in front of the graph-filter pack whose
+  // mark doubles as the join of the lane
+  if (prepare) MAPF_TRY(pack_backward_operands(p, a->message, a->flags, T, ws, sp, nullptr, nullptr));
   if (graph_tc)
     MAPF_TRY(mapf_tc_pack_b(p->gf_w, p->taps * F, a->message ? p->gf_w2 : nullptr, a->message ? F : 0, p->node_dim,
                             ws + T.wt, sp));
@@ -1478,9 +1524,10 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     i = j + 1;
   }
   double* stat = reinterpret_cast<double*>(ws + T.stat_bwd);
-  ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) == cudaSuccess;
+  const bool prepared = (a->flags & MAPF_TRAIN_PREPARED) != 0;     // packs and zeroed sums come from the forward call
+  if (!prepared) ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) == cudaSuccess;
   if (!ok) return MAPF_ERR_CUDA;
-  const int m_stat = ord.mark(sp);
+  const int m_stat = prepared ? -1 : ord.mark(sp);
 
   const float* head_act = K > 0 ? ws + T.y : ws + T.x;
   const int KF = K * F, KT = (K + (a->message ? 1 : 0)) * F;
@@ -1490,40 +1537,22 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   const bool tc_bwd = !(a->flags & MAPF_TRAIN_FFMA_BWD) && (head_in & 3) == 0 && (F & 3) == 0 && (fin & 3) == 0 &&
                       (K == 0 || (Gd & 3) == 0) && F <= 128 && Gd <= 128;
   const bool conv_tc = !(a->flags & MAPF_TRAIN_FFMA_CONV);
+  // three activation-gradient buffers in rotation: a layer's data-gradient convolution writes the buffer read two layers up,
+  // so the chain never waits for the weight-gradient kernel of the layer just above (which reads the buffer in between)
   float* da = ws + T.da0;
   float* da_next = ws + T.da1;
+  float* da_spare = ws + T.da2;
   // C[rows, Ncols] = Asrc[rows, Kd] . Wt^T with Wt [Ncols, Kd] row-major (a transposed weight): tiles of 128 output
   // columns packed on the pack lane, one GEMM launch over all tiles on the chain
-  auto nn_pack = [&](int Kd, const float* Wt, int Ncols, float* packs) -> int {
-    return mapf_tc_pack_b_tiles(Wt, Kd, Ncols, packs, sp);
-  };
   auto nn_gemm = [&](const float* Asrc, int Kd, int Ncols, const float* packs, float* Cout, int64_t ldc) -> int {
     return mapf_tc_gemm_tiles(int32_t(rows), Ncols, Kd, Asrc, Kd, packs, Cout, ldc, nullptr, 0, stream);
   };
   // ---- pack lane ----
-  int m_gfpk = -1, m_fcpk = -1, m_convpk[MAPF_MAX_CONV];
-  if (tc_bwd) {
-    if (K > 0) {
-      // dz = dy W_eff (and the W2 columns behind): W_eff^T rows are the packed B operand
-      MAPF_TRY(mapf_pack_graph_weights(p->gf_w, a->message ? p->gf_w2 : nullptr, F, K, Gd, ws + T.wtt, sp));
-      MAPF_TRY(nn_pack(Gd, ws + T.wtt, KT, ws + T.gfpk_bwd));
-      m_gfpk = ord.mark(sp);
-    }
-    MAPF_TRY(mapf_pack_graph_weights(p->fc_w, nullptr, fin, 1, F, ws + T.fcwt, sp));   // fc_w^T [fc_in][F]
-    MAPF_TRY(nn_pack(F, ws + T.fcwt, fin, ws + T.fcpk_bwd));
-    m_fcpk = ord.mark(sp);
-  }
-  for (int l = L - 1; l >= 1; --l) {
-    const int cin = p->channels[l], cout = p->channels[l + 1];
-    if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 1)) {
-      MAPF_TRY(mapf_conv_tc_layer_pack(p->conv_w[l], cin, cout, 1, ws + T.convtc_bwd[l], sp));
-    } else {
-      const int cin_pad = int(r4(cin));
-      MAPF_REQUIRE(cin_pad == cin, MAPF_ERR_UNSUPPORTED);
-      mapf_launch_pdl(pack_conv_kernel, dim3((cin_pad * cout * 9 + 255) / 256), dim3(256), 0, sp, p->conv_w[l], cout, cin, 1, ws + T.convpk_bwd[l]);
-    }
-    m_convpk[l] = ord.mark(sp);
-  }
+  BwdPackMarks pk;
+  for (int l = 0; l < MAPF_MAX_CONV; ++l) pk.conv[l] = -1;
+  if (!prepared) MAPF_TRY(pack_backward_operands(p, a->message, a->flags, T, ws, sp, &ord, &pk));
+  const int m_gfpk = pk.gf, m_fcpk = pk.fc;
+  const int* m_convpk = pk.conv;
   const int m_sp_end = ord.mark(sp);
 
   // ---- actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0] ----
@@ -1583,8 +1612,8 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   // ---- conv stack ----
   const double count = double(B) * kFovCells;
   ord.wait(s, m_stat);
-  int m_dw_prev = -1;                 // weight-gradient kernel of the layer above: it reads the buffer this layer's
-                                      // data gradient is about to overwrite
+  int m_dw_prev = -1, m_dw_prev2 = -1; // weight-gradient kernels of the two layers above: the one two layers up reads the
+                                      // buffer this layer's data gradient is about to overwrite
   for (int l = L - 1; l >= 0; --l) {
     const int cin = p->channels[l], cout = p->channels[l + 1];
     double* st = stat + int64_t(l) * N * T.cmax * 2;
@@ -1638,7 +1667,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     }
     const int m_dw = ord.mark(sw);
     if (l > 0) {
-      ord.wait(s, m_dw_prev);
+      ord.wait(s, m_dw_prev2);
       ord.wait(s, m_convpk[l]);
       // data gradient = the same 3x3 convolution with mirrored, transposed filters
       if (conv_tc && mapf_conv_tc_layer_ok(cin, cout, 1)) {
@@ -1647,8 +1676,9 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       } else {
         MAPF_TRY(launch_conv_train(s, da, cout, cin, B, N, ws + T.convpk_bwd[l], nullptr, da_next, nullptr, 0));
       }
-      float* t = da; da = da_next; da_next = t;
+      float* t = da; da = da_next; da_next = da_spare; da_spare = t;
     }
+    m_dw_prev2 = m_dw_prev;
     m_dw_prev = m_dw;
   }
   ord.wait(s, m_dw_prev);             // join both lanes

@@ -58,7 +58,8 @@ def train_flags() -> int:
            (_lib.TRAIN_TC_BWD_ALWAYS if env.get("MAPF_B200_TRAIN_TC_BWD_ALWAYS") else 0) | \
            (_lib.TRAIN_FFMA_CONV if env.get("MAPF_B200_TRAIN_FFMA_CONV") else 0) | \
            (_lib.TRAIN_SINGLE_LANE if env.get("MAPF_B200_TRAIN_SINGLE_LANE") else 0) | \
-           (_lib.TRAIN_BN_PASS if env.get("MAPF_B200_TRAIN_BN_PASS") else 0)
+           (_lib.TRAIN_BN_PASS if env.get("MAPF_B200_TRAIN_BN_PASS") else 0) | \
+           (0 if env.get("MAPF_B200_TRAIN_SELF_CONTAINED") else _lib.TRAIN_PREPARED)   # forward prepares backward's operands
 
 
 def wants_encoder_workspace(p) -> bool:

@@ -264,7 +264,7 @@ def test_training_torch_ops_are_registered_and_differentiable():
 
 
 @pytest.mark.parametrize("mode", ["MAPF_B200_TRAIN_FFMA_BWD", "MAPF_B200_TRAIN_FFMA_CONV", "MAPF_B200_TRAIN_SINGLE_LANE",
-                                  "MAPF_B200_TRAIN_BN_PASS"])
+                                  "MAPF_B200_TRAIN_BN_PASS", "MAPF_B200_TRAIN_SELF_CONTAINED"])
 @pytest.mark.parametrize("name", ["gnn_msg_k3", "gnn_k3", "baseline"])
 def test_backward_gemm_paths_match_reference(train_step, name, mode, monkeypatch):
     """The development switches against the reference's recorded gradients: FFMA2 GEMMs instead of the tensor-core

@@ -39,5 +39,8 @@ if len(idx) >= 2:
 t0 = ev[0]["ts"]
 print(f"B = {B}: {len(ev)} device activities, span {ev[-1]['ts'] + ev[-1]['dur'] - t0:.1f} us, sum of durations {sum(e['dur'] for e in ev):.1f} us")
 for e in ev:
-    nm = e["name"].split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:60]
+    nm = e["name"].replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:60]
     print(f"{e['ts'] - t0:8.1f} +{e['dur']:6.1f}  s{e.get('args', {}).get('stream', '?'):<3} {nm}")
+if os.environ.get("TIMELINE_RAW"):
+    for e in ev[5:9]:
+        print(json.dumps(e)[:600])
