@@ -88,8 +88,8 @@ TrainLayout train_layout(const mapf_net_params& p, int B, int N, int message) {
   {
     int64_t maxp = 0;
     for (int l = 0; l < p.num_conv; ++l) maxp = max(maxp, int64_t(p.channels[l]) * p.channels[l + 1]);
-    const int64_t grid = mapf_min64((rows + 31) / 32, 2 * 148);
-    T.dwpart = take(grid * (maxp * 9 + cmax));
+    const int64_t grid = mapf_min64((rows + 7) / 8, 2 * 148);      // (kCwRowsSmall rows per partial at small batches)
+    T.dwpart = take(2 * grid * (maxp * 9 + cmax));     // two sets: consecutive layers' weight gradients run on two lanes
   }
   T.fcpk = take(p.fc_out <= 128 ? mapf_tc_b_floats(p.fc_out, p.fc_in) : 0);
   for (int l = 0; l < p.num_conv; ++l) {
@@ -591,18 +591,19 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ stats, int N, i
 // and the odd-row partial sum of a tap together: half the shared-memory wavefronts and half the FMA issue slots of the
 // scalar form.
 constexpr int kCwThreads = 256;
-constexpr int kCwRows = 32;
+constexpr int kCwRows = 32;       // rows per tile when the batch fills the SMs with such tiles
+constexpr int kCwRowsSmall = 8;   // ... and when it does not (a CTA walks its row pairs serially: 15 us per 32-row tile)
 
 template <int SLOTS>
 __global__ void __launch_bounds__(kCwThreads, SLOTS == 1 ? 2 : 1)
 conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ in, int cin, int cout, int64_t rows,
-                       float* __restrict__ part) {
+                       float* __restrict__ part, int tile_rows) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
   mapf_pdl_launch();
   extern __shared__ __align__(16) float s_cw[];
   const int in_len = cin * kFovCells, out_len = cout * kFovCells;
   float2* s_du = reinterpret_cast<float2*>(s_cw);                          // [16][out_len] (even row, odd row)
-  float2* s_in = reinterpret_cast<float2*>(s_cw) + (kCwRows / 2) * out_len;   // [16][in_len]
+  float2* s_in = reinterpret_cast<float2*>(s_cw) + (tile_rows / 2) * out_len;   // [tile_rows / 2][in_len]
   const int tid = threadIdx.x;
   const int npairs = cin * cout;
   const bool small = npairs < kCwThreads;
@@ -622,7 +623,7 @@ conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ i
     // (warp -> rows, lane -> elements: no index division in the loop)
     float* d1 = reinterpret_cast<float*>(dst);
     const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < kCwRows; r += kCwThreads / 32) {
+    for (int r = warp; r < tile_rows; r += kCwThreads / 32) {
       float* drow = d1 + int64_t(r >> 1) * len * 2 + (r & 1);
       const float* srow = src + (r0 + r) * len;
       if (r < nr) {
@@ -632,10 +633,10 @@ conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ i
       }
     }
   };
-  const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
+  const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = tile * kCwRows;
-    const int nr = (rows - r0) < kCwRows ? int(rows - r0) : kCwRows;
+    const int64_t r0 = tile * tile_rows;
+    const int nr = (rows - r0) < tile_rows ? int(rows - r0) : tile_rows;
     __syncthreads();
     stage(du, out_len, r0, nr, s_du);
     stage(in, in_len, r0, nr, s_in);
@@ -647,7 +648,7 @@ conv_bwd_weight_kernel(const float* __restrict__ du, const float* __restrict__ i
       const int pp = small ? tid % npairs : tid + s * kCwThreads;
       if (pp >= npairs || (small && s > 0)) break;
       const int co = pp / cin, ci = pp - co * cin;
-      for (int rp = rstart; rp < kCwRows / 2; rp += rstep) {
+      for (int rp = rstart; rp < tile_rows / 2; rp += rstep) {
         float2 d[kFovCells], v[kFovCells];
 #pragma unroll
         for (int p = 0; p < kFovCells; ++p) {
@@ -1523,6 +1524,7 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     if (needed) ok = ok && cudaMemsetAsync(rg[i].p, 0, sizeof(float) * size_t(end - rg[i].p), sw) == cudaSuccess;
     i = j + 1;
   }
+  ord.wait(sp, ord.mark(sw));      // (the pack lane also carries every other layer's weight gradient: behind the zeroing)
   double* stat = reinterpret_cast<double*>(ws + T.stat_bwd);
   const bool prepared = (a->flags & MAPF_TRAIN_PREPARED) != 0;     // packs and zeroed sums come from the forward call
   if (!prepared) ok = ok && cudaMemsetAsync(stat, 0, sizeof(double) * size_t(2) * L * N * T.cmax, sp) == cudaSuccess;
@@ -1553,7 +1555,6 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
   if (!prepared) MAPF_TRY(pack_backward_operands(p, a->message, a->flags, T, ws, sp, &ord, &pk));
   const int m_gfpk = pk.gf, m_fcpk = pk.fc;
   const int* m_convpk = pk.conv;
-  const int m_sp_end = ord.mark(sp);
 
   // ---- actionMLP: db = colsum(dl); dW[a][g] = sum_r dl[r][a] act[r][g]; d act = (dl Wa) * [act > 0] ----
   mapf_launch_pdl(colsum_kernel, dim3(int(mapf_min64((rows + 255) / 256, 296))), dim3(256), 0, sw, a->dlogits, rows, A, G.act_b);
@@ -1643,29 +1644,35 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
         mapf_launch_pdl(bn_bwd_apply_kernel, dim3(unsigned(mapf_min64((planes * kFovCells + 255) / 256, 148 * 16))), dim3(256), 0, s, 
             da, ws + T.scsh[l], ws + T.u[l], ws + T.meaninv[l], ws + T.coef[l], N, cout, planes);
     }
-    ord.wait(sw, ord.mark(s));        // du_l (in `da`) and the BatchNorm sums
-    mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, sw, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
+    // weight gradients of consecutive layers on alternating lanes: each starts when its du is final instead of behind the
+    // layer above (a batch of 128 fills 80 CTAs per layer)
+    cudaStream_t swl = ((L - 1 - l) & 1) ? sp : sw;
+    ord.wait(swl, ord.mark(s));       // du_l (in `da`) and the BatchNorm sums
+    mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, swl, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
-      const size_t smem = sizeof(float) * size_t(kCwRows) * (cin + cout) * kFovCells;
+      const int tile_rows = (rows + kCwRows - 1) / kCwRows >= 4 * 148 ? kCwRows : kCwRowsSmall;
+      const size_t smem = sizeof(float) * size_t(tile_rows) * (cin + cout) * kFovCells;
       MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
       MAPF_REQUIRE(cin * cout <= 4 * kCwThreads, MAPF_ERR_UNSUPPORTED);
-      const int64_t ntiles = (rows + kCwRows - 1) / kCwRows;
+      const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;
       const int gridw = int(mapf_min64(ntiles, 2 * 148));
       const float* lin = l == 0 ? a->states : ws + T.a[l - 1];
-      float* part = ws + T.dwpart;
+      int64_t maxp = 0;
+      for (int q = 0; q < L; ++q) maxp = max(maxp, int64_t(p->channels[q]) * p->channels[q + 1]);
+      float* part = ws + T.dwpart + (((L - 1 - l) & 1) ? mapf_min64((rows + 7) / 8, 2 * 148) * (maxp * 9 + T.cmax) : 0);
       if (cin * cout <= kCwThreads) {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<1>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        mapf_launch_pdl(conv_bwd_weight_kernel<1>, dim3(gridw), dim3(kCwThreads), smem, sw, da, lin, cin, cout, rows, part);
+        mapf_launch_pdl(conv_bwd_weight_kernel<1>, dim3(gridw), dim3(kCwThreads), smem, swl, da, lin, cin, cout, rows, part, tile_rows);
       } else {
         if ([&]() { static int cache__[16] = {0}; return !mapf_ensure_smem(conv_bwd_weight_kernel<4>, size_t(smem), cache__); }())
           return MAPF_ERR_CUDA;
-        mapf_launch_pdl(conv_bwd_weight_kernel<4>, dim3(gridw), dim3(kCwThreads), smem, sw, da, lin, cin, cout, rows, part);
+        mapf_launch_pdl(conv_bwd_weight_kernel<4>, dim3(gridw), dim3(kCwThreads), smem, swl, da, lin, cin, cout, rows, part, tile_rows);
       }
       const int nw = cin * cout * 9;
-      mapf_launch_pdl(conv_bwd_weight_reduce_kernel, dim3((nw + cout + 31) / 32), dim3(256), 0, sw, part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
+      mapf_launch_pdl(conv_bwd_weight_reduce_kernel, dim3((nw + cout + 31) / 32), dim3(256), 0, swl, part, gridw, nw, cout, G.conv_w[l], G.conv_b[l]);
     }
-    const int m_dw = ord.mark(sw);
+    const int m_dw = ord.mark(swl);
     if (l > 0) {
       ord.wait(s, m_dw_prev2);
       ord.wait(s, m_convpk[l]);
@@ -1681,8 +1688,8 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     m_dw_prev2 = m_dw_prev;
     m_dw_prev = m_dw;
   }
-  ord.wait(s, m_dw_prev);             // join both lanes
-  ord.wait(s, m_sp_end);
+  ord.wait(s, ord.mark(sw));          // join both lanes
+  ord.wait(s, ord.mark(sp));
   MAPF_REQUIRE(ord.ok, MAPF_ERR_CUDA);
   return mapf_launch_status();
 }
