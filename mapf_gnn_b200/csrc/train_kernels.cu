@@ -475,9 +475,21 @@ __global__ void bn_bwd_apply4_kernel(float4* __restrict__ da, const float* __res
 // bn_bwd_coef + bn_bwd_apply4 in one launch for small tables (N*C <= kBnFusedMax): the coefficients go to shared memory
 __global__ void __launch_bounds__(256) bn_bwd_coef_apply4_kernel(
     float4* __restrict__ da, const float* __restrict__ scale_shift, const float4* __restrict__ u, const float* __restrict__ meaninv,
-    const double* __restrict__ stats, const float* __restrict__ gamma, int N, int C, int stat_c, double count, int64_t rows) {
+    const double* __restrict__ stats, const float* __restrict__ gamma, int N, int C, int stat_c, double count, int64_t rows,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
   mapf_pdl_wait();   // programmatic dependent launch: this grid may be resident before its predecessor completes
   mapf_pdl_launch();
+  if (blockIdx.x == 0 && threadIdx.x < C) {
+    // BatchNorm parameter gradients (bn_param_grads_kernel's arithmetic): d gamma = sum dy * xhat, d beta = sum dy over all slots
+    const int c = threadIdx.x;
+    double g = 0.0, b = 0.0;
+    for (int n = 0; n < N; ++n) {
+      b += mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2);
+      g += mapf_ld_dep(stats + (int64_t(n) * stat_c + c) * 2 + 1);
+    }
+    dgamma[c] = float(g);
+    dbeta[c] = float(b);
+  }
   __shared__ float4 s_k[kBnFusedMax];
   __shared__ float2 s_mi[kBnFusedMax], s_ss[kBnFusedMax];
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
@@ -1510,8 +1522,13 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     MAPF_REQUIRE(G.conv_w[l] && G.conv_b[l] && G.bn_gamma[l] && G.bn_beta[l], MAPF_ERR_NULL);
     want(G.conv_w[l], int64_t(p->channels[l]) * p->channels[l + 1] * 9, true);
     want(G.conv_b[l], p->channels[l + 1], true);
-    want(G.bn_gamma[l], p->channels[l + 1], false);
-    want(G.bn_beta[l], p->channels[l + 1], false);
+    // (written by bn_param_grads_kernel later on this lane: swept along where they bridge two ranges -- but not where the
+    // chain's own bn_bwd_coef_apply4_kernel writes them, which is not ordered behind this lane's memsets)
+    const bool on_chain = (p->channels[l + 1] * kFovCells) % 4 == 0 && N * p->channels[l + 1] <= kBnFusedMax && p->channels[l + 1] <= 256;
+    if (!on_chain) {
+      want(G.bn_gamma[l], p->channels[l + 1], false);
+      want(G.bn_beta[l], p->channels[l + 1], false);
+    }
   }
   for (int i = 1; i < nrg; ++i)          // insertion sort by address (at most 18 entries)
     for (int j = i; j > 0 && rg[j].p < rg[j - 1].p; --j) { const Range t = rg[j]; rg[j] = rg[j - 1]; rg[j - 1] = t; }
@@ -1629,10 +1646,12 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     else
       mapf_launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, da, ws + T.scsh[l], ws + T.u[l], ws + T.meaninv[l], B, N, cout, T.cmax, st);
     const int64_t planes = rows * cout;
+    bool bn_grads_done = false;
     if ((cout * kFovCells) % 4 == 0 && N * cout <= kBnFusedMax) {
       mapf_launch_pdl(bn_bwd_coef_apply4_kernel, dim3(unsigned(mapf_min64((planes * kFovCells / 4 + 255) / 256, 148 * 16))), dim3(256), 0, s,
           reinterpret_cast<float4*>(da), ws + T.scsh[l], reinterpret_cast<const float4*>(ws + T.u[l]),
-          ws + T.meaninv[l], st, p->bn_gamma[l], N, cout, T.cmax, count, rows);
+          ws + T.meaninv[l], st, p->bn_gamma[l], N, cout, T.cmax, count, rows, G.bn_gamma[l], G.bn_beta[l]);
+      bn_grads_done = true;
     } else {
       mapf_launch_pdl(bn_bwd_coef_kernel, dim3((N * cout + 127) / 128), dim3(128), 0, s, st, ws + T.meaninv[l], p->bn_gamma[l], N, cout, T.cmax, count,
                                                                ws + T.coef[l]);
@@ -1648,7 +1667,8 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
     // layer above (a batch of 128 fills 80 CTAs per layer)
     cudaStream_t swl = ((L - 1 - l) & 1) ? sp : sw;
     ord.wait(swl, ord.mark(s));       // du_l (in `da`) and the BatchNorm sums
-    mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, swl, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
+    if (!bn_grads_done)
+      mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, swl, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
       const int tile_rows = (rows + kCwRows - 1) / kCwRows >= 4 * 148 ? kCwRows : kCwRowsSmall;
       const size_t smem = sizeof(float) * size_t(tile_rows) * (cin + cout) * kFovCells;
