@@ -168,9 +168,12 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
   __shared__ unsigned long long s_ts[16], s_tw[8][4];
 #define TCG_WSTAMP(i) do { if (lane == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); s_tw[warp][i] = t__; } } while (0)
 #define TCG_STAMP(i) do { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); s_ts[i] = t__; } while (0)
+#define TCG_NOW(v) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v))
+  unsigned long long tq0 = 0, tq1 = 0, tq2 = 0, acc_a = 0, acc_b = 0, acc_c = 0;
   if (tid == 0) TCG_STAMP(0);
 #else
 #define TCG_STAMP(i) do {} while (0)
+#define TCG_NOW(v) do {} while (0)
 #define TCG_WSTAMP(i) do {} while (0)
 #endif
   const int m0 = blockIdx.x * kTcM, n0 = blockIdx.y * NT * NTL;
@@ -243,7 +246,9 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     uint32_t ph = 0;
     for (int c = warp; c < nchunks; c += NP, ph ^= 1) {
       load_chunk(c + NP, vn);   // next chunk's loads overlap this chunk's wait / convert / store
+      TCG_NOW(tq0);
       tc::mbar_wait(&s_empty[s], ph ^ 1);
+      TCG_NOW(tq1);
       if (lane == 0) {
         tc::mbar_expect_tx(&s_full[s], uint32_t(my_tiles) * 2 * kBBytes);
         for (int t = 0; t < my_tiles; ++t)
@@ -263,8 +268,20 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       tc::fence_proxy_async();
       tc::mbar_arrive(&s_full[s]);
       if (tid == 0 && c == 0) TCG_STAMP(2);
+      TCG_NOW(tq2);
 #pragma unroll
       for (int it = 0; it < kPerLane; ++it) v[it] = vn[it];
+#ifdef MAPF_TCG_STAMP
+      {
+        float sink = 0.f;
+#pragma unroll
+        for (int it = 0; it < kPerLane; ++it) sink += v[it].x;
+        if (sink == 123.456f) s_ts[15] = 1;      // (forces the loads to have landed before the next stamp)
+        unsigned long long t3; TCG_NOW(t3);
+        acc_a += tq1 - tq0; acc_b += tq2 - tq1; acc_c += t3 - tq2;
+        if (tid == 0) { s_ts[10] = acc_a; s_ts[11] = acc_b; s_ts[12] = acc_c; }
+      }
+#endif
     }
   } else if (warp_u < NP + NACC) {
     // ===== MMA issuers (NACC warps behind the producers: chunks c = w, w + NACC, ... into accumulator w) =====
@@ -284,8 +301,10 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
       uint32_t ph = 0;
       const uint32_t accsel = which;
       for (int c = which; c < nchunks; c += NACC) {
+        TCG_NOW(tq0);
         tc::mbar_wait(&s_full[s], ph);
         tc::fence_after_sync();
+        TCG_NOW(tq1);
         if (c == 0) TCG_STAMP(3);
         const uint64_t soff = uint64_t(uint32_t(s) * (kStageBytes >> 4));
         const bool first = c < NACC;   // first touch of this accumulator overwrites
@@ -304,11 +323,18 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
           }
         }
         tc::mma_commit(&s_empty[s]);
+#ifdef MAPF_TCG_STAMP
+        TCG_NOW(tq2);
+        acc_a += tq1 - tq0; acc_b += tq2 - tq1;
+#endif
         s += NACC;
         if (s >= NSTAGE) { s -= NSTAGE; ph ^= 1; }
       }
       tc::mma_commit(&s_done);
       if (which == 0) TCG_STAMP(4);
+#ifdef MAPF_TCG_STAMP
+      if (which == 0) { s_ts[8] = acc_a; s_ts[9] = acc_b; }
+#endif
     }
     __syncwarp();   // lanes 1-31 park here instead of spinning on s_done next to the issuing lane
   }
@@ -415,6 +441,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(TcGemmArgs g) {
     TCG_STAMP(6);
     printf("tcg<%d,%d,%d> K=%d: setup %llu first-full %llu first-mma-wake %llu last-commit %llu done-wake %llu end %llu ns\n", NT, NP, NTL, g.K,
            s_ts[1] - s_ts[0], s_ts[2] - s_ts[0], s_ts[3] - s_ts[0], s_ts[4] - s_ts[0], s_ts[5] - s_ts[0], s_ts[6] - s_ts[0]);
+    printf("   K=%d issuer 0: waiting %llu issuing %llu ns | producer 0: empty-wait %llu convert+store %llu load-wait %llu ns\n", g.K,
+           s_ts[8], s_ts[9], s_ts[10], s_ts[11], s_ts[12]);
     if (EPI == EPI_STORE)
       for (int w = 0; w < 8; ++w)
         printf("   K=%d warp %d: wake %llu ld %llu sts %llu stores %llu\n", g.K, w, s_tw[w][0] - s_ts[0], s_tw[w][1] - s_ts[0], s_tw[w][2] - s_ts[0], s_tw[w][3] - s_ts[0]);
