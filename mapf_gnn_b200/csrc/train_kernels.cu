@@ -1013,8 +1013,8 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(mapf_ce_loss_args a) {
   }
 }
 
-// Both reductions below in ONE block where the input is small (every shipped configuration: 64 k parameters, up to 8 192
-// rows): the result is stored, not accumulated -- no memset node in front of the kernel on the step's dependent chain
+// Both reductions below in ONE block where the input is small (64 k parameters; up to 2 048 rows): the result is stored,
+// not accumulated -- no memset node in front of the kernel on the step's dependent chain
 // (~4 us each at batch 128) and a fixed summation order.
 constexpr int kOneBlockThreads = 1024;
 __global__ void __launch_bounds__(kOneBlockThreads) ce_loss_one_block_kernel(mapf_ce_loss_args a) {
@@ -1719,7 +1719,7 @@ extern "C" int mapf_ce_loss(const mapf_ce_loss_args* a, mapf_stream_t stream) {
   MAPF_REQUIRE(a->rows > 0 && a->num_actions > 0, MAPF_ERR_SHAPE);
   MAPF_REQUIRE(a->num_actions <= kMaxActions, MAPF_ERR_UNSUPPORTED);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->rows <= 8 * kOneBlockThreads) {
+  if (a->rows <= 2 * kOneBlockThreads) {      // (one block walks 5 120 rows in 9.6 us, three memset-ed blocks' worth in 4)
     mapf_launch_pdl(ce_loss_one_block_kernel, dim3(1), dim3(kOneBlockThreads), 0, s, *a);
     return mapf_launch_status();
   }
