@@ -281,9 +281,12 @@ def test_backward_gemm_paths_match_reference(train_step, name, mode, monkeypatch
         assert rel_err(p.grad.cpu().numpy(), t[f"{name}/grad/{k}"], floor) < REL, k
 
 
-def test_large_batch_gradients_match_oracle():
-    """A batch that fills the machine (5120 rows, several CTAs per kernel): gradients vs the torch-CPU oracle."""
-    name, B, N = "gnn_msg_k3", 1024, 5
+@pytest.mark.parametrize("B", [1024, 3900])
+def test_large_batch_gradients_match_oracle(B):
+    """Batches that fill the machine -- 5120 rows (several CTAs per kernel, 8-row weight-gradient tiles) and 19 500 rows
+    (persistent loops, 32-row weight-gradient tiles, the single-block reductions' multi-block forms): gradients vs the
+    torch-CPU oracle."""
+    name, N = "gnn_msg_k3", 5
     rng = np.random.default_rng(12)
     states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
     adj = torch.tensor((rng.random((B, N, N)) < 0.3).astype(np.float32))
@@ -297,8 +300,16 @@ def test_large_batch_gradients_match_oracle():
     loss = torch.nn.functional.cross_entropy(net(states.cuda(), gso.cuda()).reshape(-1, 5), targets.cuda().reshape(-1))
     loss.backward()
     assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    # Tolerance: 1e-4 (the north star's figure) at 5120 rows.  At 19 500 rows 1e-3: with 30 M pre-activations a handful lie
+    # within fp32 rounding of zero, where the ReLU subgradient of two fp32 implementations differs, and ONE such element
+    # moves a gradient tensor by 1 - 4e-4 of its largest entry (here: one unit of the graph filter's output, 4.1e-4 on
+    # GFL.0.W2 and ~1e-4 on everything below it, 3e-6 above it).  The reference's own fp32 arithmetic is no closer to
+    # float64 than that (tools/grad_accuracy.py, profiles/r02_grad_accuracy.txt: torch fp32 against torch fp64 4.7e-4 at
+    # B = 1024, 3.5e-4 at B = 2048, 1.3e-4 at B = 4096 where this package is at 3e-6).  A real defect of the large-batch
+    # paths (32-row weight-gradient tiles, multi-block reductions, persistent loops) is orders of magnitude larger.
+    tol = REL if B <= 1024 else 1e-3
     for k, p in net.named_parameters():
-        assert rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy(), GRAD_FLOOR * total) < REL, k
+        assert rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy(), GRAD_FLOOR * total) < tol, k
 
 
 def test_lanes_are_ordered_under_load():
