@@ -9,6 +9,8 @@
 // one fp32 atomicAdd per CTA and output element.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -1671,7 +1673,8 @@ extern "C" int mapf_train_backward(const mapf_net_params* p, const mapf_train_bw
       mapf_launch_pdl(bn_param_grads_kernel, dim3((cout + 63) / 64), dim3(64), 0, swl, st, N, cout, T.cmax, G.bn_gamma[l], G.bn_beta[l]);
     {
       const int tile_rows = (rows + kCwRows - 1) / kCwRows >= 4 * 148 ? kCwRows : kCwRowsSmall;
-      const size_t smem = sizeof(float) * size_t(tile_rows) * (cin + cout) * kFovCells;
+      // (at least the [rstep][npairs][10] reduction scratch of the kernel's small-layer path: <= 256 x 10 floats)
+      const size_t smem = std::max(sizeof(float) * size_t(tile_rows) * (cin + cout) * kFovCells, sizeof(float) * size_t(kCwThreads) * 10);
       MAPF_REQUIRE(smem <= 220 * 1024, MAPF_ERR_UNSUPPORTED);
       MAPF_REQUIRE(cin * cout <= 4 * kCwThreads, MAPF_ERR_UNSUPPORTED);
       const int64_t ntiles = (rows + tile_rows - 1) / tile_rows;

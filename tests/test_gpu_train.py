@@ -281,6 +281,33 @@ def test_backward_gemm_paths_match_reference(train_step, name, mode, monkeypatch
         assert rel_err(p.grad.cpu().numpy(), t[f"{name}/grad/{k}"], floor) < REL, k
 
 
+def test_narrow_conv_layers_train_like_the_oracle():
+    """A general config with narrow conv layers (2 -> 4 -> 8 -> 16): few (co, ci) pairs per layer, so the weight-gradient
+    kernel's small-layer path (several row groups per pair, reduction scratch in the staging area) runs at both tile
+    sizes, and none of the layers fits the tensor-core conv kernel."""
+    import mapf_gnn_b200 as m
+    from helpers import model_config
+    for B, N in ((33, 5), (4000, 5)):
+        cfg = dict(model_config("gnn_msg_k3", N), channels=[4, 8, 16])
+        torch.manual_seed(B)
+        net = m.build_network(cfg).cuda().train()
+        rng = np.random.default_rng(B)
+        states = torch.tensor(rng.integers(0, 4, size=(B, N, 2, 5, 5))).float()
+        adj = torch.tensor((rng.random((B, N, N)) < 0.3).astype(np.float32))
+        adj[:, torch.arange(N), torch.arange(N)] = 0
+        gso = adj + torch.eye(N)
+        targets = torch.tensor(rng.integers(0, 5, size=(B, N)))
+        params = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+        loss_ref, grads_ref, _ = mo.loss_and_grads(params, states, gso, targets)
+        total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads_ref.values())))
+        loss = torch.nn.functional.cross_entropy(net(states.cuda(), gso.cuda()).reshape(-1, 5), targets.cuda().reshape(-1))
+        loss.backward()
+        assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+        tol = REL if B <= 1024 else 1e-3        # (see test_large_batch_gradients_match_oracle)
+        for k, p in net.named_parameters():
+            assert rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy(), GRAD_FLOOR * total) < tol, (B, k)
+
+
 @pytest.mark.parametrize("B", [1024, 3900])
 def test_large_batch_gradients_match_oracle(B):
     """Batches that fill the machine -- 5120 rows (several CTAs per kernel, 8-row weight-gradient tiles) and 19 500 rows
